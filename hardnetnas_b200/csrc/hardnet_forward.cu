@@ -1,0 +1,338 @@
+// HardNet.forward (hardnet/HardNet.py:312-315) behind the C ABI: weight packing (BatchNorm fold),
+// static TMA descriptors over handle-owned activation scratch, and the per-chunk launch sequence
+//   L1 (CUDA cores, input_norm fused) -> L2..L6 (tcgen05 implicit GEMM) -> head GEMM + L2Norm.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "host_common.h"
+#include "l1_norm_conv.cuh"
+#include "tc_conv.cuh"
+
+namespace hn {
+
+struct ConvLayer {
+  int cin, cout, stride, hin, hout;
+};
+// features[3], [6], [9], [12], [15] of hardnet/HardNet.py:284-298
+static const ConvLayer kConv[5] = {
+    {32, 32, 1, 32, 32}, {32, 64, 2, 32, 16}, {64, 64, 1, 16, 16}, {64, 128, 2, 16, 8}, {128, 128, 1, 8, 8}};
+
+constexpr int kHeadK = 8 * 8 * 128;
+
+}  // namespace hn
+
+struct hn_handle {
+  int chunk = 0;            // patches per conv-stack pass
+  long long head_rows = 0;  // capacity of the L6 output buffer (patches)
+  int sm_count = 0;
+  bool packed = false;
+  int act_bf16 = 0;
+  uint16_t* act[2] = {nullptr, nullptr};  // ping-pong activations, chunk * 32*32*32 elements each
+  uint16_t* l6 = nullptr;                 // [head_rows, 8, 8, 128]
+  uint16_t* wconv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [cout][9*cin]
+  uint16_t* whead = nullptr;                                           // [128][8192]
+  float* w1 = nullptr;                                                 // [9][32]
+  float* bias = nullptr;                                               // 7 x 128
+  hn::TcParams conv_params[5];
+  hn::TcParams head_params;
+};
+
+namespace hn {
+
+template <int N, int KCB, int STAGES, int LOAD, int EPI>
+static int launch_tc(const TcParams& p, int sm_count, cudaStream_t stream) {
+  auto kern = tc_kernel<N, KCB, STAGES, LOAD, EPI>;
+  constexpr size_t smem = tc_smem_bytes<N, KCB, STAGES>();
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done = true;
+  }
+  if (p.num_tiles <= 0) return HN_OK;
+  const int grid = std::min(p.num_tiles, sm_count);
+  kern<<<grid, kTcThreads, smem, stream>>>(p);
+  HN_CUDA(cudaGetLastError());
+  return HN_OK;
+}
+
+static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) {
+  switch (li) {
+    case 0: return launch_tc<32, 64, 8, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
+    case 1: return launch_tc<64, 64, 8, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
+    case 2: return launch_tc<64, 128, 6, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
+    case 3: return launch_tc<128, 128, 5, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
+    case 4: return launch_tc<128, 128, 5, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
+  }
+  return HN_ERR_INVALID;
+}
+
+static uint16_t to16(float v, int bf16) {
+  if (bf16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __half h = __float2half_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+// Static descriptors over the handle's buffers; only the tile counts change per call.
+static int build_params(hn_handle* h) {
+  for (int li = 0; li < 5; ++li) {
+    const ConvLayer& L = kConv[li];
+    TcParams& p = h->conv_params[li];
+    memset(&p, 0, sizeof(p));
+    const int kcb = (L.cin >= 64) ? 128 : 64;  // bytes of one pixel's channel chunk
+    const int kc = kcb / 2;
+    const uint16_t* in = h->act[li & 1];  // L1 wrote act[0]; layers alternate
+    const int pix_out = L.hout * L.hout;
+    p.stride = L.stride;
+    p.cin_chunks = L.cin / kc;
+    p.num_k_stages = 9 * p.cin_chunks;
+    if (pix_out >= kTileM) {
+      p.tiles_per_patch = pix_out / kTileM;
+      p.rows_per_tile = kTileM / L.hout;
+      p.patches_per_tile = 1;
+    } else {
+      p.tiles_per_patch = 0;
+      p.rows_per_tile = L.hout;
+      p.patches_per_tile = kTileM / pix_out;
+    }
+    const uint32_t box[4] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(L.hout),
+                             static_cast<uint32_t>(p.rows_per_tile), static_cast<uint32_t>(p.patches_per_tile)};
+    const uint64_t C = L.cin, W = L.hin, H = L.hin;
+    if (L.stride == 1) {
+      const uint64_t dims[4] = {C, W, H, static_cast<uint64_t>(h->chunk)};
+      const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+      HN_TRY(make_tmap_16bit(&p.tmA[0], in, 4, dims, str, box, kcb));
+    } else {
+      for (int ypar = 0; ypar < 2; ++ypar)
+        for (int xpar = 0; xpar < 2; ++xpar) {
+          const uint64_t dims[4] = {C, W / 2, H / 2, static_cast<uint64_t>(h->chunk)};
+          const uint64_t str[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
+          const uint16_t* base = in + (ypar * W + xpar) * C;
+          HN_TRY(make_tmap_16bit(&p.tmA[ypar * 2 + xpar], base, 4, dims, str, box, kcb));
+        }
+    }
+    {
+      const uint64_t K = 9ull * L.cin;
+      const uint64_t dims[2] = {K, static_cast<uint64_t>(L.cout)};
+      const uint64_t str[1] = {K * 2};
+      const uint32_t wbox[2] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(L.cout)};
+      HN_TRY(make_tmap_16bit(&p.tmB, h->wconv[li], 2, dims, str, wbox, kcb));
+    }
+    p.bias = h->bias + 128 * (li + 1);
+  }
+  {
+    TcParams& p = h->head_params;
+    memset(&p, 0, sizeof(p));
+    const uint64_t dimsA[2] = {kHeadK, static_cast<uint64_t>(h->head_rows)};
+    const uint64_t strA[1] = {kHeadK * 2ull};
+    const uint32_t boxA[2] = {64, kTileM};
+    HN_TRY(make_tmap_16bit(&p.tmA[0], h->l6, 2, dimsA, strA, boxA, 128));
+    const uint64_t dimsB[2] = {kHeadK, 128};
+    const uint32_t boxB[2] = {64, 128};
+    HN_TRY(make_tmap_16bit(&p.tmB, h->whead, 2, dimsB, strA, boxB, 128));
+    p.num_k_stages = kHeadK / 64;
+    p.bias = h->bias + 128 * 6;
+    p.l2_eps = 1e-10f;
+  }
+  return HN_OK;
+}
+
+// Runs L1..L6 for `n` patches (n <= chunk); L6 lands in l6 + l6_row * 8192.
+static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n, long long l6_row, int last_layer,
+                          cudaStream_t s) {
+  const int grid1 = std::min(n, h->sm_count * 4);
+  if (in_dtype == HN_F32) {
+    l1_norm_conv_kernel<float><<<grid1, kL1Threads, 0, s>>>(static_cast<const float*>(patches), h->act[0], h->w1,
+                                                           h->bias, n, h->act_bf16, 1);
+  } else {
+    l1_norm_conv_kernel<uint8_t><<<grid1, kL1Threads, 0, s>>>(static_cast<const uint8_t*>(patches), h->act[0], h->w1,
+                                                             h->bias, n, h->act_bf16, 1);
+  }
+  HN_CUDA(cudaGetLastError());
+  for (int li = 0; li < 5 && li + 2 <= last_layer; ++li) {
+    const ConvLayer& L = kConv[li];
+    TcParams p = h->conv_params[li];
+    const long long pix_out = static_cast<long long>(L.hout) * L.hout;
+    p.total_rows = pix_out * n;
+    p.num_tiles = static_cast<int>((p.total_rows + kTileM - 1) / kTileM);
+    p.act_bf16 = h->act_bf16;
+    p.out = (li == 4) ? static_cast<void*>(h->l6 + l6_row * kHeadK) : static_cast<void*>(h->act[(li + 1) & 1]);
+    HN_TRY(launch_conv(li, p, h->sm_count, s));
+  }
+  return HN_OK;
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows) {
+  HN_REQUIRE(out != nullptr, "hn_create: out is NULL");
+  *out = nullptr;
+  int dev = 0, major = 0;
+  HN_CUDA(cudaGetDevice(&dev));
+  HN_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("hn_create: device compute capability %d.x is not sm_100 (no fallback path exists)", major);
+    return HN_ERR_UNSUPPORTED;
+  }
+  hn_handle* h = new hn_handle();
+  int st = device_sm_count(&h->sm_count);
+  if (st != HN_OK) { delete h; return st; }
+  if (chunk_patches <= 0) chunk_patches = h->sm_count * 4;
+  chunk_patches = (chunk_patches + 1) & ~1;
+  if (head_rows <= 0) head_rows = static_cast<long long>(h->sm_count) * kTileM;
+  head_rows = std::max<long long>(head_rows, chunk_patches);
+  head_rows = (head_rows + chunk_patches - 1) / chunk_patches * chunk_patches;
+  h->chunk = chunk_patches;
+  h->head_rows = head_rows;
+  const size_t act_elems = static_cast<size_t>(chunk_patches) * 32 * 32 * 32;
+  auto fail = [&](int code) { hn_destroy(h); return code; };
+#define HN_CUDA_H(expr)                                                                                     \
+  do {                                                                                                      \
+    cudaError_t e__ = (expr);                                                                               \
+    if (e__ != cudaSuccess) {                                                                               \
+      set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));                      \
+      return fail(HN_ERR_CUDA);                                                                             \
+    }                                                                                                       \
+  } while (0)
+  HN_CUDA_H(cudaMalloc(&h->act[0], act_elems * 2));
+  HN_CUDA_H(cudaMalloc(&h->act[1], act_elems * 2));
+  HN_CUDA_H(cudaMalloc(&h->l6, static_cast<size_t>(head_rows) * kHeadK * 2));
+  // zero once so that never-written tail rows read as finite values
+  HN_CUDA_H(cudaMemset(h->act[0], 0, act_elems * 2));
+  HN_CUDA_H(cudaMemset(h->act[1], 0, act_elems * 2));
+  HN_CUDA_H(cudaMemset(h->l6, 0, static_cast<size_t>(head_rows) * kHeadK * 2));
+  for (int li = 0; li < 5; ++li)
+    HN_CUDA_H(cudaMalloc(&h->wconv[li], static_cast<size_t>(kConv[li].cout) * 9 * kConv[li].cin * 2));
+  HN_CUDA_H(cudaMalloc(&h->whead, static_cast<size_t>(128) * kHeadK * 2));
+  HN_CUDA_H(cudaMalloc(&h->w1, 9 * 32 * sizeof(float)));
+  HN_CUDA_H(cudaMalloc(&h->bias, 7 * 128 * sizeof(float)));
+#undef HN_CUDA_H
+  st = build_params(h);
+  if (st != HN_OK) return fail(st);
+  *out = h;
+  return HN_OK;
+}
+
+extern "C" int hn_destroy(hn_handle* h) {
+  if (!h) return HN_OK;
+  cudaFree(h->act[0]);
+  cudaFree(h->act[1]);
+  cudaFree(h->l6);
+  for (int li = 0; li < 5; ++li) cudaFree(h->wconv[li]);
+  cudaFree(h->whead);
+  cudaFree(h->w1);
+  cudaFree(h->bias);
+  delete h;
+  return HN_OK;
+}
+
+extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const float* const bn_mean[7],
+                               const float* const bn_var[7], float bn_eps, int act_dtype) {
+  HN_REQUIRE(h && w && bn_mean && bn_var, "hn_pack_hardnet: NULL argument");
+  HN_REQUIRE(act_dtype == HN_F16 || act_dtype == HN_BF16, "hn_pack_hardnet: act_dtype must be HN_F16 or HN_BF16");
+  for (int i = 0; i < 7; ++i) HN_REQUIRE(w[i] && bn_mean[i] && bn_var[i], "hn_pack_hardnet: NULL tensor %d", i);
+  const int bf = act_dtype == HN_BF16;
+  static const int cout[7] = {32, 32, 64, 64, 128, 128, 128};
+  std::vector<float> bias(7 * 128, 0.f);
+  std::vector<float> scale(128);
+  // stage 1: [co][1][3][3] -> [tap][co] fp32
+  {
+    std::vector<float> w1(9 * 32);
+    for (int co = 0; co < 32; ++co) {
+      const float s = 1.0f / std::sqrt(bn_var[0][co] + bn_eps);
+      bias[co] = -bn_mean[0][co] * s;
+      for (int tap = 0; tap < 9; ++tap) w1[tap * 32 + co] = w[0][co * 9 + tap] * s;
+    }
+    HN_CUDA(cudaMemcpy(h->w1, w1.data(), w1.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // 3x3 stages: OIHW -> [co][(ky*3+kx)*cin + ci], BN scale folded, 16-bit
+  for (int li = 0; li < 5; ++li) {
+    const ConvLayer& L = kConv[li];
+    const int K = 9 * L.cin;
+    std::vector<uint16_t> wp(static_cast<size_t>(L.cout) * K);
+    for (int co = 0; co < L.cout; ++co) {
+      const float s = 1.0f / std::sqrt(bn_var[li + 1][co] + bn_eps);
+      bias[128 * (li + 1) + co] = -bn_mean[li + 1][co] * s;
+      for (int ci = 0; ci < L.cin; ++ci)
+        for (int tap = 0; tap < 9; ++tap)
+          wp[static_cast<size_t>(co) * K + tap * L.cin + ci] = to16(w[li + 1][(static_cast<size_t>(co) * L.cin + ci) * 9 + tap] * s, bf);
+    }
+    HN_CUDA(cudaMemcpy(h->wconv[li], wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  }
+  // head: [co][ci][8][8] -> [co][(y*8+x)*128 + ci]
+  {
+    std::vector<uint16_t> wp(static_cast<size_t>(128) * kHeadK);
+    for (int co = 0; co < 128; ++co) {
+      const float s = 1.0f / std::sqrt(bn_var[6][co] + bn_eps);
+      bias[128 * 6 + co] = -bn_mean[6][co] * s;
+      for (int ci = 0; ci < 128; ++ci)
+        for (int yx = 0; yx < 64; ++yx)
+          wp[static_cast<size_t>(co) * kHeadK + yx * 128 + ci] = to16(w[6][(static_cast<size_t>(co) * 128 + ci) * 64 + yx] * s, bf);
+    }
+    HN_CUDA(cudaMemcpy(h->whead, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+  }
+  (void)cout;
+  HN_CUDA(cudaMemcpy(h->bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->act_bf16 = bf;
+  h->packed = true;
+  return HN_OK;
+}
+
+extern "C" int hn_forward(hn_handle* h, const void* patches, int in_dtype, long long B, void* desc_out, int out_dtype,
+                          void* stream) {
+  HN_REQUIRE(h, "hn_forward: NULL handle");
+  if (!h->packed) {
+    set_error("hn_forward: weights not packed (call hn_pack_hardnet first)");
+    return HN_ERR_STATE;
+  }
+  HN_REQUIRE(B >= 0, "hn_forward: negative batch");
+  HN_REQUIRE(in_dtype == HN_F32 || in_dtype == HN_U8, "hn_forward: in_dtype must be HN_F32 or HN_U8");
+  HN_REQUIRE(out_dtype == HN_F32 || out_dtype == HN_F16 || out_dtype == HN_BF16, "hn_forward: bad out_dtype");
+  if (B == 0) return HN_OK;
+  HN_REQUIRE(patches && desc_out, "hn_forward: NULL data pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
+  const size_t out_elem = out_dtype == HN_F32 ? 4 : 2;
+  for (long long base = 0; base < B; base += h->head_rows) {
+    const long long nb = std::min<long long>(h->head_rows, B - base);
+    for (long long off = 0; off < nb; off += h->chunk) {
+      const int n = static_cast<int>(std::min<long long>(h->chunk, nb - off));
+      const char* src = static_cast<const char*>(patches) + static_cast<size_t>(base + off) * 1024 * in_elem;
+      HN_TRY(run_conv_stack(h, src, in_dtype, n, off, 6, s));
+    }
+    TcParams p = h->head_params;
+    p.total_rows = nb;
+    p.num_tiles = static_cast<int>((nb + kTileM - 1) / kTileM);
+    p.act_bf16 = h->act_bf16;
+    p.out_dtype = out_dtype;
+    p.out = static_cast<char*>(desc_out) + static_cast<size_t>(base) * 128 * out_elem;
+    HN_TRY((launch_tc<128, 128, 5, LOAD_GEMM, EPI_BIAS_L2NORM>(p, h->sm_count, s)));
+  }
+  return HN_OK;
+}
+
+extern "C" int hn_forward_dump(hn_handle* h, const void* patches, int in_dtype, long long B, int layer, void* act_out,
+                               void* stream) {
+  HN_REQUIRE(h && patches && act_out, "hn_forward_dump: NULL argument");
+  if (!h->packed) {
+    set_error("hn_forward_dump: weights not packed");
+    return HN_ERR_STATE;
+  }
+  HN_REQUIRE(layer >= 1 && layer <= 6, "hn_forward_dump: layer must be 1..6");
+  HN_REQUIRE(B >= 1 && B <= h->chunk, "hn_forward_dump: B must be in [1, chunk=%d]", h->chunk);
+  HN_REQUIRE(in_dtype == HN_F32 || in_dtype == HN_U8, "hn_forward_dump: bad in_dtype");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HN_TRY(run_conv_stack(h, patches, in_dtype, static_cast<int>(B), 0, layer, s));
+  static const size_t per_patch[7] = {0, 32 * 32 * 32, 32 * 32 * 32, 16 * 16 * 64, 16 * 16 * 64, 8 * 8 * 128, 8 * 8 * 128};
+  const uint16_t* src = layer == 6 ? h->l6 : h->act[(layer - 1) & 1];
+  HN_CUDA(cudaMemcpyAsync(act_out, src, per_patch[layer] * 2 * static_cast<size_t>(B), cudaMemcpyDeviceToDevice, s));
+  return HN_OK;
+}

@@ -1,0 +1,181 @@
+"""Drop-in mirror of the reference's HardNet surface (hardnet/HardNet.py:275-324, hardnet/Utils.py:15-22).
+
+`HardNet` keeps the reference's module tree, so `state_dict()` / `load_state_dict()` use the same keys
+(`features.{0,3,...,19}.weight`, `features.{1,4,...,20}.running_{mean,var}`) and reference checkpoints
+(`{'epoch', 'state_dict'}`, HardNet.py:440-441) load unchanged.
+
+  * eval mode  -> the B200 kernels behind the C ABI (hn_pack_hardnet / hn_forward). CUDA tensors only;
+                  there is no CPU fallback and a missing extension raises.
+  * train mode -> the stock torch modules (batch-statistics BatchNorm and Dropout are training-time
+                  behaviour and out of the accelerated path's scope).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_DTYPES = {"fp16": _lib.HN_F16, "bf16": _lib.HN_BF16}
+_OUT_DTYPES = {torch.float32: _lib.HN_F32, torch.float16: _lib.HN_F16, torch.bfloat16: _lib.HN_BF16}
+
+
+class L2Norm(nn.Module):
+    """x / sqrt(sum(x*x, dim=1) + 1e-10) — hardnet/Utils.py:15-22."""
+
+    def __init__(self):
+        super().__init__()
+        self.eps = 1e-10
+
+    def forward(self, x):
+        norm = torch.sqrt(torch.sum(x * x, dim=1) + self.eps)
+        return x / norm.unsqueeze(-1).expand_as(x)
+
+
+def weights_init(m):
+    """Orthogonal init, gain 0.6, for every conv (hardnet/HardNet.py:317-324)."""
+    if isinstance(m, nn.Conv2d):
+        nn.init.orthogonal_(m.weight.data, gain=0.6)
+        if m.bias is not None:
+            nn.init.constant_(m.bias.data, 0.01)
+
+
+class _Engine:
+    """Owns one hn_handle on one CUDA device."""
+
+    def __init__(self, device: torch.device, chunk_patches: int, head_rows: int):
+        self.lib = _lib.load()
+        self.device = device
+        self.handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.hn_create(C.byref(self.handle), int(chunk_patches), int(head_rows)), "hn_create")
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.hn_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HardNet(nn.Module):
+    """HardNet model definition (same constructor contract as the reference: no required arguments)."""
+
+    def __init__(self, act_dtype: str = "fp16", chunk_patches: int = 0, head_rows: int = 0):
+        super().__init__()
+        self.features = nn.Sequential(
+            nn.Conv2d(1, 32, kernel_size=3, padding=1, bias=False),
+            nn.BatchNorm2d(32, affine=False),
+            nn.ReLU(),
+            nn.Conv2d(32, 32, kernel_size=3, padding=1, bias=False),
+            nn.BatchNorm2d(32, affine=False),
+            nn.ReLU(),
+            nn.Conv2d(32, 64, kernel_size=3, stride=2, padding=1, bias=False),
+            nn.BatchNorm2d(64, affine=False),
+            nn.ReLU(),
+            nn.Conv2d(64, 64, kernel_size=3, padding=1, bias=False),
+            nn.BatchNorm2d(64, affine=False),
+            nn.ReLU(),
+            nn.Conv2d(64, 128, kernel_size=3, stride=2, padding=1, bias=False),
+            nn.BatchNorm2d(128, affine=False),
+            nn.ReLU(),
+            nn.Conv2d(128, 128, kernel_size=3, padding=1, bias=False),
+            nn.BatchNorm2d(128, affine=False),
+            nn.ReLU(),
+            nn.Dropout(0.3),
+            nn.Conv2d(128, 128, kernel_size=8, bias=False),
+            nn.BatchNorm2d(128, affine=False),
+        )
+        self.features.apply(weights_init)
+        if act_dtype not in _DTYPES:
+            raise ValueError(f"act_dtype must be one of {sorted(_DTYPES)}")
+        self.act_dtype = act_dtype
+        self._chunk_patches = chunk_patches
+        self._head_rows = head_rows
+        self._engine: _Engine | None = None
+        self._packed_key = None
+
+    # ---- reference surface -------------------------------------------------------------------------
+    def input_norm(self, x):
+        flat = x.view(x.size(0), -1)
+        mp = torch.mean(flat, dim=1)
+        sp = torch.std(flat, dim=1) + 1e-7
+        return (x - mp.detach().view(-1, 1, 1, 1)) / sp.detach().view(-1, 1, 1, 1)
+
+    def forward(self, input, out_dtype: torch.dtype = torch.float32):
+        if self.training:
+            x_features = self.features(self.input_norm(input))
+            x = x_features.view(x_features.size(0), -1)
+            return L2Norm()(x)
+        return self._forward_b200(input, out_dtype)
+
+    # ---- B200 path ---------------------------------------------------------------------------------
+    def _convs_and_bns(self):
+        convs = [m for m in self.features if isinstance(m, nn.Conv2d)]
+        bns = [m for m in self.features if isinstance(m, nn.BatchNorm2d)]
+        return convs, bns
+
+    def _ensure_packed(self, device: torch.device):
+        convs, bns = self._convs_and_bns()
+        key = (device, self.act_dtype) + tuple(c.weight._version for c in convs) + tuple(
+            (b.running_mean._version, b.running_var._version) for b in bns) + tuple(c.weight.data_ptr() for c in convs)
+        if self._engine is None or self._engine.device != device:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = _Engine(device, self._chunk_patches, self._head_rows)
+            self._packed_key = None
+        if self._packed_key == key:
+            return
+        ws = [c.weight.detach().to("cpu", torch.float32).contiguous() for c in convs]
+        means = [b.running_mean.detach().to("cpu", torch.float32).contiguous() for b in bns]
+        vars_ = [b.running_var.detach().to("cpu", torch.float32).contiguous() for b in bns]
+        eng = self._engine
+        with torch.cuda.device(device):
+            _lib.check(eng.lib.hn_pack_hardnet(eng.handle, _lib.float_ptr_array(ws), _lib.float_ptr_array(means),
+                                               _lib.float_ptr_array(vars_), C.c_float(bns[0].eps),
+                                               _DTYPES[self.act_dtype]), "hn_pack_hardnet")
+        self._packed_key = key
+
+    def _check_input(self, input):
+        if not isinstance(input, torch.Tensor) or not input.is_cuda:
+            raise _lib.HardnetB200Error(
+                "HardNet eval forward runs on B200 CUDA tensors only (no CPU fallback); got a "
+                f"{'CPU tensor' if isinstance(input, torch.Tensor) else type(input).__name__}")
+        if input.dim() != 4 or tuple(input.shape[1:]) != (1, 32, 32):
+            raise ValueError(f"expected input of shape [B,1,32,32], got {tuple(input.shape)}")
+        if input.dtype == torch.float32:
+            return input.contiguous(), _lib.HN_F32
+        if input.dtype == torch.uint8:
+            return input.contiguous(), _lib.HN_U8
+        return input.float().contiguous(), _lib.HN_F32
+
+    def _forward_b200(self, input, out_dtype=torch.float32):
+        x, in_dt = self._check_input(input)
+        self._ensure_packed(x.device)
+        out = torch.empty((x.size(0), 128), dtype=out_dtype, device=x.device)
+        eng = self._engine
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(eng.lib.hn_forward(eng.handle, x.data_ptr(), in_dt, x.size(0), out.data_ptr(),
+                                          _OUT_DTYPES[out_dtype], C.c_void_p(stream)), "hn_forward")
+        return out
+
+    def forward_stage(self, input, layer: int):
+        """Test hook: NHWC activations after conv stage `layer` (1..6) as a [B,H,W,C] 16-bit tensor."""
+        x, in_dt = self._check_input(input)
+        self._ensure_packed(x.device)
+        shapes = {1: (32, 32, 32), 2: (32, 32, 32), 3: (16, 16, 64), 4: (16, 16, 64), 5: (8, 8, 128), 6: (8, 8, 128)}
+        dt = torch.float16 if self.act_dtype == "fp16" else torch.bfloat16
+        out = torch.empty((x.size(0),) + shapes[layer], dtype=dt, device=x.device)
+        eng = self._engine
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(eng.lib.hn_forward_dump(eng.handle, x.data_ptr(), in_dt, x.size(0), layer, out.data_ptr(),
+                                               C.c_void_p(stream)), "hn_forward_dump")
+        return out

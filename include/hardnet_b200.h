@@ -1,0 +1,104 @@
+/* hardnet_b200 — C ABI of the B200-native HardNet hot path.
+ *
+ * The reference (iamwangyabin/hardnetNas) is pure Python/PyTorch and has no FFI layer; its boundary is
+ * the Python surface listed below. Each entry point here replaces the torch-op sequence behind one of
+ * those Python symbols, and the Python mirror in hardnetnas_b200/ binds them with ctypes (the stub a
+ * reference maintainer would add is shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative hn_status; it never throws and never exits;
+ *     hn_last_error() returns a thread-local, human readable description of the last failure.
+ *   - data pointers are DEVICE pointers to contiguous buffers on the current CUDA device unless a
+ *     parameter is documented as host memory; the caller owns every data buffer.
+ *   - the library owns only what hangs off an hn_handle (packed weights, TMA descriptors, activation
+ *     scratch). Handles are not thread safe; distinct handles are independent.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no device-wide synchronisation
+ *     and no allocation happens on the hot calls (hn_forward / hn_dist_min / hn_loss_hardnet / hn_match).
+ *   - there is no CPU fallback: without a usable sm_100 device the calls fail with HN_ERR_CUDA.
+ */
+#ifndef HARDNET_B200_H_
+#define HARDNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hn_handle hn_handle;
+
+typedef enum hn_status {
+  HN_OK = 0,
+  HN_ERR_INVALID = -1,     /* bad argument (the reference's `assert` sites map here) */
+  HN_ERR_CUDA = -2,        /* CUDA runtime / driver failure, see hn_last_error() */
+  HN_ERR_STATE = -3,       /* e.g. forward before pack */
+  HN_ERR_UNSUPPORTED = -4
+} hn_status;
+
+typedef enum hn_dtype { HN_F32 = 0, HN_F16 = 1, HN_BF16 = 2, HN_U8 = 3 } hn_dtype;
+
+/* distance forms */
+#define HN_FORM_HARDNET 0 /* sqrt(|a|^2 + |p|^2 - 2ab + 1e-6)           hardnet/Losses.py:5-13            */
+#define HN_FORM_FDL 1     /* sqrt(clamp(2 - 2ab, 1e-8, 4))              FDLNet-master/utils/math_utils.py:8-19 */
+
+/* hn_dist_min flags */
+#define HN_FLAG_LOSS_MASK 1 /* +1e-8, diagonal +10, (<0.008) +10        hardnet/Losses.py:95-103          */
+#define HN_FLAG_SWAP 2      /* also produce column minima (anchor swap) hardnet/Losses.py:106-108         */
+
+int hn_version(void);
+const char* hn_last_error(void);
+
+/* ---- handle -------------------------------------------------------------------------------------- */
+/* chunk_patches: patches pushed through the conv stack per pass (0 = default, rounded to a multiple of
+ * 2); head_rows: descriptors accumulated before the 8x8 head GEMM runs (0 = default). Allocates all
+ * device scratch up front. */
+int hn_create(hn_handle** out, int chunk_patches, long long head_rows);
+int hn_destroy(hn_handle* h);
+
+/* ---- HardNet (hardnet/HardNet.py:275-315) --------------------------------------------------------- */
+/* Folds eval-mode BatchNorm (affine=False) into the conv weights and packs them K-major 16-bit.
+ * HOST pointers: w[i] is features.{0,3,6,9,12,15,19}.weight in PyTorch OIHW order, bn_mean / bn_var the
+ * matching running statistics of features.{1,4,7,10,13,16,20}. act_dtype: HN_F16 (default, 10-bit
+ * mantissa like TF32) or HN_BF16. */
+int hn_pack_hardnet(hn_handle* h, const float* const w[7], const float* const bn_mean[7],
+                    const float* const bn_var[7], float bn_eps, int act_dtype);
+
+/* HardNet.forward in eval mode: input_norm -> 7 conv/BN/ReLU stages -> L2Norm.
+ * patches: [B,1,32,32] (HN_F32 or HN_U8); desc_out: [B,128] (HN_F32 / HN_F16 / HN_BF16). */
+int hn_forward(hn_handle* h, const void* patches, int in_dtype, long long B, void* desc_out,
+               int out_dtype, void* stream);
+
+/* Test hook: run the stack up to and including conv stage `layer` (1..6) for B <= chunk_patches and
+ * copy that stage's NHWC 16-bit activations to act_out ([B,H,W,C]). */
+int hn_forward_dump(hn_handle* h, const void* patches, int in_dtype, long long B, int layer,
+                    void* act_out, void* stream);
+
+/* ---- distances, hardest-in-batch mining, matching ------------------------------------------------- */
+/* Bytes of device workspace hn_dist_min / hn_loss_hardnet / hn_match need for the given sizes. */
+long long hn_dist_workspace_bytes(long long Na, long long Np, int split);
+
+/* Fused distance matrix + masking + row (and column) minima; the Na x Np matrix never reaches HBM.
+ * a:[Na,128], p:[Np,128] fp32. Outputs (any may be NULL): pos[min(Na,Np)] = diagonal distances
+ * (before masking), row_min[Na] / row_arg[Na], col_min[Np] / col_arg[Np] (HN_FLAG_SWAP).
+ * Replaces distance_matrix_vector + the eye/mask/min sequence of hardnet/Losses.py:95-108. */
+int hn_dist_min(const float* a, const float* p, long long Na, long long Np, int form, int flags,
+                float* pos, float* row_min, int32_t* row_arg, float* col_min, int32_t* col_arg,
+                void* workspace, long long workspace_bytes, void* stream);
+
+/* loss_HardNet, batch_reduce='min', loss_type='triplet_margin' (hardnet/Losses.py:87-108,142-143,153;
+ * hardnetNAS/general_functions/Losses.py:27-51 is the anchor_swap=1 case). loss_out: 1 float (device). */
+int hn_loss_hardnet(const float* anchor, const float* positive, long long N, float margin,
+                    int anchor_swap, float* loss_out, void* workspace, long long workspace_bytes,
+                    void* stream);
+
+/* Brute-force matching in the FDLNet distance form: for every query row the nearest and second nearest
+ * gallery rows (D.min(dim=-1) of eval_utils.py:113-114 and sorted[:,0:2] of :168-175).
+ * q:[Nq,128], g:[Ng,128] fp32. Outputs: d1[Nq], d2[Nq] distances, i1[Nq] gallery index (+g_offset). */
+int hn_match(const float* q, const float* g, long long Nq, long long Ng, long long g_offset, float* d1,
+             float* d2, int32_t* i1, int32_t* i2, void* workspace, long long workspace_bytes,
+             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HARDNET_B200_H_ */

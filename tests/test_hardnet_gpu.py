@@ -1,0 +1,132 @@
+"""GPU parity: the B200 HardNet forward (through the C ABI) against the CPU oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hardnet_oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+# 16-bit activations (fp16: 10-bit mantissa like TF32). Gates from BASELINE.json north_star.
+DESC_MAX_ABS = 1e-3
+DESC_MIN_COS = 0.9999
+
+
+def _model(bn_seed, act_dtype="fp16", **kw):
+    from hardnetnas_b200.hardnet import HardNet
+    w, m, v = synth.hardnet_weights_from_seed(0, bn_seed)
+    torch.manual_seed(0)
+    model = HardNet(act_dtype=act_dtype, **kw)
+    sd = model.state_dict()
+    for i, (ci, bi) in enumerate(zip(synth.CONV_IDX, synth.BN_IDX)):
+        assert torch.equal(sd[f"features.{ci}.weight"], w[i])  # same init stream as the reference
+        sd[f"features.{bi}.running_mean"] = m[i]
+        sd[f"features.{bi}.running_var"] = v[i]
+    model.load_state_dict(sd)
+    return model.cuda().eval(), (w, m, v)
+
+
+def _cmp(desc, ref):
+    desc = desc.float().cpu()
+    max_abs = (desc - ref).abs().max().item()
+    nz = ref.norm(dim=1) > 0
+    cos = torch.nn.functional.cosine_similarity(desc[nz], ref[nz], dim=1).min().item()
+    return max_abs, cos
+
+
+@pytest.mark.parametrize("bn_seed", [3, None])
+def test_stage_activations_match_oracle(bn_seed):
+    model, (w, m, v) = _model(bn_seed)
+    x = synth.make_patches(64, 1234)
+    acts = hardnet_oracle.hardnet_stages(x, w, m, v, upto=6)
+    xg = x.cuda()
+    for layer in range(1, 7):
+        got = model.forward_stage(xg, layer).float().cpu().permute(0, 3, 1, 2)
+        ref = acts[layer - 1]
+        scale = ref.abs().max().item()
+        err = (got - ref).abs().max().item()
+        assert err <= 4e-3 * scale + 1e-6, f"stage {layer}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("bn_seed", [3, None])
+def test_descriptors_match_oracle_and_golden(bn_seed, golden_dir):
+    model, (w, m, v) = _model(bn_seed)
+    x = synth.make_patches(64, 1234)
+    desc = model(x.cuda())
+    ref = hardnet_oracle.hardnet_forward(x, w, m, v)
+    max_abs, cos = _cmp(desc, ref)
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+    g = np.load(golden_dir / "hardnet_forward.npz")
+    gold = torch.from_numpy(g["desc" if bn_seed == 3 else "desc_fresh_bn"])
+    max_abs, cos = _cmp(desc, gold)
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+    if bn_seed is None:
+        assert torch.all(desc[-1] == 0)  # constant patch -> exactly zero descriptor, not NaN
+    assert torch.isfinite(desc).all()
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 127, 129, 1024])
+def test_ragged_batches(batch):
+    model, (w, m, v) = _model(3, chunk_patches=64, head_rows=256)
+    x = synth.make_patches(batch, 99, edge_cases=False)
+    desc = model(x.cuda())
+    ref = hardnet_oracle.hardnet_forward(x, w, m, v)
+    max_abs, cos = _cmp(desc, ref)
+    assert desc.shape == (batch, 128)
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+
+
+def test_empty_batch():
+    model, _ = _model(3)
+    out = model(torch.empty(0, 1, 32, 32, device="cuda"))
+    assert out.shape == (0, 128)
+
+
+def test_uint8_input_and_half_output():
+    model, (w, m, v) = _model(None)
+    g = torch.Generator().manual_seed(5)
+    xu8 = torch.randint(0, 256, (96, 1, 32, 32), generator=g, dtype=torch.uint8)
+    ref = hardnet_oracle.hardnet_forward(xu8.float(), w, m, v)
+    d32 = model(xu8.cuda())
+    max_abs, cos = _cmp(d32, ref)
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+    d16 = model(xu8.cuda(), out_dtype=torch.float16)
+    assert d16.dtype == torch.float16
+    assert (d16.float() - d32).abs().max().item() <= 1e-3
+
+
+def test_bf16_activations_looser_bound():
+    # stated bf16 bound (8-bit mantissa): max-abs <= 3e-3, cosine >= 0.9999
+    model, (w, m, v) = _model(None, act_dtype="bf16")
+    x = synth.make_patches(256, 1234)
+    max_abs, cos = _cmp(model(x.cuda()), hardnet_oracle.hardnet_forward(x, w, m, v))
+    assert max_abs <= 3e-3 and cos >= 0.9999, (max_abs, cos)
+
+
+def test_train_mode_uses_stock_torch_path():
+    model, _ = _model(None)
+    model.train()
+    x = synth.make_patches(8, 3).cuda()
+    out = model(x)
+    assert out.requires_grad and out.shape == (8, 128)
+
+
+def test_cpu_input_fails_loudly():
+    from hardnetnas_b200._lib import HardnetB200Error
+    model, _ = _model(None)
+    with pytest.raises(HardnetB200Error):
+        model(synth.make_patches(4, 1))
+
+
+def test_full_size_properties():
+    """Config-sized batch: finite, unit norm, deterministic, and chunking-invariant (size-independent checks)."""
+    model, _ = _model(None)
+    x = synth.make_patches(8192, 77, edge_cases=False).cuda()
+    d1 = model(x)
+    d2 = model(x)
+    assert torch.equal(d1, d2)
+    assert torch.isfinite(d1).all()
+    assert (d1.norm(dim=1) - 1).abs().max().item() < 1e-4
+    small, _ = _model(None, chunk_patches=32, head_rows=128)
+    d3 = small(x[:1000])
+    assert torch.equal(d3, d1[:1000])
