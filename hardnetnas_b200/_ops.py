@@ -1,0 +1,92 @@
+"""Tensor-level wrappers over the distance / matching entry points of the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_ws_cache: dict = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-device scratch reused across calls (grown on demand), so the hot calls never allocate."""
+    key = (device.type, device.index)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _require_cuda_f32(name: str, t: torch.Tensor) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.HardnetB200Error(f"{name}: the fused path runs on B200 CUDA tensors only (no CPU fallback)")
+    assert t.dim() == 2, "Inputd must be a 2D matrix."
+    if t.size(1) != 128:
+        raise ValueError(f"{name}: descriptors must be 128-d, got {t.size(1)}")
+    return t.detach().float().contiguous()
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def dist_min(a: torch.Tensor, p: torch.Tensor, form: int, loss_mask: bool, swap: bool):
+    """Returns dict(pos, row_min, row_arg[, col_min, col_arg]) — see hn_dist_min in include/hardnet_b200.h."""
+    lib = _lib.load()
+    a = _require_cuda_f32("dist_min", a)
+    p = _require_cuda_f32("dist_min", p)
+    na, npos = a.size(0), p.size(0)
+    dev = a.device
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.hn_dist_workspace_bytes(na, npos, 1))
+        out = {
+            "pos": torch.empty(min(na, npos), dtype=torch.float32, device=dev) if loss_mask else None,
+            "row_min": torch.empty(na, dtype=torch.float32, device=dev),
+            "row_arg": torch.empty(na, dtype=torch.int32, device=dev),
+            "col_min": torch.empty(npos, dtype=torch.float32, device=dev) if swap else None,
+            "col_arg": torch.empty(npos, dtype=torch.int32, device=dev) if swap else None,
+        }
+        flags = (_lib.HN_FLAG_LOSS_MASK if loss_mask else 0) | (_lib.HN_FLAG_SWAP if swap else 0)
+        _lib.check(lib.hn_dist_min(_ptr(a), _ptr(p), na, npos, form, flags, _ptr(out["pos"]), _ptr(out["row_min"]),
+                                   _ptr(out["row_arg"]), _ptr(out["col_min"]), _ptr(out["col_arg"]), _ptr(ws),
+                                   ws.numel(), _stream_ptr()), "hn_dist_min")
+    return out
+
+
+def loss_hardnet(anchor: torch.Tensor, positive: torch.Tensor, margin: float, anchor_swap: bool) -> torch.Tensor:
+    lib = _lib.load()
+    a = _require_cuda_f32("loss_HardNet", anchor)
+    p = _require_cuda_f32("loss_HardNet", positive)
+    n = a.size(0)
+    dev = a.device
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.hn_dist_workspace_bytes(n, n, 1))
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        _lib.check(lib.hn_loss_hardnet(_ptr(a), _ptr(p), n, C.c_float(margin), int(bool(anchor_swap)), _ptr(out), _ptr(ws),
+                                       ws.numel(), _stream_ptr()), "hn_loss_hardnet")
+    return out
+
+
+def match_top2(q: torch.Tensor, g: torch.Tensor, g_offset: int = 0):
+    """(d1, d2, i1, i2): nearest / second-nearest gallery row per query in the FDLNet distance form."""
+    lib = _lib.load()
+    q = _require_cuda_f32("match", q)
+    g = _require_cuda_f32("match", g)
+    nq, ng = q.size(0), g.size(0)
+    dev = q.device
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.hn_dist_workspace_bytes(nq, ng, 0))
+        d1 = torch.empty(nq, dtype=torch.float32, device=dev)
+        d2 = torch.empty(nq, dtype=torch.float32, device=dev)
+        i1 = torch.empty(nq, dtype=torch.int32, device=dev)
+        i2 = torch.empty(nq, dtype=torch.int32, device=dev)
+        _lib.check(lib.hn_match(_ptr(q), _ptr(g), nq, ng, g_offset, _ptr(d1), _ptr(d2), _ptr(i1), _ptr(i2), _ptr(ws),
+                                ws.numel(), _stream_ptr()), "hn_match")
+    return d1, d2, i1, i2

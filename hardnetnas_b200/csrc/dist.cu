@@ -1,0 +1,333 @@
+// C ABI for the distance / hardest-in-batch / matching path: operand packing, the fused tcgen05
+// distance kernels (tc_dist.cuh), fp32 re-ranking of shortlisted candidates and the small finalisers.
+#include <algorithm>
+
+#include "host_common.h"
+#include "tc_dist.cuh"
+
+namespace hn {
+
+constexpr float kOperandScale = 256.0f;  // descriptors are unit vectors: x256 keeps the fp16 hi/lo split clear of subnormals
+constexpr float kDotScale = 1.0f / (kOperandScale * kOperandScale);
+
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// fp32 [n,128] -> 16-bit K-major operand rows. split == 0: [hi] (K=128). split == 1: K=384,
+// order 0 = [hi, hi, lo] (row side), order 1 = [hi, lo, hi] (column side), so that the GEMM accumulates
+// hi*hi + hi*lo + lo*hi. Also emits |x|^2 (torch.sum(x*x, dim=1), hardnet/Losses.py:8-9).
+__global__ void pack_desc_kernel(const float* __restrict__ x, long long n, uint16_t* __restrict__ out, int split, int order,
+                                 float* __restrict__ norm) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4 v = reinterpret_cast<const float4*>(x + row * 128)[lane];
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  float ss = (f[0] * f[0] + f[1] * f[1]) + (f[2] * f[2] + f[3] * f[3]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (norm && lane == 0) norm[row] = ss;
+  uint16_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float s = f[j] * kOperandScale;
+    const __half h = __float2half_rn(s);
+    const __half l = __float2half_rn(s - __half2float(h));
+    hi[j] = __half_as_ushort(h);
+    lo[j] = __half_as_ushort(l);
+  }
+  const int K = split ? 384 : 128;
+  uint16_t* dst = out + row * K + lane * 4;
+  const uint2 H = make_uint2(hi[0] | (uint32_t(hi[1]) << 16), hi[2] | (uint32_t(hi[3]) << 16));
+  const uint2 L = make_uint2(lo[0] | (uint32_t(lo[1]) << 16), lo[2] | (uint32_t(lo[3]) << 16));
+  *reinterpret_cast<uint2*>(dst) = H;
+  if (split) {
+    *reinterpret_cast<uint2*>(dst + 128) = order == 0 ? H : L;
+    *reinterpret_cast<uint2*>(dst + 256) = order == 0 ? L : H;
+  }
+}
+
+__global__ void unpack_min_kernel(const unsigned long long* __restrict__ pack, long long n, float* __restrict__ val,
+                                  int* __restrict__ arg) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long pk = pack[i];
+  if (val) val[i] = __uint_as_float(static_cast<unsigned int>(pk >> 32));
+  if (arg) arg[i] = static_cast<int>(pk & 0xffffffffu);
+}
+
+// mean(clamp(margin + pos - min_neg, 0)) with min_neg = min(row_min, col_min) — hardnet/Losses.py:105-108,
+// 142-143,153. One block, fixed summation order -> deterministic.
+__global__ void loss_finalize_kernel(const float* __restrict__ pos, const unsigned long long* __restrict__ row_pack,
+                                     const unsigned long long* __restrict__ col_pack, long long n, float margin,
+                                     float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    float mn = __uint_as_float(static_cast<unsigned int>(row_pack[i] >> 32));
+    if (col_pack) mn = fminf(mn, __uint_as_float(static_cast<unsigned int>(col_pack[i] >> 32)));
+    acc += fmaxf(margin + pos[i] - mn, 0.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) out[0] = v / static_cast<float>(n);
+  }
+}
+
+// Exact fp32 re-rank of the shortlisted chunks: one warp per query row, one candidate gallery row per lane.
+// Distances in the FDLNet form; ties resolve to the lower gallery index like torch.min / a stable sort.
+__global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q, const float* __restrict__ g,
+                                                     const int* __restrict__ cand, long long nq, long long ng, int slots,
+                                                     long long g_offset, float* __restrict__ d1, float* __restrict__ d2,
+                                                     int* __restrict__ i1, int* __restrict__ i2) {
+  __shared__ __align__(16) float sq[4][128];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 4 + w;
+  if (row >= nq) return;
+  reinterpret_cast<float4*>(sq[w])[lane] = reinterpret_cast<const float4*>(q + row * 128)[lane];
+  __syncwarp();
+  const float inf = __int_as_float(0x7f800000);
+  float b1 = inf, b2 = inf;
+  int j1 = 0x7fffffff, j2 = 0x7fffffff;
+  const int total = slots * kChunk;
+  for (int c = lane; c < total; c += 32) {
+    const int chunk = cand[row * slots + c / kChunk];
+    const long long col = static_cast<long long>(chunk) * kChunk + (c % kChunk);
+    if (chunk < 0 || col >= ng) continue;
+    const float4* gr = reinterpret_cast<const float4*>(g + col * 128);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float4 a = reinterpret_cast<const float4*>(sq[w])[k];
+      const float4 b = __ldg(gr + k);
+      s0 = fmaf(a.x, b.x, s0);
+      s1 = fmaf(a.y, b.y, s1);
+      s2 = fmaf(a.z, b.z, s2);
+      s3 = fmaf(a.w, b.w, s3);
+    }
+    const float dot = (s0 + s1) + (s2 + s3);
+    const float d = sqrtf(fminf(fmaxf(2.0f - 2.0f * dot, 1e-8f), 4.0f));
+    const int ci = static_cast<int>(col);
+    if (d < b1 || (d == b1 && ci < j1)) {
+      b2 = b1; j2 = j1; b1 = d; j1 = ci;
+    } else if (d < b2 || (d == b2 && ci < j2)) {
+      b2 = d; j2 = ci;
+    }
+  }
+  // warp merge: best (d, idx) lexicographically, then the runner-up
+  float m = b1;
+  int mj = j1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, mj, o);
+    if (od < m || (od == m && oj < mj)) { m = od; mj = oj; }
+  }
+  const bool winner = (j1 == mj) && (b1 == m);
+  float s = winner ? b2 : b1;
+  int sj = winner ? j2 : j1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, s, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, sj, o);
+    if (od < s || (od == s && oj < sj)) { s = od; sj = oj; }
+  }
+  if (lane == 0) {
+    if (d1) d1[row] = m;
+    if (i1) i1[row] = mj == 0x7fffffff ? -1 : static_cast<int>(mj + g_offset);
+    if (d2) d2[row] = s;
+    if (i2) i2[row] = sj == 0x7fffffff ? -1 : static_cast<int>(sj + g_offset);
+  }
+}
+
+static int make_desc_map(CUtensorMap* tm, const uint16_t* base, long long rows, int K) {
+  const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows)};
+  const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+  const uint32_t box[2] = {64, static_cast<uint32_t>(kDistTile)};
+  return make_tmap_16bit(tm, base, 2, dims, str, box, 128);
+}
+
+template <int MB, int EPI>
+static int launch_dist(const DistParams& p, int grid_x, int grid_y, cudaStream_t s) {
+  auto kern = dist_kernel<MB, EPI>;
+  const size_t smem = dist_smem_bytes<MB>(p.k_blocks);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_smem = smem;
+  }
+  kern<<<dim3(grid_x, grid_y), 64 + 128 * MB, smem, s>>>(p);
+  HN_CUDA(cudaGetLastError());
+  return HN_OK;
+}
+
+struct ExactWs {
+  uint16_t *a16, *p16;
+  float *na, *np, *pos;
+  unsigned long long *row_pack, *col_pack;
+  size_t bytes;
+};
+
+static ExactWs carve_exact(void* ws, long long Na, long long Np) {
+  ExactWs w;
+  char* b = static_cast<char*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t n) { char* r = b ? b + off : nullptr; off += align256(n); return r; };
+  w.a16 = reinterpret_cast<uint16_t*>(take(static_cast<size_t>(Na) * 384 * 2));
+  w.p16 = reinterpret_cast<uint16_t*>(take(static_cast<size_t>(Np) * 384 * 2));
+  w.na = reinterpret_cast<float*>(take(static_cast<size_t>(Na) * 4));
+  w.np = reinterpret_cast<float*>(take(static_cast<size_t>(Np) * 4));
+  w.pos = reinterpret_cast<float*>(take(static_cast<size_t>(std::max(Na, Np)) * 4));
+  w.row_pack = reinterpret_cast<unsigned long long*>(take(static_cast<size_t>(Na) * 8));
+  w.col_pack = reinterpret_cast<unsigned long long*>(take(static_cast<size_t>(Np) * 8));
+  w.bytes = off;
+  return w;
+}
+
+static int pick_segments(long long rows, int rows_per_block, long long cols, int sm_count, int max_seg) {
+  const long long m_blocks = (rows + rows_per_block - 1) / rows_per_block;
+  const long long n_tiles = (cols + kDistTile - 1) / kDistTile;
+  long long s = (2LL * sm_count + m_blocks - 1) / m_blocks;
+  s = std::min<long long>(s, std::min<long long>(n_tiles, max_seg));
+  return static_cast<int>(std::max<long long>(s, 1));
+}
+
+// Shared body of hn_dist_min / hn_loss_hardnet. Leaves packed minima and pos in the workspace.
+static int run_exact(const float* a, const float* p, long long Na, long long Np, int form, int flags, ExactWs& w,
+                     cudaStream_t s) {
+  int sm = 0;
+  HN_TRY(device_sm_count(&sm));
+  const int threads = 256;
+  pack_desc_kernel<<<static_cast<unsigned>((Na * 32 + threads - 1) / threads), threads, 0, s>>>(a, Na, w.a16, 1, 0, w.na);
+  pack_desc_kernel<<<static_cast<unsigned>((Np * 32 + threads - 1) / threads), threads, 0, s>>>(p, Np, w.p16, 1, 1, w.np);
+  HN_CUDA(cudaGetLastError());
+  HN_CUDA(cudaMemsetAsync(w.row_pack, 0xff, static_cast<size_t>(Na) * 8, s));
+  const bool swap = (flags & HN_FLAG_SWAP) != 0;
+  if (swap) HN_CUDA(cudaMemsetAsync(w.col_pack, 0xff, static_cast<size_t>(Np) * 8, s));
+  DistParams dp;
+  memset(&dp, 0, sizeof(dp));
+  HN_TRY(make_desc_map(&dp.side[0].tmA, w.a16, Na, 384));
+  HN_TRY(make_desc_map(&dp.side[0].tmB, w.p16, Np, 384));
+  dp.side[0].norm_a = w.na;
+  dp.side[0].norm_b = w.np;
+  dp.side[0].row_pack = w.row_pack;
+  dp.side[0].pos = w.pos;
+  dp.side[0].Na = Na;
+  dp.side[0].Nb = Np;
+  // transposed problem: rows = positives, columns = anchors (same packed operands, roles exchanged)
+  dp.side[1].tmA = dp.side[0].tmB;
+  dp.side[1].tmB = dp.side[0].tmA;
+  dp.side[1].norm_a = w.np;
+  dp.side[1].norm_b = w.na;
+  dp.side[1].row_pack = w.col_pack;
+  dp.side[1].pos = nullptr;
+  dp.side[1].Na = Np;
+  dp.side[1].Nb = Na;
+  dp.k_blocks = 6;
+  dp.form = form;
+  dp.loss_mask = (flags & HN_FLAG_LOSS_MASK) ? 1 : 0;
+  dp.dot_scale = kDotScale;
+  const long long rows = swap ? std::max(Na, Np) : Na;
+  const long long cols = swap ? std::min(Na, Np) : Np;
+  dp.segments = pick_segments(rows, kDistTile, cols, sm, 16);
+  const long long items = ((rows + kDistTile - 1) / kDistTile) * dp.segments;
+  const int grid_x = static_cast<int>(std::min<long long>(items, sm));
+  HN_TRY((launch_dist<1, EPI_EXACT>(dp, grid_x, swap ? 2 : 1, s)));
+  return HN_OK;
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" long long hn_dist_workspace_bytes(long long Na, long long Np, int split) {
+  if (Na < 0 || Np < 0) return 0;
+  (void)split;
+  ExactWs w = carve_exact(nullptr, Na, Np);
+  const size_t shortlist = align256(static_cast<size_t>(Na) * 128 * 2) + align256(static_cast<size_t>(Np) * 128 * 2) +
+                           align256(static_cast<size_t>(Na) * 16 * kTopC * 4);
+  return static_cast<long long>(std::max(w.bytes, shortlist) + 256);
+}
+
+extern "C" int hn_dist_min(const float* a, const float* p, long long Na, long long Np, int form, int flags, float* pos,
+                           float* row_min, int32_t* row_arg, float* col_min, int32_t* col_arg, void* workspace,
+                           long long workspace_bytes, void* stream) {
+  HN_REQUIRE(a && p && workspace, "hn_dist_min: NULL argument");
+  HN_REQUIRE(Na >= 1 && Np >= 1, "hn_dist_min: empty input (Na=%lld, Np=%lld)", Na, Np);
+  HN_REQUIRE(Na < (1LL << 31) && Np < (1LL << 31), "hn_dist_min: more than 2^31 rows");
+  HN_REQUIRE(form == HN_FORM_HARDNET || form == HN_FORM_FDL, "hn_dist_min: unknown distance form %d", form);
+  HN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "hn_dist_min: workspace must be 256-byte aligned");
+  HN_REQUIRE(workspace_bytes >= hn_dist_workspace_bytes(Na, Np, 1), "hn_dist_min: workspace too small");
+  if ((col_min || col_arg) && !(flags & HN_FLAG_SWAP)) {
+    set_error("hn_dist_min: column outputs need HN_FLAG_SWAP");
+    return HN_ERR_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ExactWs w = carve_exact(workspace, Na, Np);
+  HN_TRY(run_exact(a, p, Na, Np, form, flags, w, s));
+  const int threads = 256;
+  if (row_min || row_arg)
+    unpack_min_kernel<<<static_cast<unsigned>((Na + threads - 1) / threads), threads, 0, s>>>(w.row_pack, Na, row_min, row_arg);
+  if (col_min || col_arg)
+    unpack_min_kernel<<<static_cast<unsigned>((Np + threads - 1) / threads), threads, 0, s>>>(w.col_pack, Np, col_min, col_arg);
+  if (pos && (flags & HN_FLAG_LOSS_MASK))
+    HN_CUDA(cudaMemcpyAsync(pos, w.pos, static_cast<size_t>(std::min(Na, Np)) * 4, cudaMemcpyDeviceToDevice, s));
+  HN_CUDA(cudaGetLastError());
+  return HN_OK;
+}
+
+extern "C" int hn_loss_hardnet(const float* anchor, const float* positive, long long N, float margin, int anchor_swap,
+                               float* loss_out, void* workspace, long long workspace_bytes, void* stream) {
+  HN_REQUIRE(anchor && positive && loss_out && workspace, "hn_loss_hardnet: NULL argument");
+  HN_REQUIRE(N >= 1 && N < (1LL << 31), "hn_loss_hardnet: N out of range (%lld)", N);
+  HN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "hn_loss_hardnet: workspace must be 256-byte aligned");
+  HN_REQUIRE(workspace_bytes >= hn_dist_workspace_bytes(N, N, 1), "hn_loss_hardnet: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ExactWs w = carve_exact(workspace, N, N);
+  HN_TRY(run_exact(anchor, positive, N, N, HN_FORM_HARDNET, HN_FLAG_LOSS_MASK | (anchor_swap ? HN_FLAG_SWAP : 0), w, s));
+  loss_finalize_kernel<<<1, 1024, 0, s>>>(w.pos, w.row_pack, anchor_swap ? w.col_pack : nullptr, N, margin, loss_out);
+  HN_CUDA(cudaGetLastError());
+  return HN_OK;
+}
+
+extern "C" int hn_match(const float* q, const float* g, long long Nq, long long Ng, long long g_offset, float* d1,
+                        float* d2, int32_t* i1, int32_t* i2, void* workspace, long long workspace_bytes, void* stream) {
+  HN_REQUIRE(q && g && workspace, "hn_match: NULL argument");
+  HN_REQUIRE(Nq >= 1 && Ng >= 1, "hn_match: empty input (Nq=%lld, Ng=%lld)", Nq, Ng);
+  HN_REQUIRE(Nq < (1LL << 31) && Ng + g_offset < (1LL << 31), "hn_match: more than 2^31 rows");
+  HN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "hn_match: workspace must be 256-byte aligned");
+  HN_REQUIRE(workspace_bytes >= hn_dist_workspace_bytes(Nq, Ng, 0), "hn_match: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int sm = 0;
+  HN_TRY(device_sm_count(&sm));
+  char* b = static_cast<char*>(workspace);
+  uint16_t* q16 = reinterpret_cast<uint16_t*>(b);
+  uint16_t* g16 = reinterpret_cast<uint16_t*>(b + align256(static_cast<size_t>(Nq) * 256));
+  int* cand = reinterpret_cast<int*>(b + align256(static_cast<size_t>(Nq) * 256) + align256(static_cast<size_t>(Ng) * 256));
+  const int threads = 256;
+  pack_desc_kernel<<<static_cast<unsigned>((Nq * 32 + threads - 1) / threads), threads, 0, s>>>(q, Nq, q16, 0, 0, nullptr);
+  pack_desc_kernel<<<static_cast<unsigned>((Ng * 32 + threads - 1) / threads), threads, 0, s>>>(g, Ng, g16, 0, 1, nullptr);
+  HN_CUDA(cudaGetLastError());
+  DistParams dp;
+  memset(&dp, 0, sizeof(dp));
+  HN_TRY(make_desc_map(&dp.side[0].tmA, q16, Nq, 128));
+  HN_TRY(make_desc_map(&dp.side[0].tmB, g16, Ng, 128));
+  dp.side[0].cand = cand;
+  dp.side[0].Na = Nq;
+  dp.side[0].Nb = Ng;
+  dp.k_blocks = 2;
+  dp.form = HN_FORM_FDL;
+  dp.dot_scale = kDotScale;
+  dp.segments = pick_segments(Nq, 2 * kDistTile, Ng, sm, 16);
+  const long long items = ((Nq + 2 * kDistTile - 1) / (2 * kDistTile)) * dp.segments;
+  HN_TRY((launch_dist<2, EPI_SHORTLIST>(dp, static_cast<int>(std::min<long long>(items, sm)), 1, s)));
+  rerank_kernel<<<static_cast<unsigned>((Nq + 3) / 4), 128, 0, s>>>(q, g, cand, Nq, Ng, dp.segments * kTopC, g_offset, d1, d2,
+                                                                   i1, i2);
+  HN_CUDA(cudaGetLastError());
+  return HN_OK;
+}

@@ -1,0 +1,306 @@
+// Fused descriptor-distance kernels: a tcgen05 GEMM (D = A * B^T over 128-d descriptors) whose epilogue
+// reduces each 128 x 128 accumulator tile in registers, so the Na x Nb distance matrix never exists in
+// HBM. Replaces distance_matrix_vector + the masking / min / sort sequences of the reference
+// (hardnet/Losses.py:5-13,95-108; FDLNet-master/utils/math_utils.py:8-19, eval_utils.py:113-114,168-175).
+//
+// A work item is (block of MB*128 A-rows, segment of B). The A block stays resident in shared memory
+// (K <= 384), B tiles of 128 rows stream through a TMA ring, accumulators are double buffered in TMEM.
+//
+//   EPI_EXACT : operands are 3-way split fp16 (K = 384: hi*hi + hi*lo + lo*hi ~ fp32 dot). Every element
+//               goes through the reference arithmetic (norms, eps, sqrt, diagonal / duplicate masks) and
+//               feeds a per-row (value, index) minimum. Used for the loss and for hn_dist_min.
+//   EPI_SHORTLIST : single fp16 pass (K = 128). Per row, the TOPC best 8-column chunks by dot product
+//               are kept (max3 trees + a rarely taken sorted insert); a tiny fp32 kernel then re-ranks
+//               those candidates exactly. Used for bulk matching.
+#pragma once
+
+#include "../../include/hardnet_b200.h"
+#include "common.cuh"
+
+namespace hn {
+
+constexpr int kDistTile = 128;
+constexpr int kDistStages = 4;
+constexpr int kTopC = 4;     // chunks kept per row and segment
+constexpr int kChunk = 8;    // columns per chunk
+
+enum : int { EPI_EXACT = 0, EPI_SHORTLIST = 1 };
+
+struct DistSide {
+  CUtensorMap tmA;             // rows of this launch direction, [Na, K] 16-bit
+  CUtensorMap tmB;             // columns, [Nb, K]
+  const float* norm_a;         // |a_i|^2 (hardnet form)
+  const float* norm_b;
+  unsigned long long* row_pack;  // EXACT: packed (float bits << 32 | col) running minimum per row
+  float* pos;                  // EXACT: diagonal distance before masking (may be null)
+  int* cand;                   // SHORTLIST: [Na, segments, kTopC] chunk ids
+  long long Na, Nb;
+};
+
+struct DistParams {
+  DistSide side[2];            // [1] = transposed problem (anchor swap / column minima)
+  int k_blocks;                // K / 64
+  int segments;
+  int form;                    // HN_FORM_*
+  int loss_mask;               // apply +1e-8, diagonal +10, (<0.008) +10
+  float dot_scale;             // undoes the power-of-two operand scaling
+};
+
+template <int MB>
+constexpr size_t dist_smem_bytes(int k_blocks) {
+  return size_t(MB) * k_blocks * (kDistTile * 128) + size_t(kDistStages) * (kDistTile * 128) + 1024 + 256 + 2 * kDistTile * 4;
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+template <int MB, int EPI>
+__global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_constant__ DistParams p) {
+  constexpr uint32_t BLK_BYTES = kDistTile * 128;  // 128 rows x 64 fp16
+  constexpr uint32_t TMEM_COLS = 2 * MB * kDistTile;
+  const DistSide& sd = p.side[blockIdx.y];
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + MB * p.k_blocks * BLK_BYTES;
+  const uint32_t bar_base = b_base + kDistStages * BLK_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kDistStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kDistStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kDistStages + 2 + a); };
+  const uint32_t afull_bar = bar_base + 8u * (2 * kDistStages + 4);
+  const uint32_t aempty_bar = bar_base + 8u * (2 * kDistStages + 5);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kDistStages + 6);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
+  float* s_nb = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));  // [2][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = static_cast<int>((sd.Na + MB * kDistTile - 1) / (MB * kDistTile));
+  const int n_tiles = static_cast<int>((sd.Nb + kDistTile - 1) / kDistTile);
+  const int num_items = m_blocks * p.segments;
+  auto seg_range = [&](int seg, int& t0, int& t1) {
+    t0 = static_cast<int>(static_cast<long long>(n_tiles) * seg / p.segments);
+    t1 = static_cast<int>(static_cast<long long>(n_tiles) * (seg + 1) / p.segments);
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&sd.tmA);
+    tma_prefetch_desc(&sd.tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kDistStages; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 4 * MB);
+      }
+      mbar_init(afull_bar, 1);
+      mbar_init(aempty_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int mblk = item / p.segments, seg = item - mblk * p.segments;
+        int t0, t1;
+        seg_range(seg, t0, t1);
+        mbar_wait(aempty_bar, a_phase ^ 1u);
+        mbar_arrive_expect_tx(afull_bar, MB * p.k_blocks * BLK_BYTES);
+        for (int mb = 0; mb < MB; ++mb)
+          for (int kb = 0; kb < p.k_blocks; ++kb)
+            tma_load_2d(a_base + (mb * p.k_blocks + kb) * BLK_BYTES, &sd.tmA, afull_bar, kb * 64,
+                        (mblk * MB + mb) * kDistTile);
+        a_phase ^= 1u;
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), BLK_BYTES);
+            tma_load_2d(b_base + stage * BLK_BYTES, &sd.tmB, full_bar(stage), kb * 64, t * kDistTile);
+            if (++stage == kDistStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== UMMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(kDistTile, kDistTile, 0);
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int mblk = item / p.segments, seg = item - mblk * p.segments;
+        int t0, t1;
+        seg_range(seg, t0, t1);
+        mbar_wait(afull_bar, a_phase);
+        a_phase ^= 1u;
+        tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_phase = (it >> 1) & 1;
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t b_desc = make_kmajor_desc(b_base + stage * BLK_BYTES, 128);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint64_t a_desc = make_kmajor_desc(a_base + (mb * p.k_blocks + kb) * BLK_BYTES, 128);
+              const uint32_t d_tmem = tmem_base + (acc * MB + mb) * kDistTile;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+            }
+            umma_commit(empty_bar(stage));
+            if (++stage == kDistStages) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(tfull_bar(acc));
+        }
+        umma_commit(aempty_bar);  // the resident A block may be overwritten once these MMAs retired
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int q = warp & 3;
+    const int mb = (warp - 2) >> 2;
+    const int ep_tid = threadIdx.x - 64;  // 0 .. 128*MB-1
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int mblk = item / p.segments, seg = item - mblk * p.segments;
+      int t0, t1;
+      seg_range(seg, t0, t1);
+      const long long row = static_cast<long long>(mblk * MB + mb) * kDistTile + q * 32 + lane;
+      const bool row_ok = row < sd.Na;
+
+      // per-row running state
+      float best = __int_as_float(0x7f800000);
+      int best_col = 0x7fffffff;
+      float na = 0.f;
+      float tb[kTopC];
+      int tc[kTopC];
+      if (EPI == EPI_EXACT) {
+        if (p.form == HN_FORM_HARDNET && row_ok) na = sd.norm_a[row];
+      } else {
+#pragma unroll
+        for (int i = 0; i < kTopC; ++i) { tb[i] = -__int_as_float(0x7f800000); tc[i] = 0; }
+      }
+
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        const long long col0 = static_cast<long long>(t) * kDistTile;
+        if (EPI == EPI_EXACT && p.form == HN_FORM_HARDNET) {
+          // column norms of this tile -> smem (double buffered with the accumulator)
+          if (ep_tid < kDistTile) {
+            const long long c = col0 + ep_tid;
+            s_nb[acc * kDistTile + ep_tid] = c < sd.Nb ? sd.norm_b[c] : 0.f;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * MB) : "memory");
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * MB + mb) * kDistTile;
+        const bool ragged = col0 + kDistTile > sd.Nb;
+#pragma unroll
+        for (int c0 = 0; c0 < kDistTile; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c0, r);
+          tmem_ld_wait();
+          if (EPI == EPI_EXACT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const long long col = col0 + c0 + j;
+              const float dot = __uint_as_float(r[j]) * p.dot_scale;
+              float d;
+              if (p.form == HN_FORM_HARDNET) {
+                // sqrt((|a|^2 + |p|^2) - 2ab + 1e-6), hardnet/Losses.py:12-13
+                const float s = (na + s_nb[acc * kDistTile + c0 + j]) - 2.0f * dot;
+                d = sqrtf(s + 1e-6f);
+              } else {
+                // sqrt(clamp(2 - 2ab, 1e-8, 4)), FDLNet-master/utils/math_utils.py:15-18
+                d = sqrtf(fminf(fmaxf(2.0f - 2.0f * dot, 1e-8f), 4.0f));
+              }
+              if (p.loss_mask) {
+                d += 1e-8f;                                   // Losses.py:95
+                if (col == row) {
+                  if (sd.pos && row_ok) sd.pos[row] = d;      // Losses.py:99 (before masking)
+                  d += 10.0f;                                 // Losses.py:100
+                }
+                if (d < 0.008f) d += 10.0f;                   // Losses.py:101-103
+              }
+              if (col < sd.Nb && d < best) { best = d; best_col = static_cast<int>(col); }
+            }
+          } else {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (ragged) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + c0 + j >= sd.Nb) v[j] = -__int_as_float(0x7f800000);
+            }
+#pragma unroll
+            for (int s = 0; s < 32 / kChunk; ++s) {
+              const float* w = v + s * kChunk;
+              const float m = fmaxf(max3(w[0], w[1], w[2]), max3(max3(w[3], w[4], w[5]), w[6], w[7]));
+              if (m > tb[kTopC - 1]) {
+                const int id = static_cast<int>((col0 + c0) / kChunk) + s;
+                // sorted insert (descending); strict '>' keeps the earlier chunk on ties
+                const bool g0 = m > tb[0], g1 = m > tb[1], g2 = m > tb[2];
+                tb[3] = g2 ? tb[2] : m;               tc[3] = g2 ? tc[2] : id;
+                tb[2] = g2 ? (g1 ? tb[1] : m) : tb[2]; tc[2] = g2 ? (g1 ? tc[1] : id) : tc[2];
+                tb[1] = g1 ? (g0 ? tb[0] : m) : tb[1]; tc[1] = g1 ? (g0 ? tc[0] : id) : tc[1];
+                tb[0] = g0 ? m : tb[0];               tc[0] = g0 ? id : tc[0];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      }
+
+      if (row_ok) {
+        if (EPI == EPI_EXACT) {
+          if (sd.row_pack && best_col != 0x7fffffff) {
+            const unsigned long long pk =
+                (static_cast<unsigned long long>(__float_as_uint(best)) << 32) | static_cast<unsigned int>(best_col);
+            atomicMin(sd.row_pack + row, pk);  // distances are positive: bit pattern is order preserving
+          }
+        } else {
+          int4* dst = reinterpret_cast<int4*>(sd.cand + (row * p.segments + seg) * kTopC);
+          // unused slots (segment with < kTopC chunks) are marked -1
+          *dst = make_int4(tb[0] > -3.0e38f ? tc[0] : -1, tb[1] > -3.0e38f ? tc[1] : -1, tb[2] > -3.0e38f ? tc[2] : -1,
+                           tb[3] > -3.0e38f ? tc[3] : -1);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace hn

@@ -1,0 +1,137 @@
+"""Drop-in mirror of hardnet/Losses.py (and hardnetNAS/general_functions/Losses.py) for the hot path.
+
+`loss_HardNet(..., batch_reduce='min', loss_type='triplet_margin')` — the configuration the reference trains
+with (hardnet/HardNet.py:408-413) — runs as one fused B200 pass: tensor-core distance GEMM whose epilogue
+applies the eps / diagonal / duplicate masks and the row (and column) minima. The N x N matrix is never
+materialised. The other reduce / loss modes are elementwise variants outside the accelerated path and are
+evaluated with the same torch expression sequence as the reference.
+"""
+from __future__ import annotations
+
+import sys
+
+import torch
+
+from . import _lib, _ops
+
+
+def distance_matrix_vector(anchor, positive):
+    """Materialising API, kept for small N (hardnet/Losses.py:5-13). The fused paths never call it."""
+    d1_sq = torch.sum(anchor * anchor, dim=1).unsqueeze(-1)
+    d2_sq = torch.sum(positive * positive, dim=1).unsqueeze(-1)
+    eps = 1e-6
+    return torch.sqrt((d1_sq + d2_sq.t()) - 2.0 * torch.mm(anchor, positive.t()) + eps)
+
+
+def _masked_matrix(anchor, positive):
+    eps = 1e-8
+    dist_matrix = distance_matrix_vector(anchor, positive) + eps
+    eye = torch.eye(dist_matrix.size(1), device=dist_matrix.device, dtype=dist_matrix.dtype)
+    pos1 = torch.diag(dist_matrix)
+    d = dist_matrix + eye * 10
+    mask = (d.ge(0.008).float() - 1.0) * (-1)
+    d = d + mask.type_as(d) * 10
+    return pos1, d
+
+
+class _FusedHardestInBatch(torch.autograd.Function):
+    """Forward: fused kernel. Backward: gradients only flow through pos[i] and the selected negative of each
+    row (<= 2 non-zeros per row), rebuilt from the arg-indices the fused kernel returns."""
+
+    @staticmethod
+    def forward(ctx, anchor, positive, margin, anchor_swap):
+        res = _ops.dist_min(anchor, positive, _lib.HN_FORM_HARDNET, loss_mask=True, swap=anchor_swap)
+        pos, row_min = res["pos"], res["row_min"]
+        min_neg = torch.minimum(row_min, res["col_min"]) if anchor_swap else row_min
+        per_row = torch.clamp(margin + pos - min_neg, min=0.0)
+        ctx.save_for_backward(anchor, positive, pos, min_neg, row_min, res["row_arg"],
+                              res["col_min"] if anchor_swap else row_min, res["col_arg"] if anchor_swap else res["row_arg"])
+        ctx.margin, ctx.swap = margin, anchor_swap
+        return per_row.mean()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        anchor, positive, pos, min_neg, row_min, row_arg, col_min, col_arg = ctx.saved_tensors
+        n = anchor.size(0)
+        a, p = anchor.detach().float(), positive.detach().float()
+        active = ((ctx.margin + pos - min_neg) > 0).float() * (grad_out / n)
+        ga = torch.zeros_like(a)
+        gp = torch.zeros_like(p)
+        # d/da of sqrt(|a-p|^2 + 1e-6) = (a - p) / d ; pos already carries the +1e-8
+        diff = a - p
+        w = (active / (pos - 1e-8)).unsqueeze(1)
+        ga += w * diff
+        gp -= w * diff
+        idx = torch.arange(n, device=a.device)
+        use_col = (col_min < row_min) if ctx.swap else torch.zeros(n, dtype=torch.bool, device=a.device)
+        # negative taken from the row: pair (a_i, p_j*), masked values (+10) have the same gradient as d
+        j = row_arg.long()
+        sel = (~use_col).float() * active
+        dneg = (a - p[j])
+        dn = torch.sqrt((dneg * dneg).sum(1) + 1e-6).unsqueeze(1)
+        g = (sel.unsqueeze(1) * dneg / dn)
+        ga -= g
+        gp.index_add_(0, j, g)
+        if ctx.swap:
+            # negative taken from the column: pair (a_k*, p_i)
+            k = col_arg.long()
+            selc = use_col.float() * active
+            dneg = (a[k] - p)
+            dn = torch.sqrt((dneg * dneg).sum(1) + 1e-6).unsqueeze(1)
+            g = (selc.unsqueeze(1) * dneg / dn)
+            ga.index_add_(0, k, -g)
+            gp += g
+        del idx
+        return ga.to(anchor.dtype), gp.to(positive.dtype), None, None
+
+
+def loss_HardNet(anchor, positive, anchor_swap=False, anchor_ave=False, margin=1.0, batch_reduce='min',
+                 loss_type="triplet_margin"):
+    """HardNet margin loss (hardnet/Losses.py:87-154): positive distance vs closest in-batch negative."""
+    assert anchor.size() == positive.size(), "Input sizes between positive and negative must be equal."
+    assert anchor.dim() == 2, "Inputd must be a 2D matrix."
+    if batch_reduce == 'min' and loss_type == "triplet_margin":
+        if torch.is_grad_enabled() and (anchor.requires_grad or positive.requires_grad):
+            return _FusedHardestInBatch.apply(anchor, positive, float(margin), bool(anchor_swap))
+        return _ops.loss_hardnet(anchor, positive, float(margin), bool(anchor_swap))
+    # ---- modes outside the accelerated path: same expression sequence as the reference ----------------
+    eps = 1e-8
+    pos1, d = _masked_matrix(anchor, positive)
+    if batch_reduce == 'min':
+        min_neg = torch.min(d, 1)[0]
+        if anchor_swap:
+            min_neg = torch.min(min_neg, torch.min(d, 0)[0])
+        pos = pos1
+    elif batch_reduce == 'average':
+        pos = pos1.repeat(anchor.size(0)).view(-1, 1).squeeze(0)
+        min_neg = d.view(-1, 1)
+        if anchor_swap:
+            min_neg = torch.min(min_neg, torch.t(d).contiguous().view(-1, 1))
+        min_neg = min_neg.squeeze(0)
+    elif batch_reduce == 'random':
+        idxs = torch.randperm(anchor.size(0), device=anchor.device).long()
+        min_neg = d.gather(1, idxs.view(-1, 1))
+        if anchor_swap:
+            min_neg = torch.min(min_neg, torch.t(d).gather(1, idxs.view(-1, 1)))
+        min_neg = torch.t(min_neg).squeeze(0)
+        pos = pos1
+    else:
+        print('Unknown batch reduce mode. Try min, average or random')
+        sys.exit(1)
+    if loss_type == "triplet_margin":
+        loss = torch.clamp(margin + pos - min_neg, min=0.0)
+    elif loss_type == 'softmax':
+        exp_pos = torch.exp(2.0 - pos)
+        exp_den = exp_pos + torch.exp(2.0 - min_neg) + eps
+        loss = -torch.log(exp_pos / exp_den)
+    elif loss_type == 'contrastive':
+        loss = torch.clamp(margin - min_neg, min=0.0) + pos
+    else:
+        print('Unknown loss type. Try triplet_margin, softmax or contrastive')
+        sys.exit(1)
+    return torch.mean(loss)
+
+
+def loss_HardNet_nas(anchor, positive, margin=1.0):
+    """hardnetNAS/general_functions/Losses.py:27-51 — same loss with anchor swap always on."""
+    return loss_HardNet(anchor, positive, anchor_swap=True, margin=margin)

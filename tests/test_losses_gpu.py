@@ -1,0 +1,160 @@
+"""GPU parity of the fused distance / hardest-in-batch loss (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hardnet_oracle, losses_oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-4      # stated bound; the split-fp16 GEMM is fp32-class, observed ~1e-6
+DIST_TOL = 2e-5
+TIE_TAU = 1e-5       # near-tie rule: a different argmin is accepted iff the reference distances differ <= tau
+
+
+def _unit_pairs(n, seed, noise=0.05):
+    a = synth.unit_vectors(n, 128, seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    p = a + noise * torch.randn(n, 128, generator=g)
+    p = p / p.norm(dim=1, keepdim=True)
+    k = max(1, n // 5)
+    p[-k:] = synth.unit_vectors(k, 128, seed + 200)  # some rows without a true positive
+    return a.contiguous(), p.contiguous()
+
+
+def _check_args(ref_d, ref_arg, got_arg, what):
+    got_arg = got_arg.cpu().long()
+    bad = (got_arg != ref_arg).nonzero().flatten()
+    for i in bad.tolist():
+        delta = abs(ref_d[i, got_arg[i]].item() - ref_d[i, ref_arg[i]].item())
+        assert delta <= TIE_TAU, f"{what}: row {i} picked {got_arg[i]} vs {ref_arg[i]} (|dD|={delta:.3e})"
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 127, 128, 129, 500, 1024])
+@pytest.mark.parametrize("swap", [False, True])
+def test_loss_matches_oracle(n, swap):
+    from hardnetnas_b200.losses import loss_HardNet
+    a, p = _unit_pairs(n, 40 + n)
+    ref = losses_oracle.loss_hardnet(a, p, swap, 1.0).item()
+    got = loss_HardNet(a.cuda(), p.cuda(), anchor_swap=swap).item()
+    assert abs(got - ref) <= LOSS_TOL, (got, ref)
+    got05 = loss_HardNet(a.cuda(), p.cuda(), anchor_swap=swap, margin=0.5).item()
+    assert abs(got05 - losses_oracle.loss_hardnet(a, p, swap, 0.5).item()) <= LOSS_TOL
+
+
+def test_loss_matches_reference_goldens(golden_dir):
+    from hardnetnas_b200.losses import loss_HardNet, loss_HardNet_nas
+    g = np.load(golden_dir / "losses.npz")
+    ua = synth.unit_vectors(512, 128, 21)
+    up = synth.unit_vectors(512, 128, 22)
+    up[:400] = ua[:400] + 0.05 * torch.randn(400, 128, generator=torch.Generator().manual_seed(23))
+    up = up / up.norm(dim=1, keepdim=True)
+    for swap in (False, True):
+        got = loss_HardNet(ua.cuda(), up.cuda(), anchor_swap=swap).item()
+        assert abs(got - float(g[f"loss_unit_swap{int(swap)}"])) <= LOSS_TOL
+    assert abs(loss_HardNet_nas(ua.cuda(), up.cuda()).item() - float(g["loss_nas_unit"])) <= LOSS_TOL
+    # descriptors of the reference model (fresh BN), incl. the duplicate-row (<0.008 -> +10) mask cases
+    w, m, v = synth.hardnet_weights_from_seed(0, None)
+    anchors = synth.make_patches(256, 1234)
+    positives = synth.make_positives(anchors, 0.1, 7)
+    da = hardnet_oracle.hardnet_forward(anchors, w, m, v)
+    dp = hardnet_oracle.hardnet_forward(positives, w, m, v)
+    for swap in (False, True):
+        assert abs(loss_HardNet(da.cuda(), dp.cuda(), anchor_swap=swap).item() - float(g[f"loss_swap{int(swap)}"])) <= LOSS_TOL
+        assert abs(loss_HardNet(da.cuda(), dp.cuda(), anchor_swap=swap, margin=0.5).item()
+                   - float(g[f"loss_swap{int(swap)}_m05"])) <= LOSS_TOL
+    dp2 = dp.clone()
+    dp2[3] = da[3]
+    dp2[5] = da[9]
+    for swap in (False, True):
+        assert abs(loss_HardNet(da.cuda(), dp2.cuda(), anchor_swap=swap).item() - float(g[f"loss_dup_swap{int(swap)}"])) <= LOSS_TOL
+
+
+@pytest.mark.parametrize("n", [64, 300, 1024])
+def test_dist_min_parts(n):
+    from hardnetnas_b200 import _lib, _ops
+    a, p = _unit_pairs(n, 7 + n)
+    p[1] = a[1]          # exact duplicate of its anchor: positive distance below 0.008 -> masked
+    if n > 10:
+        p[4] = a[9]      # off-diagonal duplicate: excluded from the negatives by the (<0.008) mask
+    pos, min_neg, row_arg, col_min, col_arg = losses_oracle.loss_hardnet_parts(a, p, anchor_swap=False)
+    res = _ops.dist_min(a.cuda(), p.cuda(), _lib.HN_FORM_HARDNET, loss_mask=True, swap=True)
+    assert (res["pos"].cpu() - pos).abs().max().item() <= DIST_TOL
+    assert (res["row_min"].cpu() - min_neg).abs().max().item() <= DIST_TOL
+    assert (res["col_min"].cpu() - col_min).abs().max().item() <= DIST_TOL
+    # masked reference matrix for the near-tie rule
+    d = losses_oracle.distance_matrix_vector(a, p) + 1e-8
+    d = d + torch.eye(n) * 10
+    d = d + (d < 0.008).float() * 10
+    _check_args(d, row_arg, res["row_arg"], "row")
+    _check_args(d.t(), col_arg, res["col_arg"], "col")
+
+
+def test_dist_min_rectangular_fdl():
+    from hardnetnas_b200 import _lib, _ops
+    a = synth.unit_vectors(333, 128, 1)
+    p = synth.unit_vectors(777, 128, 2)
+    d = losses_oracle.distance_matrix_vector_fdl(a, p)
+    res = _ops.dist_min(a.cuda(), p.cuda(), _lib.HN_FORM_FDL, loss_mask=False, swap=True)
+    v, i = d.min(1)
+    assert (res["row_min"].cpu() - v).abs().max().item() <= DIST_TOL
+    _check_args(d, i, res["row_arg"], "row")
+    v, i = d.min(0)
+    assert (res["col_min"].cpu() - v).abs().max().item() <= DIST_TOL
+    _check_args(d.t(), i, res["col_arg"], "col")
+
+
+def test_loss_backward_matches_autograd():
+    from hardnetnas_b200.losses import loss_HardNet
+    a, p = _unit_pairs(256, 3)
+    for swap in (False, True):
+        ar, pr = a.clone().requires_grad_(True), p.clone().requires_grad_(True)
+        pos, min_neg, *_ = losses_oracle.loss_hardnet_parts(ar, pr, swap)
+        torch.mean(torch.clamp(1.0 + pos - min_neg, min=0.0)).backward()
+        ag, pg = a.cuda().requires_grad_(True), p.cuda().requires_grad_(True)
+        loss_HardNet(ag, pg, anchor_swap=swap).backward()
+        assert (ag.grad.cpu() - ar.grad).abs().max().item() <= 1e-5
+        assert (pg.grad.cpu() - pr.grad).abs().max().item() <= 1e-5
+
+
+def test_other_modes_follow_reference_expressions():
+    from hardnetnas_b200.losses import loss_HardNet
+    a, p = _unit_pairs(64, 5)
+    ac, pc = a.cuda(), p.cuda()
+    pos, d = None, None
+    # 'average' + softmax / contrastive are plain torch expressions; check one against a direct evaluation
+    pos1, min_neg, *_ = losses_oracle.loss_hardnet_parts(a, p, False)
+    ref = torch.mean(torch.clamp(1.0 - min_neg, min=0.0) + pos1).item()
+    assert abs(loss_HardNet(ac, pc, loss_type="contrastive").item() - ref) <= 1e-5
+    with pytest.raises(SystemExit):
+        loss_HardNet(ac, pc, batch_reduce="bogus")
+    with pytest.raises(AssertionError):
+        loss_HardNet(ac, pc[:10])
+
+
+def test_cpu_tensors_fail_loudly():
+    from hardnetnas_b200._lib import HardnetB200Error
+    from hardnetnas_b200.losses import loss_HardNet
+    a, p = _unit_pairs(16, 1)
+    with pytest.raises(HardnetB200Error):
+        loss_HardNet(a, p)
+
+
+def test_config2_forward_plus_loss():
+    """BASELINE config 2: HardNet forward of 1024 anchors + positives and loss_HardNet on the descriptors."""
+    from hardnetnas_b200.hardnet import HardNet
+    from hardnetnas_b200.losses import loss_HardNet
+    w, m, v = synth.hardnet_weights_from_seed(0, None)
+    torch.manual_seed(0)
+    model = HardNet().cuda().eval()
+    anchors = synth.make_patches(1024, 1234)
+    positives = synth.make_positives(anchors, 0.1, 7)
+    da, dp = model(anchors.cuda()), model(positives.cuda())
+    ra = hardnet_oracle.hardnet_forward(anchors, w, m, v)
+    rp = hardnet_oracle.hardnet_forward(positives, w, m, v)
+    for swap in (False, True):
+        # same descriptors on both sides: isolates the loss kernel
+        assert abs(loss_HardNet(ra.cuda(), rp.cuda(), anchor_swap=swap).item()
+                   - losses_oracle.loss_hardnet(ra, rp, swap).item()) <= LOSS_TOL
+        # end to end (16-bit conv stack): stated bound 1e-3
+        assert abs(loss_HardNet(da, dp, anchor_swap=swap).item() - losses_oracle.loss_hardnet(ra, rp, swap).item()) <= 1e-3

@@ -1,0 +1,103 @@
+"""GPU parity of fused brute-force matching (NN, ratio test, mutual NN) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses_oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+TIE_TAU = 1e-5
+DIST_TOL = 2e-6
+
+
+def _check(q, g, chunk=1024):
+    from hardnetnas_b200.matching import match_top2
+    d1, d2, i1, i2 = [t.cpu() for t in match_top2(q.cuda(), g.cuda())]
+    lab, ia, da, db = losses_oracle.ratio_match(q, g, 0.7, chunk) if g.size(0) >= 2 else (None, None, None, None)
+    if g.size(0) >= 2:
+        assert (d1 - da).abs().max().item() <= DIST_TOL
+        assert (d2 - db).abs().max().item() <= DIST_TOL
+        bad = (i1 != ia).nonzero().flatten().tolist()
+        if bad:
+            d = losses_oracle.distance_matrix_vector_fdl(q[bad], g)
+            for r, i in enumerate(bad):
+                assert abs(d[r, i1[i]].item() - d[r, ia[i]].item()) <= TIE_TAU, f"row {i}: {i1[i]} vs {ia[i]}"
+        got_lab = (d1 / d2) < 0.7
+        diff = (got_lab != lab).nonzero().flatten().tolist()
+        for i in diff:
+            assert abs((da[i] / db[i]).item() - 0.7) <= 1e-4
+    else:
+        v, i = losses_oracle.nn_match(q, g, chunk)
+        assert (d1 - v).abs().max().item() <= DIST_TOL and torch.equal(i1, i)
+    return d1, d2, i1, i2
+
+
+def test_matches_reference_goldens(golden_dir):
+    from hardnetnas_b200.matching import nearest_neighbor_distance_ratio_match, nearest_neighbor_match
+    g = np.load(golden_dir / "matching.npz")
+    q, gal, truth = synth.make_match_set(768, 2048, seed=11)
+    val, idx = nearest_neighbor_match(q.cuda(), gal.cuda())
+    np.testing.assert_array_equal(idx.cpu().numpy(), g["nn_idx"])
+    np.testing.assert_allclose(val.cpu().numpy(), g["nn_val"], atol=DIST_TOL)
+    kp2 = torch.arange(2048).view(-1, 1).float().cuda()
+    lab, nn_kp2 = nearest_neighbor_distance_ratio_match(q.cuda(), gal.cuda(), kp2, 0.7)
+    np.testing.assert_array_equal(lab.cpu().numpy(), g["ratio_label"])
+    np.testing.assert_array_equal(nn_kp2.view(-1).long().cpu().numpy(), g["ratio_idx"])
+
+
+@pytest.mark.parametrize("nq,ng", [(1, 1), (1, 2), (5, 7), (8, 8), (100, 9), (256, 128), (257, 129), (1000, 4097), (4096, 8192)])
+def test_ragged_sizes(nq, ng):
+    q, g, _ = synth.make_match_set(nq, ng, seed=3 + nq)
+    _check(q, g)
+
+
+def test_unstructured_descriptors_near_ties():
+    # worst case for a 16-bit shortlist: all distances close together
+    q = synth.unit_vectors(2048, 128, 5)
+    g = synth.unit_vectors(6000, 128, 6)
+    _check(q, g)
+
+
+def test_duplicate_gallery_rows_pick_first_index():
+    q, g, _ = synth.make_match_set(64, 512, seed=9)
+    g[300] = g[20]
+    g[40] = g[20]
+    q[0] = g[20]
+    d1, d2, i1, i2 = _check(q, g)
+    assert i1[0].item() == 20 and i2[0].item() == 40
+
+
+def test_mutual_nn_matches_oracle():
+    from hardnetnas_b200.matching import mutual_nearest_neighbors
+    q, g, truth = synth.make_match_set(3000, 5000, seed=21)
+    pairs = mutual_nearest_neighbors(q.cuda(), g.cuda()).cpu()
+    ref = losses_oracle.mutual_nn(q, g)
+    assert torch.equal(pairs, ref)
+    planted = truth >= 0
+    got = torch.full((3000,), -1, dtype=torch.long)
+    got[pairs[:, 0]] = pairs[:, 1]
+    assert (got[planted] == truth[planted]).float().mean().item() > 0.99
+
+
+def test_config4_full_size_properties():
+    """BASELINE config 4 (64k x 64k): planted matches are recovered, a row sample equals the oracle, and the
+    mutual check is self-consistent."""
+    from hardnetnas_b200.matching import match_top2
+    q, g, truth = synth.make_match_set(65536, 65536, seed=11)
+    qc, gc = q.cuda(), g.cuda()
+    d1, d2, i1, i2 = match_top2(qc, gc)
+    planted = (truth >= 0)
+    assert torch.equal(i1.cpu()[planted], truth[planted])
+    assert (d1 <= d2).all()
+    rows = torch.arange(0, 65536, 32)
+    lab, ia, da, db = losses_oracle.ratio_match(q[rows], g, 0.7, chunk=512)
+    assert (d1.cpu()[rows] - da).abs().max().item() <= DIST_TOL
+    assert (d2.cpu()[rows] - db).abs().max().item() <= DIST_TOL
+    mism = (i1.cpu()[rows] != ia).nonzero().flatten().tolist()
+    for r in mism:
+        assert abs(d1.cpu()[rows][r].item() - da[r].item()) <= TIE_TAU
+    # ratio test rejects the distractor queries
+    ratio = (d1 / d2).cpu()
+    assert (ratio[planted] < 0.7).float().mean().item() > 0.99
+    assert (ratio[~planted] < 0.7).float().mean().item() < 0.01
