@@ -163,6 +163,7 @@ static int launch_dist(const DistParams& p, int grid_x, int grid_y, cudaStream_t
   }
   kern<<<dim3(grid_x, grid_y), 64 + 128 * MB, smem, s>>>(p);
   HN_CUDA(cudaGetLastError());
+  count_launch();
   return HN_OK;
 }
 
@@ -206,6 +207,7 @@ static int run_exact(const float* a, const float* p, long long Na, long long Np,
   pack_desc_kernel<<<static_cast<unsigned>((Na * 32 + threads - 1) / threads), threads, 0, s>>>(a, Na, w.a16, 1, 0, w.na);
   pack_desc_kernel<<<static_cast<unsigned>((Np * 32 + threads - 1) / threads), threads, 0, s>>>(p, Np, w.p16, 1, 1, w.np);
   HN_CUDA(cudaGetLastError());
+  count_launch(2);
   HN_CUDA(cudaMemsetAsync(w.row_pack, 0xff, static_cast<size_t>(Na) * 8, s));
   const bool swap = (flags & HN_FLAG_SWAP) != 0;
   if (swap) HN_CUDA(cudaMemsetAsync(w.col_pack, 0xff, static_cast<size_t>(Np) * 8, s));
@@ -292,6 +294,7 @@ extern "C" int hn_loss_hardnet(const float* anchor, const float* positive, long 
   HN_TRY(run_exact(anchor, positive, N, N, HN_FORM_HARDNET, HN_FLAG_LOSS_MASK | (anchor_swap ? HN_FLAG_SWAP : 0), w, s));
   loss_finalize_kernel<<<1, 1024, 0, s>>>(w.pos, w.row_pack, anchor_swap ? w.col_pack : nullptr, N, margin, loss_out);
   HN_CUDA(cudaGetLastError());
+  count_launch();
   return HN_OK;
 }
 
@@ -329,5 +332,6 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   rerank_kernel<<<static_cast<unsigned>((Nq + 3) / 4), 128, 0, s>>>(q, g, cand, Nq, Ng, dp.segments * kTopC, g_offset, d1, d2,
                                                                    i1, i2);
   HN_CUDA(cudaGetLastError());
+  count_launch(3);
   return HN_OK;
 }

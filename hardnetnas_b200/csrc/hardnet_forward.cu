@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <vector>
 
@@ -39,9 +40,37 @@ struct hn_handle {
   float* bias = nullptr;                                               // 7 x 128
   hn::TcParams conv_params[5];
   hn::TcParams head_params;
+  // optional per-stage CUDA-event timing (stage 0 = L1, 1..5 = 3x3 convs, 6 = head)
+  unsigned profile_mask = 0;
+  std::vector<cudaEvent_t> ev[7];
+  size_t ev_used[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace hn {
+
+// Event pair around one launch of an instrumented stage (events are created on demand and reused).
+struct StageTimer {
+  hn_handle* h;
+  int stage;
+  cudaStream_t s;
+  bool on;
+  StageTimer(hn_handle* h_, int stage_, cudaStream_t s_) : h(h_), stage(stage_), s(s_), on((h_->profile_mask >> stage_) & 1u) {
+    if (on) record();
+  }
+  ~StageTimer() {
+    if (on) record();
+  }
+  void record() {
+    auto& v = h->ev[stage];
+    size_t& u = h->ev_used[stage];
+    if (u == v.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+      v.push_back(e);
+    }
+    cudaEventRecord(v[u++], s);
+  }
+};
 
 template <int N, int KCB, int STAGES, int LOAD, int EPI>
 static int launch_tc(const TcParams& p, int sm_count, cudaStream_t stream) {
@@ -56,6 +85,7 @@ static int launch_tc(const TcParams& p, int sm_count, cudaStream_t stream) {
   const int grid = std::min(p.num_tiles, sm_count);
   kern<<<grid, kTcThreads, smem, stream>>>(p);
   HN_CUDA(cudaGetLastError());
+  count_launch();
   return HN_OK;
 }
 
@@ -143,18 +173,18 @@ static int build_params(hn_handle* h) {
   return HN_OK;
 }
 
+static void run_l1(hn_handle* h, const void* patches, int in_dtype, int n, int grid1, cudaStream_t s);
+
 // Runs L1..L6 for `n` patches (n <= chunk); L6 lands in l6 + l6_row * 8192.
 static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n, long long l6_row, int last_layer,
                           cudaStream_t s) {
   const int grid1 = std::min(n, h->sm_count * 4);
-  if (in_dtype == HN_F32) {
-    l1_norm_conv_kernel<float><<<grid1, kL1Threads, 0, s>>>(static_cast<const float*>(patches), h->act[0], h->w1,
-                                                           h->bias, n, h->act_bf16, 1);
-  } else {
-    l1_norm_conv_kernel<uint8_t><<<grid1, kL1Threads, 0, s>>>(static_cast<const uint8_t*>(patches), h->act[0], h->w1,
-                                                             h->bias, n, h->act_bf16, 1);
+  {
+    StageTimer timer(h, 0, s);
+    run_l1(h, patches, in_dtype, n, grid1, s);
   }
   HN_CUDA(cudaGetLastError());
+  count_launch();
   for (int li = 0; li < 5 && li + 2 <= last_layer; ++li) {
     const ConvLayer& L = kConv[li];
     TcParams p = h->conv_params[li];
@@ -163,9 +193,20 @@ static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n
     p.num_tiles = static_cast<int>((p.total_rows + kTileM - 1) / kTileM);
     p.act_bf16 = h->act_bf16;
     p.out = (li == 4) ? static_cast<void*>(h->l6 + l6_row * kHeadK) : static_cast<void*>(h->act[(li + 1) & 1]);
+    StageTimer timer(h, li + 1, s);
     HN_TRY(launch_conv(li, p, h->sm_count, s));
   }
   return HN_OK;
+}
+
+static void run_l1(hn_handle* h, const void* patches, int in_dtype, int n, int grid1, cudaStream_t s) {
+  if (in_dtype == HN_F32) {
+    l1_norm_conv_kernel<float><<<grid1, kL1Threads, 0, s>>>(static_cast<const float*>(patches), h->act[0], h->w1,
+                                                           h->bias, n, h->act_bf16, 1);
+  } else {
+    l1_norm_conv_kernel<uint8_t><<<grid1, kL1Threads, 0, s>>>(static_cast<const uint8_t*>(patches), h->act[0], h->w1,
+                                                             h->bias, n, h->act_bf16, 1);
+  }
 }
 
 }  // namespace hn
@@ -230,6 +271,8 @@ extern "C" int hn_destroy(hn_handle* h) {
   cudaFree(h->whead);
   cudaFree(h->w1);
   cudaFree(h->bias);
+  for (auto& v : h->ev)
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
   delete h;
   return HN_OK;
 }
@@ -314,6 +357,7 @@ extern "C" int hn_forward(hn_handle* h, const void* patches, int in_dtype, long 
     p.act_bf16 = h->act_bf16;
     p.out_dtype = out_dtype;
     p.out = static_cast<char*>(desc_out) + static_cast<size_t>(base) * 128 * out_elem;
+    StageTimer timer(h, 6, s);
     HN_TRY((launch_tc<128, 128, 5, LOAD_GEMM, EPI_BIAS_L2NORM>(p, h->sm_count, s)));
   }
   return HN_OK;
@@ -334,5 +378,30 @@ extern "C" int hn_forward_dump(hn_handle* h, const void* patches, int in_dtype, 
   static const size_t per_patch[7] = {0, 32 * 32 * 32, 32 * 32 * 32, 16 * 16 * 64, 16 * 16 * 64, 8 * 8 * 128, 8 * 8 * 128};
   const uint16_t* src = layer == 6 ? h->l6 : h->act[(layer - 1) & 1];
   HN_CUDA(cudaMemcpyAsync(act_out, src, per_patch[layer] * 2 * static_cast<size_t>(B), cudaMemcpyDeviceToDevice, s));
+  return HN_OK;
+}
+
+extern "C" int hn_profile_enable(hn_handle* h, unsigned stage_mask) {
+  HN_REQUIRE(h, "hn_profile_enable: NULL handle");
+  h->profile_mask = stage_mask & 0x7fu;
+  for (size_t& u : h->ev_used) u = 0;
+  return HN_OK;
+}
+
+extern "C" int hn_profile_read(hn_handle* h, double ms_out[7], long long launches_out[7]) {
+  HN_REQUIRE(h && ms_out && launches_out, "hn_profile_read: NULL argument");
+  for (int st = 0; st < 7; ++st) {
+    double total = 0.0;
+    const size_t pairs = h->ev_used[st] / 2;
+    for (size_t i = 0; i < pairs; ++i) {
+      HN_CUDA(cudaEventSynchronize(h->ev[st][2 * i + 1]));
+      float ms = 0.f;
+      HN_CUDA(cudaEventElapsedTime(&ms, h->ev[st][2 * i], h->ev[st][2 * i + 1]));
+      total += ms;
+    }
+    ms_out[st] = total;
+    launches_out[st] = static_cast<long long>(pairs);
+    h->ev_used[st] = 0;
+  }
   return HN_OK;
 }

@@ -1,5 +1,6 @@
 #include "host_common.h"
 
+#include <atomic>
 #include <mutex>
 
 namespace hn {
@@ -60,6 +61,10 @@ int make_tmap_16bit(CUtensorMap* tm, const void* base, int rank, const uint64_t*
   return HN_OK;
 }
 
+static std::atomic<long long> g_launch_count{0};
+void count_launch(int n) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launch_count.load(); }
+
 int device_sm_count(int* out) {
   int dev = 0;
   HN_CUDA(cudaGetDevice(&dev));
@@ -71,3 +76,4 @@ int device_sm_count(int* out) {
 
 extern "C" const char* hn_last_error(void) { return hn::error_buffer(); }
 extern "C" int hn_version(void) { return 100; }
+extern "C" long long hn_launch_count(void) { return hn::launch_count(); }

@@ -52,4 +52,8 @@ int make_tmap_16bit(CUtensorMap* tm, const void* base, int rank, const uint64_t*
 
 int device_sm_count(int* out);
 
+// Number of kernels this library has launched (reported by bench.py as gpu_launches).
+void count_launch(int n = 1);
+long long launch_count();
+
 }  // namespace hn

@@ -108,12 +108,12 @@ class HardNet(nn.Module):
         sp = torch.std(flat, dim=1) + 1e-7
         return (x - mp.detach().view(-1, 1, 1, 1)) / sp.detach().view(-1, 1, 1, 1)
 
-    def forward(self, input, out_dtype: torch.dtype = torch.float32):
+    def forward(self, input, out_dtype: torch.dtype = torch.float32, out: torch.Tensor | None = None):
         if self.training:
             x_features = self.features(self.input_norm(input))
             x = x_features.view(x_features.size(0), -1)
             return L2Norm()(x)
-        return self._forward_b200(input, out_dtype)
+        return self._forward_b200(input, out_dtype, out)
 
     # ---- B200 path ---------------------------------------------------------------------------------
     def _convs_and_bns(self):
@@ -155,16 +155,38 @@ class HardNet(nn.Module):
             return input.contiguous(), _lib.HN_U8
         return input.float().contiguous(), _lib.HN_F32
 
-    def _forward_b200(self, input, out_dtype=torch.float32):
+    def _forward_b200(self, input, out_dtype=torch.float32, out=None):
         x, in_dt = self._check_input(input)
         self._ensure_packed(x.device)
-        out = torch.empty((x.size(0), 128), dtype=out_dtype, device=x.device)
+        if out is None:
+            out = torch.empty((x.size(0), 128), dtype=out_dtype, device=x.device)
+        else:
+            if out.shape != (x.size(0), 128) or out.device != x.device or not out.is_contiguous():
+                raise ValueError("out must be a contiguous [B,128] tensor on the input's device")
+            out_dtype = out.dtype
         eng = self._engine
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(eng.lib.hn_forward(eng.handle, x.data_ptr(), in_dt, x.size(0), out.data_ptr(),
                                           _OUT_DTYPES[out_dtype], C.c_void_p(stream)), "hn_forward")
         return out
+
+    # ---- measurement hooks (bench.py) ---------------------------------------------------------------
+    STAGE_NAMES = ("l1_norm_conv", "conv2_32x32x32", "conv3_s2_64", "conv4_64", "conv5_s2_128", "conv6_128", "head_8x8_l2norm")
+    # multiply-accumulates per patch of each stage
+    STAGE_MACS = (294912, 9437184, 4718592, 9437184, 4718592, 9437184, 1048576)
+
+    def profile_enable(self, stage_mask: int):
+        if self._engine is None:
+            raise _lib.HardnetB200Error("profile_enable: run one eval forward first")
+        _lib.check(self._engine.lib.hn_profile_enable(self._engine.handle, int(stage_mask)), "hn_profile_enable")
+
+    def profile_read(self):
+        """-> (ms per stage [7], launches per stage [7]); waits for the recorded events."""
+        ms = (C.c_double * 7)()
+        n = (C.c_longlong * 7)()
+        _lib.check(self._engine.lib.hn_profile_read(self._engine.handle, ms, n), "hn_profile_read")
+        return list(ms), list(n)
 
     def forward_stage(self, input, layer: int):
         """Test hook: NHWC activations after conv stage `layer` (1..6) as a [B,H,W,C] 16-bit tensor."""

@@ -47,6 +47,8 @@ typedef enum hn_dtype { HN_F32 = 0, HN_F16 = 1, HN_BF16 = 2, HN_U8 = 3 } hn_dtyp
 
 int hn_version(void);
 const char* hn_last_error(void);
+/* Kernels launched by this library since load (bench.py reports the delta over its timed region). */
+long long hn_launch_count(void);
 
 /* ---- handle -------------------------------------------------------------------------------------- */
 /* chunk_patches: patches pushed through the conv stack per pass (0 = default, rounded to a multiple of
@@ -72,6 +74,12 @@ int hn_forward(hn_handle* h, const void* patches, int in_dtype, long long B, voi
  * copy that stage's NHWC 16-bit activations to act_out ([B,H,W,C]). */
 int hn_forward_dump(hn_handle* h, const void* patches, int in_dtype, long long B, int layer,
                     void* act_out, void* stream);
+
+/* Measurement hooks: bracket every launch of the selected conv stages (bit 0 = stage 1 ... bit 5 = stage 6,
+ * bit 6 = head GEMM) with CUDA events on the launching stream; hn_profile_read waits for them, returns the
+ * summed milliseconds and launch counts per stage and resets the counters. */
+int hn_profile_enable(hn_handle* h, unsigned stage_mask);
+int hn_profile_read(hn_handle* h, double ms_out[7], long long launches_out[7]);
 
 /* ---- distances, hardest-in-batch mining, matching ------------------------------------------------- */
 /* Bytes of device workspace hn_dist_min / hn_loss_hardnet / hn_match need for the given sizes. */
