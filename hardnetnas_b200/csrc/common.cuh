@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda.h>          // CUtensorMap (types only; the driver entry point is resolved at run time)
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,6 +15,17 @@ namespace hn {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// One lane of a fully converged warp (warp-uniform callers only).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ uint64_t globaltimer_ns() {

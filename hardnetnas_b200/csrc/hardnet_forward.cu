@@ -72,32 +72,52 @@ struct StageTimer {
   }
 };
 
-template <int N, int KCB, int STAGES, int LOAD, int EPI>
-static int launch_tc(const TcParams& p, int sm_count, cudaStream_t stream) {
-  auto kern = tc_kernel<N, KCB, STAGES, LOAD, EPI>;
-  constexpr size_t smem = tc_smem_bytes<N, KCB, STAGES>();
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB>
+static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream) {
+  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES>;
+  auto kern = conv3x3_kernel<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, MINB>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
-    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
     attr_done = true;
   }
   if (p.num_tiles <= 0) return HN_OK;
-  const int grid = std::min(p.num_tiles, sm_count);
-  kern<<<grid, kTcThreads, smem, stream>>>(p);
+  const int grid = std::min(p.num_tiles, sm_count * MINB);
+  kern<<<grid, kTcThreads, C::SMEM, stream>>>(p);
   HN_CUDA(cudaGetLastError());
   count_launch();
   return HN_OK;
 }
 
+//                         CIN COUT HOUT STRIDE  G STAGES WRES  CTAs/SM
+#define HN_CONV_L2 launch_conv_cfg<32, 32, 32, 1, 3, 3, true, 2>
+#define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 3, 3, true, 2>
+#define HN_CONV_L4 launch_conv_cfg<64, 64, 16, 1, 3, 3, true, 1>
+#define HN_CONV_L5 launch_conv_cfg<64, 128, 8, 2, 1, 4, true, 1>
+#define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 2, 3, false, 1>
+
 static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) {
   switch (li) {
-    case 0: return launch_tc<32, 64, 8, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
-    case 1: return launch_tc<64, 64, 8, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
-    case 2: return launch_tc<64, 128, 6, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
-    case 3: return launch_tc<128, 128, 5, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
-    case 4: return launch_tc<128, 128, 5, LOAD_CONV3X3, EPI_BIAS_RELU_PACK16>(p, sm_count, s);
+    case 0: return HN_CONV_L2(p, sm_count, s);
+    case 1: return HN_CONV_L3(p, sm_count, s);
+    case 2: return HN_CONV_L4(p, sm_count, s);
+    case 3: return HN_CONV_L5(p, sm_count, s);
+    case 4: return HN_CONV_L6(p, sm_count, s);
   }
   return HN_ERR_INVALID;
+}
+
+static int launch_head(const TcParams& p, int sm_count, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    HN_CUDA(cudaFuncSetAttribute(gemm_l2norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHeadSmem)));
+    attr_done = true;
+  }
+  if (p.num_tiles <= 0) return HN_OK;
+  gemm_l2norm_kernel<<<std::min(p.num_tiles, sm_count), kTcThreads, kHeadSmem, stream>>>(p);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
 }
 
 static uint16_t to16(float v, int bf16) {
@@ -119,20 +139,10 @@ static int build_params(hn_handle* h) {
     const int kc = kcb / 2;
     const uint16_t* in = h->act[li & 1];  // L1 wrote act[0]; layers alternate
     const int pix_out = L.hout * L.hout;
-    p.stride = L.stride;
-    p.cin_chunks = L.cin / kc;
-    p.num_k_stages = 9 * p.cin_chunks;
-    if (pix_out >= kTileM) {
-      p.tiles_per_patch = pix_out / kTileM;
-      p.rows_per_tile = kTileM / L.hout;
-      p.patches_per_tile = 1;
-    } else {
-      p.tiles_per_patch = 0;
-      p.rows_per_tile = L.hout;
-      p.patches_per_tile = kTileM / pix_out;
-    }
+    const int rows_per_tile = pix_out >= kTileM ? kTileM / L.hout : L.hout;
+    const int patches_per_tile = pix_out >= kTileM ? 1 : kTileM / pix_out;
     const uint32_t box[4] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(L.hout),
-                             static_cast<uint32_t>(p.rows_per_tile), static_cast<uint32_t>(p.patches_per_tile)};
+                             static_cast<uint32_t>(rows_per_tile), static_cast<uint32_t>(patches_per_tile)};
     const uint64_t C = L.cin, W = L.hin, H = L.hin;
     if (L.stride == 1) {
       const uint64_t dims[4] = {C, W, H, static_cast<uint64_t>(h->chunk)};
@@ -166,7 +176,7 @@ static int build_params(hn_handle* h) {
     const uint64_t dimsB[2] = {kHeadK, 128};
     const uint32_t boxB[2] = {64, 128};
     HN_TRY(make_tmap_16bit(&p.tmB, h->whead, 2, dimsB, strA, boxB, 128));
-    p.num_k_stages = kHeadK / 64;
+    p.num_k_stages = kHeadK / (64 * kHeadG);
     p.bias = h->bias + 128 * 6;
     p.l2_eps = 1e-10f;
   }
@@ -358,7 +368,7 @@ extern "C" int hn_forward(hn_handle* h, const void* patches, int in_dtype, long 
     p.out_dtype = out_dtype;
     p.out = static_cast<char*>(desc_out) + static_cast<size_t>(base) * 128 * out_elem;
     StageTimer timer(h, 6, s);
-    HN_TRY((launch_tc<128, 128, 5, LOAD_GEMM, EPI_BIAS_L2NORM>(p, h->sm_count, s)));
+    HN_TRY(launch_head(p, h->sm_count, s));
   }
   return HN_OK;
 }

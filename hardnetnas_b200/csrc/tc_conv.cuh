@@ -1,19 +1,23 @@
-// Persistent, warp-specialised tcgen05 kernel for the HardNet conv stack.
+// Persistent, warp-specialised tcgen05 kernels for the HardNet conv stack.
 //
-// One kernel template covers
-//   * the 3x3 convs (features[3..17], reference hardnet/HardNet.py:284-298) as implicit GEMMs:
-//     M = output pixels (128 per tile), N = C_out, K = 9 taps x C_in. The A operand of every tap is
-//     fetched by a 4-D TMA box (C, x, y, patch) whose start coordinate is shifted by the tap offset;
-//     out-of-range coordinates are zero-filled by TMA, which is exactly the conv's zero padding, and
-//     because x/y are per-patch tensor dimensions nothing ever bleeds between patches.
-//     Stride-2 layers use four "parity" views of the input (even/odd rows x even/odd columns), so the
-//     stride never has to be expressed to TMA.
-//   * the 8x8 head conv (features[19..20] + L2Norm, HardNet.py:300-301,314-315 and Utils.py:19-22) as
-//     a plain [B, 8192] x [8192, 128] GEMM with bias + L2-normalise in the epilogue.
+//   conv3x3_kernel : the 3x3 convs (features[3..17], reference hardnet/HardNet.py:284-298) as implicit GEMMs:
+//     M = 128 output pixels per tile, N = C_out, K = 9 taps x C_in, cut into "k-blocks" of one tap x <=64
+//     channels. The A tile of a k-block is ONE 4-D TMA box (C, x, y, patch) whose start coordinate carries
+//     the tap shift; out-of-range x / y are zero-filled by TMA, which is exactly the conv's zero padding,
+//     and because x / y are per-patch tensor dimensions nothing bleeds between patches. Stride-2 layers
+//     read four "parity" views of the input (even/odd rows x even/odd columns), so the stride is never
+//     expressed to TMA. Weights stay resident in shared memory when they fit (WRES), otherwise they are
+//     streamed with the A tiles. A pipeline stage carries G k-blocks so that one mbarrier round trip
+//     feeds G * KCB/32 MMAs.
+//   gemm_l2norm_kernel : the 8x8 head conv (features[19..20] + L2Norm, HardNet.py:300-301,314-315 and
+//     Utils.py:19-22) as a [B, K] x [K, 128] GEMM with bias + L2-normalise in the epilogue (also the NAS
+//     head with K = 2048).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread UMMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU/pack or L2-normalise -> global).
-// Two accumulator buffers in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + UMMA issuer, warps 2..5 = epilogue
+// (TMEM -> registers -> bias/ReLU/pack or L2-normalise -> global). The producer / issuer loops run
+// warp-uniformly (every lane executes the control flow, elect.sync picks the lane that issues), which
+// lets the compiler keep the loop state in uniform registers. Two accumulator buffers in TMEM let the
+// epilogue of tile i overlap the MMAs of tile i+1.
 #pragma once
 
 #include "common.cuh"
@@ -23,8 +27,6 @@ namespace hn {
 constexpr int kTileM = 128;
 constexpr int kTcThreads = 192;
 
-enum : int { LOAD_CONV3X3 = 0, LOAD_GEMM = 1 };
-enum : int { EPI_BIAS_RELU_PACK16 = 0, EPI_BIAS_L2NORM = 1 };
 enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2, DT_U8 = 3 };
 
 struct TcParams {
@@ -34,26 +36,11 @@ struct TcParams {
   void* out;               // conv: 16-bit [rows, N]; head: f32/f16/bf16 [rows, N]
   long long total_rows;    // valid output rows (pixels or patches)
   int num_tiles;
-  int num_k_stages;        // conv: 9 * cin_chunks, gemm: K / (KCB / 2)
-  int stride;              // conv only: 1 or 2
-  int cin_chunks;          // conv only: C_in / (KCB / 2)
-  int tiles_per_patch;     // conv only: (H_out * W_out) / 128, or 0 when a tile holds several patches
-  int rows_per_tile;       // conv only: output image rows per tile when tiles_per_patch >= 1
-  int patches_per_tile;    // conv only: patches per tile when tiles_per_patch == 0
+  int num_k_stages;        // gemm only: K / (G * 64)
   int act_bf16;            // 16-bit activation flavour: 0 = fp16, 1 = bf16
   int out_dtype;           // head only: DT_F32 / DT_F16 / DT_BF16
-  float l2_eps;            // head only: 1e-10 (Utils.py:18)
+  float l2_eps;            // head only: 1e-10 (Utils.py:18); 0 for the NAS head
 };
-
-template <int N>
-struct TmemCols {
-  static constexpr uint32_t value = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
-};
-
-template <int N, int KCB, int STAGES>
-constexpr size_t tc_smem_bytes() {
-  return size_t(STAGES) * (size_t(kTileM) * KCB + size_t(N) * KCB) + 1024 /*align slack*/ + 256 /*barriers*/ + N * 4 /*bias*/;
-}
 
 __device__ __forceinline__ uint32_t pack16(float lo, float hi, int bf16) {
   if (bf16) {
@@ -67,26 +54,52 @@ __device__ __forceinline__ uint32_t pack16(float lo, float hi, int bf16) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int N, int KCB, int STAGES, int LOAD, int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
-  static_assert(KCB == 64 || KCB == 128, "stage rows are one 64B or 128B swizzle span");
-  static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA M=128 needs N % 16 == 0");
-  constexpr uint32_t A_BYTES = kTileM * KCB;
-  constexpr uint32_t B_BYTES = N * KCB;
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t tmem_cols_for(int n) {
+  return (2 * n <= 32) ? 32u : (2 * n <= 64) ? 64u : (2 * n <= 128) ? 128u : (2 * n <= 256) ? 256u : 512u;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 3x3 convolution
+// ------------------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES>
+struct ConvCfg {
+  static constexpr int KCB = (CIN >= 64) ? 128 : 64;            // bytes of one pixel's channel chunk
+  static constexpr int KC = KCB / 2;                             // channels per k-block
+  static constexpr int CIN_CHUNKS = CIN / KC;
+  static constexpr int KB = 9 * CIN_CHUNKS;                      // k-blocks per tile
+  static constexpr int SPT = KB / G;                             // stages per tile
+  static constexpr uint32_t A_BYTES = kTileM * KCB;
+  static constexpr uint32_t B_BYTES = COUT * KCB;
+  static constexpr uint32_t STAGE_BYTES = G * (A_BYTES + (WRES ? 0u : B_BYTES));
+  static constexpr uint32_t W_BYTES = WRES ? KB * B_BYTES : 0u;
+  static constexpr int PIX = HOUT * HOUT;
+  static constexpr int TILES_PER_PATCH = PIX >= kTileM ? PIX / kTileM : 0;
+  static constexpr int ROWS_PER_TILE = PIX >= kTileM ? kTileM / HOUT : HOUT;
+  static constexpr int PATCHES_PER_TILE = PIX >= kTileM ? 1 : kTileM / PIX;
+  static constexpr uint32_t TMEM_COLS = tmem_cols_for(COUT);
+  static constexpr size_t SMEM = size_t(W_BYTES) + size_t(STAGES) * STAGE_BYTES + 1024 + 256 + COUT * 4;
+  static_assert(KB % G == 0, "stage must hold a whole number of k-blocks");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must stay 1024B aligned");
-  constexpr uint32_t TMEM_COLS = TmemCols<N>::value;
-  constexpr int KC_ELEMS = KCB / 2;
+  static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "UMMA M=128 needs N % 16 == 0");
+};
+
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB>
+__global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_constant__ TcParams p) {
+  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES>;
+  constexpr int N = COUT;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  const uint32_t w_base = base;
+  const uint32_t ring_base = base + C::W_BYTES;
+  const uint32_t bar_base = ring_base + STAGES * C::STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t w_bar = bar_base + 8u * (2 * STAGES + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));
 
@@ -95,7 +108,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
-    if (LOAD == LOAD_CONV3X3 && p.stride == 2) {
+    if (STRIDE == 2) {
       tma_prefetch_desc(&p.tmA[1]);
       tma_prefetch_desc(&p.tmA[2]);
       tma_prefetch_desc(&p.tmA[3]);
@@ -112,10 +125,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
       }
+      mbar_init(w_bar, 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
   if (warp >= 2) {
@@ -127,74 +141,95 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int patch0 = 0, y0 = 0;
-        if (LOAD == LOAD_CONV3X3) {
-          if (p.tiles_per_patch >= 1) {
-            patch0 = tile / p.tiles_per_patch;
-            y0 = (tile - patch0 * p.tiles_per_patch) * p.rows_per_tile;
-          } else {
-            patch0 = tile * p.patches_per_tile;
-          }
-        }
-        for (int ks = 0; ks < p.num_k_stages; ++ks) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = base + stage * STAGE_BYTES;
-          const uint32_t b_dst = a_dst + A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          if (LOAD == LOAD_CONV3X3) {
-            const int tap = ks / p.cin_chunks;
-            const int cc = ks - tap * p.cin_chunks;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            if (p.stride == 1) {
-              tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), cc * KC_ELEMS, kx - 1, y0 + ky - 1, patch0);
+    // ============================== TMA producer (warp-uniform) ==============================
+    if (WRES) {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(w_bar, C::W_BYTES);
+#pragma unroll 1
+        for (int kb = 0; kb < C::KB; ++kb) tma_load_2d(w_base + kb * C::B_BYTES, &p.tmB, w_bar, kb * C::KC, 0);
+      }
+      __syncwarp();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int patch0, y0;
+      if (C::TILES_PER_PATCH >= 1) {
+        patch0 = tile / (C::TILES_PER_PATCH > 0 ? C::TILES_PER_PATCH : 1);
+        y0 = (tile - patch0 * C::TILES_PER_PATCH) * C::ROWS_PER_TILE;
+      } else {
+        patch0 = tile * C::PATCHES_PER_TILE;
+        y0 = 0;
+      }
+      int ky = 0, kx = 0, cc = 0, kb = 0;
+#pragma unroll 1
+      for (int s = 0; s < C::SPT; ++s) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t st_base = ring_base + stage * C::STAGE_BYTES;
+        const bool leader = elect_one();
+        if (leader) mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (leader) {
+            const uint32_t a_dst = st_base + g * C::A_BYTES;
+            if (STRIDE == 1) {
+              tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), cc * C::KC, kx - 1, y0 + ky - 1, patch0);
             } else {
               // input x = 2*ox + kx - 1: kx=0 -> odd column ox-1, kx=1 -> even column ox, kx=2 -> odd column ox
               const int xpar = (kx != 1), ypar = (ky != 1);
-              const int xs = (kx == 0) ? -1 : 0;
-              const int ys = y0 + ((ky == 0) ? -1 : 0);
-              tma_load_4d(a_dst, &p.tmA[ypar * 2 + xpar], full_bar(stage), cc * KC_ELEMS, xs, ys, patch0);
+              tma_load_4d(a_dst, &p.tmA[ypar * 2 + xpar], full_bar(stage), cc * C::KC, (kx == 0) ? -1 : 0,
+                          y0 + ((ky == 0) ? -1 : 0), patch0);
             }
-          } else {
-            tma_load_2d(a_dst, &p.tmA[0], full_bar(stage), ks * KC_ELEMS, tile * kTileM);
+            if (!WRES) tma_load_2d(st_base + G * C::A_BYTES + g * C::B_BYTES, &p.tmB, full_bar(stage), kb * C::KC, 0);
           }
-          tma_load_2d(b_dst, &p.tmB, full_bar(stage), ks * KC_ELEMS, 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          ++kb;
+          if (++cc == C::CIN_CHUNKS) {
+            cc = 0;
+            if (++kx == 3) { kx = 0; ++ky; }
+          }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ============================== UMMA issuer ==============================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kTileM, N, p.act_bf16);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    // ============================== UMMA issuer (warp-uniform) ==============================
+    const uint32_t idesc = make_idesc_f16(kTileM, N, p.act_bf16);
+    if (WRES) {
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N;
+#pragma unroll 1
+      for (int s = 0; s < C::SPT; ++s) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N;
-        for (int ks = 0; ks < p.num_k_stages; ++ks) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = base + stage * STAGE_BYTES;
-          const uint64_t a_desc = make_kmajor_desc(a_addr, KCB);
-          const uint64_t b_desc = make_kmajor_desc(a_addr + A_BYTES, KCB);
+        if (elect_one()) {
+          const uint32_t st_base = ring_base + stage * C::STAGE_BYTES;
 #pragma unroll
-          for (int k = 0; k < KCB / 32; ++k) {
-            // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (ks | k) != 0);
+          for (int g = 0; g < G; ++g) {
+            const uint64_t a_desc = make_kmajor_desc(st_base + g * C::A_BYTES, C::KCB);
+            const uint64_t b_desc = make_kmajor_desc(
+                WRES ? (w_base + (s * G + g) * C::B_BYTES) : (st_base + G * C::A_BYTES + g * C::B_BYTES), C::KCB);
+#pragma unroll
+            for (int k = 0; k < C::KCB / 32; ++k) {
+              // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
+              umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (s | g | k) != 0);
+            }
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          umma_commit(empty_bar(stage));                        // frees the smem slot once these MMAs have read it
+          if (s == C::SPT - 1) umma_commit(tfull_bar(acc));     // accumulator complete -> epilogue
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -210,61 +245,191 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * N;
       const long long row = static_cast<long long>(tile) * kTileM + row_in_tile;
       const bool valid = row < p.total_rows;
-      if (EPI == EPI_BIAS_RELU_PACK16) {
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + row * N);
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + row * N);
 #pragma unroll
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c0, r);
-          tmem_ld_wait();
-          uint32_t o[16];
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c0, r);
+        tmem_ld_wait();
+        uint32_t o[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float v0 = fmaxf(__uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], 0.f);
-            const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1], 0.f);
-            o[j] = pack16(v0, v1, p.act_bf16);
-          }
-          if (valid) {
+        for (int j = 0; j < 16; ++j) {
+          const float v0 = fmaxf(__uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], 0.f);
+          const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1], 0.f);
+          o[j] = pack16(v0, v1, p.act_bf16);
+        }
+        if (valid) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[c0 / 8 + j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          for (int j = 0; j < 4; ++j) dst[c0 / 8 + j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// [rows, K] x [K, 128] GEMM + bias + L2 normalisation (descriptor head)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kHeadN = 128;
+constexpr int kHeadG = 2;        // two 64-wide k-blocks per stage
+constexpr int kHeadStages = 3;
+constexpr uint32_t kHeadBlk = kTileM * 128;  // one 128 x 64 fp16 operand tile
+constexpr size_t kHeadSmem = size_t(kHeadStages) * kHeadG * 2 * kHeadBlk + 1024 + 256 + kHeadN * 4;
+
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid_constant__ TcParams p) {
+  constexpr int N = kHeadN, STAGES = kHeadStages, G = kHeadG;
+  constexpr uint32_t STAGE_BYTES = G * 2 * kHeadBlk;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(N);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 4);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < N; i += 128) s_bias[i] = p.bias[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+#pragma unroll 1
+      for (int ks = 0; ks < p.num_k_stages; ++ks) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t st_base = base + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            tma_load_2d(st_base + g * kHeadBlk, &p.tmA[0], full_bar(stage), (ks * G + g) * 64, tile * kTileM);
+            tma_load_2d(st_base + (G + g) * kHeadBlk, &p.tmB, full_bar(stage), (ks * G + g) * 64, 0);
           }
         }
-      } else {
-        // bias, then x / sqrt(sum(x*x) + eps) over the N columns of the row (Utils.py:19-22)
-        float ss = 0.f;
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16(kTileM, N, p.act_bf16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * N;
+#pragma unroll 1
+      for (int ks = 0; ks < p.num_k_stages; ++ks) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st_base = base + stage * STAGE_BYTES;
 #pragma unroll
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c0, r);
-          tmem_ld_wait();
+          for (int g = 0; g < G; ++g) {
+            const uint64_t a_desc = make_kmajor_desc(st_base + g * kHeadBlk, 128);
+            const uint64_t b_desc = make_kmajor_desc(st_base + (G + g) * kHeadBlk, 128);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = __uint_as_float(r[j]) + s_bias[c0 + j];
-            ss = fmaf(v, v, ss);
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (ks | g | k) != 0);
           }
+          umma_commit(empty_bar(stage));
+          if (ks == p.num_k_stages - 1) umma_commit(tfull_bar(acc));
         }
-        const float inv = 1.0f / sqrtf(ss + p.l2_eps);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * N;
+      const long long row = static_cast<long long>(tile) * kTileM + row_in_tile;
+      const bool valid = row < p.total_rows;
+      // bias, then x / sqrt(sum(x*x) + eps) over the N columns of the row (Utils.py:19-22)
+      float ss = 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c0, r);
-          tmem_ld_wait();
-          float v[32];
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c0, r);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(r[j]) + s_bias[c0 + j]) * inv;
-          if (valid) {
-            if (p.out_dtype == DT_F32) {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row * N + c0);
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]) + s_bias[c0 + j];
+          ss = fmaf(v, v, ss);
+        }
+      }
+      const float inv = 1.0f / sqrtf(ss + p.l2_eps);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + row * N + c0);
-              const int bf = p.out_dtype == DT_BF16;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c0, r);
+        tmem_ld_wait();
+        float v[32];
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(pack16(v[8 * j], v[8 * j + 1], bf), pack16(v[8 * j + 2], v[8 * j + 3], bf),
-                                    pack16(v[8 * j + 4], v[8 * j + 5], bf), pack16(v[8 * j + 6], v[8 * j + 7], bf));
-            }
+        for (int j = 0; j < 32; ++j) v[j] = (__uint_as_float(r[j]) + s_bias[c0 + j]) * inv;
+        if (valid) {
+          if (p.out_dtype == DT_F32) {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row * N + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + row * N + c0);
+            const int bf = p.out_dtype == DT_BF16;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack16(v[8 * j], v[8 * j + 1], bf), pack16(v[8 * j + 2], v[8 * j + 3], bf),
+                                  pack16(v[8 * j + 4], v[8 * j + 5], bf), pack16(v[8 * j + 6], v[8 * j + 7], bf));
           }
         }
       }
