@@ -72,10 +72,10 @@ struct StageTimer {
   }
 };
 
-template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB>
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT>
 static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream) {
-  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES>;
-  auto kern = conv3x3_kernel<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, MINB>;
+  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT>;
+  auto kern = conv3x3_kernel<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, MINB, ROWSHIFT>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
@@ -89,12 +89,13 @@ static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream)
   return HN_OK;
 }
 
-//                         CIN COUT HOUT STRIDE  G STAGES WRES  CTAs/SM
-#define HN_CONV_L2 launch_conv_cfg<32, 32, 32, 1, 3, 3, true, 2>
-#define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 3, 3, true, 2>
-#define HN_CONV_L4 launch_conv_cfg<64, 64, 16, 1, 3, 3, true, 1>
-#define HN_CONV_L5 launch_conv_cfg<64, 128, 8, 2, 1, 4, true, 1>
-#define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 2, 3, false, 1>
+//                         CIN COUT HOUT STRIDE  G STAGES WRES  CTAs/SM ROWSHIFT
+#define HN_CONV_L2 launch_conv_cfg<32, 32, 32, 1, 3, 2, true, 2, true>
+#define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 3, 3, true, 2, false>
+#define HN_CONV_L4 launch_conv_cfg<64, 64, 16, 1, 3, 2, true, 1, true>
+#define HN_CONV_L5 launch_conv_cfg<64, 128, 8, 2, 1, 4, true, 1, false>
+#define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 2, 3, false, 1, false>
+static const bool kRowShift[5] = {true, false, true, false, false};
 
 static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) {
   switch (li) {
@@ -142,7 +143,8 @@ static int build_params(hn_handle* h) {
     const int rows_per_tile = pix_out >= kTileM ? kTileM / L.hout : L.hout;
     const int patches_per_tile = pix_out >= kTileM ? 1 : kTileM / pix_out;
     const uint32_t box[4] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(L.hout),
-                             static_cast<uint32_t>(rows_per_tile), static_cast<uint32_t>(patches_per_tile)};
+                             static_cast<uint32_t>(rows_per_tile + (kRowShift[li] ? 2 : 0)),
+                             static_cast<uint32_t>(patches_per_tile)};
     const uint64_t C = L.cin, W = L.hin, H = L.hin;
     if (L.stride == 1) {
       const uint64_t dims[4] = {C, W, H, static_cast<uint64_t>(h->chunk)};

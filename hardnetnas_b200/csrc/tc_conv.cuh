@@ -61,31 +61,39 @@ constexpr uint32_t tmem_cols_for(int n) {
 // ------------------------------------------------------------------------------------------------------------
 // 3x3 convolution
 // ------------------------------------------------------------------------------------------------------------
-template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES>
+// ROWSHIFT (stride-1 layers whose tile is a band of whole image rows): one TMA load per (kx, channel chunk)
+// fetches the band plus one halo row above and below; the three ky taps then read that SAME shared-memory
+// tile through UMMA descriptors whose start address is advanced by ky image rows (a multiple of the 8-row
+// swizzle group, so the layout stays canonical). Cuts the L2->SMEM operand traffic from 9x to 3x(R+2)/R.
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, bool ROWSHIFT = false>
 struct ConvCfg {
   static constexpr int KCB = (CIN >= 64) ? 128 : 64;            // bytes of one pixel's channel chunk
   static constexpr int KC = KCB / 2;                             // channels per k-block
   static constexpr int CIN_CHUNKS = CIN / KC;
   static constexpr int KB = 9 * CIN_CHUNKS;                      // k-blocks per tile
-  static constexpr int SPT = KB / G;                             // stages per tile
-  static constexpr uint32_t A_BYTES = kTileM * KCB;
-  static constexpr uint32_t B_BYTES = COUT * KCB;
-  static constexpr uint32_t STAGE_BYTES = G * (A_BYTES + (WRES ? 0u : B_BYTES));
-  static constexpr uint32_t W_BYTES = WRES ? KB * B_BYTES : 0u;
   static constexpr int PIX = HOUT * HOUT;
   static constexpr int TILES_PER_PATCH = PIX >= kTileM ? PIX / kTileM : 0;
   static constexpr int ROWS_PER_TILE = PIX >= kTileM ? kTileM / HOUT : HOUT;
   static constexpr int PATCHES_PER_TILE = PIX >= kTileM ? 1 : kTileM / PIX;
+  static constexpr int UNITS = ROWSHIFT ? 3 * CIN_CHUNKS : KB;   // TMA loads of A per tile
+  static constexpr int SPT = UNITS / G;                          // stages per tile
+  static constexpr uint32_t ROW_BYTES = HOUT * KCB;              // one image row of the A tile
+  static constexpr uint32_t A_BYTES = ROWSHIFT ? (ROWS_PER_TILE + 2) * ROW_BYTES : kTileM * KCB;
+  static constexpr uint32_t B_BYTES = COUT * KCB;
+  static constexpr uint32_t STAGE_BYTES = G * (A_BYTES + (WRES ? 0u : B_BYTES));
+  static constexpr uint32_t W_BYTES = WRES ? KB * B_BYTES : 0u;
+  static_assert(!ROWSHIFT || (STRIDE == 1 && TILES_PER_PATCH >= 1 && WRES && ROW_BYTES % 1024 == 0),
+                "ROWSHIFT needs a stride-1 row-band tile, resident weights and 1024B-aligned image rows");
+  static_assert(UNITS % G == 0, "stage must hold a whole number of loads");
   static constexpr uint32_t TMEM_COLS = tmem_cols_for(COUT);
   static constexpr size_t SMEM = size_t(W_BYTES) + size_t(STAGES) * STAGE_BYTES + 1024 + 256 + COUT * 4;
-  static_assert(KB % G == 0, "stage must hold a whole number of k-blocks");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must stay 1024B aligned");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "UMMA M=128 needs N % 16 == 0");
 };
 
-template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB>
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT>
 __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_constant__ TcParams p) {
-  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES>;
+  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT>;
   constexpr int N = COUT;
 
   extern __shared__ uint8_t smem_raw[];
@@ -172,7 +180,10 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
         for (int g = 0; g < G; ++g) {
           if (leader) {
             const uint32_t a_dst = st_base + g * C::A_BYTES;
-            if (STRIDE == 1) {
+            if (ROWSHIFT) {
+              // band of ROWS_PER_TILE + 2 rows starting one row above the tile, shifted by kx - 1 columns
+              tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), cc * C::KC, kx - 1, y0 - 1, patch0);
+            } else if (STRIDE == 1) {
               tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), cc * C::KC, kx - 1, y0 + ky - 1, patch0);
             } else {
               // input x = 2*ox + kx - 1: kx=0 -> odd column ox-1, kx=1 -> even column ox, kx=2 -> odd column ox
@@ -216,13 +227,27 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
           const uint32_t st_base = ring_base + stage * C::STAGE_BYTES;
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            const uint64_t a_desc = make_kmajor_desc(st_base + g * C::A_BYTES, C::KCB);
-            const uint64_t b_desc = make_kmajor_desc(
-                WRES ? (w_base + (s * G + g) * C::B_BYTES) : (st_base + G * C::A_BYTES + g * C::B_BYTES), C::KCB);
+            if (ROWSHIFT) {
+              const int u = s * G + g;                              // load unit = (kx, channel chunk)
+              const int kx = u / C::CIN_CHUNKS, cc = u - kx * C::CIN_CHUNKS;
 #pragma unroll
-            for (int k = 0; k < C::KCB / 32; ++k) {
-              // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
-              umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (s | g | k) != 0);
+              for (int ky = 0; ky < 3; ++ky) {
+                const uint64_t a_desc = make_kmajor_desc(st_base + g * C::A_BYTES + ky * C::ROW_BYTES, C::KCB);
+                const uint64_t b_desc =
+                    make_kmajor_desc(w_base + ((ky * 3 + kx) * C::CIN_CHUNKS + cc) * C::B_BYTES, C::KCB);
+#pragma unroll
+                for (int k = 0; k < C::KCB / 32; ++k)
+                  umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (s | g | ky | k) != 0);
+              }
+            } else {
+              const uint64_t a_desc = make_kmajor_desc(st_base + g * C::A_BYTES, C::KCB);
+              const uint64_t b_desc = make_kmajor_desc(
+                  WRES ? (w_base + (s * G + g) * C::B_BYTES) : (st_base + G * C::A_BYTES + g * C::B_BYTES), C::KCB);
+#pragma unroll
+              for (int k = 0; k < C::KCB / 32; ++k) {
+                // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
+                umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (s | g | k) != 0);
+              }
             }
           }
           umma_commit(empty_bar(stage));                        // frees the smem slot once these MMAs have read it
