@@ -90,11 +90,11 @@ static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream)
 }
 
 //                         CIN COUT HOUT STRIDE  G STAGES WRES  CTAs/SM ROWSHIFT
-#define HN_CONV_L2 launch_conv_cfg<32, 32, 32, 1, 3, 2, true, 2, true>
-#define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 3, 3, true, 2, false>
-#define HN_CONV_L4 launch_conv_cfg<64, 64, 16, 1, 3, 2, true, 1, true>
+#define HN_CONV_L2 launch_conv_cfg<32, 32, 32, 1, 1, 6, true, 2, true>
+#define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 1, 9, true, 2, false>
+#define HN_CONV_L4 launch_conv_cfg<64, 64, 16, 1, 1, 7, true, 1, true>
 #define HN_CONV_L5 launch_conv_cfg<64, 128, 8, 2, 1, 4, true, 1, false>
-#define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 2, 3, false, 1, false>
+#define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 1, 6, false, 1, false>
 static const bool kRowShift[5] = {true, false, true, false, false};
 
 static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) {
