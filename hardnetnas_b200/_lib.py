@@ -29,6 +29,9 @@ SIGNATURES = {
     "hn_pack_hardnet": (C.c_int, [_P, _FPP, _FPP, _FPP, C.c_float, C.c_int]),
     "hn_forward": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P, C.c_int, _P]),
     "hn_forward_dump": (C.c_int, [_P, _P, C.c_int, C.c_longlong, C.c_int, _P, _P]),
+    "hn_pack_nas": (C.c_int, [_P, _P, C.c_int, _P, C.c_longlong, C.c_int]),
+    "hn_forward_nas": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P, C.c_int, _P]),
+    "hn_forward_nas_dump": (C.c_int, [_P, _P, C.c_int, C.c_longlong, C.c_int, _P, _P]),
     "hn_dist_workspace_bytes": (C.c_longlong, [C.c_longlong, C.c_longlong, C.c_int]),
     "hn_dist_min": (C.c_int, [_P, _P, C.c_longlong, C.c_longlong, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P,
                               C.c_longlong, _P]),

@@ -1,0 +1,37 @@
+// The opaque handle behind the C ABI: packed weights, static TMA descriptors and activation scratch.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "../../include/hardnet_b200.h"
+#include "tc_conv.cuh"
+
+namespace hn {
+struct NasState;
+void nas_state_free(NasState* s);
+// [rows, K] x [K, 128] + bias + L2 normalisation (hardnet_forward.cu); shared by the HardNet and NAS heads
+int launch_head(const TcParams& p, int sm_count, cudaStream_t stream);
+}  // namespace hn
+
+struct hn_handle {
+  int chunk = 0;            // patches per conv-stack pass
+  long long head_rows = 0;  // capacity of the L6 output buffer (patches)
+  int sm_count = 0;
+  bool packed = false;
+  int act_bf16 = 0;
+  uint16_t* act[2] = {nullptr, nullptr};  // ping-pong activations, chunk * 32*32*32 elements each
+  uint16_t* l6 = nullptr;                 // [head_rows, 8, 8, 128]
+  uint16_t* wconv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [cout][9*cin]
+  uint16_t* whead = nullptr;                                           // [128][8192]
+  float* w1 = nullptr;                                                 // [9][32]
+  float* bias = nullptr;                                               // 7 x 128
+  hn::TcParams conv_params[5];
+  hn::TcParams head_params;
+  // optional per-stage CUDA-event timing (stage 0 = L1, 1..5 = 3x3 convs, 6 = head)
+  unsigned profile_mask = 0;
+  std::vector<cudaEvent_t> ev[7];
+  size_t ev_used[7] = {0, 0, 0, 0, 0, 0, 0};
+  hn::NasState* nas = nullptr;  // NAS-derived descriptor net (nas.cu)
+};

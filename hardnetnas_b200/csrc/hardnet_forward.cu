@@ -9,6 +9,7 @@
 #include <cmath>
 #include <vector>
 
+#include "handle.h"
 #include "host_common.h"
 #include "l1_norm_conv.cuh"
 #include "tc_conv.cuh"
@@ -26,25 +27,6 @@ constexpr int kHeadK = 8 * 8 * 128;
 
 }  // namespace hn
 
-struct hn_handle {
-  int chunk = 0;            // patches per conv-stack pass
-  long long head_rows = 0;  // capacity of the L6 output buffer (patches)
-  int sm_count = 0;
-  bool packed = false;
-  int act_bf16 = 0;
-  uint16_t* act[2] = {nullptr, nullptr};  // ping-pong activations, chunk * 32*32*32 elements each
-  uint16_t* l6 = nullptr;                 // [head_rows, 8, 8, 128]
-  uint16_t* wconv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [cout][9*cin]
-  uint16_t* whead = nullptr;                                           // [128][8192]
-  float* w1 = nullptr;                                                 // [9][32]
-  float* bias = nullptr;                                               // 7 x 128
-  hn::TcParams conv_params[5];
-  hn::TcParams head_params;
-  // optional per-stage CUDA-event timing (stage 0 = L1, 1..5 = 3x3 convs, 6 = head)
-  unsigned profile_mask = 0;
-  std::vector<cudaEvent_t> ev[7];
-  size_t ev_used[7] = {0, 0, 0, 0, 0, 0, 0};
-};
 
 namespace hn {
 
@@ -108,14 +90,15 @@ static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) 
   return HN_ERR_INVALID;
 }
 
-static int launch_head(const TcParams& p, int sm_count, cudaStream_t stream) {
+int launch_head(const TcParams& p, int sm_count, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    HN_CUDA(cudaFuncSetAttribute(gemm_l2norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kHeadSmem)));
+    HN_CUDA(cudaFuncSetAttribute(gemm_l2norm_kernel<kHeadN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(kHeadSmem)));
     attr_done = true;
   }
   if (p.num_tiles <= 0) return HN_OK;
-  gemm_l2norm_kernel<<<std::min(p.num_tiles, sm_count), kTcThreads, kHeadSmem, stream>>>(p);
+  gemm_l2norm_kernel<kHeadN><<<std::min(p.num_tiles, sm_count), kTcThreads, kHeadSmem, stream>>>(p);
   HN_CUDA(cudaGetLastError());
   count_launch();
   return HN_OK;
@@ -285,6 +268,7 @@ extern "C" int hn_destroy(hn_handle* h) {
   cudaFree(h->bias);
   for (auto& v : h->ev)
     for (cudaEvent_t e : v) cudaEventDestroy(e);
+  nas_state_free(h->nas);
   delete h;
   return HN_OK;
 }

@@ -1,0 +1,679 @@
+// NAS-derived descriptor nets (hardnetNAS/fbnet_building_blocks/fbnet_builder.py + the supernet stem/head of
+// hardnetNAS/supernet_functions/model_supernet.py:57-58,64-68,84) behind the C ABI.
+//
+// The Python side compiles the module tree into a flat op list (BatchNorm folded, channel shuffle folded into
+// the producing 1x1 conv, grouped 1x1 convs expanded to block-diagonal dense matrices). Here every op is one
+// kernel over a chunk of patches, activations NHWC 16-bit in three handle-owned slots:
+//   STEM    conv 3x3 1->32 + BN + ReLU                  l1_norm_conv_kernel (no input normalisation)
+//   PW      1x1 conv + BN [+ReLU] [+residual]           pw_gemm_kernel: tcgen05 GEMM [pixels, C_in] x [C_in, C_out]
+//   DW      depthwise k3/k5, stride 1/2 + BN + ReLU     dw_conv_kernel (CUDA cores, 8 channels per thread)
+//   MAXPOOL 3x3 stride 2 pad 1                          maxpool_kernel
+//   SE      x * sigmoid(fc2(relu(fc1(avgpool(x)))))     se_kernel (one CTA per patch)
+//   HEAD    k x k full conv -> 128 + BN + y/||y||       gemm_l2norm_kernel (eps = 0, like torch.norm)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "handle.h"
+#include "host_common.h"
+#include "l1_norm_conv.cuh"
+#include "tc_conv.cuh"
+
+namespace hn {
+
+enum : int { OP_STEM = 0, OP_PW = 1, OP_DW = 2, OP_MAXPOOL = 3, OP_SE = 4, OP_HEAD = 5 };
+
+// ------------------------------------------------------------------------------------------------------------
+// pointwise (1x1) convolution as a tensor-core GEMM
+// ------------------------------------------------------------------------------------------------------------
+struct PwParams {
+  CUtensorMap tmA;       // activations [rows, C_in]
+  CUtensorMap tmB;       // weights [C_out, C_in] (BN scale folded)
+  const float* bias;     // [C_out]
+  const uint16_t* res;   // optional residual [rows, C_out]
+  uint16_t* out;         // [rows, C_out]
+  long long total_rows;
+  int num_tiles;         // m_tiles * n_tiles
+  int n_tiles;
+  int num_kb;            // C_in / (KCB / 2)
+  int cout;
+  int relu;
+  int act_bf16;
+};
+
+constexpr int kPwStages = 4;
+
+template <int NT, int KCB>
+constexpr size_t pw_smem_bytes() {
+  return size_t(kPwStages) * (size_t(kTileM) * KCB + size_t(NT) * KCB) + 1024 + 256 + 512 * 4;
+}
+
+__device__ __forceinline__ float2 unpack16(uint32_t v, int bf16) {
+  if (bf16) {
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+  }
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+
+template <int NT, int KCB>
+__global__ void __launch_bounds__(kTcThreads, 1) pw_gemm_kernel(const __grid_constant__ PwParams p) {
+  constexpr int STAGES = kPwStages;
+  constexpr uint32_t A_BYTES = kTileM * KCB;
+  constexpr uint32_t B_BYTES = NT * KCB;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(NT);
+  constexpr int KC = KCB / 2;
+  static_assert(B_BYTES % 1024 == 0, "weight tile must stay 1024B aligned");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(tfull_bar(a), 1);
+        mbar_init(tempty_bar(a), 4);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.cout; i += 128) s_bias[i] = p.bias[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+#pragma unroll 1
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          const uint32_t st_base = base + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(st_base, &p.tmA, full_bar(stage), kb * KC, mt * kTileM);
+          tma_load_2d(st_base + A_BYTES, &p.tmB, full_bar(stage), kb * KC, nt * NT);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16(kTileM, NT, p.act_bf16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * NT;
+#pragma unroll 1
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st_base = base + stage * STAGE_BYTES;
+          const uint64_t a_desc = make_kmajor_desc(st_base, KCB);
+          const uint64_t b_desc = make_kmajor_desc(st_base + A_BYTES, KCB);
+#pragma unroll
+          for (int k = 0; k < KCB / 32; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+          umma_commit(empty_bar(stage));
+          if (kb == p.num_kb - 1) umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT;
+      const long long row = static_cast<long long>(mt) * kTileM + row_in_tile;
+      const bool valid = row < p.total_rows;
+      const long long off = row * p.cout + nt * NT;
+#pragma unroll
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c0, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[nt * NT + c0 + j];
+        if (p.res != nullptr && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + off + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 rv = rp[j];
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = unpack16(w[t], p.act_bf16);
+              v[8 * j + 2 * t] += f.x;
+              v[8 * j + 2 * t + 1] += f.y;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (valid) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack16(v[8 * j], v[8 * j + 1], p.act_bf16), pack16(v[8 * j + 2], v[8 * j + 3], p.act_bf16),
+                                pack16(v[8 * j + 4], v[8 * j + 5], p.act_bf16), pack16(v[8 * j + 6], v[8 * j + 7], p.act_bf16));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CUDA-core ops on NHWC 16-bit activations
+// ------------------------------------------------------------------------------------------------------------
+// depthwise k x k conv (pad k/2) + folded BN + optional ReLU; one thread = one output pixel x 8 channels
+__global__ void __launch_bounds__(256) dw_conv_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                      const float* __restrict__ w /*[k*k][C]*/, const float* __restrict__ bias,
+                                                      long long patches, int C, int hin, int hout, int k, int stride, int relu,
+                                                      int bf16) {
+  const int cg = C >> 3;
+  const long long total = patches * hout * hout * cg;
+  const int pad = k >> 1;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cg) * 8;
+    long long t = i / cg;
+    const int ox = static_cast<int>(t % hout);
+    t /= hout;
+    const int oy = static_cast<int>(t % hout);
+    const long long n = t / hout;
+    float acc[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + c8 + 4);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+    for (int ky = 0; ky < k; ++ky) {
+      const int iy = oy * stride + ky - pad;
+      if (iy < 0 || iy >= hin) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ix = ox * stride + kx - pad;
+        if (ix < 0 || ix >= hin) continue;
+        const uint4 xv = *reinterpret_cast<const uint4*>(in + ((n * hin + iy) * hin + ix) * C + c8);
+        const float* wp = w + (ky * k + kx) * C + c8;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+        const float2 x0 = unpack16(xv.x, bf16), x1 = unpack16(xv.y, bf16), x2 = unpack16(xv.z, bf16), x3 = unpack16(xv.w, bf16);
+        acc[0] = fmaf(x0.x, w0.x, acc[0]); acc[1] = fmaf(x0.y, w0.y, acc[1]);
+        acc[2] = fmaf(x1.x, w0.z, acc[2]); acc[3] = fmaf(x1.y, w0.w, acc[3]);
+        acc[4] = fmaf(x2.x, w1.x, acc[4]); acc[5] = fmaf(x2.y, w1.y, acc[5]);
+        acc[6] = fmaf(x3.x, w1.z, acc[6]); acc[7] = fmaf(x3.y, w1.w, acc[7]);
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    *reinterpret_cast<uint4*>(out + ((n * hout + oy) * hout + ox) * C + c8) =
+        make_uint4(pack16(acc[0], acc[1], bf16), pack16(acc[2], acc[3], bf16), pack16(acc[4], acc[5], bf16),
+                   pack16(acc[6], acc[7], bf16));
+  }
+}
+
+// MaxPool2d(kernel 3, stride 2, padding 1): padding never wins (implicit -inf), like torch
+__global__ void __launch_bounds__(256) maxpool_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                      long long patches, int C, int hin, int hout, int bf16) {
+  const int cg = C >> 3;
+  const long long total = patches * hout * hout * cg;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cg) * 8;
+    long long t = i / cg;
+    const int ox = static_cast<int>(t % hout);
+    t /= hout;
+    const int oy = static_cast<int>(t % hout);
+    const long long n = t / hout;
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -__int_as_float(0x7f800000);
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 + ky - 1;
+      if (iy < 0 || iy >= hin) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 + kx - 1;
+        if (ix < 0 || ix >= hin) continue;
+        const uint4 xv = *reinterpret_cast<const uint4*>(in + ((n * hin + iy) * hin + ix) * C + c8);
+        const uint32_t wv[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack16(wv[j], bf16);
+          m[2 * j] = fmaxf(m[2 * j], f.x);
+          m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(out + ((n * hout + oy) * hout + ox) * C + c8) =
+        make_uint4(pack16(m[0], m[1], bf16), pack16(m[2], m[3], bf16), pack16(m[4], m[5], bf16), pack16(m[6], m[7], bf16));
+  }
+}
+
+// Squeeze-and-excite, in place; one CTA per patch. fc weights fp32: w1 [mid][C], w2 [C][mid].
+__global__ void __launch_bounds__(256) se_kernel(uint16_t* __restrict__ x, long long patches, int C, int h, int mid,
+                                                 const float* __restrict__ w1, const float* __restrict__ b1,
+                                                 const float* __restrict__ w2, const float* __restrict__ b2, int bf16) {
+  __shared__ float s_mean[512];
+  __shared__ float s_hid[128];
+  __shared__ float s_gate[512];
+  const int pix = h * h;
+  for (long long n = blockIdx.x; n < patches; n += gridDim.x) {
+    uint16_t* xp = x + n * pix * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int i = 0; i < pix; ++i) {
+        const uint16_t raw = xp[i * C + c];
+        s += bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&raw)) : __half2float(*reinterpret_cast<const __half*>(&raw));
+      }
+      s_mean[c] = s / static_cast<float>(pix);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < mid; j += blockDim.x) {
+      float s = b1[j];
+      for (int c = 0; c < C; ++c) s = fmaf(w1[j * C + c], s_mean[c], s);
+      s_hid[j] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = b2[c];
+      for (int j = 0; j < mid; ++j) s = fmaf(w2[c * mid + j], s_hid[j], s);
+      s_gate[c] = 1.0f / (1.0f + expf(-s));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < pix * C / 2; i += blockDim.x) {
+      uint32_t* p2 = reinterpret_cast<uint32_t*>(xp) + i;
+      const int c = (i * 2) % C;
+      const float2 f = unpack16(*p2, bf16);
+      *p2 = pack16(f.x * s_gate[c], f.y * s_gate[c + 1], bf16);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct NasState {
+  std::vector<hn_nas_op> ops;
+  std::vector<PwParams> pw;          // one per op (valid for OP_PW)
+  std::vector<size_t> w16_off;       // 16-bit weight offset per op (PW / HEAD)
+  float* params = nullptr;           // fp32 blob on the device
+  uint16_t* w16 = nullptr;
+  uint16_t* slot[3] = {nullptr, nullptr, nullptr};
+  uint16_t* head_in = nullptr;       // [head_rows, head_k]
+  size_t slot_elems = 0;             // per patch
+  int head_k = 0;
+  int act_bf16 = 0;
+  TcParams head;
+};
+
+void nas_state_free(NasState* s) {
+  if (!s) return;
+  cudaFree(s->params);
+  cudaFree(s->w16);
+  for (auto* p : s->slot) cudaFree(p);
+  cudaFree(s->head_in);
+  delete s;
+}
+
+static uint16_t f2h16(float v, int bf16) {
+  if (bf16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __half h = __float2half_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+static int pick_nt(int cout) {
+  if (cout <= 128) return cout;
+  if (cout % 128 == 0) return 128;
+  if (cout % 96 == 0) return 96;
+  if (cout % 64 == 0) return 64;
+  return 32;
+}
+
+template <int NT, int KCB>
+static int launch_pw_cfg(const PwParams& p, int sm_count, cudaStream_t s) {
+  auto kern = pw_gemm_kernel<NT, KCB>;
+  constexpr size_t smem = pw_smem_bytes<NT, KCB>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_done = true;
+  }
+  if (p.num_tiles <= 0) return HN_OK;
+  kern<<<std::min(p.num_tiles, sm_count), kTcThreads, smem, s>>>(p);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
+static int launch_pw(const PwParams& p, int nt, int kcb, int sm_count, cudaStream_t s) {
+#define HN_PW_CASE(NT_)                                                    \
+  if (nt == NT_) return kcb == 64 ? launch_pw_cfg<NT_, 64>(p, sm_count, s) : launch_pw_cfg<NT_, 128>(p, sm_count, s);
+  HN_PW_CASE(32)
+  HN_PW_CASE(64)
+  HN_PW_CASE(96)
+  HN_PW_CASE(128)
+#undef HN_PW_CASE
+  set_error("pointwise conv: unsupported output tile width %d", nt);
+  return HN_ERR_UNSUPPORTED;
+}
+
+}  // namespace hn
+
+
+namespace hn {
+// Runs ops [0, last_op] of the packed program for `n` patches (n <= chunk).
+static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype, int n, long long off, int last_op,
+                       cudaStream_t s) {
+  const int bf = st->act_bf16;
+  {
+      for (int i = 0; i <= last_op; ++i) {
+        const hn_nas_op& o = st->ops[i];
+        switch (o.kind) {
+          case OP_STEM: {
+            const int grid = std::min(n, h->sm_count * 4);
+            if (in_dtype == HN_F32)
+              l1_norm_conv_kernel<float><<<grid, kL1Threads, 0, s>>>(reinterpret_cast<const float*>(src), st->slot[o.dst],
+                                                                    st->params + o.w_off, st->params + o.b_off, n, bf, 0);
+            else
+              l1_norm_conv_kernel<uint8_t><<<grid, kL1Threads, 0, s>>>(reinterpret_cast<const uint8_t*>(src), st->slot[o.dst],
+                                                                      st->params + o.w_off, st->params + o.b_off, n, bf, 0);
+            HN_CUDA(cudaGetLastError());
+            count_launch();
+            break;
+          }
+          case OP_PW: {
+            PwParams p = st->pw[i];
+            p.total_rows = static_cast<long long>(n) * o.hin * o.hin;
+            p.num_tiles = static_cast<int>((p.total_rows + kTileM - 1) / kTileM) * p.n_tiles;
+            HN_TRY(launch_pw(p, o.cout / p.n_tiles, (o.cin % 64 == 0) ? 128 : 64, h->sm_count, s));
+            break;
+          }
+          case OP_DW: {
+            const long long total = static_cast<long long>(n) * o.hout * o.hout * (o.cin / 8);
+            const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->sm_count * 16LL));
+            dw_conv_kernel<<<grid, 256, 0, s>>>(st->slot[o.src], st->slot[o.dst], st->params + o.w_off, st->params + o.b_off, n,
+                                                o.cin, o.hin, o.hout, o.kernel, o.stride, o.relu, bf);
+            HN_CUDA(cudaGetLastError());
+            count_launch();
+            break;
+          }
+          case OP_MAXPOOL: {
+            const long long total = static_cast<long long>(n) * o.hout * o.hout * (o.cin / 8);
+            const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->sm_count * 16LL));
+            maxpool_kernel<<<grid, 256, 0, s>>>(st->slot[o.src], st->slot[o.dst], n, o.cin, o.hin, o.hout, bf);
+            HN_CUDA(cudaGetLastError());
+            count_launch();
+            break;
+          }
+          case OP_SE: {
+            se_kernel<<<std::min(n, h->sm_count * 8), 256, 0, s>>>(st->slot[o.src], n, o.cin, o.hin, o.mid, st->params + o.w_off,
+                                                                  st->params + o.b_off, st->params + o.w2_off,
+                                                                  st->params + o.b2_off, bf);
+            HN_CUDA(cudaGetLastError());
+            count_launch();
+            break;
+          }
+          case OP_HEAD: {
+            HN_CUDA(cudaMemcpyAsync(st->head_in + static_cast<size_t>(off) * st->head_k, st->slot[o.src],
+                                    static_cast<size_t>(n) * st->head_k * 2, cudaMemcpyDeviceToDevice, s));
+            break;
+          }
+        }
+      }
+    }
+  return HN_OK;
+}
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const float* params, long long n_params,
+                           int act_dtype) {
+  HN_REQUIRE(h && ops && params && n_ops >= 2 && n_params > 0, "hn_pack_nas: bad argument");
+  HN_REQUIRE(act_dtype == HN_F16 || act_dtype == HN_BF16, "hn_pack_nas: act_dtype must be HN_F16 or HN_BF16");
+  HN_REQUIRE(ops[0].kind == OP_STEM && ops[0].cout == 32 && ops[0].hin == 32, "hn_pack_nas: first op must be the 1->32 stem");
+  HN_REQUIRE(ops[n_ops - 1].kind == OP_HEAD && ops[n_ops - 1].cout == 128, "hn_pack_nas: last op must be the 128-d head");
+  const int bf = act_dtype == HN_BF16;
+  nas_state_free(h->nas);
+  h->nas = nullptr;
+  NasState* st = new NasState();
+  auto fail = [&](int code) { nas_state_free(st); return code; };
+  st->act_bf16 = bf;
+  st->ops.assign(ops, ops + n_ops);
+  st->pw.resize(n_ops);
+  st->w16_off.assign(n_ops, 0);
+  // validate + size
+  size_t w16_total = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    const hn_nas_op& o = ops[i];
+    auto in_blob = [&](long long off, long long n) { return off >= 0 && off + n <= n_params; };
+    if (o.kind != OP_STEM && (o.src < 0 || o.src > 2)) { set_error("hn_pack_nas: op %d has a bad src slot", i); return fail(HN_ERR_INVALID); }
+    if (o.kind != OP_HEAD && (o.dst < 0 || o.dst > 2)) { set_error("hn_pack_nas: op %d has a bad dst slot", i); return fail(HN_ERR_INVALID); }
+    if (o.kind != OP_STEM) st->slot_elems = std::max(st->slot_elems, static_cast<size_t>(o.cin) * o.hin * o.hin);
+    if (o.kind != OP_HEAD) st->slot_elems = std::max(st->slot_elems, static_cast<size_t>(o.cout) * o.hout * o.hout);
+    bool ok = true;
+    switch (o.kind) {
+      case OP_STEM: ok = in_blob(o.w_off, 9 * 32) && in_blob(o.b_off, 32); break;
+      case OP_PW:
+        ok = o.cin % 32 == 0 && o.cout % 32 == 0 && o.cin <= 512 && o.cout <= 512 && in_blob(o.w_off, 1LL * o.cin * o.cout) &&
+             in_blob(o.b_off, o.cout) && o.res >= -1 && o.res <= 2 && o.res != o.dst && o.src != o.dst;
+        st->w16_off[i] = w16_total;
+        w16_total += static_cast<size_t>(o.cin) * o.cout;
+        break;
+      case OP_DW:
+        ok = o.cin == o.cout && o.cin % 8 == 0 && (o.kernel == 3 || o.kernel == 5) && (o.stride == 1 || o.stride == 2) &&
+             o.hout * o.stride == o.hin && in_blob(o.w_off, 1LL * o.kernel * o.kernel * o.cin) && in_blob(o.b_off, o.cin) &&
+             o.src != o.dst;
+        break;
+      case OP_MAXPOOL: ok = o.cin == o.cout && o.cin % 8 == 0 && o.hout * 2 == o.hin && o.src != o.dst; break;
+      case OP_SE:
+        ok = o.cin <= 512 && o.mid <= 128 && o.cin % 2 == 0 && o.src == o.dst && in_blob(o.w_off, 1LL * o.mid * o.cin) &&
+             in_blob(o.b_off, o.mid) && in_blob(o.w2_off, 1LL * o.mid * o.cin) && in_blob(o.b2_off, o.cin);
+        break;
+      case OP_HEAD: {
+        const long long K = 1LL * o.kernel * o.kernel * o.cin;
+        ok = o.kernel == o.hin && K % 128 == 0 && in_blob(o.w_off, 128 * K) && in_blob(o.b_off, 128);
+        st->w16_off[i] = w16_total;
+        w16_total += static_cast<size_t>(128) * K;
+        st->head_k = static_cast<int>(K);
+        break;
+      }
+      default: ok = false;
+    }
+    if (!ok) { set_error("hn_pack_nas: op %d (kind %d) failed validation", i, o.kind); return fail(HN_ERR_INVALID); }
+  }
+#define HN_CUDA_N(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));           \
+      return fail(HN_ERR_CUDA);                                                                  \
+    }                                                                                            \
+  } while (0)
+  HN_CUDA_N(cudaMalloc(&st->params, static_cast<size_t>(n_params) * sizeof(float)));
+  HN_CUDA_N(cudaMemcpy(st->params, params, static_cast<size_t>(n_params) * sizeof(float), cudaMemcpyHostToDevice));
+  {
+    std::vector<uint16_t> w16(w16_total);
+    for (int i = 0; i < n_ops; ++i) {
+      const hn_nas_op& o = ops[i];
+      const size_t n = o.kind == OP_PW ? static_cast<size_t>(o.cin) * o.cout : o.kind == OP_HEAD ? static_cast<size_t>(128) * st->head_k : 0;
+      for (size_t j = 0; j < n; ++j) w16[st->w16_off[i] + j] = f2h16(params[o.w_off + j], bf);
+    }
+    HN_CUDA_N(cudaMalloc(&st->w16, std::max<size_t>(w16_total, 1) * 2));
+    HN_CUDA_N(cudaMemcpy(st->w16, w16.data(), w16_total * 2, cudaMemcpyHostToDevice));
+  }
+  const size_t slot_bytes = static_cast<size_t>(h->chunk) * st->slot_elems * 2;
+  for (int k = 0; k < 3; ++k) {
+    HN_CUDA_N(cudaMalloc(&st->slot[k], slot_bytes));
+    HN_CUDA_N(cudaMemset(st->slot[k], 0, slot_bytes));
+  }
+  HN_CUDA_N(cudaMalloc(&st->head_in, static_cast<size_t>(h->head_rows) * st->head_k * 2));
+  HN_CUDA_N(cudaMemset(st->head_in, 0, static_cast<size_t>(h->head_rows) * st->head_k * 2));
+#undef HN_CUDA_N
+  // static descriptors
+  for (int i = 0; i < n_ops; ++i) {
+    const hn_nas_op& o = ops[i];
+    if (o.kind == OP_PW) {
+      PwParams& p = st->pw[i];
+      memset(&p, 0, sizeof(p));
+      const int kcb = (o.cin % 64 == 0) ? 128 : 64;
+      const int kc = kcb / 2;
+      const int nt = pick_nt(o.cout);
+      const uint64_t rows_cap = static_cast<uint64_t>(h->chunk) * o.hin * o.hin;
+      const uint64_t dimsA[2] = {static_cast<uint64_t>(o.cin), rows_cap};
+      const uint64_t strA[1] = {static_cast<uint64_t>(o.cin) * 2};
+      const uint32_t boxA[2] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(kTileM)};
+      int rc = make_tmap_16bit(&p.tmA, st->slot[o.src], 2, dimsA, strA, boxA, kcb);
+      if (rc != HN_OK) return fail(rc);
+      const uint64_t dimsB[2] = {static_cast<uint64_t>(o.cin), static_cast<uint64_t>(o.cout)};
+      const uint32_t boxB[2] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(nt)};
+      rc = make_tmap_16bit(&p.tmB, st->w16 + st->w16_off[i], 2, dimsB, strA, boxB, kcb);
+      if (rc != HN_OK) return fail(rc);
+      p.bias = st->params + o.b_off;
+      p.res = o.res >= 0 ? st->slot[o.res] : nullptr;
+      p.out = st->slot[o.dst];
+      p.n_tiles = o.cout / nt;
+      p.num_kb = o.cin / kc;
+      p.cout = o.cout;
+      p.relu = o.relu;
+      p.act_bf16 = bf;
+    } else if (o.kind == OP_HEAD) {
+      TcParams& p = st->head;
+      memset(&p, 0, sizeof(p));
+      const uint64_t K = static_cast<uint64_t>(st->head_k);
+      const uint64_t dimsA[2] = {K, static_cast<uint64_t>(h->head_rows)};
+      const uint64_t strA[1] = {K * 2};
+      const uint32_t boxA[2] = {64, static_cast<uint32_t>(kTileM)};
+      int rc = make_tmap_16bit(&p.tmA[0], st->head_in, 2, dimsA, strA, boxA, 128);
+      if (rc != HN_OK) return fail(rc);
+      const uint64_t dimsB[2] = {K, 128};
+      const uint32_t boxB[2] = {64, 128};
+      rc = make_tmap_16bit(&p.tmB, st->w16 + st->w16_off[i], 2, dimsB, strA, boxB, 128);
+      if (rc != HN_OK) return fail(rc);
+      p.num_k_stages = static_cast<int>(K / (64 * kHeadG));
+      p.bias = st->params + o.b_off;
+      p.l2_eps = 0.f;  // torch.norm without eps (model_supernet.py:84)
+      p.act_bf16 = bf;
+    }
+  }
+  h->nas = st;
+  return HN_OK;
+}
+
+extern "C" int hn_forward_nas(hn_handle* h, const void* patches, int in_dtype, long long B, void* desc_out, int out_dtype,
+                              void* stream) {
+  HN_REQUIRE(h, "hn_forward_nas: NULL handle");
+  if (!h->nas) {
+    set_error("hn_forward_nas: no NAS net packed (call hn_pack_nas first)");
+    return HN_ERR_STATE;
+  }
+  HN_REQUIRE(B >= 0, "hn_forward_nas: negative batch");
+  HN_REQUIRE(in_dtype == HN_F32 || in_dtype == HN_U8, "hn_forward_nas: in_dtype must be HN_F32 or HN_U8");
+  HN_REQUIRE(out_dtype == HN_F32 || out_dtype == HN_F16 || out_dtype == HN_BF16, "hn_forward_nas: bad out_dtype");
+  if (B == 0) return HN_OK;
+  HN_REQUIRE(patches && desc_out, "hn_forward_nas: NULL data pointer");
+  NasState* st = h->nas;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
+  const size_t out_elem = out_dtype == HN_F32 ? 4 : 2;
+  const int n_ops = static_cast<int>(st->ops.size());
+  for (long long base = 0; base < B; base += h->head_rows) {
+    const long long nb = std::min<long long>(h->head_rows, B - base);
+    for (long long off = 0; off < nb; off += h->chunk) {
+      const int n = static_cast<int>(std::min<long long>(h->chunk, nb - off));
+      const char* src = static_cast<const char*>(patches) + static_cast<size_t>(base + off) * 1024 * in_elem;
+      HN_TRY(run_nas_ops(h, st, src, in_dtype, n, off, n_ops - 1, s));
+    }
+    TcParams p = st->head;
+    p.total_rows = nb;
+    p.num_tiles = static_cast<int>((nb + kTileM - 1) / kTileM);
+    p.out_dtype = out_dtype;
+    p.out = static_cast<char*>(desc_out) + static_cast<size_t>(base) * 128 * out_elem;
+    HN_TRY(launch_head(p, h->sm_count, s));
+  }
+  return HN_OK;
+}
+
+extern "C" int hn_forward_nas_dump(hn_handle* h, const void* patches, int in_dtype, long long B, int op_index, void* act_out,
+                                   void* stream) {
+  HN_REQUIRE(h && patches && act_out, "hn_forward_nas_dump: NULL argument");
+  if (!h->nas) {
+    set_error("hn_forward_nas_dump: no NAS net packed");
+    return HN_ERR_STATE;
+  }
+  NasState* st = h->nas;
+  HN_REQUIRE(op_index >= 0 && op_index < static_cast<int>(st->ops.size()) - 1, "hn_forward_nas_dump: op_index out of range");
+  HN_REQUIRE(B >= 1 && B <= h->chunk, "hn_forward_nas_dump: B must be in [1, chunk=%d]", h->chunk);
+  HN_REQUIRE(in_dtype == HN_F32 || in_dtype == HN_U8, "hn_forward_nas_dump: bad in_dtype");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  HN_TRY(run_nas_ops(h, st, static_cast<const char*>(patches), in_dtype, static_cast<int>(B), 0, op_index, s));
+  const hn_nas_op& o = st->ops[op_index];
+  HN_CUDA(cudaMemcpyAsync(act_out, st->slot[o.dst], static_cast<size_t>(B) * o.cout * o.hout * o.hout * 2,
+                          cudaMemcpyDeviceToDevice, s));
+  return HN_OK;
+}

@@ -311,8 +311,10 @@ constexpr int kHeadStages = 3;
 constexpr uint32_t kHeadBlk = kTileM * 128;  // one 128 x 64 fp16 operand tile
 constexpr size_t kHeadSmem = size_t(kHeadStages) * kHeadG * 2 * kHeadBlk + 1024 + 256 + kHeadN * 4;
 
+template <int N>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid_constant__ TcParams p) {
-  constexpr int N = kHeadN, STAGES = kHeadStages, G = kHeadG;
+  constexpr int STAGES = kHeadStages, G = kHeadG;
+  static_assert(N == kHeadN, "descriptor head is 128 wide");
   constexpr uint32_t STAGE_BYTES = G * 2 * kHeadBlk;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);

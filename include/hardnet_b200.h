@@ -81,6 +81,36 @@ int hn_forward_dump(hn_handle* h, const void* patches, int in_dtype, long long B
 int hn_profile_enable(hn_handle* h, unsigned stage_mask);
 int hn_profile_read(hn_handle* h, double ms_out[7], long long launches_out[7]);
 
+/* ---- NAS-derived descriptor nets (hardnetNAS/fbnet_building_blocks, model_supernet.py:57-58,64-68,84) ------ */
+/* One entry of the flat op list a sampled net is compiled to (hardnetnas_b200/nas/descriptor_net.py does the
+ * compilation from the nn.Module tree: BatchNorm folded, channel shuffle folded into the producing 1x1 conv,
+ * grouped 1x1 convs expanded to block-diagonal dense matrices). Activations live in three NHWC 16-bit slots. */
+enum { HN_NAS_STEM = 0, HN_NAS_PW = 1, HN_NAS_DW = 2, HN_NAS_MAXPOOL = 3, HN_NAS_SE = 4, HN_NAS_HEAD = 5 };
+typedef struct hn_nas_op {
+  int kind;           /* HN_NAS_* */
+  int cin, cout;      /* channels */
+  int kernel, stride; /* DW: 3|5, 1|2; HEAD: kernel == hin */
+  int hin, hout;      /* square spatial size in / out */
+  int relu;
+  int src, dst, res;  /* activation slots 0..2; res = residual input of a PW op or -1; STEM src = -1, HEAD dst = -1 */
+  int mid;            /* SE hidden width */
+  long long w_off, b_off, w2_off, b2_off; /* float offsets into `params` (fp32):
+      STEM  w[9][32] (tap-major), b[32]            PW    w[cout][cin] dense, b[cout]
+      DW    w[k*k][C], b[C]                        SE    w1[mid][C], b1[mid], w2[C][mid], b2[C]
+      HEAD  w[128][(y*k+x)*cin + c], b[128] */
+} hn_nas_op;
+
+/* ops / params are HOST memory. Replaces any previously packed NAS net of the handle. */
+int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const float* params, long long n_params,
+                int act_dtype);
+/* Eval forward of the packed net: [B,1,32,32] patches -> [B,128] unit descriptors (y / ||y||, no eps). */
+int hn_forward_nas(hn_handle* h, const void* patches, int in_dtype, long long B, void* desc_out,
+                   int out_dtype, void* stream);
+
+/* Test hook: run ops [0, op_index] for B <= chunk_patches and copy that op's NHWC 16-bit output ([B,H,W,C]). */
+int hn_forward_nas_dump(hn_handle* h, const void* patches, int in_dtype, long long B, int op_index,
+                        void* act_out, void* stream);
+
 /* ---- distances, hardest-in-batch mining, matching ------------------------------------------------- */
 /* Bytes of device workspace hn_dist_min / hn_loss_hardnet / hn_match need for the given sizes. */
 long long hn_dist_workspace_bytes(long long Na, long long Np, int split);

@@ -117,3 +117,20 @@ def weights_fingerprint(ws) -> np.ndarray:
         f = w.double().flatten()
         rows.append(np.concatenate([[f.sum().item(), f.abs().sum().item()], f[:8].numpy()]))
     return np.stack(rows)
+
+
+def randomize_nas_state(state_dict: dict, seed: int = 4) -> dict:
+    """Randomise every BatchNorm of a NAS net (running stats and, where present, the affine parameters):
+    running_mean ~ 0.1 N, running_var ~ U(0.5,1.5), weight ~ U(0.5,1.5), bias ~ 0.1 N. Keys are visited in sorted
+    order so that two state_dicts with the same keys receive the same values."""
+    g = torch.Generator().manual_seed(seed)
+    out = dict(state_dict)
+    bn_prefixes = sorted(k[: -len("running_mean")] for k in out if k.endswith("running_mean"))
+    for pre in bn_prefixes:
+        n = out[pre + "running_mean"].numel()
+        out[pre + "running_mean"] = 0.1 * torch.randn(n, generator=g)
+        out[pre + "running_var"] = 0.5 + torch.rand(n, generator=g)
+        if pre + "weight" in out:
+            out[pre + "weight"] = 0.5 + torch.rand(n, generator=g)
+            out[pre + "bias"] = 0.1 * torch.randn(n, generator=g)
+    return out

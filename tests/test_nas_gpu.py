@@ -1,0 +1,86 @@
+"""GPU parity of the NAS-derived descriptor nets (BASELINE config 5) against the CPU oracle and reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from hardnetnas_b200.nas import SampledDescriptorNet
+from hardnetnas_b200.nas.fbnet_modeldef import arch_ops
+from oracle import nas_oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+MIXED = ["ir_k3_e3_se", "ir_k5_s4", "ir_k3_s2_se", "ir_k5_e3", "ir_k3_s4_se", "ir_k3_e1_se"]
+DESC_MAX_ABS = 1e-3
+DESC_MIN_COS = 0.9999
+
+
+def build(arch, **kw):
+    ops = MIXED if arch == "mixed_se" else arch_ops(arch)
+    torch.manual_seed(0)
+    net = SampledDescriptorNet(ops, **kw)
+    net.load_state_dict(synth.randomize_nas_state(net.state_dict(), 4))
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    return net.cuda().eval(), ops, sd
+
+
+def _cmp(got, ref):
+    got = got.float().cpu()
+    return (got - ref).abs().max().item(), torch.nn.functional.cosine_similarity(got, ref, dim=1).min().item()
+
+
+@pytest.mark.parametrize("arch", ["wang2", "wang3", "wang4", "mixed_se"])
+def test_stage_outputs_match_oracle(arch):
+    net, ops, sd = build(arch)
+    x = synth.make_patches(32, 1234, edge_cases=False)
+    _, feats = nas_oracle.nas_forward(x, ops, sd, return_features=True)
+    prog = net.compile_program()
+    for stage, op_index in enumerate(prog.stage_end):
+        got = net.forward_op(x.cuda(), op_index).float().cpu().permute(0, 3, 1, 2)
+        ref = feats[stage]
+        scale = ref.abs().max().item()
+        err = (got - ref).abs().max().item()
+        assert err <= 6e-3 * scale + 1e-5, f"{arch} stage {stage} (op {op_index}): err {err:.3e} scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("arch", ["wang2", "wang3", "wang4", "mixed_se"])
+def test_descriptors_match_oracle_and_golden(arch, golden_dir):
+    net, ops, sd = build(arch)
+    x = synth.make_patches(32, 1234, edge_cases=False)
+    got = net(x.cuda())
+    ref = nas_oracle.nas_forward(x, ops, sd)
+    max_abs, cos = _cmp(got, ref)
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+    gold = torch.from_numpy(np.load(golden_dir / "nas_forward.npz")[f"{arch}_desc"])
+    max_abs, cos = _cmp(got, gold)
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+
+
+@pytest.mark.parametrize("batch", [1, 3, 127, 700])
+def test_ragged_batches(batch):
+    net, ops, sd = build("wang2", chunk_patches=64, head_rows=256)
+    x = synth.make_patches(batch, 5, edge_cases=False)
+    max_abs, cos = _cmp(net(x.cuda()), nas_oracle.nas_forward(x, ops, sd))
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+
+
+def test_config5_batch_64k_properties():
+    """BASELINE config 5: wang2 at batch 65 536 — finite, unit norm, deterministic, equal to small-batch results."""
+    net, ops, sd = build("wang2")
+    x = synth.make_patches(65536, 9, edge_cases=False).cuda()
+    d1 = net(x)
+    d2 = net(x)
+    assert torch.equal(d1, d2) and torch.isfinite(d1).all()
+    assert (d1.norm(dim=1) - 1).abs().max().item() < 1e-3
+    ref = nas_oracle.nas_forward(x[:256].cpu(), ops, sd)
+    max_abs, cos = _cmp(d1[:256], ref)
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+
+
+def test_train_mode_is_stock_torch_and_cpu_eval_fails():
+    from hardnetnas_b200._lib import HardnetB200Error
+    net, _, _ = build("wang3")
+    with pytest.raises(HardnetB200Error):
+        net(synth.make_patches(4, 1))
+    net.train()
+    out = net(synth.make_patches(8, 1, edge_cases=False).cuda())
+    assert out.requires_grad and out.shape == (8, 128)
