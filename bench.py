@@ -383,6 +383,19 @@ def side_measurements(device, model, rank, world):
         t = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if rank == 0:
+        # configs[4]: NAS-derived descriptor net (wang2) forward at batch 65 536
+        from hardnetnas_b200.nas import SampledDescriptorNet
+        torch.manual_seed(0)
+        nas = SampledDescriptorNet("wang2").to(device).eval()
+        xb = torch.nn.functional.avg_pool2d(torch.rand((65536, 1, 32, 32), generator=g, device=device), 5, 1, 2)
+        ob = nas(xb)
+        nas_ms = timeit(lambda: nas(xb), 5)
+        res["config4_nas_wang2_batch65536_ms"] = nas_ms
+        res["config4_nas_wang2_patches_per_sec"] = 65536 / (nas_ms / 1e3)
+        res["config4_nas_wang2_frac_of_bf16_peak"] = 65536 * 7272448 / (nas_ms / 1e3) / 1e12 / load_peaks()["tflops_sustained"]
+        res["config4_nas_wang2_algorithmic_GBps"] = 65536 * 4608 / (nas_ms / 1e3) / 1e9
+        del nas, xb, ob
     res["config3_match_65536x65536_ms"] = ms
     res["config3_match_pairs_per_sec"] = n * n / (ms / 1e3)
     res["config3_match_frac_of_bf16_peak"] = n * n * 256 / (ms / 1e3) / 1e12 / (load_peaks()["tflops_sustained"] * world)

@@ -221,7 +221,7 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   hn_handle* h = new hn_handle();
   int st = device_sm_count(&h->sm_count);
   if (st != HN_OK) { delete h; return st; }
-  if (chunk_patches <= 0) chunk_patches = h->sm_count * 4;
+  if (chunk_patches <= 0) chunk_patches = h->sm_count * 128;  // measured: larger passes amortise launch + prologue cost
   chunk_patches = (chunk_patches + 1) & ~1;
   if (head_rows <= 0) head_rows = static_cast<long long>(h->sm_count) * kTileM;
   head_rows = std::max<long long>(head_rows, chunk_patches);

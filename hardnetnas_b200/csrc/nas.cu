@@ -363,6 +363,7 @@ struct NasState {
   uint16_t* slot[3] = {nullptr, nullptr, nullptr};
   uint16_t* head_in = nullptr;       // [head_rows, head_k]
   size_t slot_elems = 0;             // per patch
+  int chunk = 0;                     // patches per pass (<= handle chunk, capped so the three slots stay <= 4 GiB)
   int head_k = 0;
   int act_bf16 = 0;
   TcParams head;
@@ -567,7 +568,11 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
     HN_CUDA_N(cudaMalloc(&st->w16, std::max<size_t>(w16_total, 1) * 2));
     HN_CUDA_N(cudaMemcpy(st->w16, w16.data(), w16_total * 2, cudaMemcpyHostToDevice));
   }
-  const size_t slot_bytes = static_cast<size_t>(h->chunk) * st->slot_elems * 2;
+  {
+    const size_t cap = (size_t(4) << 30) / (6 * st->slot_elems);
+    st->chunk = static_cast<int>(std::min<size_t>(h->chunk, std::max<size_t>(cap, 64))) & ~1;
+  }
+  const size_t slot_bytes = static_cast<size_t>(st->chunk) * st->slot_elems * 2;
   for (int k = 0; k < 3; ++k) {
     HN_CUDA_N(cudaMalloc(&st->slot[k], slot_bytes));
     HN_CUDA_N(cudaMemset(st->slot[k], 0, slot_bytes));
@@ -584,7 +589,7 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
       const int kcb = (o.cin % 64 == 0) ? 128 : 64;
       const int kc = kcb / 2;
       const int nt = pick_nt(o.cout);
-      const uint64_t rows_cap = static_cast<uint64_t>(h->chunk) * o.hin * o.hin;
+      const uint64_t rows_cap = static_cast<uint64_t>(st->chunk) * o.hin * o.hin;
       const uint64_t dimsA[2] = {static_cast<uint64_t>(o.cin), rows_cap};
       const uint64_t strA[1] = {static_cast<uint64_t>(o.cin) * 2};
       const uint32_t boxA[2] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(kTileM)};
@@ -644,8 +649,8 @@ extern "C" int hn_forward_nas(hn_handle* h, const void* patches, int in_dtype, l
   const int n_ops = static_cast<int>(st->ops.size());
   for (long long base = 0; base < B; base += h->head_rows) {
     const long long nb = std::min<long long>(h->head_rows, B - base);
-    for (long long off = 0; off < nb; off += h->chunk) {
-      const int n = static_cast<int>(std::min<long long>(h->chunk, nb - off));
+    for (long long off = 0; off < nb; off += st->chunk) {
+      const int n = static_cast<int>(std::min<long long>(st->chunk, nb - off));
       const char* src = static_cast<const char*>(patches) + static_cast<size_t>(base + off) * 1024 * in_elem;
       HN_TRY(run_nas_ops(h, st, src, in_dtype, n, off, n_ops - 1, s));
     }
@@ -668,7 +673,7 @@ extern "C" int hn_forward_nas_dump(hn_handle* h, const void* patches, int in_dty
   }
   NasState* st = h->nas;
   HN_REQUIRE(op_index >= 0 && op_index < static_cast<int>(st->ops.size()) - 1, "hn_forward_nas_dump: op_index out of range");
-  HN_REQUIRE(B >= 1 && B <= h->chunk, "hn_forward_nas_dump: B must be in [1, chunk=%d]", h->chunk);
+  HN_REQUIRE(B >= 1 && B <= st->chunk, "hn_forward_nas_dump: B must be in [1, chunk=%d]", st->chunk);
   HN_REQUIRE(in_dtype == HN_F32 || in_dtype == HN_U8, "hn_forward_nas_dump: bad in_dtype");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   HN_TRY(run_nas_ops(h, st, static_cast<const char*>(patches), in_dtype, static_cast<int>(B), 0, op_index, s));
