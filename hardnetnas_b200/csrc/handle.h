@@ -13,6 +13,9 @@ struct NasState;
 void nas_state_free(NasState* s);
 // [rows, K] x [K, 128] + bias + L2 normalisation (hardnet_forward.cu); shared by the HardNet and NAS heads
 int launch_head(const TcParams& p, int sm_count, cudaStream_t stream);
+// input_norm (optional) + conv 1->32 k3 + BN + ReLU on the tensor core (hardnet_forward.cu); also the NAS stem
+int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, int n, int act_bf16,
+              int do_norm, int sm_count, cudaStream_t s);
 }  // namespace hn
 
 struct hn_handle {

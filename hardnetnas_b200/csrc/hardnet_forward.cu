@@ -11,7 +11,7 @@
 
 #include "handle.h"
 #include "host_common.h"
-#include "l1_norm_conv.cuh"
+#include "l1_tc.cuh"
 #include "tc_conv.cuh"
 
 namespace hn {
@@ -88,6 +88,25 @@ static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) 
     case 4: return HN_CONV_L6(p, sm_count, s);
   }
   return HN_ERR_INVALID;
+}
+
+// Stage 1 (input_norm + conv 1->32 + BN + ReLU) on the tensor core; do_norm = 0 gives the NAS stem.
+int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, int n, int act_bf16,
+              int do_norm, int sm_count, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    HN_CUDA(cudaFuncSetAttribute(l1_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kL1TcSmem)));
+    HN_CUDA(cudaFuncSetAttribute(l1_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kL1TcSmem)));
+    attr_done = true;
+  }
+  if (n <= 0) return HN_OK;
+  const int grid = std::min(n, sm_count);
+  if (in_dtype == HN_F32)
+    l1_tc_kernel<float><<<grid, kL1TcThreads, kL1TcSmem, s>>>(static_cast<const float*>(patches), out, w, bias, n, act_bf16, do_norm);
+  else
+    l1_tc_kernel<uint8_t><<<grid, kL1TcThreads, kL1TcSmem, s>>>(static_cast<const uint8_t*>(patches), out, w, bias, n, act_bf16, do_norm);
+  HN_CUDA(cudaGetLastError());
+  return HN_OK;
 }
 
 int launch_head(const TcParams& p, int sm_count, cudaStream_t stream) {
@@ -195,13 +214,8 @@ static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n
 }
 
 static void run_l1(hn_handle* h, const void* patches, int in_dtype, int n, int grid1, cudaStream_t s) {
-  if (in_dtype == HN_F32) {
-    l1_norm_conv_kernel<float><<<grid1, kL1Threads, 0, s>>>(static_cast<const float*>(patches), h->act[0], h->w1,
-                                                           h->bias, n, h->act_bf16, 1);
-  } else {
-    l1_norm_conv_kernel<uint8_t><<<grid1, kL1Threads, 0, s>>>(static_cast<const uint8_t*>(patches), h->act[0], h->w1,
-                                                             h->bias, n, h->act_bf16, 1);
-  }
+  (void)grid1;
+  launch_l1(patches, in_dtype, h->act[0], h->w1, h->bias, n, h->act_bf16, 1, h->sm_count, s);
 }
 
 }  // namespace hn

@@ -20,7 +20,6 @@
 
 #include "handle.h"
 #include "host_common.h"
-#include "l1_norm_conv.cuh"
 #include "tc_conv.cuh"
 
 namespace hn {
@@ -436,14 +435,7 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
         const hn_nas_op& o = st->ops[i];
         switch (o.kind) {
           case OP_STEM: {
-            const int grid = std::min(n, h->sm_count * 4);
-            if (in_dtype == HN_F32)
-              l1_norm_conv_kernel<float><<<grid, kL1Threads, 0, s>>>(reinterpret_cast<const float*>(src), st->slot[o.dst],
-                                                                    st->params + o.w_off, st->params + o.b_off, n, bf, 0);
-            else
-              l1_norm_conv_kernel<uint8_t><<<grid, kL1Threads, 0, s>>>(reinterpret_cast<const uint8_t*>(src), st->slot[o.dst],
-                                                                      st->params + o.w_off, st->params + o.b_off, n, bf, 0);
-            HN_CUDA(cudaGetLastError());
+            HN_TRY(launch_l1(src, in_dtype, st->slot[o.dst], st->params + o.w_off, st->params + o.b_off, n, bf, 0, h->sm_count, s));
             count_launch();
             break;
           }
