@@ -14,12 +14,13 @@ void nas_state_free(NasState* s);
 // [rows, K] x [K, 128] + bias + L2 normalisation (hardnet_forward.cu); shared by the HardNet and NAS heads
 int launch_head(const TcParams& p, int sm_count, cudaStream_t stream);
 // input_norm (optional) + conv 1->32 k3 + BN + ReLU on the tensor core (hardnet_forward.cu); also the NAS stem
-int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, int n, int act_bf16,
-              int do_norm, int sm_count, cudaStream_t s);
+int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, float2* stats, int n,
+              int act_bf16, int sm_count, cudaStream_t s);
 }  // namespace hn
 
 struct hn_handle {
   int chunk = 0;            // patches per conv-stack pass
+  int front_chunk = 0;      // patches per stage-1 + conv2 sub-pass (keeps the stage-1 output L2 resident)
   long long head_rows = 0;  // capacity of the L6 output buffer (patches)
   int sm_count = 0;
   bool packed = false;
@@ -30,6 +31,7 @@ struct hn_handle {
   uint16_t* whead = nullptr;                                           // [128][8192]
   float* w1 = nullptr;                                                 // [9][32]
   float* bias = nullptr;                                               // 7 x 128
+  float2* stats = nullptr;                                             // per-patch (mean, 1/std), chunk entries
   hn::TcParams conv_params[5];
   hn::TcParams head_params;
   // optional per-stage CUDA-event timing (stage 0 = L1, 1..5 = 3x3 convs, 6 = head)

@@ -91,8 +91,8 @@ static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) 
 }
 
 // Stage 1 (input_norm + conv 1->32 + BN + ReLU) on the tensor core; do_norm = 0 gives the NAS stem.
-int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, int n, int act_bf16,
-              int do_norm, int sm_count, cudaStream_t s) {
+int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, float2* stats, int n,
+              int act_bf16, int sm_count, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     HN_CUDA(cudaFuncSetAttribute(l1_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kL1TcSmem)));
@@ -101,11 +101,18 @@ int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, 
   }
   if (n <= 0) return HN_OK;
   const int grid = std::min(n, sm_count);
-  if (in_dtype == HN_F32)
-    l1_tc_kernel<float><<<grid, kL1TcThreads, kL1TcSmem, s>>>(static_cast<const float*>(patches), out, w, bias, n, act_bf16, do_norm);
-  else
-    l1_tc_kernel<uint8_t><<<grid, kL1TcThreads, kL1TcSmem, s>>>(static_cast<const uint8_t*>(patches), out, w, bias, n, act_bf16, do_norm);
+  const int sgrid = std::min((n + 7) / 8, sm_count * 8);
+  if (in_dtype == HN_F32) {
+    const float* x = static_cast<const float*>(patches);
+    if (stats) patch_stats_kernel<float><<<sgrid, 256, 0, s>>>(x, stats, n);
+    l1_tc_kernel<float><<<grid, kL1TcThreads, kL1TcSmem, s>>>(x, out, w, bias, stats, n, act_bf16);
+  } else {
+    const uint8_t* x = static_cast<const uint8_t*>(patches);
+    if (stats) patch_stats_kernel<uint8_t><<<sgrid, 256, 0, s>>>(x, stats, n);
+    l1_tc_kernel<uint8_t><<<grid, kL1TcThreads, kL1TcSmem, s>>>(x, out, w, bias, stats, n, act_bf16);
+  }
   HN_CUDA(cudaGetLastError());
+  count_launch(stats ? 2 : 1);
   return HN_OK;
 }
 
@@ -187,19 +194,32 @@ static int build_params(hn_handle* h) {
   return HN_OK;
 }
 
-static void run_l1(hn_handle* h, const void* patches, int in_dtype, int n, int grid1, cudaStream_t s);
-
 // Runs L1..L6 for `n` patches (n <= chunk); L6 lands in l6 + l6_row * 8192.
+// Stage 1 and conv2 run in sub-passes of `front_chunk` patches that reuse the head of act[0], so the 64 KB/patch
+// stage-1 output is produced and consumed inside the L2 instead of making an HBM round trip; conv2 writes into
+// the full-size act[1] and the deeper (smaller) stages run once over the whole pass.
 static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n, long long l6_row, int last_layer,
                           cudaStream_t s) {
-  const int grid1 = std::min(n, h->sm_count * 4);
-  {
-    StageTimer timer(h, 0, s);
-    run_l1(h, patches, in_dtype, n, grid1, s);
+  const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
+  const int front = last_layer >= 2 ? std::min(h->front_chunk, n) : n;
+  for (int off = 0; off < n; off += front) {
+    const int m = std::min(front, n - off);
+    {
+      StageTimer timer(h, 0, s);
+      HN_TRY(launch_l1(static_cast<const char*>(patches) + static_cast<size_t>(off) * 1024 * in_elem, in_dtype, h->act[0],
+                       h->w1, h->bias, h->stats, m, h->act_bf16, h->sm_count, s));
+    }
+    if (last_layer >= 2) {
+      TcParams p = h->conv_params[0];
+      p.total_rows = 1024LL * m;
+      p.num_tiles = static_cast<int>(p.total_rows / kTileM);
+      p.act_bf16 = h->act_bf16;
+      p.out = h->act[1] + static_cast<size_t>(off) * 32 * 32 * 32;
+      StageTimer timer(h, 1, s);
+      HN_TRY(launch_conv(0, p, h->sm_count, s));
+    }
   }
-  HN_CUDA(cudaGetLastError());
-  count_launch();
-  for (int li = 0; li < 5 && li + 2 <= last_layer; ++li) {
+  for (int li = 1; li < 5 && li + 2 <= last_layer; ++li) {
     const ConvLayer& L = kConv[li];
     TcParams p = h->conv_params[li];
     const long long pix_out = static_cast<long long>(L.hout) * L.hout;
@@ -213,10 +233,6 @@ static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n
   return HN_OK;
 }
 
-static void run_l1(hn_handle* h, const void* patches, int in_dtype, int n, int grid1, cudaStream_t s) {
-  (void)grid1;
-  launch_l1(patches, in_dtype, h->act[0], h->w1, h->bias, n, h->act_bf16, 1, h->sm_count, s);
-}
 
 }  // namespace hn
 
@@ -241,6 +257,10 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   head_rows = std::max<long long>(head_rows, chunk_patches);
   head_rows = (head_rows + chunk_patches - 1) / chunk_patches * chunk_patches;
   h->chunk = chunk_patches;
+  {
+    const char* e = getenv("HN_FRONT_CHUNK");
+    h->front_chunk = e ? std::max(2, atoi(e)) : chunk_patches;
+  }
   h->head_rows = head_rows;
   const size_t act_elems = static_cast<size_t>(chunk_patches) * 32 * 32 * 32;
   auto fail = [&](int code) { hn_destroy(h); return code; };
@@ -264,6 +284,7 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   HN_CUDA_H(cudaMalloc(&h->whead, static_cast<size_t>(128) * kHeadK * 2));
   HN_CUDA_H(cudaMalloc(&h->w1, 9 * 32 * sizeof(float)));
   HN_CUDA_H(cudaMalloc(&h->bias, 7 * 128 * sizeof(float)));
+  HN_CUDA_H(cudaMalloc(&h->stats, static_cast<size_t>(chunk_patches) * sizeof(float2)));
 #undef HN_CUDA_H
   st = build_params(h);
   if (st != HN_OK) return fail(st);
@@ -280,6 +301,7 @@ extern "C" int hn_destroy(hn_handle* h) {
   cudaFree(h->whead);
   cudaFree(h->w1);
   cudaFree(h->bias);
+  cudaFree(h->stats);
   for (auto& v : h->ev)
     for (cudaEvent_t e : v) cudaEventDestroy(e);
   nas_state_free(h->nas);

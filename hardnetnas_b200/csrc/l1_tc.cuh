@@ -21,10 +21,11 @@ constexpr int kL1TcThreads = 17 * 32;
 constexpr int kL1PPitch = 40;                               // halfs per row of the haloed patch (34 used)
 constexpr uint32_t kL1ABytes = 8 * 4096;                    // eight 128x16 im2col tiles
 constexpr uint32_t kL1PBytes = 34 * kL1PPitch * 2;          // 2720
-constexpr uint32_t kL1BufBytes = kL1ABytes + 3072;          // P padded to keep the next buffer 1024B aligned
+constexpr uint32_t kL1BufBytes = kL1ABytes;
+constexpr uint32_t kL1StageBytes = 8 * 2 * 2048;            // per epilogue warp: two 32-row x 64 B output staging buffers
 // > half of the SM's shared memory on purpose: one CTA per SM, because each CTA allocates all 512 TMEM columns
 constexpr size_t kL1TcSmem = 120 * 1024;
-static_assert(2 * kL1BufBytes + 1024 /*W*/ + 1024 /*align*/ + 256 /*barriers*/ + 256 /*bias, stats*/ <= kL1TcSmem, "smem budget");
+static_assert(2 * kL1BufBytes + 1024 /*W*/ + kL1StageBytes + 1024 /*align*/ + 256 /*barriers*/ + 256 /*bias*/ <= kL1TcSmem, "smem budget");
 
 __device__ __forceinline__ uint64_t make_noswizzle_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -44,17 +45,64 @@ __device__ __forceinline__ uint16_t to16bits(float v, int bf16) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 
+// Per-patch (mean, 1 / (unbiased std + 1e-7)) of HardNet.input_norm (hardnet/HardNet.py:306-310); one warp per
+// patch. Pure pairwise trees, so a constant patch has mean == value exactly and normalises to exactly 0, like the
+// reference's 0 / 1e-7.
+template <typename TIn>
+__global__ void __launch_bounds__(256) patch_stats_kernel(const TIn* __restrict__ in, float2* __restrict__ stats,
+                                                          int num_patches) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int patch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; patch < num_patches; patch += warps) {
+    float x[32];
+    const TIn* src = in + static_cast<size_t>(patch) * 1024;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if constexpr (sizeof(TIn) == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
+        x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+      } else {
+        const uchar4 q = *reinterpret_cast<const uchar4*>(src + (i * 32 + lane) * 4);
+        x[4 * i] = q.x; x[4 * i + 1] = q.y; x[4 * i + 2] = q.z; x[4 * i + 3] = q.w;
+      }
+    }
+    float t[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t[i] = x[i];
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+      for (int i = 0; i < w; ++i) t[i] = t[2 * i] + t[2 * i + 1];
+    float s = t[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / 1024.f);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const float d = x[i] - mean; t[i] = d * d; }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1)
+#pragma unroll
+      for (int i = 0; i < w; ++i) t[i] = t[2 * i] + t[2 * i + 1];
+    float v = t[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) stats[patch] = make_float2(mean, 1.f / (sqrtf(v * (1.f / 1023.f)) + 1e-7f));  // torch.std is unbiased
+  }
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(kL1TcThreads, 1)
 l1_tc_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out, const float* __restrict__ w /*[9][32] folded*/,
-             const float* __restrict__ bias /*[32]*/, int num_patches, int act_bf16, int do_norm) {
+             const float* __restrict__ bias /*[32]*/, const float2* __restrict__ stats /*null: no normalisation*/,
+             int num_patches, int act_bf16) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
   // layout: [buf0: A (32 KB) | P (3 KB)] [buf1 ...] [W 1 KB] [barriers] [bias 32 f] [red 8 f] [stat 2 f]
   const uint32_t w_addr = base + 2 * kL1BufBytes;
-  const uint32_t bar_base = w_addr + 1024;
+  const uint32_t stage_addr = w_addr + 1024;   // epilogue output staging
+  const uint32_t bar_base = stage_addr + kL1StageBytes;
   auto a_full = [&](int b) { return bar_base + 8u * b; };
   auto a_empty = [&](int b) { return bar_base + 8u * (2 + b); };
   auto t_full = [&](int b) { return bar_base + 8u * (4 + b); };
@@ -62,8 +110,6 @@ l1_tc_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out, const float
   const uint32_t tmem_slot = bar_base + 64;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
   float* s_bias = reinterpret_cast<float*>(gbase + (bar_base + 256 - base));
-  float* s_red = s_bias + 32;
-  float* s_stat = s_red + 8;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,11 +132,6 @@ l1_tc_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out, const float
     if (threadIdx.x < 32) s_bias[threadIdx.x] = bias[threadIdx.x];
   } else if (warp >= 9) {
     const int l = threadIdx.x - 9 * 32;  // 0..255
-    // zero both haloed patches (the halo stays zero for the kernel's lifetime)
-    for (int b = 0; b < 2; ++b) {
-      uint32_t* P = reinterpret_cast<uint32_t*>(gbase + b * kL1BufBytes + kL1ABytes);
-      for (int i = l; i < static_cast<int>(kL1PBytes / 4); i += 256) P[i] = 0u;
-    }
     // weights -> canonical no-swizzle [32 x 16] tile: (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2
     uint16_t* W = reinterpret_cast<uint16_t*>(gbase + (w_addr - base));
     for (int i = l; i < 32 * 16; i += 256) {
@@ -107,68 +148,46 @@ l1_tc_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out, const float
 
   if (warp >= 9) {
     // ============================== loaders: normalise + im2col ==============================
+    // Every thread owns 4 consecutive pixels and reads its own 3 x 6 window straight from global memory (the 4 KB
+    // patch is L1 resident), so the loader warps never synchronise with each other.
     const int l = threadIdx.x - 9 * 32;
-    const int lw = l >> 5;             // loader warp 0..7
     const int py = l >> 3;             // pixel row handled by this thread
     const int px0 = (l & 7) * 4;       // first of 4 consecutive pixels
     int it = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      float x[4];
-      {
-        const TIn* src = in + static_cast<size_t>(patch) * 1024 + l * 4;
-        if constexpr (sizeof(TIn) == 4) {
-          const float4 v = *reinterpret_cast<const float4*>(src);
-          x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-        } else {
-          const uchar4 v = *reinterpret_cast<const uchar4*>(src);
-          x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
-        }
-      }
       float mean = 0.f, inv = 1.f;
-      if (do_norm) {
-        // pure pairwise trees: a constant patch gives mean == value exactly (-> all-zero input like the reference)
-        float s = (x[0] + x[1]) + (x[2] + x[3]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) s_red[lw] = s;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mean = (((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]))) * (1.f / 1024.f);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float d0 = x[0] - mean, d1 = x[1] - mean, d2 = x[2] - mean, d3 = x[3] - mean;
-        float v = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[lw] = v;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float var = (((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]))) * (1.f / 1023.f);
-        inv = 1.f / (sqrtf(var) + 1e-7f);  // torch.std is the unbiased estimator
+      if (stats != nullptr) {
+        const float2 st = __ldg(stats + patch);
+        mean = st.x;
+        inv = st.y;
       }
-      // the MMAs that read this buffer two patches ago must have retired before P / A are overwritten
-      mbar_wait(a_empty(b), ph ^ 1u);
-      uint16_t* P = reinterpret_cast<uint16_t*>(gbase + b * kL1BufBytes + kL1ABytes);
-      {
-        const uint32_t lo = to16bits((x[0] - mean) * inv, act_bf16) | (static_cast<uint32_t>(to16bits((x[1] - mean) * inv, act_bf16)) << 16);
-        const uint32_t hi = to16bits((x[2] - mean) * inv, act_bf16) | (static_cast<uint32_t>(to16bits((x[3] - mean) * inv, act_bf16)) << 16);
-        // P[(py+1)][px0+1 .. px0+4]: odd start column -> scalar 16-bit stores
-        uint16_t* row = P + (py + 1) * kL1PPitch + px0 + 1;
-        row[0] = static_cast<uint16_t>(lo & 0xffff);
-        row[1] = static_cast<uint16_t>(lo >> 16);
-        row[2] = static_cast<uint16_t>(hi & 0xffff);
-        row[3] = static_cast<uint16_t>(hi >> 16);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      // im2col of this thread's 4 pixels: window rows py..py+2, columns px0..px0+5 of the haloed patch
+      const TIn* src = in + static_cast<size_t>(patch) * 1024;
       uint16_t win[3][6];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        const uint16_t* wr = P + (py + r) * kL1PPitch + px0;
-        const uint2 a = *reinterpret_cast<const uint2*>(wr);          // 4 halfs, 8-byte aligned
-        const uint32_t c = *reinterpret_cast<const uint32_t*>(wr + 4);
-        win[r][0] = a.x & 0xffff; win[r][1] = a.x >> 16; win[r][2] = a.y & 0xffff; win[r][3] = a.y >> 16;
-        win[r][4] = c & 0xffff;   win[r][5] = c >> 16;
+        const int y = py + r - 1;
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool ok[6] = {false, false, false, false, false, false};
+        if (y >= 0 && y < 32) {
+          const TIn* row = src + y * 32 + px0;
+          if constexpr (sizeof(TIn) == 4) {
+            const float4 q = *reinterpret_cast<const float4*>(row);
+            v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
+          } else {
+            const uchar4 q = *reinterpret_cast<const uchar4*>(row);
+            v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
+          }
+          ok[1] = ok[2] = ok[3] = ok[4] = true;
+          if (px0 > 0) { v[0] = static_cast<float>(row[-1]); ok[0] = true; }
+          if (px0 < 28) { v[5] = static_cast<float>(row[4]); ok[5] = true; }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) win[r][c] = ok[c] ? to16bits((v[c] - mean) * inv, act_bf16) : static_cast<uint16_t>(0);
       }
+      // the MMAs that read this buffer two patches ago must have retired before A is overwritten
+      mbar_wait(a_empty(b), ph ^ 1u);
       uint8_t* A = gbase + b * kL1BufBytes;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -213,9 +232,13 @@ l1_tc_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out, const float
     }
   } else {
     // ============================== epilogue ==============================
+    // Each warp owns 32 consecutive pixels of a tile = 2 KB of contiguous NHWC output: rows are staged in shared
+    // memory and leave through one bulk (async-proxy) store per warp and tile, fully coalesced and off the LSU.
     const int q = warp & 3;
     const int half = warp >> 2;
-    int it = 0;
+    const uint32_t my_stage = stage_addr + warp * 4096;
+    uint8_t* my_stage_ptr = gbase + (my_stage - base);
+    int it = 0, sbuf = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
       const int b = it & 1;
       const uint32_t ph = (it >> 1) & 1;
@@ -234,14 +257,25 @@ l1_tc_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out, const float
           const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[2 * j + 1], 0.f);
           o[j] = pack16(v0, v1, act_bf16);
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(patch) * 1024 + t * 128 + q * 32 + lane) * 32);
+        // the bulk store that last read this staging buffer (two tiles ago) must be done reading it
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        uint4* srow = reinterpret_cast<uint4*>(my_stage_ptr + sbuf * 2048 + lane * 64);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) srow[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_store(out + (static_cast<size_t>(patch) * 1024 + t * 128 + q * 32) * 32, my_stage + sbuf * 2048, 2048);
+          bulk_commit();
+        }
+        sbuf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(t_empty(b));
     }
+    if (lane == 0) bulk_wait_all<0>();   // outstanding stores must complete before the CTA (and its smem) goes away
   }
 
   tc_fence_before();

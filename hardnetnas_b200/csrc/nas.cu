@@ -435,8 +435,7 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
         const hn_nas_op& o = st->ops[i];
         switch (o.kind) {
           case OP_STEM: {
-            HN_TRY(launch_l1(src, in_dtype, st->slot[o.dst], st->params + o.w_off, st->params + o.b_off, n, bf, 0, h->sm_count, s));
-            count_launch();
+            HN_TRY(launch_l1(src, in_dtype, st->slot[o.dst], st->params + o.w_off, st->params + o.b_off, nullptr, n, bf, h->sm_count, s));
             break;
           }
           case OP_PW: {
