@@ -1,0 +1,328 @@
+// Fused front of the HardNet stack: input_norm + conv 1->32 + BN + ReLU (features[0..2]) and conv 32->32 + BN + ReLU
+// (features[3..5], reference hardnet/HardNet.py:281-286,306-310) in ONE persistent kernel. The 64 KB/patch stage-1
+// activation never leaves the SM: its epilogue writes it to shared memory in a channel-planar, row-haloed layout
+//     act1[plane = c / 8][slot = (y + 1) * 32 + x][c % 8]            (fp16/bf16, 16 B per slot, 34 x 32 slots per plane)
+// which IS a UMMA no-swizzle K-major operand (8 consecutive slots x 16 B = one core matrix, SBO = 128 B,
+// LBO = plane pitch), so a ky tap of conv2 is the same buffer viewed 32 slots further on - no im2col copy.
+//
+// conv2 runs with the three kx taps STACKED ON N:  D'[p, kx * 32 + co] = sum_{ky, ci} act1[p + (ky - 1) row, ci] *
+// w[ky, kx, ci, co]  (M = 128 pixels = 4 image rows, N = 96, K = 3 x 32), so each A tile is read from shared memory
+// 3 times instead of 9 (SS-mode UMMA is bound by the 128 B/clk shared-memory port when N is small). The epilogue
+// finishes the conv with two lane shuffles per value:  out[y, x] = D'0[y, x - 1] + D'1[y, x] + D'2[y, x + 1]; a TMEM lane
+// quarter is exactly one image row, so the shuffle's edge lanes are the conv's zero padding in x.
+//
+// Warps (21): 0-3 stage-1 epilogue (TMEM -> act1 in smem), 4-11 conv2 epilogue (two groups of four, one per
+// accumulator buffer), 12 TMEM owner + UMMA issuer, 13-20 loaders (normalise + im2col of the 1-channel input, K = 9 -> 16).
+#pragma once
+
+#include "common.cuh"
+#include "l1_tc.cuh"
+#include "tc_conv.cuh"
+
+namespace hn {
+
+constexpr int kFfThreads = 21 * 32;
+constexpr int kFfIssuer = 12;
+constexpr int kFfLoader0 = 13;
+constexpr uint32_t kFfPlane = 34 * 32 * 16;   // one 8-channel plane of the haloed stage-1 output
+constexpr uint32_t kFfAct1 = 4 * kFfPlane;    // 69 632 B per buffer
+constexpr uint32_t kFfA1 = 8 * 4096;          // eight 128 x 16 im2col tiles of the input patch
+constexpr uint32_t kFfW2Tap = 96 * 32 * 2;    // one ky: [kx * 32 + co][ci]
+constexpr uint32_t kFfW2 = 3 * kFfW2Tap;      // 18 432 B
+constexpr uint32_t kFfW1 = 1024;
+constexpr size_t kFfSmem = kFfA1 + 2 * kFfAct1 + kFfW2 + kFfW1 + 256 /*barriers*/ + 256 /*biases*/ + 1024 /*align*/;
+static_assert(kFfSmem <= 227 * 1024, "smem budget");
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(kFfThreads, 1)
+front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][32][32][32] NHWC*/,
+                   const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
+                   const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
+                   const float* __restrict__ bias2 /*[32]*/, const float2* __restrict__ stats /*null: no normalisation*/,
+                   int num_patches, int act_bf16) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw_addr);
+  const uint32_t a1_addr = base;
+  const uint32_t act1_addr = a1_addr + kFfA1;
+  const uint32_t w2_addr = act1_addr + 2 * kFfAct1;
+  const uint32_t w1_addr = w2_addr + kFfW2;
+  const uint32_t bar_base = w1_addr + kFfW1;
+  const uint32_t a1_full = bar_base, a1_empty = bar_base + 8, l1_full = bar_base + 16, l1_empty = bar_base + 24;
+  auto act1_full = [&](int b) { return bar_base + 32u + 8u * b; };
+  auto act1_empty = [&](int b) { return bar_base + 48u + 8u * b; };
+  auto c2_full = [&](int a) { return bar_base + 64u + 8u * a; };
+  auto c2_empty = [&](int a) { return bar_base + 80u + 8u * a; };
+  const uint32_t tmem_slot = bar_base + 128;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
+  float* s_bias1 = reinterpret_cast<float*>(gbase + (bar_base + 256 - base));
+  float* s_bias2 = s_bias1 + 32;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---------------------------------------------- one-time setup ----------------------------------------------
+  if (warp == kFfIssuer) {
+    if (lane == 0) {
+      mbar_init(a1_full, 8);    // one arrive per loader warp
+      mbar_init(a1_empty, 1);   // tcgen05.commit
+      mbar_init(l1_full, 1);    // tcgen05.commit
+      mbar_init(l1_empty, 4);   // one arrive per stage-1 epilogue warp
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(act1_full(b), 4);
+        mbar_init(act1_empty(b), 1);
+        mbar_init(c2_full(b), 1);
+        mbar_init(c2_empty(b), 4);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  } else {
+    const int t = threadIdx.x - (warp > kFfIssuer ? 32 : 0);  // 0..639 over the non-issuer threads
+    // conv2 weights: copy the prepared shared-memory image
+    for (int i = t; i < static_cast<int>(kFfW2 / 16); i += kFfThreads - 32)
+      *reinterpret_cast<uint4*>(gbase + (w2_addr - base) + i * 16) = __ldg(w2img + i);
+    // halo rows of both act1 buffers (slots [0, 32) and [33 * 32, 34 * 32) of every plane) are zero and stay zero
+    for (int i = t; i < 2 * 4 * 2 * 32; i += kFfThreads - 32) {
+      const int slot = i & 31, top = (i >> 5) & 1, plane = (i >> 6) & 3, b = i >> 8;
+      *reinterpret_cast<uint4*>(gbase + (act1_addr - base) + b * kFfAct1 + plane * kFfPlane +
+                                (top ? 33 * 32 + slot : slot) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    // stage-1 weights -> canonical no-swizzle [32 x 16] tile: (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2
+    uint16_t* W = reinterpret_cast<uint16_t*>(gbase + (w1_addr - base));
+    for (int i = t; i < 32 * 16; i += kFfThreads - 32) {
+      const int n = i >> 4, k = i & 15;
+      const float v = k < 9 ? w1[k * 32 + n] : 0.f;
+      W[((n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) >> 1] = to16bits(v, act_bf16);
+    }
+    if (t < 32) s_bias1[t] = bias1[t];
+    else if (t < 64) s_bias2[t - 32] = bias2[t - 32];
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tm_l1 = tmem_base;            // columns [0, 256): eight 128 x 32 stage-1 accumulators
+  const uint32_t tm_c2 = tmem_base + 256;      // columns [256, 512): two 128 x 96 conv2 accumulators, pitch 128
+
+  if (warp >= kFfLoader0) {
+    // ============================== loaders: normalise + im2col of the input patch ==============================
+    const int l = threadIdx.x - kFfLoader0 * 32;  // 0..255
+    const int py = l >> 3;                        // pixel row handled by this thread
+    const int px0 = (l & 7) * 4;                  // first of 4 consecutive pixels
+    const int rot = (l >> 1) & 3;                 // store order rotation: a quarter-warp hits 8 distinct 16 B bank groups
+    int it = 0;
+    for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
+      float mean = 0.f, inv = 1.f;
+      if (stats != nullptr) {
+        const float2 st = __ldg(stats + patch);
+        mean = st.x;
+        inv = st.y;
+      }
+      const TIn* src = in + static_cast<size_t>(patch) * 1024;
+      uint16_t win[3][6];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int y = py + r - 1;
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool ok[6] = {false, false, false, false, false, false};
+        if (y >= 0 && y < 32) {
+          const TIn* row = src + y * 32 + px0;
+          if constexpr (sizeof(TIn) == 4) {
+            const float4 q = *reinterpret_cast<const float4*>(row);
+            v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
+          } else {
+            const uchar4 q = *reinterpret_cast<const uchar4*>(row);
+            v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
+          }
+          ok[1] = ok[2] = ok[3] = ok[4] = true;
+          if (px0 > 0) { v[0] = static_cast<float>(row[-1]); ok[0] = true; }
+          if (px0 < 28) { v[5] = static_cast<float>(row[4]); ok[5] = true; }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) win[r][c] = ok[c] ? to16bits((v[c] - mean) * inv, act_bf16) : static_cast<uint16_t>(0);
+      }
+      // the stage-1 MMAs of the previous patch must have retired before A1 is overwritten
+      mbar_wait(a1_empty, (it & 1) ^ 1u);
+      uint8_t* A = gbase + (a1_addr - base);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint4 k0, k1;
+        int j;
+        // j = (jj + rot) & 3 with compile-time register indexing
+        uint32_t w00, w01, w02, w10, w11, w12, w20, w21, w22;
+#define HN_FF_PICK(J)                                                                          \
+  { w00 = win[0][J]; w01 = win[0][J + 1]; w02 = win[0][J + 2]; w10 = win[1][J]; w11 = win[1][J + 1]; \
+    w12 = win[1][J + 2]; w20 = win[2][J]; w21 = win[2][J + 1]; w22 = win[2][J + 2]; }
+        j = (jj + rot) & 3;
+        if (j == 0) HN_FF_PICK(0) else if (j == 1) HN_FF_PICK(1) else if (j == 2) HN_FF_PICK(2) else HN_FF_PICK(3)
+#undef HN_FF_PICK
+        const int pix = py * 32 + px0 + j;
+        const int tile = pix >> 7, r = pix & 127;
+        uint8_t* dst = A + tile * 4096 + (r >> 3) * 256 + (r & 7) * 16;
+        k0.x = w00 | (w01 << 16);
+        k0.y = w02 | (w10 << 16);
+        k0.z = w11 | (w12 << 16);
+        k0.w = w20 | (w21 << 16);
+        k1.x = w22;
+        k1.y = 0u; k1.z = 0u; k1.w = 0u;
+        *reinterpret_cast<uint4*>(dst) = k0;
+        *reinterpret_cast<uint4*>(dst + 128) = k1;
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a1_full);
+    }
+  } else if (warp == kFfIssuer) {
+    // ============================== UMMA issuer ==============================
+    const uint32_t idesc1 = make_idesc_f16(kTileM, 32, act_bf16);
+    const uint32_t idesc2 = make_idesc_f16(kTileM, 96, act_bf16);
+    const uint64_t b1_desc = make_noswizzle_desc(w1_addr, 128, 256);
+    const int n_local = (num_patches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    auto issue_l1 = [&]() {
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          umma_f16(tm_l1 + t * 32, make_noswizzle_desc(a1_addr + t * 4096, 128, 256), b1_desc, idesc1, 0u);
+        umma_commit(a1_empty);
+        umma_commit(l1_full);
+      }
+      __syncwarp();
+    };
+    if (n_local > 0) {
+      mbar_wait(a1_full, 0);
+      tc_fence_after();
+      issue_l1();
+    }
+    uint32_t use = 0;  // conv2 tiles issued so far (accumulator buffer = use & 1)
+    for (int it = 0; it < n_local; ++it) {
+      const int b = it & 1;
+      if (it + 1 < n_local) {
+        // stage 1 of the NEXT patch goes first, so its epilogue overlaps the conv2 MMAs of this patch
+        mbar_wait(a1_full, (it + 1) & 1);
+        mbar_wait(l1_empty, it & 1);
+        tc_fence_after();
+        issue_l1();
+      }
+      mbar_wait(act1_full(b), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t act = act1_addr + b * kFfAct1;
+#pragma unroll 1
+      for (int t = 0; t < 8; ++t, ++use) {
+        const int a = use & 1;
+        mbar_wait(c2_empty(a), ((use >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d = tm_c2 + a * 128;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              // A: 128 slots starting at image row 4t + ky - 1 (slot (4t + ky) * 32), channels 16k .. 16k + 15
+              const uint64_t a_desc = make_noswizzle_desc(act + (t * 128 + ky * 32) * 16 + k * 2 * kFfPlane, kFfPlane, 128);
+              const uint64_t b_desc = make_noswizzle_desc(w2_addr + ky * kFfW2Tap + k * 256, 128, 512);
+              umma_f16(d, a_desc, b_desc, idesc2, (ky | k) != 0);
+            }
+          }
+          umma_commit(c2_full(a));
+          if (t == 7) umma_commit(act1_empty(b));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 4) {
+    // ============================== stage-1 epilogue: TMEM -> bias, ReLU, pack -> act1 (smem) ==============================
+    const int q = warp;
+    int it = 0;
+    for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
+      const int b = it & 1;
+      mbar_wait(l1_full, it & 1);
+      mbar_wait(act1_empty(b), ((it >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      uint8_t* act = gbase + (act1_addr - base) + b * kFfAct1;
+#pragma unroll 1
+      for (int t = 0; t < 8; ++t) {
+        uint32_t r[32];
+        tmem_ld32(tm_l1 + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float v0 = fmaxf(__uint_as_float(r[2 * j]) + s_bias1[2 * j], 0.f);
+          const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias1[2 * j + 1], 0.f);
+          o[j] = pack16(v0, v1, act_bf16);
+        }
+        // pixel p = t * 128 + q * 32 + lane  ->  slot p + 32 (one halo row on top)
+        uint8_t* dst = act + (t * 128 + q * 32 + lane + 32) * 16;
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl)
+          *reinterpret_cast<uint4*>(dst + pl * kFfPlane) = make_uint4(o[4 * pl], o[4 * pl + 1], o[4 * pl + 2], o[4 * pl + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(act1_full(b));
+        mbar_arrive(l1_empty);
+      }
+    }
+  } else {
+    // ============================== conv2 epilogue: kx shift-and-add, bias, ReLU, pack -> global ==============================
+    const int q = warp & 3;
+    const int g = (warp - 4) >> 2;  // accumulator buffer owned by this group of four warps
+    const uint32_t t_row = tm_c2 + (static_cast<uint32_t>(q * 32) << 16) + g * 128;
+    uint32_t use = 0;
+    for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x) {
+      uint16_t* opatch = out + static_cast<size_t>(patch) * 32768;
+#pragma unroll 1
+      for (int tt = 0; tt < 4; ++tt, ++use) {
+        const int t = 2 * tt + g;
+        mbar_wait(c2_full(g), use & 1);
+        tc_fence_after();
+        uint4* dst = reinterpret_cast<uint4*>(opatch + (t * 128 + q * 32 + lane) * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r0[8], r1[8], r2[8];
+          tmem_ld8(t_row + c * 8, r0);
+          tmem_ld8(t_row + 32 + c * 8, r1);
+          tmem_ld8(t_row + 64 + c * 8, r2);
+          tmem_ld_wait();
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);     // D'0 of pixel x - 1
+            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);  // D'2 of pixel x + 1
+            if (lane == 0) left = 0.f;
+            if (lane == 31) right = 0.f;
+            v[j] = fmaxf(left + __uint_as_float(r1[j]) + right + s_bias2[c * 8 + j], 0.f);
+          }
+          dst[c] = make_uint4(pack16(v[0], v[1], act_bf16), pack16(v[2], v[3], act_bf16), pack16(v[4], v[5], act_bf16),
+                              pack16(v[6], v[7], act_bf16));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(c2_empty(g));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kFfIssuer) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace hn

@@ -30,6 +30,8 @@ struct hn_handle {
   uint16_t* wconv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [cout][9*cin]
   uint16_t* whead = nullptr;                                           // [128][8192]
   float* w1 = nullptr;                                                 // [9][32]
+  uint16_t* w2img = nullptr;  // conv2 weights as the fused front kernel's shared-memory image (front_fused.cuh)
+  int fused_front = 1;        // stage 1 + conv2 in one kernel (HN_FUSED_FRONT=0 selects the two-kernel path)
   float* bias = nullptr;                                               // 7 x 128
   float2* stats = nullptr;                                             // per-patch (mean, 1/std), chunk entries
   hn::TcParams conv_params[5];

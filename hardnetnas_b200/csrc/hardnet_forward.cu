@@ -9,6 +9,7 @@
 #include <cmath>
 #include <vector>
 
+#include "front_fused.cuh"
 #include "handle.h"
 #include "host_common.h"
 #include "l1_tc.cuh"
@@ -116,6 +117,32 @@ int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, 
   return HN_OK;
 }
 
+// Stage 1 + conv2 fused (front_fused.cuh): patches -> conv2 output (NHWC 16-bit), stage-1 activation stays on chip.
+static int launch_front_fused(hn_handle* h, const void* patches, int in_dtype, uint16_t* out, int n, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    HN_CUDA(cudaFuncSetAttribute(front_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFfSmem)));
+    HN_CUDA(cudaFuncSetAttribute(front_fused_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFfSmem)));
+    attr_done = true;
+  }
+  if (n <= 0) return HN_OK;
+  const int grid = std::min(n, h->sm_count);
+  const int sgrid = std::min((n + 7) / 8, h->sm_count * 8);
+  const uint4* w2 = reinterpret_cast<const uint4*>(h->w2img);
+  if (in_dtype == HN_F32) {
+    const float* x = static_cast<const float*>(patches);
+    patch_stats_kernel<float><<<sgrid, 256, 0, s>>>(x, h->stats, n);
+    front_fused_kernel<float><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, h->bias + 128, h->stats, n, h->act_bf16);
+  } else {
+    const uint8_t* x = static_cast<const uint8_t*>(patches);
+    patch_stats_kernel<uint8_t><<<sgrid, 256, 0, s>>>(x, h->stats, n);
+    front_fused_kernel<uint8_t><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, h->bias + 128, h->stats, n, h->act_bf16);
+  }
+  HN_CUDA(cudaGetLastError());
+  count_launch(2);
+  return HN_OK;
+}
+
 int launch_head(const TcParams& p, int sm_count, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
@@ -201,8 +228,12 @@ static int build_params(hn_handle* h) {
 static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n, long long l6_row, int last_layer,
                           cudaStream_t s) {
   const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
+  if (h->fused_front && last_layer >= 2) {
+    StageTimer timer(h, 1, s);  // reported as the conv2 stage (stage 1 is inside it)
+    HN_TRY(launch_front_fused(h, patches, in_dtype, h->act[1], n, s));
+  }
   const int front = last_layer >= 2 ? std::min(h->front_chunk, n) : n;
-  for (int off = 0; off < n; off += front) {
+  for (int off = 0; off < n && !(h->fused_front && last_layer >= 2); off += front) {
     const int m = std::min(front, n - off);
     {
       StageTimer timer(h, 0, s);
@@ -260,6 +291,8 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   {
     const char* e = getenv("HN_FRONT_CHUNK");
     h->front_chunk = e ? std::max(2, atoi(e)) : chunk_patches;
+    const char* f = getenv("HN_FUSED_FRONT");
+    h->fused_front = f ? atoi(f) : 1;
   }
   h->head_rows = head_rows;
   const size_t act_elems = static_cast<size_t>(chunk_patches) * 32 * 32 * 32;
@@ -283,6 +316,7 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
     HN_CUDA_H(cudaMalloc(&h->wconv[li], static_cast<size_t>(kConv[li].cout) * 9 * kConv[li].cin * 2));
   HN_CUDA_H(cudaMalloc(&h->whead, static_cast<size_t>(128) * kHeadK * 2));
   HN_CUDA_H(cudaMalloc(&h->w1, 9 * 32 * sizeof(float)));
+  HN_CUDA_H(cudaMalloc(&h->w2img, kFfW2));
   HN_CUDA_H(cudaMalloc(&h->bias, 7 * 128 * sizeof(float)));
   HN_CUDA_H(cudaMalloc(&h->stats, static_cast<size_t>(chunk_patches) * sizeof(float2)));
 #undef HN_CUDA_H
@@ -300,6 +334,7 @@ extern "C" int hn_destroy(hn_handle* h) {
   for (int li = 0; li < 5; ++li) cudaFree(h->wconv[li]);
   cudaFree(h->whead);
   cudaFree(h->w1);
+  cudaFree(h->w2img);
   cudaFree(h->bias);
   cudaFree(h->stats);
   for (auto& v : h->ev)
@@ -341,6 +376,19 @@ extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const floa
           wp[static_cast<size_t>(co) * K + tap * L.cin + ci] = to16(w[li + 1][(static_cast<size_t>(co) * L.cin + ci) * 9 + tap] * s, bf);
     }
     HN_CUDA(cudaMemcpy(h->wconv[li], wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+    if (li == 0) {
+      // fused front kernel: per ky a [n = kx * 32 + co][k = ci] tile in the UMMA no-swizzle K-major core-matrix order
+      std::vector<uint16_t> img(kFfW2 / 2);
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx)
+          for (int co = 0; co < 32; ++co)
+            for (int ci = 0; ci < 32; ++ci) {
+              const int nn = kx * 32 + co;
+              const size_t byte = static_cast<size_t>(ky) * kFfW2Tap + (nn >> 3) * 512 + (ci >> 3) * 128 + (nn & 7) * 16 + (ci & 7) * 2;
+              img[byte / 2] = wp[static_cast<size_t>(co) * K + (ky * 3 + kx) * 32 + ci];
+            }
+      HN_CUDA(cudaMemcpy(h->w2img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    }
   }
   // head: [co][ci][8][8] -> [co][(y*8+x)*128 + ci]
   {
