@@ -42,7 +42,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 
 template <typename TIn>
 __global__ void __launch_bounds__(kFfThreads, 1)
-front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][32][32][32] NHWC*/,
+front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]*/,
                    const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
                    const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
                    const float* __restrict__ bias2 /*[32]*/, const float2* __restrict__ stats /*null: no normalisation*/,
@@ -290,7 +290,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         const int t = 2 * tt + g;
         mbar_wait(c2_full(g), use & 1);
         tc_fence_after();
-        uint4* dst = reinterpret_cast<uint4*>(opatch + (t * 128 + q * 32 + lane) * 32);
+        // channel-planar parity layout for the stride-2 conv3: [plane][ypar][xpar][16][16][8]
+        uint4* dst = reinterpret_cast<uint4*>(opatch) + planar_pixel_slot<32, true>(4 * t + q, lane);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t r0[8], r1[8], r2[8];
@@ -307,7 +308,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
             if (lane == 31) right = 0.f;
             v[j] = fmaxf(left + __uint_as_float(r1[j]) + right + s_bias2[c * 8 + j], 0.f);
           }
-          dst[c] = make_uint4(pack16(v[0], v[1], act_bf16), pack16(v[2], v[3], act_bf16), pack16(v[4], v[5], act_bf16),
+          dst[c * 1024] = make_uint4(pack16(v[0], v[1], act_bf16), pack16(v[2], v[3], act_bf16), pack16(v[4], v[5], act_bf16),
                               pack16(v[6], v[7], act_bf16));
         }
         tc_fence_before();

@@ -20,7 +20,6 @@ int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, 
 
 struct hn_handle {
   int chunk = 0;            // patches per conv-stack pass
-  int front_chunk = 0;      // patches per stage-1 + conv2 sub-pass (keeps the stage-1 output L2 resident)
   long long head_rows = 0;  // capacity of the L6 output buffer (patches)
   int sm_count = 0;
   bool packed = false;
@@ -31,7 +30,6 @@ struct hn_handle {
   uint16_t* whead = nullptr;                                           // [128][8192]
   float* w1 = nullptr;                                                 // [9][32]
   uint16_t* w2img = nullptr;  // conv2 weights as the fused front kernel's shared-memory image (front_fused.cuh)
-  int fused_front = 1;        // stage 1 + conv2 in one kernel (HN_FUSED_FRONT=0 selects the two-kernel path)
   float* bias = nullptr;                                               // 7 x 128
   float2* stats = nullptr;                                             // per-patch (mean, 1/std), chunk entries
   hn::TcParams conv_params[5];

@@ -1,6 +1,7 @@
 // HardNet.forward (hardnet/HardNet.py:312-315) behind the C ABI: weight packing (BatchNorm fold),
 // static TMA descriptors over handle-owned activation scratch, and the per-chunk launch sequence
-//   L1 (CUDA cores, input_norm fused) -> L2..L6 (tcgen05 implicit GEMM) -> head GEMM + L2Norm.
+//   fused front (input_norm + conv1 + conv2, front_fused.cuh) -> conv3..conv6 (tcgen05 implicit GEMM over
+//   channel-planar activations) -> head GEMM + L2Norm.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -55,10 +56,10 @@ struct StageTimer {
   }
 };
 
-template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT>
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT, bool OUT_PARITY>
 static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream) {
   using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT>;
-  auto kern = conv3x3_kernel<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, MINB, ROWSHIFT>;
+  auto kern = conv3x3_kernel<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, MINB, ROWSHIFT, OUT_PARITY>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
@@ -72,17 +73,16 @@ static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream)
   return HN_OK;
 }
 
-//                         CIN COUT HOUT STRIDE  G STAGES WRES  CTAs/SM ROWSHIFT
-#define HN_CONV_L2 launch_conv_cfg<32, 32, 32, 1, 1, 6, true, 2, true>
-#define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 1, 9, true, 2, false>
-#define HN_CONV_L4 launch_conv_cfg<64, 64, 16, 1, 1, 7, true, 1, true>
-#define HN_CONV_L5 launch_conv_cfg<64, 128, 8, 2, 1, 4, true, 1, false>
-#define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 1, 6, false, 1, false>
+// conv2 (li = 0) lives in the fused front kernel. OUT_PARITY: the consumer is a stride-2 conv and wants parity sub-planes.
+//                         CIN COUT HOUT STRIDE  G STAGES WRES  CTAs/SM ROWSHIFT OUT_PARITY
+#define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 1, 9, true, 2, false, false>
+#define HN_CONV_L4 launch_conv_cfg<64, 64, 16, 1, 1, 7, true, 1, true, true>
+#define HN_CONV_L5 launch_conv_cfg<64, 128, 8, 2, 1, 4, true, 1, false, false>
+#define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 1, 6, false, 1, false, false>
 static const bool kRowShift[5] = {true, false, true, false, false};
 
 static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) {
   switch (li) {
-    case 0: return HN_CONV_L2(p, sm_count, s);
     case 1: return HN_CONV_L3(p, sm_count, s);
     case 2: return HN_CONV_L4(p, sm_count, s);
     case 3: return HN_CONV_L5(p, sm_count, s);
@@ -178,21 +178,24 @@ static int build_params(hn_handle* h) {
     const int pix_out = L.hout * L.hout;
     const int rows_per_tile = pix_out >= kTileM ? kTileM / L.hout : L.hout;
     const int patches_per_tile = pix_out >= kTileM ? 1 : kTileM / pix_out;
-    const uint32_t box[4] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(L.hout),
+    // channel-planar input [patch][plane][y][x][8] seen as (x * 8, y, patch, plane); box = whole rows of NPL planes
+    const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8),
                              static_cast<uint32_t>(rows_per_tile + (kRowShift[li] ? 2 : 0)),
-                             static_cast<uint32_t>(patches_per_tile)};
+                             static_cast<uint32_t>(patches_per_tile), static_cast<uint32_t>(kc / 8)};
     const uint64_t C = L.cin, W = L.hin, H = L.hin;
+    if (li == 0) continue;  // conv2 is part of the fused front kernel
     if (L.stride == 1) {
-      const uint64_t dims[4] = {C, W, H, static_cast<uint64_t>(h->chunk)};
-      const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
-      HN_TRY(make_tmap_16bit(&p.tmA[0], in, 4, dims, str, box, kcb));
+      const uint64_t dims[4] = {W * 8, H, static_cast<uint64_t>(h->chunk), C / 8};
+      const uint64_t str[3] = {W * 16, C * H * W * 2, H * W * 16};
+      HN_TRY(make_tmap_16bit(&p.tmA[0], in, 4, dims, str, box, 0));
     } else {
+      // parity sub-planes [patch][plane][ypar][xpar][y/2][x/2][8]
       for (int ypar = 0; ypar < 2; ++ypar)
         for (int xpar = 0; xpar < 2; ++xpar) {
-          const uint64_t dims[4] = {C, W / 2, H / 2, static_cast<uint64_t>(h->chunk)};
-          const uint64_t str[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
-          const uint16_t* base = in + (ypar * W + xpar) * C;
-          HN_TRY(make_tmap_16bit(&p.tmA[ypar * 2 + xpar], base, 4, dims, str, box, kcb));
+          const uint64_t dims[4] = {W / 2 * 8, H / 2, static_cast<uint64_t>(h->chunk), C / 8};
+          const uint64_t str[3] = {W / 2 * 16, C * H * W * 2, H * W * 16};
+          const uint16_t* base = in + (ypar * 2 + xpar) * (H / 2) * (W / 2) * 8;
+          HN_TRY(make_tmap_16bit(&p.tmA[ypar * 2 + xpar], base, 4, dims, str, box, 0));
         }
     }
     {
@@ -221,34 +224,15 @@ static int build_params(hn_handle* h) {
   return HN_OK;
 }
 
-// Runs L1..L6 for `n` patches (n <= chunk); L6 lands in l6 + l6_row * 8192.
-// Stage 1 and conv2 run in sub-passes of `front_chunk` patches that reuse the head of act[0], so the 64 KB/patch
-// stage-1 output is produced and consumed inside the L2 instead of making an HBM round trip; conv2 writes into
-// the full-size act[1] and the deeper (smaller) stages run once over the whole pass.
+// Runs the conv stack up to `last_layer` for `n` patches (n <= chunk); the conv6 output lands in l6 + l6_row * 8192.
 static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n, long long l6_row, int last_layer,
                           cudaStream_t s) {
-  const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
-  if (h->fused_front && last_layer >= 2) {
-    StageTimer timer(h, 1, s);  // reported as the conv2 stage (stage 1 is inside it)
+  if (last_layer >= 2) {
+    StageTimer timer(h, 1, s);  // stage 1 + conv2 (the stage-1 activation never reaches global memory)
     HN_TRY(launch_front_fused(h, patches, in_dtype, h->act[1], n, s));
-  }
-  const int front = last_layer >= 2 ? std::min(h->front_chunk, n) : n;
-  for (int off = 0; off < n && !(h->fused_front && last_layer >= 2); off += front) {
-    const int m = std::min(front, n - off);
-    {
-      StageTimer timer(h, 0, s);
-      HN_TRY(launch_l1(static_cast<const char*>(patches) + static_cast<size_t>(off) * 1024 * in_elem, in_dtype, h->act[0],
-                       h->w1, h->bias, h->stats, m, h->act_bf16, h->sm_count, s));
-    }
-    if (last_layer >= 2) {
-      TcParams p = h->conv_params[0];
-      p.total_rows = 1024LL * m;
-      p.num_tiles = static_cast<int>(p.total_rows / kTileM);
-      p.act_bf16 = h->act_bf16;
-      p.out = h->act[1] + static_cast<size_t>(off) * 32 * 32 * 32;
-      StageTimer timer(h, 1, s);
-      HN_TRY(launch_conv(0, p, h->sm_count, s));
-    }
+  } else {
+    StageTimer timer(h, 0, s);  // stage 1 alone (activation dump only), NHWC
+    HN_TRY(launch_l1(patches, in_dtype, h->act[0], h->w1, h->bias, h->stats, n, h->act_bf16, h->sm_count, s));
   }
   for (int li = 1; li < 5 && li + 2 <= last_layer; ++li) {
     const ConvLayer& L = kConv[li];
@@ -288,12 +272,6 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   head_rows = std::max<long long>(head_rows, chunk_patches);
   head_rows = (head_rows + chunk_patches - 1) / chunk_patches * chunk_patches;
   h->chunk = chunk_patches;
-  {
-    const char* e = getenv("HN_FRONT_CHUNK");
-    h->front_chunk = e ? std::max(2, atoi(e)) : chunk_patches;
-    const char* f = getenv("HN_FUSED_FRONT");
-    h->fused_front = f ? atoi(f) : 1;
-  }
   h->head_rows = head_rows;
   const size_t act_elems = static_cast<size_t>(chunk_patches) * 32 * 32 * 32;
   auto fail = [&](int code) { hn_destroy(h); return code; };
@@ -390,7 +368,7 @@ extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const floa
       HN_CUDA(cudaMemcpy(h->w2img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
     }
   }
-  // head: [co][ci][8][8] -> [co][(y*8+x)*128 + ci]
+  // head: [co][ci][8][8] -> [co][(ci/8)*512 + (y*8+x)*8 + ci%8]  (K order of the channel-planar conv6 output)
   {
     std::vector<uint16_t> wp(static_cast<size_t>(128) * kHeadK);
     for (int co = 0; co < 128; ++co) {
@@ -398,7 +376,7 @@ extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const floa
       bias[128 * 6 + co] = -bn_mean[6][co] * s;
       for (int ci = 0; ci < 128; ++ci)
         for (int yx = 0; yx < 64; ++yx)
-          wp[static_cast<size_t>(co) * kHeadK + yx * 128 + ci] = to16(w[6][(static_cast<size_t>(co) * 128 + ci) * 64 + yx] * s, bf);
+          wp[static_cast<size_t>(co) * kHeadK + (ci >> 3) * 512 + yx * 8 + (ci & 7)] = to16(w[6][(static_cast<size_t>(co) * 128 + ci) * 64 + yx] * s, bf);
     }
     HN_CUDA(cudaMemcpy(h->whead, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
   }

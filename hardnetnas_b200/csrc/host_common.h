@@ -46,7 +46,7 @@ inline void set_error(const char* fmt, ...) {
   } while (0)
 
 // 16-bit element tiled tensor map. dims[0] is the contiguous dimension; strides_bytes has rank-1 entries
-// (dims 1..rank-1). swizzle_bytes is 64 or 128 and must equal box[0] * 2.
+// (dims 1..rank-1). swizzle_bytes is 32 / 64 / 128 (and must equal box[0] * 2) or 0 for a dense, unswizzled box.
 int make_tmap_16bit(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 

@@ -27,15 +27,6 @@ constexpr uint32_t kL1StageBytes = 8 * 2 * 2048;            // per epilogue warp
 constexpr size_t kL1TcSmem = 120 * 1024;
 static_assert(2 * kL1BufBytes + 1024 /*W*/ + kL1StageBytes + 1024 /*align*/ + 256 /*barriers*/ + 256 /*bias*/ <= kL1TcSmem, "smem budget");
 
-__device__ __forceinline__ uint64_t make_noswizzle_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
-  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
-  d |= 1ull << 46;
-  return d;  // layout type 0 = no swizzle
-}
-
 __device__ __forceinline__ uint16_t to16bits(float v, int bf16) {
   if (bf16) {
     __nv_bfloat16 h = __float2bfloat16_rn(v);

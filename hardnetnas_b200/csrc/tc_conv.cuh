@@ -1,14 +1,17 @@
 // Persistent, warp-specialised tcgen05 kernels for the HardNet conv stack.
 //
-//   conv3x3_kernel : the 3x3 convs (features[3..17], reference hardnet/HardNet.py:284-298) as implicit GEMMs:
+//   conv3x3_kernel : the 3x3 convs (features[6..17], reference hardnet/HardNet.py:287-298) as implicit GEMMs:
 //     M = 128 output pixels per tile, N = C_out, K = 9 taps x C_in, cut into "k-blocks" of one tap x <=64
-//     channels. The A tile of a k-block is ONE 4-D TMA box (C, x, y, patch) whose start coordinate carries
-//     the tap shift; out-of-range x / y are zero-filled by TMA, which is exactly the conv's zero padding,
-//     and because x / y are per-patch tensor dimensions nothing bleeds between patches. Stride-2 layers
-//     read four "parity" views of the input (even/odd rows x even/odd columns), so the stride is never
-//     expressed to TMA. Weights stay resident in shared memory when they fit (WRES), otherwise they are
-//     streamed with the A tiles. A pipeline stage carries G k-blocks so that one mbarrier round trip
-//     feeds G * KCB/32 MMAs.
+//     channels. Activations live in global memory CHANNEL-PLANAR: [patch][plane = c / 8][y][x][c % 8] (16 B per
+//     pixel and plane; stride-2 consumers get the four row/column parity sub-planes [plane][ypar][xpar][y/2][x/2][8]).
+//     The A tile of a k-block is ONE 4-D TMA box (x * 8, y, patch, plane) whose start coordinate carries the tap
+//     shift; out-of-range x / y are zero-filled by TMA, which is exactly the conv's zero padding, and because
+//     x / y are per-patch tensor dimensions nothing bleeds between patches. The box lands in shared memory as
+//     [plane][pixel][8 channels], which is the UMMA no-swizzle K-major layout (core matrix = 8 pixels x 16 B,
+//     SBO = 128 B, LBO = plane pitch). The planar layout is what makes the epilogue's stores coalesce: a warp
+//     writes 32 pixels x 16 B = 512 contiguous bytes per instruction (NHWC rows would touch 32 cache lines).
+//     Weights stay resident in shared memory when they fit (WRES), otherwise they are streamed with the A
+//     tiles. A pipeline stage carries G k-blocks so that one mbarrier round trip feeds G * KCB/32 MMAs.
 //   gemm_l2norm_kernel : the 8x8 head conv (features[19..20] + L2Norm, HardNet.py:300-301,314-315 and
 //     Utils.py:19-22) as a [B, K] x [K, 128] GEMM with bias + L2-normalise in the epilogue (also the NAS
 //     head with K = 2048).
@@ -33,7 +36,7 @@ struct TcParams {
   CUtensorMap tmA[4];      // conv stride 1 / gemm: [0]; conv stride 2: parity views [ypar * 2 + xpar]
   CUtensorMap tmB;         // weights, [C_out, K] K-major
   const float* bias;       // [N] folded BatchNorm shift
-  void* out;               // conv: 16-bit [rows, N]; head: f32/f16/bf16 [rows, N]
+  void* out;               // conv: 16-bit channel-planar (see above); head: f32/f16/bf16 [rows, N]
   long long total_rows;    // valid output rows (pixels or patches)
   int num_tiles;
   int num_k_stages;        // gemm only: K / (G * 64)
@@ -77,13 +80,15 @@ struct ConvCfg {
   static constexpr int PATCHES_PER_TILE = PIX >= kTileM ? 1 : kTileM / PIX;
   static constexpr int UNITS = ROWSHIFT ? 3 * CIN_CHUNKS : KB;   // TMA loads of A per tile
   static constexpr int SPT = UNITS / G;                          // stages per tile
-  static constexpr uint32_t ROW_BYTES = HOUT * KCB;              // one image row of the A tile
-  static constexpr uint32_t A_BYTES = ROWSHIFT ? (ROWS_PER_TILE + 2) * ROW_BYTES : kTileM * KCB;
+  static constexpr int NPL = KC / 8;                              // 8-channel planes per k-block
+  static constexpr uint32_t ROW_BYTES = HOUT * 16;               // one image row inside one plane of the A tile
+  static constexpr uint32_t PLANE_BYTES = ROWSHIFT ? (ROWS_PER_TILE + 2) * ROW_BYTES : kTileM * 16;
+  static constexpr uint32_t A_BYTES = NPL * PLANE_BYTES;
   static constexpr uint32_t B_BYTES = COUT * KCB;
   static constexpr uint32_t STAGE_BYTES = G * (A_BYTES + (WRES ? 0u : B_BYTES));
   static constexpr uint32_t W_BYTES = WRES ? KB * B_BYTES : 0u;
-  static_assert(!ROWSHIFT || (STRIDE == 1 && TILES_PER_PATCH >= 1 && WRES && ROW_BYTES % 1024 == 0),
-                "ROWSHIFT needs a stride-1 row-band tile, resident weights and 1024B-aligned image rows");
+  static_assert(!ROWSHIFT || (STRIDE == 1 && TILES_PER_PATCH >= 1 && WRES && ROW_BYTES % 128 == 0),
+                "ROWSHIFT needs a stride-1 row-band tile, resident weights and image rows that are whole core matrices");
   static_assert(UNITS % G == 0, "stage must hold a whole number of loads");
   static constexpr uint32_t TMEM_COLS = tmem_cols_for(COUT);
   static constexpr size_t SMEM = size_t(W_BYTES) + size_t(STAGES) * STAGE_BYTES + 1024 + 256 + COUT * 4;
@@ -91,7 +96,23 @@ struct ConvCfg {
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "UMMA M=128 needs N % 16 == 0");
 };
 
-template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT>
+__device__ __forceinline__ uint64_t make_noswizzle_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;   // K direction: next 8-channel core matrix
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;   // M/N direction: next 8-row core matrix
+  d |= 1ull << 46;
+  return d;  // layout type 0 = no swizzle
+}
+
+// Element offset of pixel (y, x) inside one 8-channel plane of a W x W image (units of 8-channel groups).
+template <int W, bool PARITY>
+__device__ __forceinline__ int planar_pixel_slot(int y, int x) {
+  if (PARITY) return ((y & 1) * 2 + (x & 1)) * (W * W / 4) + (y >> 1) * (W / 2) + (x >> 1);
+  return y * W + x;
+}
+
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT, bool OUT_PARITY>
 __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_constant__ TcParams p) {
   using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT>;
   constexpr int N = COUT;
@@ -182,14 +203,14 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
             const uint32_t a_dst = st_base + g * C::A_BYTES;
             if (ROWSHIFT) {
               // band of ROWS_PER_TILE + 2 rows starting one row above the tile, shifted by kx - 1 columns
-              tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), cc * C::KC, kx - 1, y0 - 1, patch0);
+              tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), (kx - 1) * 8, y0 - 1, patch0, cc * C::NPL);
             } else if (STRIDE == 1) {
-              tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), cc * C::KC, kx - 1, y0 + ky - 1, patch0);
+              tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), (kx - 1) * 8, y0 + ky - 1, patch0, cc * C::NPL);
             } else {
               // input x = 2*ox + kx - 1: kx=0 -> odd column ox-1, kx=1 -> even column ox, kx=2 -> odd column ox
               const int xpar = (kx != 1), ypar = (ky != 1);
-              tma_load_4d(a_dst, &p.tmA[ypar * 2 + xpar], full_bar(stage), cc * C::KC, (kx == 0) ? -1 : 0,
-                          y0 + ((ky == 0) ? -1 : 0), patch0);
+              tma_load_4d(a_dst, &p.tmA[ypar * 2 + xpar], full_bar(stage), (kx == 0) ? -8 : 0,
+                          y0 + ((ky == 0) ? -1 : 0), patch0, cc * C::NPL);
             }
             if (!WRES) tma_load_2d(st_base + G * C::A_BYTES + g * C::B_BYTES, &p.tmB, full_bar(stage), kb * C::KC, 0);
           }
@@ -232,21 +253,23 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
               const int kx = u / C::CIN_CHUNKS, cc = u - kx * C::CIN_CHUNKS;
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky) {
-                const uint64_t a_desc = make_kmajor_desc(st_base + g * C::A_BYTES + ky * C::ROW_BYTES, C::KCB);
+                const uint32_t a_addr = st_base + g * C::A_BYTES + ky * C::ROW_BYTES;
                 const uint64_t b_desc =
                     make_kmajor_desc(w_base + ((ky * 3 + kx) * C::CIN_CHUNKS + cc) * C::B_BYTES, C::KCB);
 #pragma unroll
                 for (int k = 0; k < C::KCB / 32; ++k)
-                  umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (s | g | ky | k) != 0);
+                  umma_f16(d_tmem, make_noswizzle_desc(a_addr + 2 * k * C::PLANE_BYTES, C::PLANE_BYTES, 128), b_desc + 2u * k,
+                           idesc, (s | g | ky | k) != 0);
               }
             } else {
-              const uint64_t a_desc = make_kmajor_desc(st_base + g * C::A_BYTES, C::KCB);
+              const uint32_t a_addr = st_base + g * C::A_BYTES;
               const uint64_t b_desc = make_kmajor_desc(
                   WRES ? (w_base + (s * G + g) * C::B_BYTES) : (st_base + G * C::A_BYTES + g * C::B_BYTES), C::KCB);
 #pragma unroll
               for (int k = 0; k < C::KCB / 32; ++k) {
-                // advance 16 K-elements = 32 bytes inside the swizzle span: +2 in the (addr >> 4) field
-                umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (s | g | k) != 0);
+                // A: 16 K-elements = two 8-channel planes; B: 32 bytes inside the swizzle span = +2 in the (addr >> 4) field
+                umma_f16(d_tmem, make_noswizzle_desc(a_addr + 2 * k * C::PLANE_BYTES, C::PLANE_BYTES, 128), b_desc + 2u * k,
+                         idesc, (s | g | k) != 0);
               }
             }
           }
@@ -270,7 +293,11 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * N;
       const long long row = static_cast<long long>(tile) * kTileM + row_in_tile;
       const bool valid = row < p.total_rows;
-      uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + row * N);
+      // channel-planar output: [patch][plane][pixel slot][8]; consecutive lanes = consecutive pixels = consecutive 16 B
+      const long long patch = row / C::PIX;
+      const int pix = static_cast<int>(row - patch * C::PIX);
+      const int slot = planar_pixel_slot<HOUT, OUT_PARITY>(pix / HOUT, pix % HOUT);
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + patch * (static_cast<long long>(N) * C::PIX)) + slot;
 #pragma unroll
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t r[32];
@@ -285,7 +312,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
         }
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[c0 / 8 + j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          for (int j = 0; j < 4; ++j) dst[(c0 / 8 + j) * C::PIX] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         }
       }
       tc_fence_before();

@@ -200,4 +200,14 @@ class HardNet(nn.Module):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(eng.lib.hn_forward_dump(eng.handle, x.data_ptr(), in_dt, x.size(0), layer, out.data_ptr(),
                                                C.c_void_p(stream)), "hn_forward_dump")
-        return out
+        if layer == 1:
+            return out
+        # stages 2..6 are channel-planar on the device ([B][C/8][H][W][8]; stages feeding a stride-2 conv hold the
+        # four row/column parity sub-planes [B][C/8][ypar][xpar][H/2][W/2][8]) -> NHWC for the caller
+        H, W, Cc = shapes[layer]
+        raw = out.view(-1)
+        if layer in (2, 4):
+            v = raw.view(x.size(0), Cc // 8, 2, 2, H // 2, W // 2, 8).permute(0, 4, 2, 5, 3, 1, 6)
+        else:
+            v = raw.view(x.size(0), Cc // 8, H, W, 8).permute(0, 2, 3, 1, 4)
+        return v.reshape(x.size(0), H, W, Cc).contiguous()
