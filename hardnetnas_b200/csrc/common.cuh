@@ -152,6 +152,30 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same instruction with the two 64-bit shared-memory descriptors given as (lo, hi) words. The issue loops keep the
+// hi words (SBO, version, layout) as compile-time constants and advance only the lo word (start address >> 4, plus the
+// constant LBO field), so stepping to the next operand tile is ONE 32-bit add instead of rebuilding a descriptor.
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// lo / hi words of the two descriptor flavours (see make_kmajor_desc below and make_noswizzle_desc in tc_conv.cuh)
+__host__ __device__ constexpr uint32_t kmajor_desc_hi(uint32_t row_bytes) {
+  return ((8u * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u)) << 29);
+}
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__host__ __device__ constexpr uint32_t noswizzle_desc_hi(uint32_t sbo_bytes) { return (sbo_bytes >> 4) | (1u << 14); }
+__device__ __forceinline__ uint32_t noswizzle_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+
 // Arrives (count 1) on the mbarrier once every previously issued tcgen05.mma of this thread retired.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(

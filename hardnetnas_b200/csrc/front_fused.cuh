@@ -11,8 +11,12 @@
 // finishes the conv with two lane shuffles per value:  out[y, x] = D'0[y, x - 1] + D'1[y, x] + D'2[y, x + 1]; a TMEM lane
 // quarter is exactly one image row, so the shuffle's edge lanes are the conv's zero padding in x.
 //
-// Warps (21): 0-3 stage-1 epilogue (TMEM -> act1 in smem), 4-11 conv2 epilogue (two groups of four, one per
-// accumulator buffer), 12 TMEM owner + UMMA issuer, 13-20 loaders (normalise + im2col of the 1-channel input, K = 9 -> 16).
+// The stage-1 BatchNorm shift rides in the spare K slots of the stage-1 GEMM (K = 9 taps padded to 16): im2col columns 9
+// and 10 are the constant 1 and the matching weight rows hold the shift split into a 16-bit hi + lo pair, so the tensor
+// core adds it in fp32 and the stage-1 epilogue is just TMEM -> ReLU/pack (one F2FP per two values) -> shared memory.
+//
+// Warps (17): 0-3 stage-1 epilogue (TMEM -> act1 in smem), 4-11 conv2 epilogue (two groups of four, one per
+// accumulator buffer), 12 TMEM owner + UMMA issuer, 13-16 loaders (normalise + im2col of the 1-channel input).
 #pragma once
 
 #include "common.cuh"
@@ -21,9 +25,9 @@
 
 namespace hn {
 
-constexpr int kFfThreads = 21 * 32;
+constexpr int kFfThreads = 17 * 32;
 constexpr int kFfIssuer = 12;
-constexpr int kFfLoader0 = 13;
+constexpr int kFfLoader0 = 13;   // 4 loader warps: 13..16
 constexpr uint32_t kFfPlane = 34 * 32 * 16;   // one 8-channel plane of the haloed stage-1 output
 constexpr uint32_t kFfAct1 = 4 * kFfPlane;    // 69 632 B per buffer
 constexpr uint32_t kFfA1 = 8 * 4096;          // eight 128 x 16 im2col tiles of the input patch
@@ -38,6 +42,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
                : "memory");
+}
+
+// {lo, hi} -> two 16-bit values with ReLU and saturation to the largest finite value, one instruction (F2FP.SATFINITE.RELU)
+__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi, int bf16) {
+  uint32_t r;
+  if (bf16) asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack16_plain(float lo, float hi, int bf16) {
+  uint32_t r;
+  if (bf16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 template <typename TIn>
@@ -63,8 +81,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   auto c2_empty = [&](int a) { return bar_base + 80u + 8u * a; };
   const uint32_t tmem_slot = bar_base + 128;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
-  float* s_bias1 = reinterpret_cast<float*>(gbase + (bar_base + 256 - base));
-  float* s_bias2 = s_bias1 + 32;
+  float* s_bias2 = reinterpret_cast<float*>(gbase + (bar_base + 256 - base));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -72,7 +89,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   // ---------------------------------------------- one-time setup ----------------------------------------------
   if (warp == kFfIssuer) {
     if (lane == 0) {
-      mbar_init(a1_full, 8);    // one arrive per loader warp
+      mbar_init(a1_full, 4);    // one arrive per loader warp
       mbar_init(a1_empty, 1);   // tcgen05.commit
       mbar_init(l1_full, 1);    // tcgen05.commit
       mbar_init(l1_empty, 4);   // one arrive per stage-1 epilogue warp
@@ -88,7 +105,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   } else {
-    const int t = threadIdx.x - (warp > kFfIssuer ? 32 : 0);  // 0..639 over the non-issuer threads
+    const int t = threadIdx.x - (warp > kFfIssuer ? 32 : 0);  // dense index over the non-issuer threads
     // conv2 weights: copy the prepared shared-memory image
     for (int i = t; i < static_cast<int>(kFfW2 / 16); i += kFfThreads - 32)
       *reinterpret_cast<uint4*>(gbase + (w2_addr - base) + i * 16) = __ldg(w2img + i);
@@ -102,11 +119,17 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     uint16_t* W = reinterpret_cast<uint16_t*>(gbase + (w1_addr - base));
     for (int i = t; i < 32 * 16; i += kFfThreads - 32) {
       const int n = i >> 4, k = i & 15;
-      const float v = k < 9 ? w1[k * 32 + n] : 0.f;
+      float v = k < 9 ? w1[k * 32 + n] : 0.f;
+      if (k == 9 || k == 10) {   // BatchNorm shift as hi + lo against the constant-1 im2col columns
+        const float bsh = bias1[n];
+        const uint16_t hi = to16bits(bsh, act_bf16);
+        const float hif = act_bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&hi))
+                                   : __half2float(*reinterpret_cast<const __half*>(&hi));
+        v = k == 9 ? hif : bsh - hif;
+      }
       W[((n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) >> 1] = to16bits(v, act_bf16);
     }
-    if (t < 32) s_bias1[t] = bias1[t];
-    else if (t < 64) s_bias2[t - 32] = bias2[t - 32];
+    if (t < 32) s_bias2[t] = bias2[t];
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -118,10 +141,10 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
 
   if (warp >= kFfLoader0) {
     // ============================== loaders: normalise + im2col of the input patch ==============================
-    const int l = threadIdx.x - kFfLoader0 * 32;  // 0..255
-    const int py = l >> 3;                        // pixel row handled by this thread
-    const int px0 = (l & 7) * 4;                  // first of 4 consecutive pixels
-    const int rot = (l >> 1) & 3;                 // store order rotation: a quarter-warp hits 8 distinct 16 B bank groups
+    // Thread = image column x (lane) x 8 consecutive rows (warp): every global load is one coalesced 128 B row segment
+    // and every im2col store phase touches 8 consecutive pixels = 8 distinct 16 B bank groups (conflict free).
+    const int lw = warp - kFfLoader0;      // rows 8 * lw .. 8 * lw + 7
+    const uint32_t one16 = act_bf16 ? 0x3F80u : 0x3C00u;
     int it = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
       float mean = 0.f, inv = 1.f;
@@ -130,53 +153,41 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         mean = st.x;
         inv = st.y;
       }
-      const TIn* src = in + static_cast<size_t>(patch) * 1024;
-      uint16_t win[3][6];
+      const TIn* src = in + static_cast<size_t>(patch) * 1024 + lane;
+      // 30 independent, branch-free loads (clamped addresses, masked afterwards) so they are all in flight together
+      float v[10][3];
+      const int xl = lane > 0 ? -1 : 0, xr = lane < 31 ? 1 : 0;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int y = py + r - 1;
-        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        bool ok[6] = {false, false, false, false, false, false};
-        if (y >= 0 && y < 32) {
-          const TIn* row = src + y * 32 + px0;
-          if constexpr (sizeof(TIn) == 4) {
-            const float4 q = *reinterpret_cast<const float4*>(row);
-            v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
-          } else {
-            const uchar4 q = *reinterpret_cast<const uchar4*>(row);
-            v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
-          }
-          ok[1] = ok[2] = ok[3] = ok[4] = true;
-          if (px0 > 0) { v[0] = static_cast<float>(row[-1]); ok[0] = true; }
-          if (px0 < 28) { v[5] = static_cast<float>(row[4]); ok[5] = true; }
-        }
+      for (int r = 0; r < 10; ++r) {
+        const int y = 8 * lw + r - 1;              // warp-uniform
+        const TIn* row = src + min(max(y, 0), 31) * 32;
+        v[r][0] = static_cast<float>(row[xl]);
+        v[r][1] = static_cast<float>(row[0]);
+        v[r][2] = static_cast<float>(row[xr]);
+      }
 #pragma unroll
-        for (int c = 0; c < 6; ++c) win[r][c] = ok[c] ? to16bits((v[c] - mean) * inv, act_bf16) : static_cast<uint16_t>(0);
+      for (int r = 0; r < 10; ++r) {
+        const int y = 8 * lw + r - 1;
+        const bool rowok = y >= 0 && y < 32;       // rows / columns outside the patch are the conv's zero padding
+        v[r][0] = (rowok && lane > 0) ? (v[r][0] - mean) * inv : 0.f;
+        v[r][1] = rowok ? (v[r][1] - mean) * inv : 0.f;
+        v[r][2] = (rowok && lane < 31) ? (v[r][2] - mean) * inv : 0.f;
       }
       // the stage-1 MMAs of the previous patch must have retired before A1 is overwritten
       mbar_wait(a1_empty, (it & 1) ^ 1u);
-      uint8_t* A = gbase + (a1_addr - base);
+      // pixel (y, x): tile y / 4, row r = (y % 4) * 32 + x  ->  (r / 8) * 256 + (r % 8) * 16
+      uint8_t* A = gbase + (a1_addr - base) + lw * 2 * 4096 + (lane >> 3) * 256 + (lane & 7) * 16;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
+      for (int j = 0; j < 8; ++j) {
         uint4 k0, k1;
-        int j;
-        // j = (jj + rot) & 3 with compile-time register indexing
-        uint32_t w00, w01, w02, w10, w11, w12, w20, w21, w22;
-#define HN_FF_PICK(J)                                                                          \
-  { w00 = win[0][J]; w01 = win[0][J + 1]; w02 = win[0][J + 2]; w10 = win[1][J]; w11 = win[1][J + 1]; \
-    w12 = win[1][J + 2]; w20 = win[2][J]; w21 = win[2][J + 1]; w22 = win[2][J + 2]; }
-        j = (jj + rot) & 3;
-        if (j == 0) HN_FF_PICK(0) else if (j == 1) HN_FF_PICK(1) else if (j == 2) HN_FF_PICK(2) else HN_FF_PICK(3)
-#undef HN_FF_PICK
-        const int pix = py * 32 + px0 + j;
-        const int tile = pix >> 7, r = pix & 127;
-        uint8_t* dst = A + tile * 4096 + (r >> 3) * 256 + (r & 7) * 16;
-        k0.x = w00 | (w01 << 16);
-        k0.y = w02 | (w10 << 16);
-        k0.z = w11 | (w12 << 16);
-        k0.w = w20 | (w21 << 16);
-        k1.x = w22;
-        k1.y = 0u; k1.z = 0u; k1.w = 0u;
+        k0.x = pack16_plain(v[j][0], v[j][1], act_bf16);
+        k0.y = pack16_plain(v[j][2], v[j + 1][0], act_bf16);
+        k0.z = pack16_plain(v[j + 1][1], v[j + 1][2], act_bf16);
+        k0.w = pack16_plain(v[j + 2][0], v[j + 2][1], act_bf16);
+        k1.x = pack16_plain(v[j + 2][2], 0.f, act_bf16) | (one16 << 16);   // k = 8 (tap 2,2), k = 9: constant 1
+        k1.y = one16;                                                       // k = 10: constant 1
+        k1.z = 0u; k1.w = 0u;
+        uint8_t* dst = A + (j >> 2) * 4096 + (j & 3) * 1024;   // row y = 8 lw + j: tile 2 lw + j / 4, 32-row group j % 4
         *reinterpret_cast<uint4*>(dst) = k0;
         *reinterpret_cast<uint4*>(dst + 128) = k1;
       }
@@ -186,15 +197,20 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     }
   } else if (warp == kFfIssuer) {
     // ============================== UMMA issuer ==============================
+    // Descriptor hi words are constants; lo words are `buffer base + compile-time offset` (tile loop fully unrolled).
     const uint32_t idesc1 = make_idesc_f16(kTileM, 32, act_bf16);
     const uint32_t idesc2 = make_idesc_f16(kTileM, 96, act_bf16);
-    const uint64_t b1_desc = make_noswizzle_desc(w1_addr, 128, 256);
+    constexpr uint32_t L1A_HI = noswizzle_desc_hi(256), L1B_HI = noswizzle_desc_hi(256);
+    constexpr uint32_t C2A_HI = noswizzle_desc_hi(128), C2B_HI = noswizzle_desc_hi(512);
+    const uint32_t a1_lo = noswizzle_desc_lo(a1_addr, 128);
+    const uint32_t b1_lo = noswizzle_desc_lo(w1_addr, 128);
+    const uint32_t act_lo0 = noswizzle_desc_lo(act1_addr, kFfPlane);
+    const uint32_t w2_lo = noswizzle_desc_lo(w2_addr, 128);
     const int n_local = (num_patches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     auto issue_l1 = [&]() {
       if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          umma_f16(tm_l1 + t * 32, make_noswizzle_desc(a1_addr + t * 4096, 128, 256), b1_desc, idesc1, 0u);
+        for (int t = 0; t < 8; ++t) umma_f16_w(tm_l1 + t * 32, a1_lo + t * (4096 >> 4), L1A_HI, b1_lo, L1B_HI, idesc1, 0u);
         umma_commit(a1_empty);
         umma_commit(l1_full);
       }
@@ -205,7 +221,6 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       tc_fence_after();
       issue_l1();
     }
-    uint32_t use = 0;  // conv2 tiles issued so far (accumulator buffer = use & 1)
     for (int it = 0; it < n_local; ++it) {
       const int b = it & 1;
       if (it + 1 < n_local) {
@@ -217,11 +232,11 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       }
       mbar_wait(act1_full(b), (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t act = act1_addr + b * kFfAct1;
-#pragma unroll 1
-      for (int t = 0; t < 8; ++t, ++use) {
-        const int a = use & 1;
-        mbar_wait(c2_empty(a), ((use >> 1) & 1) ^ 1u);
+      const uint32_t act_lo = act_lo0 + b * (kFfAct1 >> 4);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int a = t & 1;                       // 8 tiles per patch: the accumulator buffer is simply the tile parity
+        mbar_wait(c2_empty(a), (((it * 4 + (t >> 1)) & 1) ^ 1u));
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d = tm_c2 + a * 128;
@@ -230,9 +245,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               // A: 128 slots starting at image row 4t + ky - 1 (slot (4t + ky) * 32), channels 16k .. 16k + 15
-              const uint64_t a_desc = make_noswizzle_desc(act + (t * 128 + ky * 32) * 16 + k * 2 * kFfPlane, kFfPlane, 128);
-              const uint64_t b_desc = make_noswizzle_desc(w2_addr + ky * kFfW2Tap + k * 256, 128, 512);
-              umma_f16(d, a_desc, b_desc, idesc2, (ky | k) != 0);
+              umma_f16_w(d, act_lo + (((t * 128 + ky * 32) * 16 + k * 2 * kFfPlane) >> 4), C2A_HI,
+                         w2_lo + ((ky * kFfW2Tap + k * 256) >> 4), C2B_HI, idesc2, (ky | k) != 0);
             }
           }
           umma_commit(c2_full(a));
@@ -258,11 +272,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         tmem_ld_wait();
         uint32_t o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float v0 = fmaxf(__uint_as_float(r[2 * j]) + s_bias1[2 * j], 0.f);
-          const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias1[2 * j + 1], 0.f);
-          o[j] = pack16(v0, v1, act_bf16);
-        }
+        for (int j = 0; j < 16; ++j) o[j] = pack16_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), act_bf16);
         // pixel p = t * 128 + q * 32 + lane  ->  slot p + 32 (one halo row on top)
         uint8_t* dst = act + (t * 128 + q * 32 + lane + 32) * 16;
 #pragma unroll
@@ -282,6 +292,11 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     const int q = warp & 3;
     const int g = (warp - 4) >> 2;  // accumulator buffer owned by this group of four warps
     const uint32_t t_row = tm_c2 + (static_cast<uint32_t>(q * 32) << 16) + g * 128;
+    float bias[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bias[j] = s_bias2[j];
+    const float m_left = lane == 0 ? 0.f : 1.f;     // x - 1 / x + 1 outside the row = the conv's zero padding
+    const float m_right = lane == 31 ? 0.f : 1.f;
     uint32_t use = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x) {
       uint16_t* opatch = out + static_cast<size_t>(patch) * 32768;
@@ -302,14 +317,12 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);     // D'0 of pixel x - 1
-            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);  // D'2 of pixel x + 1
-            if (lane == 0) left = 0.f;
-            if (lane == 31) right = 0.f;
-            v[j] = fmaxf(left + __uint_as_float(r1[j]) + right + s_bias2[c * 8 + j], 0.f);
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);     // D'0 of pixel x - 1
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);  // D'2 of pixel x + 1
+            v[j] = fmaf(right, m_right, fmaf(left, m_left, __uint_as_float(r1[j]) + bias[c * 8 + j]));
           }
-          dst[c * 1024] = make_uint4(pack16(v[0], v[1], act_bf16), pack16(v[2], v[3], act_bf16), pack16(v[4], v[5], act_bf16),
-                              pack16(v[6], v[7], act_bf16));
+          dst[c * 1024] = make_uint4(pack16_relu(v[0], v[1], act_bf16), pack16_relu(v[2], v[3], act_bf16),
+                                     pack16_relu(v[4], v[5], act_bf16), pack16_relu(v[6], v[7], act_bf16));
         }
         tc_fence_before();
         __syncwarp();

@@ -226,7 +226,14 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ============================== UMMA issuer (warp-uniform) ==============================
+    // The k-loop is fully unrolled: taps, channel chunks and k-steps are compile-time constants, so every descriptor
+    // is `stage base (one multiply-add per stage) + constant` in its lo word; the hi words never change.
     const uint32_t idesc = make_idesc_f16(kTileM, N, p.act_bf16);
+    constexpr uint32_t A_HI = noswizzle_desc_hi(128);
+    constexpr uint32_t B_HI = kmajor_desc_hi(C::KCB);
+    const uint32_t ring_a_lo = noswizzle_desc_lo(ring_base, C::PLANE_BYTES);
+    const uint32_t ring_b_lo = kmajor_desc_lo(ring_base + G * C::A_BYTES);   // streamed weights live behind the A tiles
+    const uint32_t w_lo = kmajor_desc_lo(w_base);
     if (WRES) {
       mbar_wait(w_bar, 0);
       tc_fence_after();
@@ -240,12 +247,14 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * N;
-#pragma unroll 1
+#pragma unroll
       for (int s = 0; s < C::SPT; ++s) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t st_base = ring_base + stage * C::STAGE_BYTES;
+          const uint32_t st_off = static_cast<uint32_t>(stage) * (C::STAGE_BYTES >> 4);
+          const uint32_t a_lo = ring_a_lo + st_off;
+          const uint32_t b_lo = WRES ? w_lo : ring_b_lo + st_off;
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             if (ROWSHIFT) {
@@ -253,23 +262,18 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
               const int kx = u / C::CIN_CHUNKS, cc = u - kx * C::CIN_CHUNKS;
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky) {
-                const uint32_t a_addr = st_base + g * C::A_BYTES + ky * C::ROW_BYTES;
-                const uint64_t b_desc =
-                    make_kmajor_desc(w_base + ((ky * 3 + kx) * C::CIN_CHUNKS + cc) * C::B_BYTES, C::KCB);
 #pragma unroll
                 for (int k = 0; k < C::KCB / 32; ++k)
-                  umma_f16(d_tmem, make_noswizzle_desc(a_addr + 2 * k * C::PLANE_BYTES, C::PLANE_BYTES, 128), b_desc + 2u * k,
-                           idesc, (s | g | ky | k) != 0);
+                  umma_f16_w(d_tmem, a_lo + ((g * C::A_BYTES + ky * C::ROW_BYTES + 2 * k * C::PLANE_BYTES) >> 4), A_HI,
+                             b_lo + ((((ky * 3 + kx) * C::CIN_CHUNKS + cc) * C::B_BYTES) >> 4) + 2 * k, B_HI, idesc,
+                             (s | g | ky | k) != 0);
               }
             } else {
-              const uint32_t a_addr = st_base + g * C::A_BYTES;
-              const uint64_t b_desc = make_kmajor_desc(
-                  WRES ? (w_base + (s * G + g) * C::B_BYTES) : (st_base + G * C::A_BYTES + g * C::B_BYTES), C::KCB);
 #pragma unroll
               for (int k = 0; k < C::KCB / 32; ++k) {
                 // A: 16 K-elements = two 8-channel planes; B: 32 bytes inside the swizzle span = +2 in the (addr >> 4) field
-                umma_f16(d_tmem, make_noswizzle_desc(a_addr + 2 * k * C::PLANE_BYTES, C::PLANE_BYTES, 128), b_desc + 2u * k,
-                         idesc, (s | g | k) != 0);
+                umma_f16_w(d_tmem, a_lo + ((g * C::A_BYTES + 2 * k * C::PLANE_BYTES) >> 4), A_HI,
+                           b_lo + (((WRES ? (s * G + g) : g) * C::B_BYTES) >> 4) + 2 * k, B_HI, idesc, (s | g | k) != 0);
               }
             }
           }
