@@ -44,20 +44,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "memory");
 }
 
-// {lo, hi} -> two 16-bit values with ReLU and saturation to the largest finite value, one instruction (F2FP.SATFINITE.RELU)
-__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi, int bf16) {
-  uint32_t r;
-  if (bf16) asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ uint32_t pack16_plain(float lo, float hi, int bf16) {
-  uint32_t r;
-  if (bf16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
 template <typename TIn>
 __global__ void __launch_bounds__(kFfThreads, 1)
 front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]*/,

@@ -56,17 +56,18 @@ struct StageTimer {
   }
 };
 
-template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT, bool OUT_PARITY>
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT, bool OUT_PARITY,
+          int TILES = 1, int KCB_ = 0>
 static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream) {
-  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT>;
-  auto kern = conv3x3_kernel<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, MINB, ROWSHIFT, OUT_PARITY>;
+  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT, TILES, KCB_>;
+  auto kern = conv3x3_kernel<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, MINB, ROWSHIFT, OUT_PARITY, TILES, KCB_>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
     attr_done = true;
   }
   if (p.num_tiles <= 0) return HN_OK;
-  const int grid = std::min(p.num_tiles, sm_count * MINB);
+  const int grid = std::min((p.num_tiles + TILES - 1) / TILES, sm_count * MINB);
   kern<<<grid, kTcThreads, C::SMEM, stream>>>(p);
   HN_CUDA(cudaGetLastError());
   count_launch();
@@ -77,9 +78,12 @@ static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream)
 //                         CIN COUT HOUT STRIDE  G STAGES WRES  CTAs/SM ROWSHIFT OUT_PARITY
 #define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 1, 9, true, 2, false, false>
 #define HN_CONV_L4 launch_conv_cfg<64, 64, 16, 1, 1, 7, true, 1, true, true>
-#define HN_CONV_L5 launch_conv_cfg<64, 128, 8, 2, 1, 4, true, 1, false, false>
-#define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 1, 6, false, 1, false, false>
-static const bool kRowShift[5] = {true, false, true, false, false};
+//   conv5: weights streamed so that TILES = 2 doubles the activation bytes in flight per stage
+//   conv6: ROWSHIFT over two-patch tiles + TILES = 2: 132 KB / patch through the SM's L2 port instead of 288 KB
+#define HN_CONV_L5 launch_conv_cfg<64, 128, 8, 2, 1, 4, false, 1, false, false, 2>
+#define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 1, 4, false, 1, true, false, 2, 64>
+static const bool kRowShift[5] = {true, false, true, false, true};
+static const int kKcb[5] = {64, 64, 128, 128, 64};   // bytes of one pixel's channel chunk per k-block (ConvCfg::KCB)
 
 static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) {
   switch (li) {
@@ -172,24 +176,32 @@ static int build_params(hn_handle* h) {
     const ConvLayer& L = kConv[li];
     TcParams& p = h->conv_params[li];
     memset(&p, 0, sizeof(p));
-    const int kcb = (L.cin >= 64) ? 128 : 64;  // bytes of one pixel's channel chunk
+    const int kcb = kKcb[li];  // bytes of one pixel's channel chunk
     const int kc = kcb / 2;
     const uint16_t* in = h->act[li & 1];  // L1 wrote act[0]; layers alternate
     const int pix_out = L.hout * L.hout;
     const int rows_per_tile = pix_out >= kTileM ? kTileM / L.hout : L.hout;
     const int patches_per_tile = pix_out >= kTileM ? 1 : kTileM / pix_out;
-    // channel-planar input [patch][plane][y][x][8] seen as (x * 8, y, patch, plane); box = whole rows of NPL planes
-    const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8),
-                             static_cast<uint32_t>(rows_per_tile + (kRowShift[li] ? 2 : 0)),
-                             static_cast<uint32_t>(patches_per_tile), static_cast<uint32_t>(kc / 8)};
+    // channel-planar input [patch][plane][y][x][8] seen as (x * 8, y, patch, plane); box = whole rows of NPL planes.
+    // ROWSHIFT layers order the box (x * 8, patch, y, plane) instead (see ConvCfg).
     const uint64_t C = L.cin, W = L.hin, H = L.hin;
     if (li == 0) continue;  // conv2 is part of the fused front kernel
-    if (L.stride == 1) {
+    if (L.stride == 1 && kRowShift[li]) {
+      const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8), static_cast<uint32_t>(patches_per_tile),
+                               static_cast<uint32_t>(rows_per_tile + 2), static_cast<uint32_t>(kc / 8)};
+      const uint64_t dims[4] = {W * 8, static_cast<uint64_t>(h->chunk), H, C / 8};
+      const uint64_t str[3] = {C * H * W * 2, W * 16, H * W * 16};
+      HN_TRY(make_tmap_16bit(&p.tmA[0], in, 4, dims, str, box, 0));
+    } else if (L.stride == 1) {
+      const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8), static_cast<uint32_t>(rows_per_tile),
+                               static_cast<uint32_t>(patches_per_tile), static_cast<uint32_t>(kc / 8)};
       const uint64_t dims[4] = {W * 8, H, static_cast<uint64_t>(h->chunk), C / 8};
       const uint64_t str[3] = {W * 16, C * H * W * 2, H * W * 16};
       HN_TRY(make_tmap_16bit(&p.tmA[0], in, 4, dims, str, box, 0));
     } else {
       // parity sub-planes [patch][plane][ypar][xpar][y/2][x/2][8]
+      const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8), static_cast<uint32_t>(rows_per_tile),
+                               static_cast<uint32_t>(patches_per_tile), static_cast<uint32_t>(kc / 8)};
       for (int ypar = 0; ypar < 2; ++ypar)
         for (int xpar = 0; xpar < 2; ++xpar) {
           const uint64_t dims[4] = {W / 2 * 8, H / 2, static_cast<uint64_t>(h->chunk), C / 8};

@@ -64,13 +64,18 @@ constexpr uint32_t tmem_cols_for(int n) {
 // ------------------------------------------------------------------------------------------------------------
 // 3x3 convolution
 // ------------------------------------------------------------------------------------------------------------
-// ROWSHIFT (stride-1 layers whose tile is a band of whole image rows): one TMA load per (kx, channel chunk)
-// fetches the band plus one halo row above and below; the three ky taps then read that SAME shared-memory
-// tile through UMMA descriptors whose start address is advanced by ky image rows (a multiple of the 8-row
-// swizzle group, so the layout stays canonical). Cuts the L2->SMEM operand traffic from 9x to 3x(R+2)/R.
-template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, bool ROWSHIFT = false>
+// ROWSHIFT (stride-1 layers): one TMA load per (kx, channel chunk) fetches the tile's band of image rows plus one
+// halo row above and below; the three ky taps then read that SAME shared-memory tile through UMMA descriptors whose
+// start address is advanced by ky image rows (whole 8-row core matrices). Cuts the L2->SMEM operand traffic from 9x
+// to 3x(R+2)/R. When a tile spans several small patches (8x8 images: two patches) the box is ordered
+// (x, patch, y, plane), so that shared memory holds [plane][y][patch][x] and a ky shift is still one uniform offset;
+// the tile's M rows are then ordered (y, patch, x).
+// TILES: accumulator tiles per pass. With TILES = 2 every streamed weight block feeds two A tiles (halves the weight
+// traffic through the SM's L2 port) and each pipeline stage carries twice the bytes in flight.
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, bool ROWSHIFT = false, int TILES = 1,
+          int KCB_ = 0>
 struct ConvCfg {
-  static constexpr int KCB = (CIN >= 64) ? 128 : 64;            // bytes of one pixel's channel chunk
+  static constexpr int KCB = KCB_ ? KCB_ : ((CIN >= 64) ? 128 : 64);   // bytes of one pixel's channel chunk
   static constexpr int KC = KCB / 2;                             // channels per k-block
   static constexpr int CIN_CHUNKS = CIN / KC;
   static constexpr int KB = 9 * CIN_CHUNKS;                      // k-blocks per tile
@@ -81,19 +86,24 @@ struct ConvCfg {
   static constexpr int UNITS = ROWSHIFT ? 3 * CIN_CHUNKS : KB;   // TMA loads of A per tile
   static constexpr int SPT = UNITS / G;                          // stages per tile
   static constexpr int NPL = KC / 8;                              // 8-channel planes per k-block
-  static constexpr uint32_t ROW_BYTES = HOUT * 16;               // one image row inside one plane of the A tile
+  // one image row (of all the tile's patches when ROWSHIFT) inside one plane of the A tile
+  static constexpr uint32_t ROW_BYTES = (ROWSHIFT ? PATCHES_PER_TILE : 1) * HOUT * 16;
   static constexpr uint32_t PLANE_BYTES = ROWSHIFT ? (ROWS_PER_TILE + 2) * ROW_BYTES : kTileM * 16;
   static constexpr uint32_t A_BYTES = NPL * PLANE_BYTES;
   static constexpr uint32_t B_BYTES = COUT * KCB;
-  static constexpr uint32_t STAGE_BYTES = G * (A_BYTES + (WRES ? 0u : B_BYTES));
+  static constexpr int B_PER_STAGE = WRES ? 0 : (ROWSHIFT ? 3 : G);   // streamed weight k-blocks per stage
+  static constexpr uint32_t STAGE_BYTES = G * TILES * A_BYTES + B_PER_STAGE * B_BYTES;
   static constexpr uint32_t W_BYTES = WRES ? KB * B_BYTES : 0u;
-  static_assert(!ROWSHIFT || (STRIDE == 1 && TILES_PER_PATCH >= 1 && WRES && ROW_BYTES % 128 == 0),
-                "ROWSHIFT needs a stride-1 row-band tile, resident weights and image rows that are whole core matrices");
+  static_assert(!ROWSHIFT || (STRIDE == 1 && ROW_BYTES % 128 == 0 && (WRES || G == 1)),
+                "ROWSHIFT needs a stride-1 layer whose image rows are whole core matrices");
   static_assert(UNITS % G == 0, "stage must hold a whole number of loads");
-  static constexpr uint32_t TMEM_COLS = tmem_cols_for(COUT);
+  static_assert(2 * TILES * COUT <= 512, "two accumulator buffers must fit the tensor memory");
+  static constexpr uint32_t TMEM_COLS = tmem_cols_for(TILES * COUT);
   static constexpr size_t SMEM = size_t(W_BYTES) + size_t(STAGES) * STAGE_BYTES + 1024 + 256 + COUT * 4;
-  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "operand tiles must stay 1024B aligned");
+  static_assert((G * TILES * A_BYTES) % 1024 == 0 && B_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0,
+                "swizzled weight tiles must stay 1024B aligned");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "UMMA M=128 needs N % 16 == 0");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ uint64_t make_noswizzle_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -112,10 +122,26 @@ __device__ __forceinline__ int planar_pixel_slot(int y, int x) {
   return y * W + x;
 }
 
-template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT, bool OUT_PARITY>
+// {lo, hi} -> two 16-bit values with ReLU and saturation to the largest finite value, one instruction (F2FP.SATFINITE.RELU)
+__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi, int bf16) {
+  uint32_t r;
+  if (bf16) asm("cvt.rn.relu.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack16_plain(float lo, float hi, int bf16) {
+  uint32_t r;
+  if (bf16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES, int MINB, bool ROWSHIFT, bool OUT_PARITY,
+          int TILES, int KCB_>
 __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_constant__ TcParams p) {
-  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT>;
+  using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT, TILES, KCB_>;
   constexpr int N = COUT;
+  constexpr int PPT = C::PATCHES_PER_TILE;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -134,6 +160,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int num_groups = (p.num_tiles + TILES - 1) / TILES;   // a pass works on TILES consecutive tiles
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
@@ -181,15 +208,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
     }
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int patch0, y0;
-      if (C::TILES_PER_PATCH >= 1) {
-        patch0 = tile / (C::TILES_PER_PATCH > 0 ? C::TILES_PER_PATCH : 1);
-        y0 = (tile - patch0 * C::TILES_PER_PATCH) * C::ROWS_PER_TILE;
-      } else {
-        patch0 = tile * C::PATCHES_PER_TILE;
-        y0 = 0;
-      }
+    for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
       int ky = 0, kx = 0, cc = 0, kb = 0;
 #pragma unroll 1
       for (int s = 0; s < C::SPT; ++s) {
@@ -200,19 +219,42 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           if (leader) {
-            const uint32_t a_dst = st_base + g * C::A_BYTES;
-            if (ROWSHIFT) {
-              // band of ROWS_PER_TILE + 2 rows starting one row above the tile, shifted by kx - 1 columns
-              tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), (kx - 1) * 8, y0 - 1, patch0, cc * C::NPL);
-            } else if (STRIDE == 1) {
-              tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), (kx - 1) * 8, y0 + ky - 1, patch0, cc * C::NPL);
-            } else {
-              // input x = 2*ox + kx - 1: kx=0 -> odd column ox-1, kx=1 -> even column ox, kx=2 -> odd column ox
-              const int xpar = (kx != 1), ypar = (ky != 1);
-              tma_load_4d(a_dst, &p.tmA[ypar * 2 + xpar], full_bar(stage), (kx == 0) ? -8 : 0,
-                          y0 + ((ky == 0) ? -1 : 0), patch0, cc * C::NPL);
+#pragma unroll
+            for (int tl = 0; tl < TILES; ++tl) {
+              // tiles past the end of the batch read out-of-range patch coordinates: TMA zero-fills them
+              const int tile = grp * TILES + tl;
+              int patch0, y0;
+              if (C::TILES_PER_PATCH >= 1) {
+                patch0 = tile / (C::TILES_PER_PATCH > 0 ? C::TILES_PER_PATCH : 1);
+                y0 = (tile - patch0 * C::TILES_PER_PATCH) * C::ROWS_PER_TILE;
+              } else {
+                patch0 = tile * PPT;
+                y0 = 0;
+              }
+              const uint32_t a_dst = st_base + (g * TILES + tl) * C::A_BYTES;
+              if (ROWSHIFT) {
+                // band of ROWS_PER_TILE + 2 rows starting one row above the tile, shifted by kx - 1 columns;
+                // box order (x, patch, y, plane)
+                tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), (kx - 1) * 8, patch0, y0 - 1, cc * C::NPL);
+              } else if (STRIDE == 1) {
+                tma_load_4d(a_dst, &p.tmA[0], full_bar(stage), (kx - 1) * 8, y0 + ky - 1, patch0, cc * C::NPL);
+              } else {
+                // input x = 2*ox + kx - 1: kx=0 -> odd column ox-1, kx=1 -> even column ox, kx=2 -> odd column ox
+                const int xpar = (kx != 1), ypar = (ky != 1);
+                tma_load_4d(a_dst, &p.tmA[ypar * 2 + xpar], full_bar(stage), (kx == 0) ? -8 : 0,
+                            y0 + ((ky == 0) ? -1 : 0), patch0, cc * C::NPL);
+              }
             }
-            if (!WRES) tma_load_2d(st_base + G * C::A_BYTES + g * C::B_BYTES, &p.tmB, full_bar(stage), kb * C::KC, 0);
+            if (!WRES) {
+              const uint32_t b_dst = st_base + G * TILES * C::A_BYTES;
+              if (ROWSHIFT) {
+#pragma unroll
+                for (int t3 = 0; t3 < 3; ++t3)   // the three ky taps of this (kx, channel chunk) unit
+                  tma_load_2d(b_dst + t3 * C::B_BYTES, &p.tmB, full_bar(stage), ((t3 * 3 + kx) * C::CIN_CHUNKS + cc) * C::KC, 0);
+              } else {
+                tma_load_2d(b_dst + g * C::B_BYTES, &p.tmB, full_bar(stage), kb * C::KC, 0);
+              }
+            }
           }
           ++kb;
           if (++cc == C::CIN_CHUNKS) {
@@ -232,7 +274,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
     constexpr uint32_t A_HI = noswizzle_desc_hi(128);
     constexpr uint32_t B_HI = kmajor_desc_hi(C::KCB);
     const uint32_t ring_a_lo = noswizzle_desc_lo(ring_base, C::PLANE_BYTES);
-    const uint32_t ring_b_lo = kmajor_desc_lo(ring_base + G * C::A_BYTES);   // streamed weights live behind the A tiles
+    const uint32_t ring_b_lo = kmajor_desc_lo(ring_base + G * TILES * C::A_BYTES);   // streamed weights live behind the A tiles
     const uint32_t w_lo = kmajor_desc_lo(w_base);
     if (WRES) {
       mbar_wait(w_bar, 0);
@@ -241,12 +283,12 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * N;
+      const uint32_t d_tmem = tmem_base + acc * (TILES * N);
 #pragma unroll
       for (int s = 0; s < C::SPT; ++s) {
         mbar_wait(full_bar(stage), phase);
@@ -262,23 +304,30 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
               const int kx = u / C::CIN_CHUNKS, cc = u - kx * C::CIN_CHUNKS;
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky) {
+                const uint32_t b_off = WRES ? ((((ky * 3 + kx) * C::CIN_CHUNKS + cc) * C::B_BYTES) >> 4) : ((ky * C::B_BYTES) >> 4);
 #pragma unroll
-                for (int k = 0; k < C::KCB / 32; ++k)
-                  umma_f16_w(d_tmem, a_lo + ((g * C::A_BYTES + ky * C::ROW_BYTES + 2 * k * C::PLANE_BYTES) >> 4), A_HI,
-                             b_lo + ((((ky * 3 + kx) * C::CIN_CHUNKS + cc) * C::B_BYTES) >> 4) + 2 * k, B_HI, idesc,
-                             (s | g | ky | k) != 0);
+                for (int tl = 0; tl < TILES; ++tl) {
+#pragma unroll
+                  for (int k = 0; k < C::KCB / 32; ++k)
+                    umma_f16_w(d_tmem + tl * N,
+                               a_lo + (((g * TILES + tl) * C::A_BYTES + ky * C::ROW_BYTES + 2 * k * C::PLANE_BYTES) >> 4), A_HI,
+                               b_lo + b_off + 2 * k, B_HI, idesc, (s | g | ky | k) != 0);
+                }
               }
             } else {
 #pragma unroll
-              for (int k = 0; k < C::KCB / 32; ++k) {
-                // A: 16 K-elements = two 8-channel planes; B: 32 bytes inside the swizzle span = +2 in the (addr >> 4) field
-                umma_f16_w(d_tmem, a_lo + ((g * C::A_BYTES + 2 * k * C::PLANE_BYTES) >> 4), A_HI,
-                           b_lo + (((WRES ? (s * G + g) : g) * C::B_BYTES) >> 4) + 2 * k, B_HI, idesc, (s | g | k) != 0);
+              for (int tl = 0; tl < TILES; ++tl) {
+#pragma unroll
+                for (int k = 0; k < C::KCB / 32; ++k) {
+                  // A: 16 K-elements = two 8-channel planes; B: 32 bytes inside the swizzle span = +2 in the (addr >> 4) field
+                  umma_f16_w(d_tmem + tl * N, a_lo + (((g * TILES + tl) * C::A_BYTES + 2 * k * C::PLANE_BYTES) >> 4), A_HI,
+                             b_lo + (((WRES ? (s * G + g) : g) * C::B_BYTES) >> 4) + 2 * k, B_HI, idesc, (s | g | k) != 0);
+                }
               }
             }
           }
           umma_commit(empty_bar(stage));                        // frees the smem slot once these MMAs have read it
-          if (s == C::SPT - 1) umma_commit(tfull_bar(acc));     // accumulator complete -> epilogue
+          if (s == C::SPT - 1) umma_commit(tfull_bar(acc));     // accumulators complete -> epilogue
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -288,35 +337,46 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
     // ============================== epilogue ==============================
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int row_in_tile = q * 32 + lane;
+    const long long total_patches = p.total_rows / C::PIX;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int grp = blockIdx.x; grp < num_groups; grp += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * N;
-      const long long row = static_cast<long long>(tile) * kTileM + row_in_tile;
-      const bool valid = row < p.total_rows;
-      // channel-planar output: [patch][plane][pixel slot][8]; consecutive lanes = consecutive pixels = consecutive 16 B
-      const long long patch = row / C::PIX;
-      const int pix = static_cast<int>(row - patch * C::PIX);
-      const int slot = planar_pixel_slot<HOUT, OUT_PARITY>(pix / HOUT, pix % HOUT);
-      uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + patch * (static_cast<long long>(N) * C::PIX)) + slot;
 #pragma unroll
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(t_row + c0, r);
-        tmem_ld_wait();
-        uint32_t o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float v0 = fmaxf(__uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], 0.f);
-          const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1], 0.f);
-          o[j] = pack16(v0, v1, p.act_bf16);
+      for (int tl = 0; tl < TILES; ++tl) {
+        const int tile = grp * TILES + tl;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (TILES * N) + tl * N;
+        // which output pixel this accumulator row is
+        long long patch;
+        int pix;
+        if (ROWSHIFT && PPT > 1) {   // rows ordered (y, patch, x)
+          patch = static_cast<long long>(tile) * PPT + (row_in_tile / HOUT) % PPT;
+          pix = (row_in_tile / (HOUT * PPT)) * HOUT + row_in_tile % HOUT;
+        } else {                     // rows ordered (patch, y, x)
+          const long long row = static_cast<long long>(tile) * kTileM + row_in_tile;
+          patch = row / C::PIX;
+          pix = static_cast<int>(row - patch * C::PIX);
         }
-        if (valid) {
+        const bool valid = patch < total_patches;
+        // channel-planar output: [patch][plane][pixel slot][8]; consecutive lanes = consecutive pixels = consecutive 16 B
+        const int slot = planar_pixel_slot<HOUT, OUT_PARITY>(pix / HOUT, pix % HOUT);
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + patch * (static_cast<long long>(N) * C::PIX)) + slot;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[(c0 / 8 + j) * C::PIX] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c0, r);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            o[j] = pack16_relu(__uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], __uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1],
+                               p.act_bf16);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[(c0 / 8 + j) * C::PIX] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
         }
       }
       tc_fence_before();
