@@ -473,6 +473,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_f16(kTileM, N, p.act_bf16);
+    constexpr uint32_t HI = kmajor_desc_hi(128);
+    const uint32_t ring_lo = kmajor_desc_lo(base);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -487,13 +489,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t st_base = base + stage * STAGE_BYTES;
+          const uint32_t lo = ring_lo + static_cast<uint32_t>(stage) * (STAGE_BYTES >> 4);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            const uint64_t a_desc = make_kmajor_desc(st_base + g * kHeadBlk, 128);
-            const uint64_t b_desc = make_kmajor_desc(st_base + (G + g) * kHeadBlk, 128);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (ks | g | k) != 0);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_w(d_tmem, lo + ((g * kHeadBlk) >> 4) + 2u * k, HI, lo + (((G + g) * kHeadBlk) >> 4) + 2u * k, HI, idesc,
+                         (ks | g | k) != 0);
           }
           umma_commit(empty_bar(stage));
           if (ks == p.num_k_stages - 1) umma_commit(tfull_bar(acc));

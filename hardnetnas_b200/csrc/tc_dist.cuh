@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
+    // ============================== TMA producer (warp-uniform) ==============================
+    {
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -123,26 +123,36 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
         int t0, t1;
         seg_range(seg, t0, t1);
         mbar_wait(aempty_bar, a_phase ^ 1u);
-        mbar_arrive_expect_tx(afull_bar, MB * p.k_blocks * BLK_BYTES);
-        for (int mb = 0; mb < MB; ++mb)
-          for (int kb = 0; kb < p.k_blocks; ++kb)
-            tma_load_2d(a_base + (mb * p.k_blocks + kb) * BLK_BYTES, &sd.tmA, afull_bar, kb * 64,
-                        (mblk * MB + mb) * kDistTile);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(afull_bar, MB * p.k_blocks * BLK_BYTES);
+          for (int mb = 0; mb < MB; ++mb)
+            for (int kb = 0; kb < p.k_blocks; ++kb)
+              tma_load_2d(a_base + (mb * p.k_blocks + kb) * BLK_BYTES, &sd.tmA, afull_bar, kb * 64,
+                          (mblk * MB + mb) * kDistTile);
+        }
+        __syncwarp();
         a_phase ^= 1u;
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(stage), BLK_BYTES);
-            tma_load_2d(b_base + stage * BLK_BYTES, &sd.tmB, full_bar(stage), kb * 64, t * kDistTile);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(full_bar(stage), BLK_BYTES);
+              tma_load_2d(b_base + stage * BLK_BYTES, &sd.tmB, full_bar(stage), kb * 64, t * kDistTile);
+            }
+            __syncwarp();
             if (++stage == kDistStages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ============================== UMMA issuer ==============================
-    if (lane == 0) {
+    // ============================== UMMA issuer (warp-uniform) ==============================
+    // Every lane runs the control flow, elect.sync picks the issuing lane; descriptors advance by adding to their lo word.
+    {
       const uint32_t idesc = make_idesc_f16(kDistTile, kDistTile, 0);
+      constexpr uint32_t HI = kmajor_desc_hi(128);
+      const uint32_t a_lo0 = kmajor_desc_lo(a_base);
+      const uint32_t b_lo0 = kmajor_desc_lo(b_base);
       int stage = 0;
       uint32_t phase = 0, a_phase = 0;
       int it = 0;
@@ -161,20 +171,24 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint64_t b_desc = make_kmajor_desc(b_base + stage * BLK_BYTES, 128);
+            if (elect_one()) {
+              const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(stage) * (BLK_BYTES >> 4);
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-              const uint64_t a_desc = make_kmajor_desc(a_base + (mb * p.k_blocks + kb) * BLK_BYTES, 128);
-              const uint32_t d_tmem = tmem_base + (acc * MB + mb) * kDistTile;
+              for (int mb = 0; mb < MB; ++mb) {
+                const uint32_t a_lo = a_lo0 + static_cast<uint32_t>(mb * p.k_blocks + kb) * (BLK_BYTES >> 4);
+                const uint32_t d_tmem = tmem_base + (acc * MB + mb) * kDistTile;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0);
+                for (int k = 0; k < 4; ++k) umma_f16_w(d_tmem, a_lo + 2u * k, HI, b_lo + 2u * k, HI, idesc, (kb | k) != 0);
+              }
+              umma_commit(empty_bar(stage));
+              if (kb == p.k_blocks - 1) umma_commit(tfull_bar(acc));
             }
-            umma_commit(empty_bar(stage));
+            __syncwarp();
             if (++stage == kDistStages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(tfull_bar(acc));
         }
-        umma_commit(aempty_bar);  // the resident A block may be overwritten once these MMAs retired
+        if (elect_one()) umma_commit(aempty_bar);  // the resident A block may be overwritten once these MMAs retired
+        __syncwarp();
       }
     }
   } else {
