@@ -33,6 +33,8 @@ struct hn_handle {
   float* bias = nullptr;                                               // 7 x 128
   float2* stats = nullptr;                                             // per-patch (mean, 1/std), chunk entries
   hn::TcParams conv_params[5];
+  hn::TcParams pair_params[5];   // same layers for the CTA-pair kernels (tc_conv_pair.cuh)
+  unsigned pair_mask = 0;        // bit li: layer li runs on CTA pairs
   hn::TcParams head_params;
   // optional per-stage CUDA-event timing (stage 0 = L1, 1..5 = 3x3 convs, 6 = head)
   unsigned profile_mask = 0;

@@ -15,6 +15,7 @@
 #include "host_common.h"
 #include "l1_tc.cuh"
 #include "tc_conv.cuh"
+#include "tc_conv_pair.cuh"
 
 namespace hn {
 
@@ -74,6 +75,24 @@ static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream)
   return HN_OK;
 }
 
+template <int CIN, int COUT, int HOUT, int STRIDE, int STAGES, bool ROWSHIFT, bool OUT_PARITY, int KCB_ = 0>
+static int launch_conv_pair_cfg(const TcParams& p, int sm_count, cudaStream_t stream) {
+  using C = PairCfg<CIN, COUT, HOUT, STRIDE, STAGES, ROWSHIFT, KCB_>;
+  auto kern = conv3x3_pair_kernel<CIN, COUT, HOUT, STRIDE, STAGES, ROWSHIFT, OUT_PARITY, KCB_>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
+    attr_done = true;
+  }
+  if (p.num_tiles <= 0) return HN_OK;
+  const int groups = (p.num_tiles + 1) / 2;
+  const int grid = 2 * std::min(groups, sm_count / 2);   // whole CTA pairs (__cluster_dims__(2, 1, 1))
+  kern<<<grid, kTcThreads, C::SMEM, stream>>>(p);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
 // conv2 (li = 0) lives in the fused front kernel. OUT_PARITY: the consumer is a stride-2 conv and wants parity sub-planes.
 //                         CIN COUT HOUT STRIDE  G STAGES WRES  CTAs/SM ROWSHIFT OUT_PARITY
 #define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 1, 9, true, 2, false, false>
@@ -82,8 +101,27 @@ static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream)
 //   conv6: ROWSHIFT over two-patch tiles + TILES = 2: 132 KB / patch through the SM's L2 port instead of 288 KB
 #define HN_CONV_L5 launch_conv_cfg<64, 128, 8, 2, 1, 4, false, 1, false, false, 2>
 #define HN_CONV_L6 launch_conv_cfg<128, 128, 8, 1, 1, 4, false, 1, true, false, 2, 64>
+// CTA-pair (cta_group::2) variants: weights resident (half per CTA), M = 256 per MMA
+//                                   CIN COUT HOUT STRIDE STAGES ROWSHIFT OUT_PARITY KCB
+#define HN_PAIR_L3 launch_conv_pair_cfg<32, 64, 16, 2, 9, false, false>
+#define HN_PAIR_L4 launch_conv_pair_cfg<64, 64, 16, 1, 9, true, true>
+#define HN_PAIR_L5 launch_conv_pair_cfg<64, 128, 8, 2, 9, false, false>
+#define HN_PAIR_L6 launch_conv_pair_cfg<128, 128, 8, 1, 4, true, false>
 static const bool kRowShift[5] = {true, false, true, false, true};
+static const bool kPairRowShift[5] = {false, false, true, false, true};
+static const int kPairKcb[5] = {64, 64, 128, 128, 128};
+static const unsigned kDefaultPairMask = 0x1c;   // conv4, conv5, conv6 (conv3 is faster with two independent CTAs per SM)
 static const int kKcb[5] = {64, 64, 128, 128, 64};   // bytes of one pixel's channel chunk per k-block (ConvCfg::KCB)
+
+static int launch_conv_pair(int li, const TcParams& p, int sm_count, cudaStream_t s) {
+  switch (li) {
+    case 1: return HN_PAIR_L3(p, sm_count, s);
+    case 2: return HN_PAIR_L4(p, sm_count, s);
+    case 3: return HN_PAIR_L5(p, sm_count, s);
+    case 4: return HN_PAIR_L6(p, sm_count, s);
+  }
+  return HN_ERR_INVALID;
+}
 
 static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) {
   switch (li) {
@@ -170,54 +208,58 @@ static uint16_t to16(float v, int bf16) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 
-// Static descriptors over the handle's buffers; only the tile counts change per call.
+// Static descriptors of one 3x3 layer over the handle's buffers; only the tile counts change per call.
+// kcb = bytes of one pixel's channel chunk per k-block; half_b: weight box of C_out / 2 rows (CTA-pair kernels).
+static int build_conv_params(hn_handle* h, int li, int kcb, bool rowshift, bool half_b, TcParams& p) {
+  const ConvLayer& L = kConv[li];
+  memset(&p, 0, sizeof(p));
+  const int kc = kcb / 2;
+  const uint16_t* in = h->act[li & 1];  // the front kernel writes act[1]; layers alternate
+  const int pix_out = L.hout * L.hout;
+  const int rows_per_tile = pix_out >= kTileM ? kTileM / L.hout : L.hout;
+  const int patches_per_tile = pix_out >= kTileM ? 1 : kTileM / pix_out;
+  // channel-planar input [patch][plane][y][x][8] seen as (x * 8, y, patch, plane); box = whole rows of NPL planes.
+  // ROWSHIFT layers order the box (x * 8, patch, y, plane) instead (see ConvCfg).
+  const uint64_t C = L.cin, W = L.hin, H = L.hin;
+  if (L.stride == 1 && rowshift) {
+    const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8), static_cast<uint32_t>(patches_per_tile),
+                             static_cast<uint32_t>(rows_per_tile + 2), static_cast<uint32_t>(kc / 8)};
+    const uint64_t dims[4] = {W * 8, static_cast<uint64_t>(h->chunk), H, C / 8};
+    const uint64_t str[3] = {C * H * W * 2, W * 16, H * W * 16};
+    HN_TRY(make_tmap_16bit(&p.tmA[0], in, 4, dims, str, box, 0));
+  } else if (L.stride == 1) {
+    const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8), static_cast<uint32_t>(rows_per_tile),
+                             static_cast<uint32_t>(patches_per_tile), static_cast<uint32_t>(kc / 8)};
+    const uint64_t dims[4] = {W * 8, H, static_cast<uint64_t>(h->chunk), C / 8};
+    const uint64_t str[3] = {W * 16, C * H * W * 2, H * W * 16};
+    HN_TRY(make_tmap_16bit(&p.tmA[0], in, 4, dims, str, box, 0));
+  } else {
+    // parity sub-planes [patch][plane][ypar][xpar][y/2][x/2][8]
+    const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8), static_cast<uint32_t>(rows_per_tile),
+                             static_cast<uint32_t>(patches_per_tile), static_cast<uint32_t>(kc / 8)};
+    for (int ypar = 0; ypar < 2; ++ypar)
+      for (int xpar = 0; xpar < 2; ++xpar) {
+        const uint64_t dims[4] = {W / 2 * 8, H / 2, static_cast<uint64_t>(h->chunk), C / 8};
+        const uint64_t str[3] = {W / 2 * 16, C * H * W * 2, H * W * 16};
+        const uint16_t* base = in + (ypar * 2 + xpar) * (H / 2) * (W / 2) * 8;
+        HN_TRY(make_tmap_16bit(&p.tmA[ypar * 2 + xpar], base, 4, dims, str, box, 0));
+      }
+  }
+  {
+    const uint64_t K = 9ull * L.cin;
+    const uint64_t dims[2] = {K, static_cast<uint64_t>(L.cout)};
+    const uint64_t str[1] = {K * 2};
+    const uint32_t wbox[2] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(half_b ? L.cout / 2 : L.cout)};
+    HN_TRY(make_tmap_16bit(&p.tmB, h->wconv[li], 2, dims, str, wbox, kcb));
+  }
+  p.bias = h->bias + 128 * (li + 1);
+  return HN_OK;
+}
+
 static int build_params(hn_handle* h) {
-  for (int li = 0; li < 5; ++li) {
-    const ConvLayer& L = kConv[li];
-    TcParams& p = h->conv_params[li];
-    memset(&p, 0, sizeof(p));
-    const int kcb = kKcb[li];  // bytes of one pixel's channel chunk
-    const int kc = kcb / 2;
-    const uint16_t* in = h->act[li & 1];  // L1 wrote act[0]; layers alternate
-    const int pix_out = L.hout * L.hout;
-    const int rows_per_tile = pix_out >= kTileM ? kTileM / L.hout : L.hout;
-    const int patches_per_tile = pix_out >= kTileM ? 1 : kTileM / pix_out;
-    // channel-planar input [patch][plane][y][x][8] seen as (x * 8, y, patch, plane); box = whole rows of NPL planes.
-    // ROWSHIFT layers order the box (x * 8, patch, y, plane) instead (see ConvCfg).
-    const uint64_t C = L.cin, W = L.hin, H = L.hin;
-    if (li == 0) continue;  // conv2 is part of the fused front kernel
-    if (L.stride == 1 && kRowShift[li]) {
-      const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8), static_cast<uint32_t>(patches_per_tile),
-                               static_cast<uint32_t>(rows_per_tile + 2), static_cast<uint32_t>(kc / 8)};
-      const uint64_t dims[4] = {W * 8, static_cast<uint64_t>(h->chunk), H, C / 8};
-      const uint64_t str[3] = {C * H * W * 2, W * 16, H * W * 16};
-      HN_TRY(make_tmap_16bit(&p.tmA[0], in, 4, dims, str, box, 0));
-    } else if (L.stride == 1) {
-      const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8), static_cast<uint32_t>(rows_per_tile),
-                               static_cast<uint32_t>(patches_per_tile), static_cast<uint32_t>(kc / 8)};
-      const uint64_t dims[4] = {W * 8, H, static_cast<uint64_t>(h->chunk), C / 8};
-      const uint64_t str[3] = {W * 16, C * H * W * 2, H * W * 16};
-      HN_TRY(make_tmap_16bit(&p.tmA[0], in, 4, dims, str, box, 0));
-    } else {
-      // parity sub-planes [patch][plane][ypar][xpar][y/2][x/2][8]
-      const uint32_t box[4] = {static_cast<uint32_t>(L.hout * 8), static_cast<uint32_t>(rows_per_tile),
-                               static_cast<uint32_t>(patches_per_tile), static_cast<uint32_t>(kc / 8)};
-      for (int ypar = 0; ypar < 2; ++ypar)
-        for (int xpar = 0; xpar < 2; ++xpar) {
-          const uint64_t dims[4] = {W / 2 * 8, H / 2, static_cast<uint64_t>(h->chunk), C / 8};
-          const uint64_t str[3] = {W / 2 * 16, C * H * W * 2, H * W * 16};
-          const uint16_t* base = in + (ypar * 2 + xpar) * (H / 2) * (W / 2) * 8;
-          HN_TRY(make_tmap_16bit(&p.tmA[ypar * 2 + xpar], base, 4, dims, str, box, 0));
-        }
-    }
-    {
-      const uint64_t K = 9ull * L.cin;
-      const uint64_t dims[2] = {K, static_cast<uint64_t>(L.cout)};
-      const uint64_t str[1] = {K * 2};
-      const uint32_t wbox[2] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(L.cout)};
-      HN_TRY(make_tmap_16bit(&p.tmB, h->wconv[li], 2, dims, str, wbox, kcb));
-    }
-    p.bias = h->bias + 128 * (li + 1);
+  for (int li = 1; li < 5; ++li) {   // conv2 (li = 0) is part of the fused front kernel
+    HN_TRY(build_conv_params(h, li, kKcb[li], kRowShift[li], false, h->conv_params[li]));
+    HN_TRY(build_conv_params(h, li, kPairKcb[li], kPairRowShift[li], true, h->pair_params[li]));
   }
   {
     TcParams& p = h->head_params;
@@ -248,14 +290,15 @@ static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n
   }
   for (int li = 1; li < 5 && li + 2 <= last_layer; ++li) {
     const ConvLayer& L = kConv[li];
-    TcParams p = h->conv_params[li];
+    const bool pair = (h->pair_mask >> li) & 1;
+    TcParams p = pair ? h->pair_params[li] : h->conv_params[li];
     const long long pix_out = static_cast<long long>(L.hout) * L.hout;
     p.total_rows = pix_out * n;
     p.num_tiles = static_cast<int>((p.total_rows + kTileM - 1) / kTileM);
     p.act_bf16 = h->act_bf16;
     p.out = (li == 4) ? static_cast<void*>(h->l6 + l6_row * kHeadK) : static_cast<void*>(h->act[(li + 1) & 1]);
     StageTimer timer(h, li + 1, s);
-    HN_TRY(launch_conv(li, p, h->sm_count, s));
+    HN_TRY(pair ? launch_conv_pair(li, p, h->sm_count, s) : launch_conv(li, p, h->sm_count, s));
   }
   return HN_OK;
 }
@@ -285,6 +328,10 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   head_rows = (head_rows + chunk_patches - 1) / chunk_patches * chunk_patches;
   h->chunk = chunk_patches;
   h->head_rows = head_rows;
+  {
+    const char* e = getenv("HN_PAIR_MASK");   // bit li: run 3x3 layer li (1 = conv3 .. 4 = conv6) on CTA pairs
+    h->pair_mask = e ? static_cast<unsigned>(strtoul(e, nullptr, 0)) : kDefaultPairMask;
+  }
   const size_t act_elems = static_cast<size_t>(chunk_patches) * 32 * 32 * 32;
   auto fail = [&](int code) { hn_destroy(h); return code; };
 #define HN_CUDA_H(expr)                                                                                     \

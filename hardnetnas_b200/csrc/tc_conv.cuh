@@ -103,7 +103,6 @@ struct ConvCfg {
   static_assert((G * TILES * A_BYTES) % 1024 == 0 && B_BYTES % 1024 == 0 && STAGE_BYTES % 1024 == 0,
                 "swizzled weight tiles must stay 1024B aligned");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "UMMA M=128 needs N % 16 == 0");
-  static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ uint64_t make_noswizzle_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -140,6 +139,7 @@ template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES,
           int TILES, int KCB_>
 __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_constant__ TcParams p) {
   using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT, TILES, KCB_>;
+  static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
   constexpr int N = COUT;
   constexpr int PPT = C::PATCHES_PER_TILE;
 
