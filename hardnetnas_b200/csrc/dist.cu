@@ -82,7 +82,8 @@ __global__ void loss_finalize_kernel(const float* __restrict__ pos, const unsign
 // Exact fp32 re-rank of the shortlisted chunks: one warp per query row, one candidate gallery row per lane.
 // Distances in the FDLNet form; ties resolve to the lower gallery index like torch.min / a stable sort.
 __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q, const float* __restrict__ g,
-                                                     const int* __restrict__ cand, long long nq, long long ng, int slots,
+                                                     const int* __restrict__ cand, const float* __restrict__ cand_val,
+                                                     float margin, long long nq, long long ng, int slots,
                                                      long long g_offset, float* __restrict__ d1, float* __restrict__ d2,
                                                      int* __restrict__ i1, int* __restrict__ i2) {
   __shared__ __align__(16) float sq[4][128];
@@ -91,6 +92,24 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q
   if (row >= nq) return;
   reinterpret_cast<float4*>(sq[w])[lane] = reinterpret_cast<const float4*>(q + row * 128)[lane];
   __syncwarp();
+  // A chunk can hold one of the two nearest columns only if its approximate maximum reaches the second largest
+  // chunk maximum minus twice the error bound of the 16-bit-operand dot product (`margin`, same scaled units).
+  float thr;
+  {
+    float m1 = -__int_as_float(0x7f800000), m2 = m1;
+    for (int c = lane; c < slots; c += 32) {
+      const float v = cand[row * slots + c] >= 0 ? cand_val[row * slots + c] : -__int_as_float(0x7f800000);
+      if (v > m1) { m2 = m1; m1 = v; } else if (v > m2) { m2 = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float o1 = __shfl_xor_sync(0xffffffffu, m1, o), o2 = __shfl_xor_sync(0xffffffffu, m2, o);
+      const float lo = fminf(m1, o1);
+      m1 = fmaxf(m1, o1);
+      m2 = fmaxf(fmaxf(m2, o2), lo);
+    }
+    thr = m2 - margin;   // -inf when fewer than two chunks exist: everything is re-ranked
+  }
   const float inf = __int_as_float(0x7f800000);
   float b1 = inf, b2 = inf;
   int j1 = 0x7fffffff, j2 = 0x7fffffff;
@@ -98,7 +117,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q
   for (int c = lane; c < total; c += 32) {
     const int chunk = cand[row * slots + c / kChunk];
     const long long col = static_cast<long long>(chunk) * kChunk + (c % kChunk);
-    if (chunk < 0 || col >= ng) continue;
+    if (chunk < 0 || col >= ng || cand_val[row * slots + c / kChunk] < thr) continue;
     const float4* gr = reinterpret_cast<const float4*>(g + col * 128);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 8
@@ -252,7 +271,7 @@ extern "C" long long hn_dist_workspace_bytes(long long Na, long long Np, int spl
   (void)split;
   ExactWs w = carve_exact(nullptr, Na, Np);
   const size_t shortlist = align256(static_cast<size_t>(Na) * 128 * 2) + align256(static_cast<size_t>(Np) * 128 * 2) +
-                           align256(static_cast<size_t>(Na) * 16 * kTopC * 4);
+                           2 * align256(static_cast<size_t>(Na) * 16 * kTopC * 4);
   return static_cast<long long>(std::max(w.bytes, shortlist) + 256);
 }
 
@@ -312,6 +331,7 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   uint16_t* q16 = reinterpret_cast<uint16_t*>(b);
   uint16_t* g16 = reinterpret_cast<uint16_t*>(b + align256(static_cast<size_t>(Nq) * 256));
   int* cand = reinterpret_cast<int*>(b + align256(static_cast<size_t>(Nq) * 256) + align256(static_cast<size_t>(Ng) * 256));
+  float* cand_val = reinterpret_cast<float*>(reinterpret_cast<char*>(cand) + align256(static_cast<size_t>(Nq) * 16 * kTopC * 4));
   const int threads = 256;
   pack_desc_kernel<<<static_cast<unsigned>((Nq * 32 + threads - 1) / threads), threads, 0, s>>>(q, Nq, q16, 0, 0, nullptr);
   pack_desc_kernel<<<static_cast<unsigned>((Ng * 32 + threads - 1) / threads), threads, 0, s>>>(g, Ng, g16, 0, 1, nullptr);
@@ -321,6 +341,7 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   HN_TRY(make_desc_map(&dp.side[0].tmA, q16, Nq, 128));
   HN_TRY(make_desc_map(&dp.side[0].tmB, g16, Ng, 128));
   dp.side[0].cand = cand;
+  dp.side[0].cand_val = cand_val;
   dp.side[0].Na = Nq;
   dp.side[0].Nb = Ng;
   dp.k_blocks = 2;
@@ -329,8 +350,11 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   dp.segments = pick_segments(Nq, 2 * kDistTile, Ng, sm, 16);
   const long long items = ((Nq + 2 * kDistTile - 1) / (2 * kDistTile)) * dp.segments;
   HN_TRY((launch_dist<2, EPI_SHORTLIST>(dp, static_cast<int>(std::min<long long>(items, sm)), 1, s)));
-  rerank_kernel<<<static_cast<unsigned>((Nq + 3) / 4), 128, 0, s>>>(q, g, cand, Nq, Ng, dp.segments * kTopC, g_offset, d1, d2,
-                                                                   i1, i2);
+  // |fp16-operand dot - exact dot| <= 2^-10 for rows of norm <= 1 (L2-normalised descriptors, the only input this path
+  // is defined for: FDLNet-master/utils/math_utils.py:15-18 clamps 2 - 2ab to [1e-8, 4]); keep 4x that as the margin.
+  const float margin = 4.0f * (1.0f / 1024.0f) / kDotScale;
+  rerank_kernel<<<static_cast<unsigned>((Nq + 3) / 4), 128, 0, s>>>(q, g, cand, cand_val, margin, Nq, Ng, dp.segments * kTopC,
+                                                                   g_offset, d1, d2, i1, i2);
   HN_CUDA(cudaGetLastError());
   count_launch(3);
   return HN_OK;

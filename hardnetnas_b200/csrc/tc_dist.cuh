@@ -34,6 +34,7 @@ struct DistSide {
   unsigned long long* row_pack;  // EXACT: packed (float bits << 32 | col) running minimum per row
   float* pos;                  // EXACT: diagonal distance before masking (may be null)
   int* cand;                   // SHORTLIST: [Na, segments, kTopC] chunk ids
+  float* cand_val;             // SHORTLIST: the chunks' approximate (fp16-operand, scaled) dot-product maxima
   long long Na, Nb;
 };
 
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
           // unused slots (segment with < kTopC chunks) are marked -1
           *dst = make_int4(tb[0] > -3.0e38f ? tc[0] : -1, tb[1] > -3.0e38f ? tc[1] : -1, tb[2] > -3.0e38f ? tc[2] : -1,
                            tb[3] > -3.0e38f ? tc[3] : -1);
+          *reinterpret_cast<float4*>(sd.cand_val + (row * p.segments + seg) * kTopC) = make_float4(tb[0], tb[1], tb[2], tb[3]);
         }
       }
     }
