@@ -20,6 +20,7 @@ int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, 
 
 struct hn_handle {
   int chunk = 0;            // patches per conv-stack pass
+  int front_chunk = 0;      // patches per front-kernel + conv3 sub-pass (keeps the conv2 output L2 resident)
   long long head_rows = 0;  // capacity of the L6 output buffer (patches)
   int sm_count = 0;
   bool packed = false;

@@ -279,27 +279,41 @@ static int build_params(hn_handle* h) {
 }
 
 // Runs the conv stack up to `last_layer` for `n` patches (n <= chunk); the conv6 output lands in l6 + l6_row * 8192.
+static int run_one_conv(hn_handle* h, int li, int n, void* out, cudaStream_t s) {
+  const ConvLayer& L = kConv[li];
+  const bool pair = (h->pair_mask >> li) & 1;
+  TcParams p = pair ? h->pair_params[li] : h->conv_params[li];
+  const long long pix_out = static_cast<long long>(L.hout) * L.hout;
+  p.total_rows = pix_out * n;
+  p.num_tiles = static_cast<int>((p.total_rows + kTileM - 1) / kTileM);
+  p.act_bf16 = h->act_bf16;
+  p.out = out;
+  StageTimer timer(h, li + 1, s);
+  return pair ? launch_conv_pair(li, p, h->sm_count, s) : launch_conv(li, p, h->sm_count, s);
+}
+
 static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n, long long l6_row, int last_layer,
                           cudaStream_t s) {
-  if (last_layer >= 2) {
-    StageTimer timer(h, 1, s);  // stage 1 + conv2 (the stage-1 activation never reaches global memory)
-    HN_TRY(launch_front_fused(h, patches, in_dtype, h->act[1], n, s));
-  } else {
+  if (last_layer < 2) {
     StageTimer timer(h, 0, s);  // stage 1 alone (activation dump only), NHWC
-    HN_TRY(launch_l1(patches, in_dtype, h->act[0], h->w1, h->bias, h->stats, n, h->act_bf16, h->sm_count, s));
+    return launch_l1(patches, in_dtype, h->act[0], h->w1, h->bias, h->stats, n, h->act_bf16, h->sm_count, s);
   }
-  for (int li = 1; li < 5 && li + 2 <= last_layer; ++li) {
-    const ConvLayer& L = kConv[li];
-    const bool pair = (h->pair_mask >> li) & 1;
-    TcParams p = pair ? h->pair_params[li] : h->conv_params[li];
-    const long long pix_out = static_cast<long long>(L.hout) * L.hout;
-    p.total_rows = pix_out * n;
-    p.num_tiles = static_cast<int>((p.total_rows + kTileM - 1) / kTileM);
-    p.act_bf16 = h->act_bf16;
-    p.out = (li == 4) ? static_cast<void*>(h->l6 + l6_row * kHeadK) : static_cast<void*>(h->act[(li + 1) & 1]);
-    StageTimer timer(h, li + 1, s);
-    HN_TRY(pair ? launch_conv_pair(li, p, h->sm_count, s) : launch_conv(li, p, h->sm_count, s));
+  // The 64 KB/patch conv2 output is the largest tensor of the stack. The front kernel and conv3 run in sub-passes of
+  // `front_chunk` patches over the SAME head of act[1], so it is produced and consumed inside the 126 MB L2 instead of
+  // making an HBM round trip; conv3 writes into the full-size act[0] and the deeper stages run once over the whole pass.
+  const int front = last_layer >= 3 ? std::min(h->front_chunk, n) : n;
+  const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
+  for (int off = 0; off < n; off += front) {
+    const int m = std::min(front, n - off);
+    {
+      StageTimer timer(h, 1, s);  // stage 1 + conv2 (the stage-1 activation never reaches global memory)
+      HN_TRY(launch_front_fused(h, static_cast<const char*>(patches) + static_cast<size_t>(off) * 1024 * in_elem, in_dtype,
+                                h->act[1], m, s));
+    }
+    if (last_layer >= 3) HN_TRY(run_one_conv(h, 1, m, h->act[0] + static_cast<size_t>(off) * 16 * 16 * 64, s));
   }
+  for (int li = 2; li < 5 && li + 2 <= last_layer; ++li)
+    HN_TRY(run_one_conv(h, li, n, (li == 4) ? static_cast<void*>(h->l6 + l6_row * kHeadK) : static_cast<void*>(h->act[(li + 1) & 1]), s));
   return HN_OK;
 }
 
@@ -328,6 +342,10 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   head_rows = (head_rows + chunk_patches - 1) / chunk_patches * chunk_patches;
   h->chunk = chunk_patches;
   h->head_rows = head_rows;
+  {
+    const char* e = getenv("HN_FRONT_CHUNK");   // patches per front-kernel + conv3 sub-pass
+    h->front_chunk = e ? std::max(2, atoi(e)) : chunk_patches;
+  }
   {
     const char* e = getenv("HN_PAIR_MASK");   // bit li: run 3x3 layer li (1 = conv3 .. 4 = conv6) on CTA pairs
     h->pair_mask = e ? static_cast<unsigned>(strtoul(e, nullptr, 0)) : kDefaultPairMask;

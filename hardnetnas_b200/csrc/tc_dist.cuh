@@ -234,6 +234,39 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
         tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * MB + mb) * kDistTile;
         const bool ragged = col0 + kDistTile > sd.Nb;
+        if (EPI == EPI_SHORTLIST) {
+          // all four TMEM loads are issued before the single wait: one exposed round trip per tile instead of four
+          uint32_t r[4][32];
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) tmem_ld32(t_row + gq * 32, r[gq]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const int c0 = gq * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[gq][j]);
+            if (ragged) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + c0 + j >= sd.Nb) v[j] = -__int_as_float(0x7f800000);
+            }
+#pragma unroll
+            for (int s = 0; s < 32 / kChunk; ++s) {
+              const float* w = v + s * kChunk;
+              const float m = fmaxf(max3(w[0], w[1], w[2]), max3(max3(w[3], w[4], w[5]), w[6], w[7]));
+              if (m > tb[kTopC - 1]) {
+                const int id = static_cast<int>((col0 + c0) / kChunk) + s;
+                // sorted insert (descending); strict '>' keeps the earlier chunk on ties
+                const bool g0 = m > tb[0], g1 = m > tb[1], g2 = m > tb[2];
+                tb[3] = g2 ? tb[2] : m;               tc[3] = g2 ? tc[2] : id;
+                tb[2] = g2 ? (g1 ? tb[1] : m) : tb[2]; tc[2] = g2 ? (g1 ? tc[1] : id) : tc[2];
+                tb[1] = g1 ? (g0 ? tb[0] : m) : tb[1]; tc[1] = g1 ? (g0 ? tc[0] : id) : tc[1];
+                tb[0] = g0 ? m : tb[0];               tc[0] = g0 ? id : tc[0];
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int c0 = 0; c0 < kDistTile; c0 += 32) {
           uint32_t r[32];
@@ -287,6 +320,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
               }
             }
           }
+        }
         }
         tc_fence_before();
         __syncwarp();

@@ -172,9 +172,11 @@ class HardNet(nn.Module):
         return out
 
     # ---- measurement hooks (bench.py) ---------------------------------------------------------------
-    STAGE_NAMES = ("l1_norm_conv", "conv2_32x32x32", "conv3_s2_64", "conv4_64", "conv5_s2_128", "conv6_128", "head_8x8_l2norm")
-    # multiply-accumulates per patch of each stage
-    STAGE_MACS = (294912, 9437184, 4718592, 9437184, 4718592, 9437184, 1048576)
+    # stage 0 (input_norm + conv1 on its own) only runs for activation dumps: the forward path fuses it into stage 1
+    STAGE_NAMES = ("conv1_only_dump_path", "front_fused_norm_conv1_conv2", "conv3_s2_64", "conv4_64", "conv5_s2_128", "conv6_128",
+                   "head_8x8_l2norm")
+    # multiply-accumulates per patch of each stage; stage 1 = a2 + a3
+    STAGE_MACS = (294912, 294912 + 9437184, 4718592, 9437184, 4718592, 9437184, 1048576)
 
     def profile_enable(self, stage_mask: int):
         if self._engine is None:
