@@ -34,7 +34,9 @@ constexpr uint32_t kFfA1 = 8 * 4096;          // eight 128 x 16 im2col tiles of 
 constexpr uint32_t kFfW2Tap = 96 * 32 * 2;    // one ky: [kx * 32 + co][ci]
 constexpr uint32_t kFfW2 = 3 * kFfW2Tap;      // 18 432 B
 constexpr uint32_t kFfW1 = 1024;
-constexpr size_t kFfSmem = kFfA1 + 2 * kFfAct1 + kFfW2 + kFfW1 + 256 /*barriers*/ + 256 /*biases*/ + 1024 /*align*/;
+constexpr int kFfRawDepth = 4;                 // raw input patches prefetched ahead of the loaders (bulk async copies)
+constexpr uint32_t kFfRaw = kFfRawDepth * 4096;
+constexpr size_t kFfSmem = kFfA1 + 2 * kFfAct1 + kFfW2 + kFfW1 + kFfRaw + 256 /*barriers*/ + 256 /*biases*/ + 1024 /*align*/;
 static_assert(kFfSmem <= 227 * 1024, "smem budget");
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -59,12 +61,15 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   const uint32_t act1_addr = a1_addr + kFfA1;
   const uint32_t w2_addr = act1_addr + 2 * kFfAct1;
   const uint32_t w1_addr = w2_addr + kFfW2;
-  const uint32_t bar_base = w1_addr + kFfW1;
+  const uint32_t raw_addr0 = w1_addr + kFfW1;
+  const uint32_t bar_base = raw_addr0 + kFfRaw;
   const uint32_t a1_full = bar_base, a1_empty = bar_base + 8, l1_full = bar_base + 16, l1_empty = bar_base + 24;
   auto act1_full = [&](int b) { return bar_base + 32u + 8u * b; };
   auto act1_empty = [&](int b) { return bar_base + 48u + 8u * b; };
   auto c2_full = [&](int a) { return bar_base + 64u + 8u * a; };
-  auto c2_empty = [&](int a) { return bar_base + 80u + 8u * a; };
+  auto c2_empty = [&](int a) { return bar_base + 96u + 8u * a; };
+  auto raw_full = [&](int d) { return bar_base + 136u + 8u * d; };
+  auto raw_empty = [&](int d) { return bar_base + 168u + 8u * d; };
   const uint32_t tmem_slot = bar_base + 128;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
   float* s_bias2 = reinterpret_cast<float*>(gbase + (bar_base + 256 - base));
@@ -82,8 +87,14 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       for (int b = 0; b < 2; ++b) {
         mbar_init(act1_full(b), 4);
         mbar_init(act1_empty(b), 1);
-        mbar_init(c2_full(b), 1);
-        mbar_init(c2_empty(b), 4);
+      }
+      for (int a = 0; a < 4; ++a) {
+        mbar_init(c2_full(a), 1);
+        mbar_init(c2_empty(a), 4);
+      }
+      for (int d = 0; d < kFfRawDepth; ++d) {
+        mbar_init(raw_full(d), 1);    // arrive.expect_tx of the prefetching lane + the copy's complete_tx
+        mbar_init(raw_empty(d), 4);   // one arrive per loader warp
       }
       fence_mbar_init();
     }
@@ -122,25 +133,45 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tm_l1 = tmem_base;            // columns [0, 256): eight 128 x 32 stage-1 accumulators
-  const uint32_t tm_c2 = tmem_base + 256;      // columns [256, 512): two 128 x 96 conv2 accumulators, pitch 128
+  // Tensor memory: stage 1 runs in two halves of four 128 x 32 tiles (columns [0, 128)), which leaves room for FOUR
+  // 128 x 96 conv2 accumulators (columns [128, 512)): each epilogue group owns two, so the MMAs of its next tile are
+  // already done when it finishes the current one.
+  const uint32_t tm_l1 = tmem_base;
+  const uint32_t tm_c2 = tmem_base + 128;
 
   if (warp >= kFfLoader0) {
     // ============================== loaders: normalise + im2col of the input patch ==============================
     // Thread = image column x (lane) x 8 consecutive rows (warp): every global load is one coalesced 128 B row segment
     // and every im2col store phase touches 8 consecutive pixels = 8 distinct 16 B bank groups (conflict free).
+    // The raw patch comes from a shared-memory ring that one lane keeps kFfRawDepth - 1 patches ahead with bulk async
+    // copies, so the HBM latency of the input is off the loaders' critical path.
     const int lw = warp - kFfLoader0;      // rows 8 * lw .. 8 * lw + 7
     const uint32_t one16 = act_bf16 ? 0x3F80u : 0x3C00u;
+    constexpr uint32_t RAW_BYTES = 1024 * sizeof(TIn);
+    const int n_loc = (num_patches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    auto prefetch = [&](int j) {           // lane 0 of loader warp 0 only
+      const int d = j % kFfRawDepth;
+      mbar_wait(raw_empty(d), ((j / kFfRawDepth) & 1) ^ 1u);
+      mbar_arrive_expect_tx(raw_full(d), RAW_BYTES);
+      const TIn* g = in + (static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x) * 1024;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       raw_addr0 + d * 4096), "l"(g), "r"(RAW_BYTES), "r"(raw_full(d))
+                   : "memory");
+    };
+    if (lw == 0 && lane == 0)
+      for (int j = 0; j < kFfRawDepth - 1 && j < n_loc; ++j) prefetch(j);
+    float2 st_next = make_float2(0.f, 1.f);
+    if (stats != nullptr && n_loc > 0) st_next = __ldg(stats + blockIdx.x);
     int it = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
-      float mean = 0.f, inv = 1.f;
-      if (stats != nullptr) {
-        const float2 st = __ldg(stats + patch);
-        mean = st.x;
-        inv = st.y;
-      }
-      const TIn* src = in + static_cast<size_t>(patch) * 1024 + lane;
-      // 30 independent, branch-free loads (clamped addresses, masked afterwards) so they are all in flight together
+      if (lw == 0 && lane == 0 && it + kFfRawDepth - 1 < n_loc) prefetch(it + kFfRawDepth - 1);
+      __syncwarp();
+      const float mean = st_next.x, inv = st_next.y;
+      if (stats != nullptr && patch + static_cast<int>(gridDim.x) < num_patches) st_next = __ldg(stats + patch + gridDim.x);
+      const int d = it % kFfRawDepth;
+      mbar_wait(raw_full(d), (it / kFfRawDepth) & 1);
+      const TIn* src = reinterpret_cast<const TIn*>(gbase + (raw_addr0 - base) + d * 4096) + lane;
+      // 30 branch-free shared-memory loads (clamped addresses, masked afterwards)
       float v[10][3];
       const int xl = lane > 0 ? -1 : 0, xr = lane < 31 ? 1 : 0;
 #pragma unroll
@@ -159,6 +190,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         v[r][1] = rowok ? (v[r][1] - mean) * inv : 0.f;
         v[r][2] = (rowok && lane < 31) ? (v[r][2] - mean) * inv : 0.f;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(raw_empty(d));   // the raw slot may be refilled
       // the stage-1 MMAs of the previous patch must have retired before A1 is overwritten
       mbar_wait(a1_empty, (it & 1) ^ 1u);
       // pixel (y, x): tile y / 4, row r = (y % 4) * 32 + x  ->  (r / 8) * 256 + (r % 8) * 16
@@ -193,11 +226,12 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     const uint32_t act_lo0 = noswizzle_desc_lo(act1_addr, kFfPlane);
     const uint32_t w2_lo = noswizzle_desc_lo(w2_addr, 128);
     const int n_local = (num_patches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-    auto issue_l1 = [&]() {
+    auto issue_l1_half = [&](int half) {
       if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) umma_f16_w(tm_l1 + t * 32, a1_lo + t * (4096 >> 4), L1A_HI, b1_lo, L1B_HI, idesc1, 0u);
-        umma_commit(a1_empty);
+        for (int t = 0; t < 4; ++t)
+          umma_f16_w(tm_l1 + t * 32, a1_lo + (half * 4 + t) * (4096 >> 4), L1A_HI, b1_lo, L1B_HI, idesc1, 0u);
+        if (half == 1) umma_commit(a1_empty);
         umma_commit(l1_full);
       }
       __syncwarp();
@@ -205,27 +239,36 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     if (n_local > 0) {
       mbar_wait(a1_full, 0);
       tc_fence_after();
-      issue_l1();
+      issue_l1_half(0);
+      mbar_wait(l1_empty, 0);
+      tc_fence_after();
+      issue_l1_half(1);
     }
     for (int it = 0; it < n_local; ++it) {
       const int b = it & 1;
-      if (it + 1 < n_local) {
-        // stage 1 of the NEXT patch goes first, so its epilogue overlaps the conv2 MMAs of this patch
+      const bool more = it + 1 < n_local;
+      if (more) {
+        // stage 1 of the NEXT patch is interleaved with the conv2 tiles of this one, so its epilogue overlaps them
         mbar_wait(a1_full, (it + 1) & 1);
-        mbar_wait(l1_empty, it & 1);
+        mbar_wait(l1_empty, 1);          // second half of patch `it` has been drained
         tc_fence_after();
-        issue_l1();
+        issue_l1_half(0);
       }
       mbar_wait(act1_full(b), (it >> 1) & 1);
       tc_fence_after();
       const uint32_t act_lo = act_lo0 + b * (kFfAct1 >> 4);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
-        const int a = t & 1;                       // 8 tiles per patch: the accumulator buffer is simply the tile parity
-        mbar_wait(c2_empty(a), (((it * 4 + (t >> 1)) & 1) ^ 1u));
+        if (t == 4 && more) {
+          mbar_wait(l1_empty, 0);        // first half of patch `it + 1` has been drained
+          tc_fence_after();
+          issue_l1_half(1);
+        }
+        const int a = t & 3;             // 8 tiles per patch over 4 buffers: each buffer is used twice per patch
+        mbar_wait(c2_empty(a), ((t >> 2) & 1) ^ 1u);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d = tm_c2 + a * 128;
+          const uint32_t d = tm_c2 + a * 96;
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -247,72 +290,84 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     int it = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
       const int b = it & 1;
-      mbar_wait(l1_full, it & 1);
       mbar_wait(act1_empty(b), ((it >> 1) & 1) ^ 1u);
-      tc_fence_after();
       uint8_t* act = gbase + (act1_addr - base) + b * kFfAct1;
 #pragma unroll 1
-      for (int t = 0; t < 8; ++t) {
-        uint32_t r[32];
-        tmem_ld32(tm_l1 + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
-        tmem_ld_wait();
-        uint32_t o[16];
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(l1_full, half);
+        tc_fence_after();
+#pragma unroll 1
+        for (int tq = 0; tq < 4; ++tq) {
+          const int t = half * 4 + tq;
+          uint32_t r[32];
+          tmem_ld32(tm_l1 + (static_cast<uint32_t>(q * 32) << 16) + tq * 32, r);
+          tmem_ld_wait();
+          uint32_t o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = pack16_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), act_bf16);
-        // pixel p = t * 128 + q * 32 + lane  ->  slot p + 32 (one halo row on top)
-        uint8_t* dst = act + (t * 128 + q * 32 + lane + 32) * 16;
+          for (int j = 0; j < 16; ++j) o[j] = pack16_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), act_bf16);
+          // pixel p = t * 128 + q * 32 + lane  ->  slot p + 32 (one halo row on top)
+          uint8_t* dst = act + (t * 128 + q * 32 + lane + 32) * 16;
 #pragma unroll
-        for (int pl = 0; pl < 4; ++pl)
-          *reinterpret_cast<uint4*>(dst + pl * kFfPlane) = make_uint4(o[4 * pl], o[4 * pl + 1], o[4 * pl + 2], o[4 * pl + 3]);
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(act1_full(b));
-        mbar_arrive(l1_empty);
+          for (int pl = 0; pl < 4; ++pl)
+            *reinterpret_cast<uint4*>(dst + pl * kFfPlane) = make_uint4(o[4 * pl], o[4 * pl + 1], o[4 * pl + 2], o[4 * pl + 3]);
+        }
+        if (half == 1) fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (half == 1) mbar_arrive(act1_full(b));
+          mbar_arrive(l1_empty);
+        }
       }
     }
   } else {
     // ============================== conv2 epilogue: kx shift-and-add, bias, ReLU, pack -> global ==============================
     const int q = warp & 3;
-    const int g = (warp - 4) >> 2;  // accumulator buffer owned by this group of four warps
-    const uint32_t t_row = tm_c2 + (static_cast<uint32_t>(q * 32) << 16) + g * 128;
-    float bias[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) bias[j] = s_bias2[j];
+    const int g = (warp - 4) >> 2;  // this group of four warps owns accumulator buffers g and g + 2
+    const uint32_t t_row0 = tm_c2 + (static_cast<uint32_t>(q * 32) << 16);
     const float m_left = lane == 0 ? 0.f : 1.f;     // x - 1 / x + 1 outside the row = the conv's zero padding
     const float m_right = lane == 31 ? 0.f : 1.f;
-    uint32_t use = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x) {
       uint16_t* opatch = out + static_cast<size_t>(patch) * 32768;
 #pragma unroll 1
-      for (int tt = 0; tt < 4; ++tt, ++use) {
+      for (int tt = 0; tt < 4; ++tt) {
         const int t = 2 * tt + g;
-        mbar_wait(c2_full(g), use & 1);
+        const int a = t & 3;
+        const uint32_t t_row = t_row0 + a * 96;
+        mbar_wait(c2_full(a), (t >> 2) & 1);
         tc_fence_after();
         // channel-planar parity layout for the stride-2 conv3: [plane][ypar][xpar][16][16][8]
         uint4* dst = reinterpret_cast<uint4*>(opatch) + planar_pixel_slot<32, true>(4 * t + q, lane);
+        // six TMEM loads (two 8-channel chunks) are in flight per wait: half the exposed round trips of a per-chunk wait
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r0[8], r1[8], r2[8];
-          tmem_ld8(t_row + c * 8, r0);
-          tmem_ld8(t_row + 32 + c * 8, r1);
-          tmem_ld8(t_row + 64 + c * 8, r2);
-          tmem_ld_wait();
+        for (int h2 = 0; h2 < 2; ++h2) {
+        uint32_t r0[2][8], r1[2][8], r2[2][8];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          tmem_ld8(t_row + (2 * h2 + cc) * 8, r0[cc]);
+          tmem_ld8(t_row + 32 + (2 * h2 + cc) * 8, r1[cc]);
+          tmem_ld8(t_row + 64 + (2 * h2 + cc) * 8, r2[cc]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 2 * h2 + cc;
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias2 + c * 8), b1 = *reinterpret_cast<const float4*>(s_bias2 + c * 8 + 4);
+          const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[j]), 1);     // D'0 of pixel x - 1
-            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[j]), 1);  // D'2 of pixel x + 1
-            v[j] = fmaf(right, m_right, fmaf(left, m_left, __uint_as_float(r1[j]) + bias[c * 8 + j]));
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(r0[cc][j]), 1);     // D'0 of pixel x - 1
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[cc][j]), 1);  // D'2 of pixel x + 1
+            v[j] = fmaf(right, m_right, fmaf(left, m_left, __uint_as_float(r1[cc][j]) + bias[j]));
           }
           dst[c * 1024] = make_uint4(pack16_relu(v[0], v[1], act_bf16), pack16_relu(v[2], v[3], act_bf16),
                                      pack16_relu(v[4], v[5], act_bf16), pack16_relu(v[6], v[7], act_bf16));
         }
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(c2_empty(g));
+        if (lane == 0) mbar_arrive(c2_empty(a));
       }
     }
   }
