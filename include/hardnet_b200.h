@@ -71,12 +71,14 @@ int hn_forward(hn_handle* h, const void* patches, int in_dtype, long long B, voi
                int out_dtype, void* stream);
 
 /* Test hook: run the stack up to and including conv stage `layer` (1..6) for B <= chunk_patches and
- * copy that stage's NHWC 16-bit activations to act_out ([B,H,W,C]). */
+ * copy that stage's 16-bit activations to act_out in the device layout: stage 1 NHWC [B,H,W,C]; stages 2..6
+ * channel-planar [B][C/8][H][W][8], where stages 2 and 4 (inputs of the stride-2 convs) hold the four
+ * row/column parity sub-planes [B][C/8][ypar][xpar][H/2][W/2][8]. */
 int hn_forward_dump(hn_handle* h, const void* patches, int in_dtype, long long B, int layer,
                     void* act_out, void* stream);
 
-/* Measurement hooks: bracket every launch of the selected conv stages (bit 0 = stage 1 ... bit 5 = stage 6,
- * bit 6 = head GEMM) with CUDA events on the launching stream; hn_profile_read waits for them, returns the
+/* Measurement hooks: bracket every launch of the selected stages (bit 0 = stage 1 alone (dump path only),
+ * bit 1 = fused front kernel = stages 1 + 2, bits 2..5 = stages 3..6, bit 6 = head GEMM) with CUDA events on the launching stream; hn_profile_read waits for them, returns the
  * summed milliseconds and launch counts per stage and resets the counters. */
 int hn_profile_enable(hn_handle* h, unsigned stage_mask);
 int hn_profile_read(hn_handle* h, double ms_out[7], long long launches_out[7]);
