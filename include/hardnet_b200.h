@@ -138,6 +138,16 @@ int hn_match(const float* q, const float* g, long long Nq, long long Ng, long lo
              float* d2, int32_t* i1, int32_t* i2, void* workspace, long long workspace_bytes,
              void* stream);
 
+/* ---- patch extraction (FDLNet-master/utils/image_utils.py:11-158, clip_patch) ------------------------ */
+/* Crops a psize x psize patch around every keypoint with the reference's similarity transform
+ * (scale / im_info[b][0] / 2, optional rotation (cos, sin)) and bilinear interpolation with clamped taps.
+ * images [B,1,H,W] fp32; kpts_byxc [N,4] int64 (b, y, x, 0); kpts_scale [N]; kpts_ori [N,2] or NULL;
+ * im_info [B,2]; out [N,1,psize,psize] fp32 (the input layout of hn_forward). N must be a multiple of B
+ * (the reference reshapes the keypoints with view(B, -1)). */
+int hn_clip_patches(const float* images, long long B, int H, int W, const long long* kpts_byxc,
+                    const float* kpts_scale, const float* kpts_ori, const float* im_info, long long N,
+                    int psize, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

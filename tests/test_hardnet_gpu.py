@@ -130,3 +130,27 @@ def test_full_size_properties():
     small, _ = _model(None, chunk_patches=32, head_rows=128)
     d3 = small(x[:1000])
     assert torch.equal(d3, d1[:1000])
+
+
+def test_fpr95_agrees_with_reference_path():
+    """FPR95 on a synthetic patch-pair set must agree to 0.1 pt (BASELINE.json north_star): label-1 pairs are
+    (patch, patch + 0.1 * noise), label-0 pairs are independent patches."""
+    import numpy as np
+    from hardnetnas_b200 import metrics
+    from oracle import losses_oracle
+    model, (w, m, v) = _model(3)
+    n = 50000   # SURVEY.md section 8d; the oracle forward of the 200 000 patches takes ~40 s of host time
+    a = synth.make_patches(2 * n, 11, edge_cases=False)
+    p = torch.cat([synth.make_positives(a[:n], 0.1, 7), synth.make_patches(n, 12, edge_cases=False)])
+    labels = torch.cat([torch.ones(n), torch.zeros(n)]).long()
+    da, dp = model(a.cuda()), model(p.cuda())
+    dist = metrics.pair_distances(da, dp)
+    fpr_dev = metrics.ErrorRateAt95Recall(labels.cuda(), 1.0 / (dist + 1e-8))
+    ra = torch.cat([hardnet_oracle.hardnet_forward(c, w, m, v) for c in a.split(8192)])
+    rp = torch.cat([hardnet_oracle.hardnet_forward(c, w, m, v) for c in p.split(8192)])
+    rdist = torch.sqrt(torch.sum((ra - rp) ** 2, 1)).numpy()
+    fpr_ref = losses_oracle.error_rate_at_95_recall(labels.numpy(), 1.0 / (rdist + 1e-8))
+    assert abs(fpr_dev - fpr_ref) <= 1e-3, (fpr_dev, fpr_ref)
+    assert 0.0 < fpr_ref < 0.5   # the set is non-degenerate
+    # the device metric itself equals the reference metric on identical inputs
+    assert metrics.ErrorRateAt95Recall(labels, torch.from_numpy(1.0 / (rdist + 1e-8))) == fpr_ref
