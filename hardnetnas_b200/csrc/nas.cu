@@ -272,6 +272,85 @@ __global__ void __launch_bounds__(256) dw_conv_kernel(const uint16_t* __restrict
   }
 }
 
+// Register-blocked depthwise conv for the shapes the NAS nets use (k in {3, 5}, stride in {1, 2}): a thread owns
+// 8 channels x a strip of 4 output pixels of one row. Per ky it loads the K weight vectors once and walks the
+// (4 - 1) * S + K input columns once, so an input vector is fetched and unpacked once per row instead of once per
+// tap (k = 5, stride 1: 40 loads / 4 outputs instead of 100) and the tap loops are compile-time unrolled.
+template <int K, int S>
+__global__ void __launch_bounds__(256) dw_conv_strip_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                            const float* __restrict__ w /*[k*k][C]*/,
+                                                            const float* __restrict__ bias, long long patches, int C, int hin,
+                                                            int hout, int relu, int bf16) {
+  constexpr int SW = 4;                       // outputs per thread (hout is a multiple of 4 for every NAS stage)
+  constexpr int NIN = (SW - 1) * S + K;       // input columns a strip touches
+  constexpr int PAD = K >> 1;
+  const int cg = C >> 3;
+  const int strips = hout / SW;
+  const long long total = patches * hout * strips * cg;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cg) * 8;
+    long long t = i / cg;
+    const int sx = static_cast<int>(t % strips);
+    t /= strips;
+    const int oy = static_cast<int>(t % hout);
+    const long long n = t / hout;
+    // accumulators, inputs and weights are kept as float2 pairs: FFMA2 (fma.rn.f32x2, sm_100) does two FMAs per instruction
+    float2 acc[SW][4];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + c8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + c8 + 4);
+#pragma unroll
+      for (int j = 0; j < SW; ++j) {
+        acc[j][0] = make_float2(b0.x, b0.y); acc[j][1] = make_float2(b0.z, b0.w);
+        acc[j][2] = make_float2(b1.x, b1.y); acc[j][3] = make_float2(b1.z, b1.w);
+      }
+    }
+    const int ix0 = sx * SW * S - PAD;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * S + ky - PAD;
+      if (iy < 0 || iy >= hin) continue;       // warp-uniform: a warp covers one output row
+      float2 wk[K][4];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const float* wp = w + (ky * K + kx) * C + c8;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+        wk[kx][0] = make_float2(w0.x, w0.y); wk[kx][1] = make_float2(w0.z, w0.w);
+        wk[kx][2] = make_float2(w1.x, w1.y); wk[kx][3] = make_float2(w1.z, w1.w);
+      }
+      const uint16_t* row = in + ((n * hin + iy) * hin) * C + c8;
+#pragma unroll
+      for (int c = 0; c < NIN; ++c) {
+        const int ix = ix0 + c;
+        if (ix < 0 || ix >= hin) continue;
+        const uint4 xv = *reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * C);
+        const float2 x[4] = {unpack16(xv.x, bf16), unpack16(xv.y, bf16), unpack16(xv.z, bf16), unpack16(xv.w, bf16)};
+#pragma unroll
+        for (int j = 0; j < SW; ++j) {
+          const int kx = c - j * S;            // compile-time after unrolling
+          if (kx >= 0 && kx < K) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][e] = __ffma2_rn(x[e], wk[kx][e], acc[j][e]);
+          }
+        }
+      }
+    }
+    uint16_t* orow = out + ((n * hout + oy) * hout + sx * SW) * C + c8;
+#pragma unroll
+    for (int j = 0; j < SW; ++j) {
+      if (relu) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = make_float2(fmaxf(acc[j][e].x, 0.f), fmaxf(acc[j][e].y, 0.f));
+      }
+      *reinterpret_cast<uint4*>(orow + static_cast<long long>(j) * C) =
+          make_uint4(pack16(acc[j][0].x, acc[j][0].y, bf16), pack16(acc[j][1].x, acc[j][1].y, bf16),
+                     pack16(acc[j][2].x, acc[j][2].y, bf16), pack16(acc[j][3].x, acc[j][3].y, bf16));
+    }
+  }
+}
+
 // MaxPool2d(kernel 3, stride 2, padding 1): padding never wins (implicit -inf), like torch
 __global__ void __launch_bounds__(256) maxpool_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                                                       long long patches, int C, int hin, int hout, int bf16) {
@@ -446,10 +525,20 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
             break;
           }
           case OP_DW: {
-            const long long total = static_cast<long long>(n) * o.hout * o.hout * (o.cin / 8);
+            const bool strip = (o.kernel == 3 || o.kernel == 5) && (o.stride == 1 || o.stride == 2) && o.hout % 4 == 0;
+            const long long total = static_cast<long long>(n) * o.hout * (strip ? o.hout / 4 : o.hout) * (o.cin / 8);
             const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->sm_count * 16LL));
-            dw_conv_kernel<<<grid, 256, 0, s>>>(st->slot[o.src], st->slot[o.dst], st->params + o.w_off, st->params + o.b_off, n,
-                                                o.cin, o.hin, o.hout, o.kernel, o.stride, o.relu, bf);
+            const uint16_t* src = st->slot[o.src];
+            uint16_t* dst = st->slot[o.dst];
+            const float* wv = st->params + o.w_off;
+            const float* bv = st->params + o.b_off;
+#define HN_DW_STRIP(KK, SS) dw_conv_strip_kernel<KK, SS><<<grid, 256, 0, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, o.relu, bf)
+            if (!strip) dw_conv_kernel<<<grid, 256, 0, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, o.kernel, o.stride, o.relu, bf);
+            else if (o.kernel == 3 && o.stride == 1) HN_DW_STRIP(3, 1);
+            else if (o.kernel == 3) HN_DW_STRIP(3, 2);
+            else if (o.stride == 1) HN_DW_STRIP(5, 1);
+            else HN_DW_STRIP(5, 2);
+#undef HN_DW_STRIP
             HN_CUDA(cudaGetLastError());
             count_launch();
             break;
