@@ -384,6 +384,16 @@ def side_measurements(device, model, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     if rank == 0:
+        # "existing implementation on the same box" (BASELINE.md section 3): the reference's stock torch modules on this
+        # GPU (cuDNN / cuBLAS), fp32 with TF32 allowed and fp16 autocast + channels_last; 65 536-patch batches
+        xs = torch.nn.functional.avg_pool2d(torch.rand((65536, 1, 32, 32), generator=g, device=device), 5, 1, 2)
+        with torch.no_grad():
+            ms_tf32 = timeit(lambda: model.forward_stock(xs), 5)
+            res["stock_torch_gpu_tf32_patches_per_sec"] = 65536 / (ms_tf32 / 1e3)
+            with torch.autocast("cuda", dtype=torch.float16):
+                ms_amp = timeit(lambda: model.forward_stock(xs), 5)
+            res["stock_torch_gpu_fp16_autocast_patches_per_sec"] = 65536 / (ms_amp / 1e3)
+        del xs
         # configs[4]: NAS-derived descriptor net (wang2) forward at batch 65 536
         from hardnetnas_b200.nas import SampledDescriptorNet
         torch.manual_seed(0)
@@ -395,6 +405,8 @@ def side_measurements(device, model, rank, world):
         res["config4_nas_wang2_patches_per_sec"] = 65536 / (nas_ms / 1e3)
         res["config4_nas_wang2_frac_of_bf16_peak"] = 65536 * 7272448 / (nas_ms / 1e3) / 1e12 / load_peaks()["tflops_sustained"]
         res["config4_nas_wang2_algorithmic_GBps"] = 65536 * 4608 / (nas_ms / 1e3) / 1e9
+        # layer-at-a-time NHWC 16-bit activations move ~562 KB/patch: the HBM fraction that implies
+        res["config4_nas_wang2_layerwise_hbm_frac"] = 65536 * 562e3 / (nas_ms / 1e3) / 1e9 / load_peaks()["hbm_gbs"]
         del nas, xb, ob
     res["config3_match_65536x65536_ms"] = ms
     res["config3_match_pairs_per_sec"] = n * n / (ms / 1e3)

@@ -115,6 +115,13 @@ class HardNet(nn.Module):
             return L2Norm()(x)
         return self._forward_b200(input, out_dtype, out)
 
+    def forward_stock(self, input):
+        """The reference's own op sequence (HardNet.py:312-315) on whatever device the stock torch modules live on.
+        Comparison arm for bench.py (cuDNN / cuBLAS on the same B200); never used by the accelerated path."""
+        x_features = self.features(self.input_norm(input))
+        x = x_features.view(x_features.size(0), -1)
+        return L2Norm()(x)
+
     # ---- B200 path ---------------------------------------------------------------------------------
     def _convs_and_bns(self):
         convs = [m for m in self.features if isinstance(m, nn.Conv2d)]
