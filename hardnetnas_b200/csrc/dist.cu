@@ -4,6 +4,7 @@
 
 #include "host_common.h"
 #include "tc_dist.cuh"
+#include "tc_dist_pair.cuh"
 
 namespace hn {
 
@@ -164,10 +165,10 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q
   }
 }
 
-static int make_desc_map(CUtensorMap* tm, const uint16_t* base, long long rows, int K) {
+static int make_desc_map(CUtensorMap* tm, const uint16_t* base, long long rows, int K, int box_rows = kDistTile) {
   const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows)};
   const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
-  const uint32_t box[2] = {64, static_cast<uint32_t>(kDistTile)};
+  const uint32_t box[2] = {64, static_cast<uint32_t>(box_rows)};
   return make_tmap_16bit(tm, base, 2, dims, str, box, 128);
 }
 
@@ -338,8 +339,12 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   HN_CUDA(cudaGetLastError());
   DistParams dp;
   memset(&dp, 0, sizeof(dp));
+  // CTA pairs (tc_dist_pair.cuh) once the problem is large enough to fill the machine with 512-row query blocks
+  const char* pe = getenv("HN_MATCH_PAIR");   // 0 / 1 force the single-CTA / CTA-pair kernel (tests), default: by size
+  const int pair_env = pe ? atoi(pe) : -1;
+  const bool use_pair = pair_env >= 0 ? pair_env != 0 : (Nq >= 8192 && Ng >= 1024);
   HN_TRY(make_desc_map(&dp.side[0].tmA, q16, Nq, 128));
-  HN_TRY(make_desc_map(&dp.side[0].tmB, g16, Ng, 128));
+  HN_TRY(make_desc_map(&dp.side[0].tmB, g16, Ng, 128, use_pair ? 64 : kDistTile));
   dp.side[0].cand = cand;
   dp.side[0].cand_val = cand_val;
   dp.side[0].Na = Nq;
@@ -347,9 +352,23 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   dp.k_blocks = 2;
   dp.form = HN_FORM_FDL;
   dp.dot_scale = kDotScale;
-  dp.segments = pick_segments(Nq, 2 * kDistTile, Ng, sm, 16);
-  const long long items = ((Nq + 2 * kDistTile - 1) / (2 * kDistTile)) * dp.segments;
-  HN_TRY((launch_dist<2, EPI_SHORTLIST>(dp, static_cast<int>(std::min<long long>(items, sm)), 1, s)));
+  if (use_pair) {
+    const int pairs = std::max(sm / 2, 1);
+    dp.segments = pick_segments(Nq, 4 * kDistTile, Ng, pairs, 16);
+    const long long items = ((Nq + 4 * kDistTile - 1) / (4 * kDistTile)) * dp.segments;
+    static bool attr_done = false;
+    if (!attr_done) {
+      HN_CUDA(cudaFuncSetAttribute(match_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMpSmem)));
+      attr_done = true;
+    }
+    match_pair_kernel<<<2 * static_cast<int>(std::min<long long>(items, pairs)), 64 + 256, kMpSmem, s>>>(dp);
+    HN_CUDA(cudaGetLastError());
+    count_launch();
+  } else {
+    dp.segments = pick_segments(Nq, 2 * kDistTile, Ng, sm, 16);
+    const long long items = ((Nq + 2 * kDistTile - 1) / (2 * kDistTile)) * dp.segments;
+    HN_TRY((launch_dist<2, EPI_SHORTLIST>(dp, static_cast<int>(std::min<long long>(items, sm)), 1, s)));
+  }
   // |fp16-operand dot - exact dot| <= 2^-10 for rows of norm <= 1 (L2-normalised descriptors, the only input this path
   // is defined for: FDLNet-master/utils/math_utils.py:15-18 clamps 2 - 2ab to [1e-8, 4]); keep 4x that as the margin.
   const float margin = 4.0f * (1.0f / 1024.0f) / kDotScale;

@@ -52,6 +52,25 @@ def test_ragged_sizes(nq, ng):
     _check(q, g)
 
 
+@pytest.mark.parametrize("nq,ng", [(1, 1), (5, 7), (257, 129), (511, 64), (513, 4097), (1000, 130), (4096, 8192), (9000, 20000)])
+def test_ragged_sizes_cta_pair_kernel(nq, ng, monkeypatch):
+    """Same checks with the CTA-pair (cta_group::2) matching kernel forced on (by default it is used from 8192 queries)."""
+    monkeypatch.setenv("HN_MATCH_PAIR", "1")
+    q, g, _ = synth.make_match_set(nq, ng, seed=3 + nq)
+    _check(q, g)
+
+
+def test_single_and_pair_kernels_agree(monkeypatch):
+    from hardnetnas_b200.matching import match_top2
+    q, g, _ = synth.make_match_set(3000, 9000, seed=8)
+    outs = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("HN_MATCH_PAIR", mode)
+        outs.append([t.cpu() for t in match_top2(q.cuda(), g.cuda())])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def test_unstructured_descriptors_near_ties():
     # worst case for a 16-bit shortlist: all distances close together
     q = synth.unit_vectors(2048, 128, 5)
