@@ -288,7 +288,7 @@ def run_b200(args):
     h_out = torch.empty((P, 128), dtype=torch.float32, pin_memory=True)
     del x, out
     torch.cuda.empty_cache()
-    ext = DescriptorExtractor(model, batch=65536, device=device)
+    ext = DescriptorExtractor(model, device=device)
     ext(h_in, h_out)
     e2e_steps = max(1, min(args.steps, 5))
     barrier()
@@ -300,7 +300,7 @@ def run_b200(args):
     barrier()
     e2e = {"value": world * P * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": world * P * 4096,
            "d2h_bytes_per_step": world * P * 512, "steps": e2e_steps,
-           "api": "hardnetnas_b200.extract.DescriptorExtractor (pinned host in/out, 65536-patch pipelined batches)"}
+           "api": f"hardnetnas_b200.extract.DescriptorExtractor (pinned host in/out, {ext.batch}-patch pipelined batches)"}
 
     extras = {}
     if not args.no_extras:

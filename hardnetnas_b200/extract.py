@@ -11,11 +11,15 @@ import torch
 
 
 class DescriptorExtractor:
-    def __init__(self, model, batch: int = 65536, out_dtype: torch.dtype = torch.float32, device=None,
+    def __init__(self, model, batch: int | None = None, out_dtype: torch.dtype = torch.float32, device=None,
                  in_dtype: torch.dtype = torch.float32):
         self.model = model
-        self.batch = int(batch)
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if batch is None:
+            # one conv-stack pass of the engine (128 patches per SM unless the model was built with chunk_patches): no
+            # partial passes inside a batch and a short pipeline fill / drain
+            batch = getattr(model, "_chunk_patches", 0) or 128 * torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.batch = int(batch)
         self.out_dtype = out_dtype
         with torch.cuda.device(self.device):
             self.copy_in = torch.cuda.Stream()
@@ -59,5 +63,5 @@ class DescriptorExtractor:
         return out_host
 
 
-def extract_descriptors(model, patches_host: torch.Tensor, batch: int = 65536, out_dtype=torch.float32) -> torch.Tensor:
+def extract_descriptors(model, patches_host: torch.Tensor, batch: int | None = None, out_dtype=torch.float32) -> torch.Tensor:
     return DescriptorExtractor(model, batch=batch, out_dtype=out_dtype, in_dtype=patches_host.dtype)(patches_host)

@@ -154,3 +154,16 @@ def test_fpr95_agrees_with_reference_path():
     assert 0.0 < fpr_ref < 0.5   # the set is non-degenerate
     # the device metric itself equals the reference metric on identical inputs
     assert metrics.ErrorRateAt95Recall(labels, torch.from_numpy(1.0 / (rdist + 1e-8))) == fpr_ref
+
+
+def test_host_pipeline_matches_direct_forward():
+    """extract_descriptors (pinned host in / out, H2D + forward + D2H pipelined) returns what forward() returns."""
+    from hardnetnas_b200.extract import DescriptorExtractor, extract_descriptors
+    model, _ = _model(3, chunk_patches=256, head_rows=512)
+    x = synth.make_patches(1500, 21, edge_cases=False)
+    ref = model(x.cuda()).cpu()
+    out = extract_descriptors(model, x.pin_memory())
+    assert torch.equal(out, ref)
+    ext = DescriptorExtractor(model, batch=300)          # ragged: 5 batches, the last one partial
+    assert torch.equal(ext(x.pin_memory()), ref)
+    assert torch.equal(ext(x[:7].pin_memory()), ref[:7])
