@@ -8,8 +8,9 @@
 // conv2 runs with the three kx taps STACKED ON N:  D'[p, kx * 32 + co] = sum_{ky, ci} act1[p + (ky - 1) row, ci] *
 // w[ky, kx, ci, co]  (M = 128 pixels = 4 image rows, N = 96, K = 3 x 32), so each A tile is read from shared memory
 // 3 times instead of 9 (SS-mode UMMA is bound by the 128 B/clk shared-memory port when N is small). The epilogue
-// finishes the conv with one lane shuffle per value (fp16 pairs):  out[y, x] = D'0[y, x - 1] + D'1[y, x] + D'2[y, x + 1]; a TMEM lane
-// quarter is exactly one image row, so the shuffle's edge lanes are the conv's zero padding in x.
+// finishes the conv:  out[y, x] = D'0[y, x - 1] + D'1[y, x] + D'2[y, x + 1]. A TMEM lane quarter is exactly one image row,
+// so D'2 is moved one lane down with tcgen05.shift (in tensor memory, behind the MMAs), D'0 one lane up with half a
+// shuffle per value (fp16 pairs), and the edge lanes are masked = the conv's zero padding in x.
 //
 // The stage-1 BatchNorm shift rides in the spare K slots of the stage-1 GEMM (K = 9 taps padded to 16): im2col columns 9
 // and 10 are the constant 1 and the matching weight rows hold the shift split into a 16-bit hi + lo pair, so the tensor
@@ -70,6 +71,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   auto c2_empty = [&](int a) { return bar_base + 96u + 8u * a; };
   auto raw_full = [&](int d) { return bar_base + 136u + 8u * d; };
   auto raw_empty = [&](int d) { return bar_base + 168u + 8u * d; };
+  auto mma_done = [&](int a) { return bar_base + 200u + 8u * a; };
   const uint32_t tmem_slot = bar_base + 128;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
   float* s_bias2 = reinterpret_cast<float*>(gbase + (bar_base + 256 - base));
@@ -91,6 +93,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       for (int a = 0; a < 4; ++a) {
         mbar_init(c2_full(a), 1);
         mbar_init(c2_empty(a), 4);
+        mbar_init(mma_done(a), 1);
       }
       for (int d = 0; d < kFfRawDepth; ++d) {
         mbar_init(raw_full(d), 1);    // arrive.expect_tx of the prefetching lane + the copy's complete_tx
@@ -278,8 +281,29 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
                          w2_lo + ((ky * kFfW2Tap + k * 256) >> 4), C2B_HI, idesc2, (ky | k) != 0);
             }
           }
-          umma_commit(c2_full(a));
-          if (t == 7) umma_commit(act1_empty(b));
+          umma_commit(mma_done(a));
+        }
+        __syncwarp();
+        // D'2 (columns 64..95) is needed one pixel to the left: tcgen05.shift moves every 32-lane quarter (= one image
+        // row) down by one lane, 8 columns per instruction (lane 31 keeps its value and is masked in the epilogue).
+        // The shift is NOT ordered behind earlier MMAs by itself, so it is issued for the PREVIOUS tile once that tile's
+        // MMAs have retired - by then this tile's MMAs are already queued and the tensor pipe stays busy.
+        const int sh = (t == 0) ? -1 : t - 1;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const int ts = pass == 0 ? sh : (t == 7 ? 7 : -1);   // after the last tile also finish that tile itself
+          if (ts < 0) continue;
+          const int as = ts & 3;
+          mbar_wait(mma_done(as), (ts >> 2) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t ds = tm_c2 + as * 96 + 64;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(ds + c8 * 8) : "memory");
+            umma_commit(c2_full(as));
+            if (ts == 7) umma_commit(act1_empty(b));
+          }
+          __syncwarp();
         }
         __syncwarp();
       }
@@ -354,19 +378,17 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
           const int c = 2 * h2 + cc;
           const float4 b0 = *reinterpret_cast<const float4*>(s_bias2 + c * 8), b1 = *reinterpret_cast<const float4*>(s_bias2 + c * 8 + 4);
           const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          // The two neighbour partial sums cross lanes as fp16 pairs: one shuffle moves two values (the shuffles are the
-          // most expensive part of this epilogue: ~0.8 clk each on the shared-memory pipe). |D'| stays far inside the
-          // fp16 range and the extra rounding (2^-11 relative on two of the three addends) is of the size of the
-          // output's own 16-bit rounding: measured descriptor error 6.5e-5 vs 5.0e-5 with fp32 shuffles. Sums are fp32.
+          // The left neighbour's partial sum crosses lanes as fp16 pairs: one shuffle moves two values (shuffles run on
+          // the shared-memory pipe, the busiest unit of this kernel). |D'| stays far inside the fp16 range and the extra
+          // rounding (2^-11 relative on one addend) is below the output's own 16-bit rounding. Sums are fp32.
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; j += 2) {
             const uint32_t lp = __shfl_up_sync(0xffffffffu, pack16_plain(__uint_as_float(r0[cc][j]), __uint_as_float(r0[cc][j + 1]), 0), 1);
-            const uint32_t rp = __shfl_down_sync(0xffffffffu, pack16_plain(__uint_as_float(r2[cc][j]), __uint_as_float(r2[cc][j + 1]), 0), 1);
             const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lp));    // D'0 of pixel x - 1
-            const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rp));    // D'2 of pixel x + 1
-            v[j] = fmaf(rf.x, m_right, fmaf(lf.x, m_left, __uint_as_float(r1[cc][j]) + bias[j]));
-            v[j + 1] = fmaf(rf.y, m_right, fmaf(lf.y, m_left, __uint_as_float(r1[cc][j + 1]) + bias[j + 1]));
+            // r2 already holds D'2 of pixel x + 1 (shifted in tensor memory by the issuer)
+            v[j] = fmaf(__uint_as_float(r2[cc][j]), m_right, fmaf(lf.x, m_left, __uint_as_float(r1[cc][j]) + bias[j]));
+            v[j + 1] = fmaf(__uint_as_float(r2[cc][j + 1]), m_right, fmaf(lf.y, m_left, __uint_as_float(r1[cc][j + 1]) + bias[j + 1]));
           }
           dst[c * 1024] = make_uint4(pack16_relu(v[0], v[1], act_bf16), pack16_relu(v[2], v[3], act_bf16),
                                      pack16_relu(v[4], v[5], act_bf16), pack16_relu(v[6], v[7], act_bf16));
