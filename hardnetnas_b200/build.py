@@ -47,7 +47,7 @@ def _compile(src: Path, force: bool, verbose: bool) -> Path:
     obj = OBJ / (src.stem + ".o")
     if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, _newest_header_mtime()):
         return obj
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("HN_EXTRA_NVCC_FLAGS", "").split(), "-c", str(src), "-o", str(obj)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = OBJ / (src.stem + ".ptxas.log")
     log.write_text(r.stdout + r.stderr)

@@ -47,6 +47,16 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "memory");
 }
 
+#ifdef HN_FF_TRACE
+// Diagnostic build only (-DHN_FF_TRACE): cycles each role of CTA 0 spends blocked on each barrier, summed over the launch.
+__device__ unsigned long long hn_ff_trace[32];
+#define HN_FF_T0() const long long t0__ = clock64()
+#define HN_FF_ACC(slot) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&hn_ff_trace[slot], static_cast<unsigned long long>(clock64() - t0__)); } while (0)
+#define HN_FF_WAIT(slot, bar, par) do { HN_FF_T0(); mbar_wait(bar, par); HN_FF_ACC(slot); } while (0)
+#else
+#define HN_FF_WAIT(slot, bar, par) mbar_wait(bar, par)
+#endif
+
 template <typename TIn>
 __global__ void __launch_bounds__(kFfThreads, 1)
 front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]*/,
@@ -78,6 +88,9 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef HN_FF_TRACE
+  const long long hn_ff_start = clock64();
+#endif
 
   // ---------------------------------------------- one-time setup ----------------------------------------------
   if (warp == kFfIssuer) {
@@ -172,7 +185,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       const float mean = st_next.x, inv = st_next.y;
       if (stats != nullptr && patch + static_cast<int>(gridDim.x) < num_patches) st_next = __ldg(stats + patch + gridDim.x);
       const int d = it % kFfRawDepth;
-      mbar_wait(raw_full(d), (it / kFfRawDepth) & 1);
+      HN_FF_WAIT(0, raw_full(d), (it / kFfRawDepth) & 1);
       const TIn* src = reinterpret_cast<const TIn*>(gbase + (raw_addr0 - base) + d * 4096) + lane;
       // 30 branch-free shared-memory loads (clamped addresses, masked afterwards)
       float v[10][3];
@@ -196,7 +209,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       __syncwarp();
       if (lane == 0) mbar_arrive(raw_empty(d));   // the raw slot may be refilled
       // the stage-1 MMAs of the previous patch must have retired before A1 is overwritten
-      mbar_wait(a1_empty, (it & 1) ^ 1u);
+      HN_FF_WAIT(1, a1_empty, (it & 1) ^ 1u);
       // pixel (y, x): tile y / 4, row r = (y % 4) * 32 + x  ->  (r / 8) * 256 + (r % 8) * 16
       uint8_t* A = gbase + (a1_addr - base) + lw * 2 * 4096 + (lane >> 3) * 256 + (lane & 7) * 16;
 #pragma unroll
@@ -252,23 +265,23 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       const bool more = it + 1 < n_local;
       if (more) {
         // stage 1 of the NEXT patch is interleaved with the conv2 tiles of this one, so its epilogue overlaps them
-        mbar_wait(a1_full, (it + 1) & 1);
-        mbar_wait(l1_empty, 1);          // second half of patch `it` has been drained
+        HN_FF_WAIT(2, a1_full, (it + 1) & 1);
+        HN_FF_WAIT(3, l1_empty, 1);          // second half of patch `it` has been drained
         tc_fence_after();
         issue_l1_half(0);
       }
-      mbar_wait(act1_full(b), (it >> 1) & 1);
+      HN_FF_WAIT(4, act1_full(b), (it >> 1) & 1);
       tc_fence_after();
       const uint32_t act_lo = act_lo0 + b * (kFfAct1 >> 4);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         if (t == 4 && more) {
-          mbar_wait(l1_empty, 0);        // first half of patch `it + 1` has been drained
+          HN_FF_WAIT(5, l1_empty, 0);        // first half of patch `it + 1` has been drained
           tc_fence_after();
           issue_l1_half(1);
         }
         const int a = t & 3;             // 8 tiles per patch over 4 buffers: each buffer is used twice per patch
-        mbar_wait(c2_empty(a), ((t >> 2) & 1) ^ 1u);
+        HN_FF_WAIT(6, c2_empty(a), ((t >> 2) & 1) ^ 1u);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d = tm_c2 + a * 96;
@@ -294,7 +307,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
           const int ts = pass == 0 ? sh : (t == 7 ? 7 : -1);   // after the last tile also finish that tile itself
           if (ts < 0) continue;
           const int as = ts & 3;
-          mbar_wait(mma_done(as), (ts >> 2) & 1);
+          HN_FF_WAIT(7, mma_done(as), (ts >> 2) & 1);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t ds = tm_c2 + as * 96 + 64;
@@ -314,11 +327,11 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     int it = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
       const int b = it & 1;
-      mbar_wait(act1_empty(b), ((it >> 1) & 1) ^ 1u);
+      HN_FF_WAIT(8, act1_empty(b), ((it >> 1) & 1) ^ 1u);
       uint8_t* act = gbase + (act1_addr - base) + b * kFfAct1;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
-        mbar_wait(l1_full, half);
+        HN_FF_WAIT(9, l1_full, half);
         tc_fence_after();
 #pragma unroll 1
         for (int tq = 0; tq < 4; ++tq) {
@@ -358,7 +371,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         const int t = 2 * tt + g;
         const int a = t & 3;
         const uint32_t t_row = t_row0 + a * 96;
-        mbar_wait(c2_full(a), (t >> 2) & 1);
+        HN_FF_WAIT(10, c2_full(a), (t >> 2) & 1);
         tc_fence_after();
         // channel-planar parity layout for the stride-2 conv3: [plane][ypar][xpar][16][16][8]
         uint4* dst = reinterpret_cast<uint4*>(opatch) + planar_pixel_slot<32, true>(4 * t + q, lane);
@@ -403,6 +416,12 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
 
   tc_fence_before();
   __syncthreads();
+#ifdef HN_FF_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&hn_ff_trace[15], static_cast<unsigned long long>(clock64() - hn_ff_start));
+    atomicAdd(&hn_ff_trace[16], static_cast<unsigned long long>((num_patches + gridDim.x - 1) / gridDim.x));
+  }
+#endif
   if (warp == kFfIssuer) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

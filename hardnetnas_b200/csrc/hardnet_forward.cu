@@ -540,3 +540,15 @@ extern "C" int hn_profile_read(hn_handle* h, double ms_out[7], long long launche
   }
   return HN_OK;
 }
+
+#ifdef HN_FF_TRACE
+extern "C" int hn_debug_ff_trace(unsigned long long* out32, int reset) {
+  HN_CUDA(cudaDeviceSynchronize());
+  HN_CUDA(cudaMemcpyFromSymbol(out32, hn::hn_ff_trace, 32 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    HN_CUDA(cudaMemcpyToSymbol(hn::hn_ff_trace, z, sizeof(z)));
+  }
+  return HN_OK;
+}
+#endif
