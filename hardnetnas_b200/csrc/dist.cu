@@ -114,49 +114,45 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q
   const float inf = __int_as_float(0x7f800000);
   float b1 = inf, b2 = inf;
   int j1 = 0x7fffffff, j2 = 0x7fffffff;
-  const int total = slots * kChunk;
-  for (int c = lane; c < total; c += 32) {
-    const int chunk = cand[row * slots + c / kChunk];
-    const long long col = static_cast<long long>(chunk) * kChunk + (c % kChunk);
-    if (chunk < 0 || col >= ng || cand_val[row * slots + c / kChunk] < thr) continue;
-    const float4* gr = reinterpret_cast<const float4*>(g + col * 128);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-      const float4 a = reinterpret_cast<const float4*>(sq[w])[k];
-      const float4 b = __ldg(gr + k);
-      s0 = fmaf(a.x, b.x, s0);
-      s1 = fmaf(a.y, b.y, s1);
-      s2 = fmaf(a.z, b.z, s2);
-      s3 = fmaf(a.w, b.w, s3);
-    }
-    const float dot = (s0 + s1) + (s2 + s3);
-    const float d = sqrtf(fminf(fmaxf(2.0f - 2.0f * dot, 1e-8f), 4.0f));
-    const int ci = static_cast<int>(col);
-    if (d < b1 || (d == b1 && ci < j1)) {
-      b2 = b1; j2 = j1; b1 = d; j1 = ci;
-    } else if (d < b2 || (d == b2 && ci < j2)) {
-      b2 = d; j2 = ci;
-    }
-  }
-  // warp merge: best (d, idx) lexicographically, then the runner-up
-  float m = b1;
-  int mj = j1;
+  // The warp walks the surviving chunks together: a gallery row is ONE coalesced 512 B read (lane = float4 index) and
+  // the 128-term dot is finished with a butterfly, so every lane ends up with the same (d, index) stream. Per-lane
+  // row reads (one lane per candidate) cost 32 L1 wavefronts per row instead of 4.
+  const float4 qv = reinterpret_cast<const float4*>(sq[w])[lane];
+  for (int c = 0; c < slots; ++c) {
+    const int chunk = cand[row * slots + c];
+    if (chunk < 0 || cand_val[row * slots + c] < thr) continue;   // warp-uniform
+    const long long col0 = static_cast<long long>(chunk) * kChunk;
+    float part[kChunk];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, m, o);
-    const int oj = __shfl_xor_sync(0xffffffffu, mj, o);
-    if (od < m || (od == m && oj < mj)) { m = od; mj = oj; }
-  }
-  const bool winner = (j1 == mj) && (b1 == m);
-  float s = winner ? b2 : b1;
-  int sj = winner ? j2 : j1;
+    for (int r = 0; r < kChunk; ++r) {
+      const long long col = col0 + r;
+      part[r] = 0.f;
+      if (col < ng) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + col * 128) + lane);
+        part[r] = fmaf(qv.x, gv.x, fmaf(qv.y, gv.y, fmaf(qv.z, gv.z, qv.w * gv.w)));
+      }
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float od = __shfl_xor_sync(0xffffffffu, s, o);
-    const int oj = __shfl_xor_sync(0xffffffffu, sj, o);
-    if (od < s || (od == s && oj < sj)) { s = od; sj = oj; }
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < kChunk; ++r) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < kChunk; ++r) {
+      const long long col = col0 + r;
+      if (col >= ng) continue;
+      const float d = sqrtf(fminf(fmaxf(2.0f - 2.0f * part[r], 1e-8f), 4.0f));
+      const int ci = static_cast<int>(col);
+      if (d < b1 || (d == b1 && ci < j1)) {
+        b2 = b1; j2 = j1; b1 = d; j1 = ci;
+      } else if (d < b2 || (d == b2 && ci < j2)) {
+        b2 = d; j2 = ci;
+      }
+    }
   }
+  // every lane holds the same top-2 now
+  const float m = b1, s = b2;
+  const int mj = j1, sj = j2;
   if (lane == 0) {
     if (d1) d1[row] = m;
     if (i1) i1[row] = mj == 0x7fffffff ? -1 : static_cast<int>(mj + g_offset);
