@@ -36,8 +36,6 @@ struct hn_handle {
   hn::TcParams conv_params[5];
   hn::TcParams pair_params[5];   // same layers for the CTA-pair kernels (tc_conv_pair.cuh)
   unsigned pair_mask = 0;        // bit li: layer li runs on CTA pairs
-  hn::TcParams whole4_params;    // conv4, CTA pairs, whole-patch loads (conv3x3_pair_whole_kernel)
-  int whole4 = 1;
   hn::TcParams head_params;
   // optional per-stage CUDA-event timing (stage 0 = L1, 1..5 = 3x3 convs, 6 = head)
   unsigned profile_mask = 0;

@@ -93,24 +93,6 @@ static int launch_conv_pair_cfg(const TcParams& p, int sm_count, cudaStream_t st
   return HN_OK;
 }
 
-// conv4 on CTA pairs with one padded whole-patch load per channel chunk (tc_conv_pair.cuh)
-static int launch_conv4_whole(const TcParams& p, int sm_count, cudaStream_t stream) {
-  using C = PairWholeCfg<64, 64, 16, 4>;
-  auto kern = conv3x3_pair_whole_kernel<64, 64, 16, 4, true>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
-    attr_done = true;
-  }
-  const long long patches = p.total_rows / C::PIX;
-  if (patches <= 0) return HN_OK;
-  const int grid = 2 * static_cast<int>(std::min<long long>((patches + 1) / 2, sm_count / 2));
-  kern<<<grid, kTcThreads, C::SMEM, stream>>>(p);
-  HN_CUDA(cudaGetLastError());
-  count_launch();
-  return HN_OK;
-}
-
 // conv2 (li = 0) lives in the fused front kernel. OUT_PARITY: the consumer is a stride-2 conv and wants parity sub-planes.
 //                         CIN COUT HOUT STRIDE  G STAGES WRES  CTAs/SM ROWSHIFT OUT_PARITY
 #define HN_CONV_L3 launch_conv_cfg<32, 64, 16, 2, 1, 9, true, 2, false, false>
@@ -280,17 +262,6 @@ static int build_params(hn_handle* h) {
     HN_TRY(build_conv_params(h, li, kPairKcb[li], kPairRowShift[li], true, h->pair_params[li]));
   }
   {
-    // conv4 "whole patch" variant: same maps as the pair kernel except the A box = the zero-bordered 18 x 18 image
-    TcParams& p = h->whole4_params;
-    p = h->pair_params[2];
-    const ConvLayer& L = kConv[2];
-    const uint64_t C = L.cin, W = L.hin, H = L.hin;
-    const uint32_t box[4] = {static_cast<uint32_t>((L.hout + 2) * 8), static_cast<uint32_t>(L.hout + 2), 1u, 8u};
-    const uint64_t dims[4] = {W * 8, H, static_cast<uint64_t>(h->chunk), C / 8};
-    const uint64_t str[3] = {W * 16, C * H * W * 2, H * W * 16};
-    HN_TRY(make_tmap_16bit(&p.tmA[0], h->act[2 & 1], 4, dims, str, box, 0));
-  }
-  {
     TcParams& p = h->head_params;
     memset(&p, 0, sizeof(p));
     const uint64_t dimsA[2] = {kHeadK, static_cast<uint64_t>(h->head_rows)};
@@ -311,15 +282,13 @@ static int build_params(hn_handle* h) {
 static int run_one_conv(hn_handle* h, int li, int n, void* out, cudaStream_t s) {
   const ConvLayer& L = kConv[li];
   const bool pair = (h->pair_mask >> li) & 1;
-  const bool whole = li == 2 && h->whole4 && pair;
-  TcParams p = whole ? h->whole4_params : pair ? h->pair_params[li] : h->conv_params[li];
+  TcParams p = pair ? h->pair_params[li] : h->conv_params[li];
   const long long pix_out = static_cast<long long>(L.hout) * L.hout;
   p.total_rows = pix_out * n;
   p.num_tiles = static_cast<int>((p.total_rows + kTileM - 1) / kTileM);
   p.act_bf16 = h->act_bf16;
   p.out = out;
   StageTimer timer(h, li + 1, s);
-  if (whole) return launch_conv4_whole(p, h->sm_count, s);
   return pair ? launch_conv_pair(li, p, h->sm_count, s) : launch_conv(li, p, h->sm_count, s);
 }
 
@@ -378,8 +347,6 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
     h->front_chunk = e ? std::max(2, atoi(e)) : chunk_patches;
   }
   {
-    const char* wv = getenv("HN_CONV4_WHOLE");   // 1: conv4 with one whole-patch load per chunk (default), 0: band loads
-    h->whole4 = wv ? atoi(wv) : 1;
     const char* e = getenv("HN_PAIR_MASK");   // bit li: run 3x3 layer li (1 = conv3 .. 4 = conv6) on CTA pairs
     h->pair_mask = e ? static_cast<unsigned>(strtoul(e, nullptr, 0)) : kDefaultPairMask;
   }

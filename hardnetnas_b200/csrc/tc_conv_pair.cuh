@@ -322,208 +322,4 @@ conv3x3_pair_kernel(const __grid_constant__ TcParams p) {
   }
 }
 
-
-// ------------------------------------------------------------------------------------------------------------
-// "Whole patch" variant for stride-1 layers on 16 x 16 images (conv4): instead of three kx-shifted band loads per tile
-// (ROWSHIFT), ONE TMA box per patch and channel chunk brings in the whole image with a one-pixel zero border on every
-// side (box start (-1, -1), out-of-range = zero), i.e. shared memory holds [plane][18 rows][18 slots][16 B]. All nine
-// taps of BOTH tiles of the patch are then descriptor offsets into that image: a tile is a column half (16 rows x 8
-// columns), so that its 8-pixel core matrices sit one padded row (18 slots = SBO 288 B) apart. A third of the TMA bytes
-// written into shared memory per patch (41 KB instead of 120 KB) on a layer that is bound by the shared-memory pipe.
-template <int CIN, int COUT, int HOUT, int STAGES>
-struct PairWholeCfg {
-  static constexpr int KCB = (CIN >= 64) ? 128 : 64;
-  static constexpr int KC = KCB / 2, CIN_CHUNKS = CIN / KC, NPL = KC / 8, KB = 9 * CIN_CHUNKS, PIX = HOUT * HOUT;
-  static constexpr int P = HOUT + 2;                                    // padded pitch in slots
-  static constexpr uint32_t PLANE_BYTES = P * P * 16;
-  static constexpr uint32_t A_BYTES = NPL * PLANE_BYTES;
-  static constexpr uint32_t BH_BYTES = (COUT / 2) * KCB;
-  static constexpr uint32_t W_BYTES = KB * BH_BYTES;
-  static constexpr uint32_t STAGE_BYTES = A_BYTES;
-  static constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * COUT);        // two tiles per pass, two passes in flight
-  static constexpr size_t SMEM = size_t(W_BYTES) + size_t(STAGES) * STAGE_BYTES + 1024 + 256 + COUT * 4;
-  static_assert(HOUT == 16, "a tile is 16 rows x 8 columns: two column halves of a 16 x 16 image");
-  static_assert(BH_BYTES % 1024 == 0 && W_BYTES % 1024 == 0, "swizzled weight tiles must stay 1024B aligned");
-  static_assert(A_BYTES % 128 == 0 && 4 * COUT <= 512, "operand / accumulator budget");
-  static_assert(SMEM <= 227 * 1024, "shared memory budget");
-};
-
-template <int CIN, int COUT, int HOUT, int STAGES, bool OUT_PARITY>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-conv3x3_pair_whole_kernel(const __grid_constant__ TcParams p) {
-  using C = PairWholeCfg<CIN, COUT, HOUT, STAGES>;
-  constexpr int N = COUT;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  const uint32_t w_base = base;
-  const uint32_t ring_base = base + C::W_BYTES;
-  const uint32_t bar_base = ring_base + STAGES * C::STAGE_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t w_bar = bar_base + 8u * (2 * STAGES + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const long long total_patches = p.total_rows / C::PIX;
-  const int num_groups = static_cast<int>((total_patches + 1) / 2);   // a pass of the pair covers two patches
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA[0]);
-    tma_prefetch_desc(&p.tmB);
-  }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
-        mbar_init(full_bar(s), 2);
-        mbar_init(empty_bar(s), 1);
-      }
-      for (int a = 0; a < 2; ++a) {
-        mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), 8);
-      }
-      mbar_init(w_bar, 2);
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish_pair();
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < N; i += 128) s_bias[i] = p.bias[i];
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-
-  if (warp == 0) {
-    // ============================== TMA producer (both CTAs) ==============================
-    const uint32_t lead_w_bar = mapa_cluster(w_bar, 0);
-    if (elect_one()) {
-      mbar_arrive_expect_tx_cluster(lead_w_bar, C::W_BYTES);
-#pragma unroll 1
-      for (int kb = 0; kb < C::KB; ++kb)
-        tma_load_2d_pair(w_base + kb * C::BH_BYTES, &p.tmB, lead_w_bar, kb * C::KC, static_cast<int>(rank) * (COUT / 2));
-    }
-    __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int grp = pair; grp < num_groups; grp += num_pairs) {
-      const int patch = grp * 2 + static_cast<int>(rank);   // past the end: the box is out of range and reads as zeros
-#pragma unroll 1
-      for (int cc = 0; cc < C::CIN_CHUNKS; ++cc) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (elect_one()) {
-          const uint32_t lead_full = mapa_cluster(full_bar(stage), 0);
-          mbar_arrive_expect_tx_cluster(lead_full, C::STAGE_BYTES);
-          tma_load_4d_pair(ring_base + stage * C::STAGE_BYTES, &p.tmA[0], lead_full, -8, -1, patch, cc * C::NPL);
-        }
-        __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    // ============================== UMMA issuer (leader CTA only) ==============================
-    if (rank == 0) {
-      const uint32_t idesc = make_idesc_f16(2 * kTileM, N, p.act_bf16);
-      constexpr uint32_t A_HI = noswizzle_desc_hi(C::P * 16);
-      constexpr uint32_t B_HI = kmajor_desc_hi(C::KCB);
-      const uint32_t ring_a_lo = noswizzle_desc_lo(ring_base, C::PLANE_BYTES);
-      const uint32_t w_lo = kmajor_desc_lo(w_base);
-      mbar_wait(w_bar, 0);
-      tc_fence_after();
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int grp = pair; grp < num_groups; grp += num_pairs, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < C::CIN_CHUNKS; ++cc) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_lo = ring_a_lo + static_cast<uint32_t>(stage) * (C::STAGE_BYTES >> 4);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t d_tmem = tmem_base + acc * (2 * N) + h * N;
-#pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                const int ky = tap / 3, kx = tap % 3;
-#pragma unroll
-                for (int k = 0; k < C::KCB / 32; ++k)
-                  umma_f16_pair_w(d_tmem, a_lo + (((ky * C::P + 8 * h + kx) * 16 + 2 * k * C::PLANE_BYTES) >> 4), A_HI,
-                                  w_lo + (((tap * C::CIN_CHUNKS + cc) * C::BH_BYTES) >> 4) + 2 * k, B_HI, idesc,
-                                  (cc | tap | k) != 0);
-              }
-            }
-            umma_commit_pair(empty_bar(stage));
-            if (cc == C::CIN_CHUNKS - 1) umma_commit_pair(tfull_bar(acc));
-          }
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-  } else {
-    // ============================== epilogue (both CTAs, each its own patch) ==============================
-    const int q = warp & 3;
-    const int row_in_tile = q * 32 + lane;
-    const uint32_t lead_tempty[2] = {mapa_cluster(tempty_bar(0), 0), mapa_cluster(tempty_bar(1), 0)};
-    int it = 0;
-    for (int grp = pair; grp < num_groups; grp += num_pairs, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const long long patch = static_cast<long long>(grp) * 2 + rank;
-      const bool valid = patch < total_patches;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (2 * N) + h * N;
-        const int y = row_in_tile >> 3, x = 8 * h + (row_in_tile & 7);   // tile = column half h
-        const int slot = planar_pixel_slot<HOUT, OUT_PARITY>(y, x);
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + patch * (static_cast<long long>(N) * C::PIX)) + slot;
-#pragma unroll
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(t_row + c0, r);
-          tmem_ld_wait();
-          uint32_t o[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            o[j] = pack16_relu(__uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], __uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1],
-                               p.act_bf16);
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[(c0 / 8 + j) * C::PIX] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_tempty[acc]);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
-  }
-}
-
 }  // namespace hn
