@@ -37,7 +37,7 @@ constexpr uint32_t kFfW2 = 3 * kFfW2Tap;      // 18 432 B
 constexpr uint32_t kFfW1 = 1024;
 constexpr int kFfRawDepth = 4;                 // raw input patches prefetched ahead of the loaders (bulk async copies)
 constexpr uint32_t kFfRaw = kFfRawDepth * 4096;
-constexpr size_t kFfSmem = kFfA1 + 2 * kFfAct1 + kFfW2 + kFfW1 + kFfRaw + 256 /*barriers*/ + 256 /*biases*/ + 1024 /*align*/;
+constexpr size_t kFfSmem = kFfA1 + 2 * kFfAct1 + kFfW2 + kFfW1 + kFfRaw + 256 /*barriers*/ + 256 /*biases + reductions*/ + 1024 /*align*/;
 static_assert(kFfSmem <= 227 * 1024, "smem budget");
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kFfThreads, 1)
 front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]*/,
                    const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
                    const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
-                   const float* __restrict__ bias2 /*[32]*/, const float2* __restrict__ stats /*null: no normalisation*/,
+                   const float* __restrict__ bias2 /*[32]*/, int do_norm /*0: no input normalisation*/,
                    int num_patches, int act_bf16) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -176,14 +176,11 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     };
     if (lw == 0 && lane == 0)
       for (int j = 0; j < kFfRawDepth - 1 && j < n_loc; ++j) prefetch(j);
-    float2 st_next = make_float2(0.f, 1.f);
-    if (stats != nullptr && n_loc > 0) st_next = __ldg(stats + blockIdx.x);
+    float* s_red = reinterpret_cast<float*>(gbase + (bar_base + 384 - base));   // [sum | sum of squares][patch parity][4 warps]
     int it = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
       if (lw == 0 && lane == 0 && it + kFfRawDepth - 1 < n_loc) prefetch(it + kFfRawDepth - 1);
       __syncwarp();
-      const float mean = st_next.x, inv = st_next.y;
-      if (stats != nullptr && patch + static_cast<int>(gridDim.x) < num_patches) st_next = __ldg(stats + patch + gridDim.x);
       const int d = it % kFfRawDepth;
       HN_FF_WAIT(0, raw_full(d), (it / kFfRawDepth) & 1);
       const TIn* src = reinterpret_cast<const TIn*>(gbase + (raw_addr0 - base) + d * 4096) + lane;
@@ -197,6 +194,29 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         v[r][0] = static_cast<float>(row[xl]);
         v[r][1] = static_cast<float>(row[0]);
         v[r][2] = static_cast<float>(row[xr]);
+      }
+      // HardNet.input_norm (hardnet/HardNet.py:306-310): per-patch mean and unbiased std + 1e-7, fused into this load.
+      // Every partial sum is a balanced pairwise tree (8 values per lane, xor butterfly over the warp, 2 x 2 warps), so a
+      // constant patch has mean == value exactly and normalises to exactly 0, like the reference's 0 / 1e-7.
+      float mean = 0.f, inv = 1.f;
+      if (do_norm) {
+        float* red = s_red + (it & 1) * 4;
+        float s8 = ((v[1][1] + v[2][1]) + (v[3][1] + v[4][1])) + ((v[5][1] + v[6][1]) + (v[7][1] + v[8][1]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s8 += __shfl_xor_sync(0xffffffffu, s8, o);
+        if (lane == 0) red[lw] = s8;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mean = ((red[0] + red[1]) + (red[2] + red[3])) * (1.f / 1024.f);
+        float dq[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { const float dd = v[r + 1][1] - mean; dq[r] = dd * dd; }
+        float q8 = ((dq[0] + dq[1]) + (dq[2] + dq[3])) + ((dq[4] + dq[5]) + (dq[6] + dq[7]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q8 += __shfl_xor_sync(0xffffffffu, q8, o);
+        if (lane == 0) red[8 + lw] = q8;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float var = ((red[8] + red[9]) + (red[10] + red[11])) * (1.f / 1023.f);   // torch.std is unbiased
+        inv = 1.f / (sqrtf(var) + 1e-7f);
       }
 #pragma unroll
       for (int r = 0; r < 10; ++r) {

@@ -169,19 +169,16 @@ static int launch_front_fused(hn_handle* h, const void* patches, int in_dtype, u
   }
   if (n <= 0) return HN_OK;
   const int grid = std::min(n, h->sm_count);
-  const int sgrid = std::min((n + 7) / 8, h->sm_count * 8);
   const uint4* w2 = reinterpret_cast<const uint4*>(h->w2img);
   if (in_dtype == HN_F32) {
     const float* x = static_cast<const float*>(patches);
-    patch_stats_kernel<float><<<sgrid, 256, 0, s>>>(x, h->stats, n);
-    front_fused_kernel<float><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, h->bias + 128, h->stats, n, h->act_bf16);
+    front_fused_kernel<float><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, h->bias + 128, 1, n, h->act_bf16);
   } else {
     const uint8_t* x = static_cast<const uint8_t*>(patches);
-    patch_stats_kernel<uint8_t><<<sgrid, 256, 0, s>>>(x, h->stats, n);
-    front_fused_kernel<uint8_t><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, h->bias + 128, h->stats, n, h->act_bf16);
+    front_fused_kernel<uint8_t><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, h->bias + 128, 1, n, h->act_bf16);
   }
   HN_CUDA(cudaGetLastError());
-  count_launch(2);
+  count_launch(1);
   return HN_OK;
 }
 
