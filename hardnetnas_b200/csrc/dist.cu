@@ -172,11 +172,10 @@ template <int MB, int EPI>
 static int launch_dist(const DistParams& p, int grid_x, int grid_y, cudaStream_t s) {
   auto kern = dist_kernel<MB, EPI>;
   const size_t smem = dist_smem_bytes<MB>(p.k_blocks);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_smem = smem;
-  }
+  // the size depends on k_blocks (MB = 1: up to 6 for the 3-way split, MB = 2: always 2): raise the limit once per device
+  static DeviceOnce attr_once;
+  if (attr_once.first_time())
+    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dist_smem_bytes<MB>(MB == 1 ? 6 : 2))));
   kern<<<dim3(grid_x, grid_y), 64 + 128 * MB, smem, s>>>(p);
   HN_CUDA(cudaGetLastError());
   count_launch();
@@ -352,10 +351,9 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
     const int pairs = std::max(sm / 2, 1);
     dp.segments = pick_segments(Nq, 4 * kDistTile, Ng, pairs, 16);
     const long long items = ((Nq + 4 * kDistTile - 1) / (4 * kDistTile)) * dp.segments;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static DeviceOnce attr_once;
+    if (attr_once.first_time()) {
       HN_CUDA(cudaFuncSetAttribute(match_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMpSmem)));
-      attr_done = true;
     }
     match_pair_kernel<<<2 * static_cast<int>(std::min<long long>(items, pairs)), 64 + 256, kMpSmem, s>>>(dp);
     HN_CUDA(cudaGetLastError());

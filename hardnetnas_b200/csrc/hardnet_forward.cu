@@ -62,10 +62,9 @@ template <int CIN, int COUT, int HOUT, int STRIDE, int G, int STAGES, bool WRES,
 static int launch_conv_cfg(const TcParams& p, int sm_count, cudaStream_t stream) {
   using C = ConvCfg<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, ROWSHIFT, TILES, KCB_>;
   auto kern = conv3x3_kernel<CIN, COUT, HOUT, STRIDE, G, STAGES, WRES, MINB, ROWSHIFT, OUT_PARITY, TILES, KCB_>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static DeviceOnce attr_once;  // per instantiation
+  if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
-    attr_done = true;
   }
   if (p.num_tiles <= 0) return HN_OK;
   const int grid = std::min((p.num_tiles + TILES - 1) / TILES, sm_count * MINB);
@@ -79,10 +78,9 @@ template <int CIN, int COUT, int HOUT, int STRIDE, int STAGES, bool ROWSHIFT, bo
 static int launch_conv_pair_cfg(const TcParams& p, int sm_count, cudaStream_t stream) {
   using C = PairCfg<CIN, COUT, HOUT, STRIDE, STAGES, ROWSHIFT, KCB_>;
   auto kern = conv3x3_pair_kernel<CIN, COUT, HOUT, STRIDE, STAGES, ROWSHIFT, OUT_PARITY, KCB_>;
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
+  static DeviceOnce attr_once;  // per instantiation
+  if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
-    attr_done = true;
   }
   if (p.num_tiles <= 0) return HN_OK;
   const int groups = (p.num_tiles + 1) / 2;
@@ -136,11 +134,10 @@ static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) 
 // Stage 1 (input_norm + conv 1->32 + BN + ReLU) on the tensor core; do_norm = 0 gives the NAS stem.
 int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, float2* stats, int n,
               int act_bf16, int sm_count, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(l1_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kL1TcSmem)));
     HN_CUDA(cudaFuncSetAttribute(l1_tc_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kL1TcSmem)));
-    attr_done = true;
   }
   if (n <= 0) return HN_OK;
   const int grid = std::min(n, sm_count);
@@ -161,11 +158,10 @@ int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, 
 
 // Stage 1 + conv2 fused (front_fused.cuh): patches -> conv2 output (NHWC 16-bit), stage-1 activation stays on chip.
 static int launch_front_fused(hn_handle* h, const void* patches, int in_dtype, uint16_t* out, int n, cudaStream_t s) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(front_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFfSmem)));
     HN_CUDA(cudaFuncSetAttribute(front_fused_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFfSmem)));
-    attr_done = true;
   }
   if (n <= 0) return HN_OK;
   const int grid = std::min(n, h->sm_count);
@@ -183,11 +179,10 @@ static int launch_front_fused(hn_handle* h, const void* patches, int in_dtype, u
 }
 
 int launch_head(const TcParams& p, int sm_count, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(gemm_l2norm_kernel<kHeadN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(kHeadSmem)));
-    attr_done = true;
   }
   if (p.num_tiles <= 0) return HN_OK;
   gemm_l2norm_kernel<kHeadN><<<std::min(p.num_tiles, sm_count), kTcThreads, kHeadSmem, stream>>>(p);

@@ -52,6 +52,20 @@ int make_tmap_16bit(CUtensorMap* tm, const void* base, int rank, const uint64_t*
 
 int device_sm_count(int* out);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember per kernel instantiation (one static
+// DeviceOnce per call site) on which devices it has been raised, so one process may drive several GPUs.
+struct DeviceOnce {
+  unsigned long long done[2] = {0, 0};   // up to 128 devices
+  bool first_time() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return true;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done[dev >> 6] & bit) return false;
+    done[dev >> 6] |= bit;
+    return true;
+  }
+};
+
 // Number of kernels this library has launched (reported by bench.py as gpu_launches).
 void count_launch(int n = 1);
 long long launch_count();

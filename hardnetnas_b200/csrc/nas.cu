@@ -477,10 +477,9 @@ template <int NT, int KCB>
 static int launch_pw_cfg(const PwParams& p, int sm_count, cudaStream_t s) {
   auto kern = pw_gemm_kernel<NT, KCB>;
   constexpr size_t smem = pw_smem_bytes<NT, KCB>();
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_done = true;
   }
   if (p.num_tiles <= 0) return HN_OK;
   kern<<<std::min(p.num_tiles, sm_count), kTcThreads, smem, s>>>(p);

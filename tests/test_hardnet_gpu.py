@@ -178,3 +178,25 @@ def test_single_cta_and_cta_pair_conv_kernels(mask, monkeypatch):
     x = synth.make_patches(333, 31, edge_cases=False)
     max_abs, cos = _cmp(model(x.cuda()), hardnet_oracle.hardnet_forward(x, w, m, v))
     assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (mask, max_abs, cos)
+
+
+def test_second_gpu_in_the_same_process():
+    """Kernel attributes (dynamic shared memory limits) are per device: a process may use more than one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    model0, (w, m, v) = _model(3)
+    x = synth.make_patches(200, 41, edge_cases=False)
+    ref = hardnet_oracle.hardnet_forward(x, w, m, v)
+    d0 = model0(x.cuda(0))
+    model1, _ = _model(3)
+    model1 = model1.to("cuda:1")
+    d1 = model1(x.to("cuda:1"))
+    for d in (d0, d1):
+        max_abs, cos = _cmp(d, ref)
+        assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS
+    from hardnetnas_b200.matching import match_top2
+    q, g, _ = synth.make_match_set(300, 900, seed=4)
+    a = [t.cpu() for t in match_top2(q.cuda(0), g.cuda(0))]
+    b = [t.cpu() for t in match_top2(q.to("cuda:1"), g.to("cuda:1"))]
+    for s, t in zip(a, b):
+        assert torch.equal(s, t)
