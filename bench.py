@@ -72,6 +72,26 @@ def cpu_reference_throughput(sample: int, repeats: int = 1):
     return sample / best, best
 
 
+def cpu_side_baselines():
+    """The oracle port of the other two hot-path pieces on the host cores (bounded samples): loss_HardNet at N = 1024
+    (hardnet/Losses.py:87-154) and NN + ratio matching of an 8192-query chunk against 65 536 gallery rows
+    (FDLNet-master/utils/eval_utils.py:113-114,168-175; the reference's full-row sort is replaced by top-2)."""
+    from oracle import losses_oracle, synth
+    a = synth.unit_vectors(1024, 128, 3)
+    p = torch.nn.functional.normalize(a + 0.3 * synth.unit_vectors(1024, 128, 4), dim=1)
+    losses_oracle.loss_hardnet(a, p, True)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        losses_oracle.loss_hardnet(a, p, True)
+    loss_ms = (time.perf_counter() - t0) / 10 * 1e3
+    q, g, _ = synth.make_match_set(8192, 65536, seed=11)
+    t0 = time.perf_counter()
+    losses_oracle.ratio_match(q, g, 0.7)
+    match_s = time.perf_counter() - t0
+    return {"loss_hardnet_n1024_ms": loss_ms, "match_8192x65536_s": match_s,
+            "match_pairs_per_sec": 8192 * 65536 / match_s}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -314,6 +334,7 @@ def run_b200(args):
         v, t = cpu_reference_throughput(sample)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"{sample} patches ({t:.1f} s), oracle/hardnet_oracle.py (torch CPU fp32 restatement of the reference forward)"}
+        cpu_baseline.update(cpu_side_baselines())
 
     if rank == 0:
         line = {
