@@ -267,7 +267,7 @@ extern "C" long long hn_dist_workspace_bytes(long long Na, long long Np, int spl
   (void)split;
   ExactWs w = carve_exact(nullptr, Na, Np);
   const size_t shortlist = align256(static_cast<size_t>(Na) * 128 * 2) + align256(static_cast<size_t>(Np) * 128 * 2) +
-                           2 * align256(static_cast<size_t>(Na) * 16 * kTopC * 4);
+                           2 * align256(static_cast<size_t>(Na) * 32 * kTopC * 4);
   return static_cast<long long>(std::max(w.bytes, shortlist) + 256);
 }
 
@@ -327,7 +327,7 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   uint16_t* q16 = reinterpret_cast<uint16_t*>(b);
   uint16_t* g16 = reinterpret_cast<uint16_t*>(b + align256(static_cast<size_t>(Nq) * 256));
   int* cand = reinterpret_cast<int*>(b + align256(static_cast<size_t>(Nq) * 256) + align256(static_cast<size_t>(Ng) * 256));
-  float* cand_val = reinterpret_cast<float*>(reinterpret_cast<char*>(cand) + align256(static_cast<size_t>(Nq) * 16 * kTopC * 4));
+  float* cand_val = reinterpret_cast<float*>(reinterpret_cast<char*>(cand) + align256(static_cast<size_t>(Nq) * 32 * kTopC * 4));
   const int threads = 256;
   pack_desc_kernel<<<static_cast<unsigned>((Nq * 32 + threads - 1) / threads), threads, 0, s>>>(q, Nq, q16, 0, 0, nullptr);
   pack_desc_kernel<<<static_cast<unsigned>((Ng * 32 + threads - 1) / threads), threads, 0, s>>>(g, Ng, g16, 0, 1, nullptr);
@@ -355,7 +355,7 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
     if (attr_once.first_time()) {
       HN_CUDA(cudaFuncSetAttribute(match_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMpSmem)));
     }
-    match_pair_kernel<<<2 * static_cast<int>(std::min<long long>(items, pairs)), 64 + 256, kMpSmem, s>>>(dp);
+    match_pair_kernel<<<2 * static_cast<int>(std::min<long long>(items, pairs)), kMpThreads, kMpSmem, s>>>(dp);
     HN_CUDA(cudaGetLastError());
     count_launch();
   } else {
@@ -366,8 +366,9 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   // |fp16-operand dot - exact dot| <= 2^-10 for rows of norm <= 1 (L2-normalised descriptors, the only input this path
   // is defined for: FDLNet-master/utils/math_utils.py:15-18 clamps 2 - 2ab to [1e-8, 4]); keep 4x that as the margin.
   const float margin = 4.0f * (1.0f / 1024.0f) / kDotScale;
-  rerank_kernel<<<static_cast<unsigned>((Nq + 3) / 4), 128, 0, s>>>(q, g, cand, cand_val, margin, Nq, Ng, dp.segments * kTopC,
-                                                                   g_offset, d1, d2, i1, i2);
+  // the CTA-pair kernel keeps two top-kTopC lists per row and segment (one per 64-column half of its tiles)
+  rerank_kernel<<<static_cast<unsigned>((Nq + 3) / 4), 128, 0, s>>>(q, g, cand, cand_val, margin, Nq, Ng,
+                                                                   dp.segments * kTopC * (use_pair ? 2 : 1), g_offset, d1, d2, i1, i2);
   HN_CUDA(cudaGetLastError());
   count_launch(3);
   return HN_OK;

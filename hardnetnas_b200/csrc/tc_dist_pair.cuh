@@ -17,8 +17,13 @@ constexpr uint32_t kMpABlk = kDistTile * 128;      // one 128-row x 64-element A
 constexpr uint32_t kMpBBlk = 64 * 128;             // this CTA's 64-row x 64-element half of a B k-block
 constexpr uint32_t kMpStage = 2 * kMpBBlk;         // both k-blocks of a half tile
 constexpr size_t kMpSmem = 4 * kMpABlk + kMpStages * kMpStage + 1024 + 256;
+// The epilogue (per row: maxima of sixteen 8-column chunks per tile + a sorted insert) is the longest step per tile, so
+// every 32-row lane quarter of an accumulator is shared by TWO warps, each reducing 64 of the 128 columns into its own
+// top-kTopC list (the lists of the two halves are separate slots of the candidate table).
+constexpr int kMpEpiWarps = 16;
+constexpr int kMpThreads = 64 + kMpEpiWarps * 32;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256, 1) match_pair_kernel(const __grid_constant__ DistParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMpThreads, 1) match_pair_kernel(const __grid_constant__ DistParams p) {
   constexpr int MB = 2;
   const DistSide& sd = p.side[0];
   extern __shared__ uint8_t smem_raw[];
@@ -61,7 +66,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256, 1) match_p
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);    // multicast tcgen05.commit
-        mbar_init(tempty_bar(a), 16);  // eight epilogue warps of each CTA (leader's copy)
+        mbar_init(tempty_bar(a), 2 * kMpEpiWarps);  // the epilogue warps of both CTAs (leader's copy)
       }
       mbar_init(afull_bar, 2);
       mbar_init(aempty_bar, 1);        // multicast tcgen05.commit
@@ -160,7 +165,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256, 1) match_p
   } else {
     // ============================== epilogue (both CTAs): top-kTopC chunks per row ==============================
     const int q = warp & 3;
-    const int mb = (warp - 2) >> 2;
+    const int mb = (warp - 2) >> 3;          // M-block of this CTA
+    const int half = ((warp - 2) >> 2) & 1;  // which 64 of the tile's 128 columns
     int it = 0;
     for (int item = pair; item < num_items; item += num_pairs) {
       const int mblk = item / p.segments, seg = item - mblk * p.segments;
@@ -176,17 +182,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256, 1) match_p
       for (int t = t0; t < t1; ++t, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        const long long col0 = static_cast<long long>(t) * kDistTile;
+        const long long col0 = static_cast<long long>(t) * kDistTile + half * 64;
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * MB + mb) * kDistTile;
-        const bool ragged = col0 + kDistTile > sd.Nb;
-        uint32_t r[4][32];
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * MB + mb) * kDistTile + half * 64;
+        const bool ragged = col0 + 64 > sd.Nb;
+        uint32_t r[2][32];
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) tmem_ld32(t_row + gq * 32, r[gq]);
+        for (int gq = 0; gq < 2; ++gq) tmem_ld32(t_row + gq * 32, r[gq]);
         tmem_ld_wait();
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
+        for (int gq = 0; gq < 2; ++gq) {
           const int c0 = gq * 32;
           float v[32];
 #pragma unroll
@@ -215,10 +221,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256, 1) match_p
         if (lane == 0) mbar_arrive_cluster(acc ? lead_tempty1 : lead_tempty0);
       }
       if (row_ok) {
-        int4* dst = reinterpret_cast<int4*>(sd.cand + (row * p.segments + seg) * kTopC);
+        int4* dst = reinterpret_cast<int4*>(sd.cand + ((row * p.segments + seg) * 2 + half) * kTopC);
         *dst = make_int4(tb[0] > -3.0e38f ? tc[0] : -1, tb[1] > -3.0e38f ? tc[1] : -1, tb[2] > -3.0e38f ? tc[2] : -1,
                          tb[3] > -3.0e38f ? tc[3] : -1);
-        *reinterpret_cast<float4*>(sd.cand_val + (row * p.segments + seg) * kTopC) = make_float4(tb[0], tb[1], tb[2], tb[3]);
+        *reinterpret_cast<float4*>(sd.cand_val + ((row * p.segments + seg) * 2 + half) * kTopC) = make_float4(tb[0], tb[1], tb[2], tb[3]);
       }
     }
   }
