@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -351,6 +352,127 @@ __global__ void __launch_bounds__(256) dw_conv_strip_kernel(const uint16_t* __re
   }
 }
 
+// Depthwise conv through shared memory. A patch's NHWC map is contiguous in HBM, so a unit of G consecutive patches is
+// ONE bulk async copy into a two-deep shared-memory ring (the copy of unit u+1 runs under the arithmetic of unit u) and
+// every input byte crosses HBM -> L2 -> SM exactly once. A thread owns 8 channels x a VERTICAL strip of SH output rows
+// at one output column; consecutive threads walk (channel group, column), so a warp's 16-byte shared loads and its
+// 16-byte global stores are contiguous. Per kx the K weight vectors sit in registers and the (SH-1)*S+K input rows are
+// loaded once each. Out-of-image taps read a clamped address and are zeroed by select - no divergent branches.
+template <int K, int S, int SH>
+__global__ void __launch_bounds__(256) dw_conv_smem_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                           const float* __restrict__ w /*[k*k][C]*/,
+                                                           const float* __restrict__ bias, int patches, int C, int hin,
+                                                           int hout, int G, int relu, int bf16) {
+  extern __shared__ __align__(128) uint8_t dw_smem[];
+  constexpr int PAD = K >> 1;
+  constexpr int NR = (SH - 1) * S + K;         // input rows a strip touches
+  const int cg = C >> 3;
+  const int map_elems = hin * hin * C;
+  const uint32_t unit_bytes = static_cast<uint32_t>(G) * map_elems * 2;
+  float* s_w = reinterpret_cast<float*>(dw_smem);                    // [K*K][C] weights, then [C] bias
+  const int w_floats = (K * K + 1) * C;
+  const uint32_t buf_off = (static_cast<uint32_t>(w_floats) * 4 + 127) & ~127u;
+  const uint32_t bar0 = smem_u32(dw_smem + buf_off + 2 * unit_bytes);
+  for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_w[K * K * C + i] = bias[i];
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int units = (patches + G - 1) / G;
+  auto issue = [&](int u, int slot) {          // one thread: bulk copy of unit u (the tail unit may hold fewer patches)
+    const int np = min(G, patches - u * G);
+    const uint32_t bytes = static_cast<uint32_t>(np) * map_elems * 2;
+    const uint32_t bar = bar0 + 8 * slot;
+    mbar_arrive_expect_tx(bar, bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + static_cast<size_t>(u) * unit_bytes;
+    const uint32_t dst = smem_u32(dw_smem + buf_off + slot * unit_bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768) {
+      const uint32_t n = min(32768u, bytes - o);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + o),
+                   "l"(src + o), "r"(n), "r"(bar)
+                   : "memory");
+    }
+  };
+  if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < units) issue(blockIdx.x, 0);
+  const int strips = hout / SH;
+  const int items_per_patch = strips * hout * cg;
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int slot = it & 1;
+    if (threadIdx.x == 0 && u + static_cast<int>(gridDim.x) < units) issue(u + gridDim.x, slot ^ 1);
+    mbar_wait(bar0 + 8 * slot, (it >> 1) & 1);
+    const uint16_t* buf = reinterpret_cast<const uint16_t*>(dw_smem + buf_off + slot * unit_bytes);
+    const int np = min(G, patches - u * G);
+    for (int e = threadIdx.x; e < np * items_per_patch; e += blockDim.x) {
+      const int c8 = (e % cg) * 8;
+      int t = e / cg;
+      const int ox = t % hout;
+      t /= hout;
+      const int ys = t % strips;
+      const int pl = t / strips;
+      const uint16_t* map = buf + pl * map_elems + c8;
+      float2 acc[SH][4];
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(s_w + K * K * C + c8);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_w + K * K * C + c8 + 4);
+#pragma unroll
+        for (int j = 0; j < SH; ++j) {
+          acc[j][0] = make_float2(b0.x, b0.y); acc[j][1] = make_float2(b0.z, b0.w);
+          acc[j][2] = make_float2(b1.x, b1.y); acc[j][3] = make_float2(b1.z, b1.w);
+        }
+      }
+      const int iy0 = ys * SH * S - PAD;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int ix = ox * S + kx - PAD;
+        const bool x_ok = ix >= 0 && ix < hin;
+        const int ixc = min(max(ix, 0), hin - 1);
+        float2 wk[K][4];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const float* wp = s_w + (ky * K + kx) * C + c8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);
+          const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+          wk[ky][0] = make_float2(w0.x, w0.y); wk[ky][1] = make_float2(w0.z, w0.w);
+          wk[ky][2] = make_float2(w1.x, w1.y); wk[ky][3] = make_float2(w1.z, w1.w);
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int iy = iy0 + r;
+          const bool ok = x_ok && iy >= 0 && iy < hin;
+          const int iyc = min(max(iy, 0), hin - 1);
+          uint4 xv = *reinterpret_cast<const uint4*>(map + (iyc * hin + ixc) * C);
+          if (!ok) xv = make_uint4(0u, 0u, 0u, 0u);
+          const float2 x[4] = {unpack16(xv.x, bf16), unpack16(xv.y, bf16), unpack16(xv.z, bf16), unpack16(xv.w, bf16)};
+#pragma unroll
+          for (int j = 0; j < SH; ++j) {
+            const int ky = r - j * S;          // compile-time after unrolling
+            if (ky >= 0 && ky < K) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[j][q] = __ffma2_rn(x[q], wk[ky][q], acc[j][q]);
+            }
+          }
+        }
+      }
+      uint16_t* optr = out + ((static_cast<size_t>(u) * G + pl) * hout + ys * SH) * hout * C + ox * C + c8;
+#pragma unroll
+      for (int j = 0; j < SH; ++j) {
+        if (relu) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[j][q] = make_float2(fmaxf(acc[j][q].x, 0.f), fmaxf(acc[j][q].y, 0.f));
+        }
+        *reinterpret_cast<uint4*>(optr + static_cast<size_t>(j) * hout * C) =
+            make_uint4(pack16(acc[j][0].x, acc[j][0].y, bf16), pack16(acc[j][1].x, acc[j][1].y, bf16),
+                       pack16(acc[j][2].x, acc[j][2].y, bf16), pack16(acc[j][3].x, acc[j][3].y, bf16));
+      }
+    }
+    __syncthreads();                           // every thread is done with this slot before it is refilled
+  }
+}
+
 // MaxPool2d(kernel 3, stride 2, padding 1): padding never wins (implicit -inf), like torch
 __global__ void __launch_bounds__(256) maxpool_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                                                       long long patches, int C, int hin, int hout, int bf16) {
@@ -504,6 +626,11 @@ static int launch_pw(const PwParams& p, int nt, int kcb, int sm_count, cudaStrea
 
 
 namespace hn {
+static bool dw_via_smem() {                    // HN_NAS_DW_SMEM=0 selects the register-strip kernel (A/B measurements, tests)
+  const char* e = std::getenv("HN_NAS_DW_SMEM");
+  return !(e && e[0] == '0');
+}
+
 // Runs ops [0, last_op] of the packed program for `n` patches (n <= chunk).
 static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype, int n, long long off, int last_op,
                        cudaStream_t s) {
@@ -531,6 +658,36 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
             uint16_t* dst = st->slot[o.dst];
             const float* wv = st->params + o.w_off;
             const float* bv = st->params + o.b_off;
+            // shared-memory kernel whenever two units of whole maps fit next to the weights (every shape of SEARCH_SPACE2
+            // with expansion 1); wider expansions fall through to the register-strip kernel below
+            if (strip && dw_via_smem()) {
+              const size_t map_bytes = static_cast<size_t>(o.hin) * o.hin * o.cin * 2;
+              const int items = (o.hout / 4) * o.hout * (o.cin / 8);
+              int G = std::max(1, 256 / items);
+              const size_t w_bytes = ((static_cast<size_t>(o.kernel) * o.kernel + 1) * o.cin * 4 + 127) & ~size_t(127);
+              while (G > 1 && w_bytes + 2 * G * map_bytes + 16 > 110 * 1024) G >>= 1;
+              const size_t smem = w_bytes + 2 * G * map_bytes + 16;
+              if (smem <= 227 * 1024) {
+                const int units = (n + G - 1) / G;
+                const int per_sm = std::max(1, std::min(4, static_cast<int>((227 * 1024) / (smem + 1024))));
+                const int sgrid = std::min(units, h->sm_count * per_sm);
+#define HN_DW_SMEM(KK, SS)                                                                                            \
+  do {                                                                                                                \
+    static DeviceOnce once;                                                                                           \
+    if (once.first_time())                                                                                            \
+      HN_CUDA(cudaFuncSetAttribute(dw_conv_smem_kernel<KK, SS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    dw_conv_smem_kernel<KK, SS, 4><<<sgrid, 256, smem, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, G, o.relu, bf);   \
+  } while (0)
+                if (o.kernel == 3 && o.stride == 1) HN_DW_SMEM(3, 1);
+                else if (o.kernel == 3) HN_DW_SMEM(3, 2);
+                else if (o.stride == 1) HN_DW_SMEM(5, 1);
+                else HN_DW_SMEM(5, 2);
+#undef HN_DW_SMEM
+                HN_CUDA(cudaGetLastError());
+                count_launch();
+                break;
+              }
+            }
 #define HN_DW_STRIP(KK, SS) dw_conv_strip_kernel<KK, SS><<<grid, 256, 0, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, o.relu, bf)
             if (!strip) dw_conv_kernel<<<grid, 256, 0, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, o.kernel, o.stride, o.relu, bf);
             else if (o.kernel == 3 && o.stride == 1) HN_DW_STRIP(3, 1);
