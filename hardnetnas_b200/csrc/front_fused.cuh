@@ -57,9 +57,12 @@ __device__ unsigned long long hn_ff_trace[32];
 #define HN_FF_WAIT(slot, bar, par) mbar_wait(bar, par)
 #endif
 
-template <typename TIn>
+// PW2 = true is the NAS front (stem + the first block's 1x1 expansion, hardnetNAS fbnet_builder.py IRFBlock `pw`): the
+// second stage is a pointwise 32 -> 32 conv, i.e. only the centre tap of the same weight image, two N = 32 MMAs per
+// tile, no shift-and-add, and the output is plain NHWC ([n][32][32][32]) for the NAS op kernels.
+template <typename TIn, bool PW2 = false>
 __global__ void __launch_bounds__(kFfThreads, 1)
-front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]*/,
+front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]; PW2: NHWC*/,
                    const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
                    const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
                    const float* __restrict__ bias2 /*[32]*/, int do_norm /*0: no input normalisation*/,
@@ -254,7 +257,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     // ============================== UMMA issuer ==============================
     // Descriptor hi words are constants; lo words are `buffer base + compile-time offset` (tile loop fully unrolled).
     const uint32_t idesc1 = make_idesc_f16(kTileM, 32, act_bf16);
-    const uint32_t idesc2 = make_idesc_f16(kTileM, 96, act_bf16);
+    const uint32_t idesc2 = make_idesc_f16(kTileM, PW2 ? 32 : 96, act_bf16);
     constexpr uint32_t L1A_HI = noswizzle_desc_hi(256), L1B_HI = noswizzle_desc_hi(256);
     constexpr uint32_t C2A_HI = noswizzle_desc_hi(128), C2B_HI = noswizzle_desc_hi(512);
     const uint32_t a1_lo = noswizzle_desc_lo(a1_addr, 128);
@@ -303,6 +306,20 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         const int a = t & 3;             // 8 tiles per patch over 4 buffers: each buffer is used twice per patch
         HN_FF_WAIT(6, c2_empty(a), ((t >> 2) & 1) ^ 1u);
         tc_fence_after();
+        if constexpr (PW2) {
+          if (elect_one()) {
+            const uint32_t d = tm_c2 + a * 96;
+            // centre tap only: A = the tile's own 128 slots (image row 4t -> slot (4t + 1) * 32), B = rows [32, 64) of ky = 1
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_f16_w(d, act_lo + (((t * 128 + 32) * 16 + k * 2 * kFfPlane) >> 4), C2A_HI,
+                         w2_lo + ((kFfW2Tap + 4 * 512 + k * 256) >> 4), C2B_HI, idesc2, k != 0);
+            umma_commit(c2_full(a));
+            if (t == 7) umma_commit(act1_empty(b));
+          }
+          __syncwarp();
+          continue;
+        }
         if (elect_one()) {
           const uint32_t d = tm_c2 + a * 96;
 #pragma unroll
@@ -393,6 +410,25 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         const uint32_t t_row = t_row0 + a * 96;
         HN_FF_WAIT(10, c2_full(a), (t >> 2) & 1);
         tc_fence_after();
+        if constexpr (PW2) {
+          uint32_t r[32];
+          tmem_ld32(t_row, r);
+          tmem_ld_wait();
+          uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(patch) * 1024 + (4 * t + q) * 32 + lane) * 32);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias2 + c * 8), b1 = *reinterpret_cast<const float4*>(s_bias2 + c * 8 + 4);
+            const uint32_t* rr = r + c * 8;
+            dst[c] = make_uint4(pack16_relu(__uint_as_float(rr[0]) + b0.x, __uint_as_float(rr[1]) + b0.y, act_bf16),
+                                pack16_relu(__uint_as_float(rr[2]) + b0.z, __uint_as_float(rr[3]) + b0.w, act_bf16),
+                                pack16_relu(__uint_as_float(rr[4]) + b1.x, __uint_as_float(rr[5]) + b1.y, act_bf16),
+                                pack16_relu(__uint_as_float(rr[6]) + b1.z, __uint_as_float(rr[7]) + b1.w, act_bf16));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(c2_empty(a));
+          continue;
+        }
         // channel-planar parity layout for the stride-2 conv3: [plane][ypar][xpar][16][16][8]
         uint4* dst = reinterpret_cast<uint4*>(opatch) + planar_pixel_slot<32, true>(4 * t + q, lane);
         // six TMEM loads (two 8-channel chunks) are in flight per wait: half the exposed round trips of a per-chunk wait

@@ -178,6 +178,38 @@ static int launch_front_fused(hn_handle* h, const void* patches, int in_dtype, u
   return HN_OK;
 }
 
+// NAS front: stem (1 -> 32, 3x3, folded BN, ReLU) + the first block's pointwise 32 -> 32 conv (folded BN, ReLU) in one
+// launch of the fused front kernel (PW2 variant); `w2img` is a front-kernel weight image whose centre tap is the 1x1 conv.
+int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const float* w1, const float* bias1,
+                    const uint16_t* w2img, const float* bias2, int n, int act_bf16, int sm_count, cudaStream_t s) {
+  static DeviceOnce attr_once;
+  if (attr_once.first_time()) {
+    HN_CUDA(cudaFuncSetAttribute(front_fused_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFfSmem)));
+    HN_CUDA(cudaFuncSetAttribute(front_fused_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFfSmem)));
+  }
+  if (n <= 0) return HN_OK;
+  const int grid = std::min(n, sm_count);
+  const uint4* w2 = reinterpret_cast<const uint4*>(w2img);
+  if (in_dtype == HN_F32)
+    front_fused_kernel<float, true><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const float*>(patches), out, w1, bias1, w2, bias2, 0, n, act_bf16);
+  else
+    front_fused_kernel<uint8_t, true><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const uint8_t*>(patches), out, w1, bias1, w2, bias2, 0, n, act_bf16);
+  HN_CUDA(cudaGetLastError());
+  count_launch(1);
+  return HN_OK;
+}
+
+// Front-kernel weight image (front_fused.cuh) of a pointwise 32 -> 32 conv: [co][ci] 16-bit weights at the centre tap.
+void front_pw_weight_image(const uint16_t* w /*[32][32]*/, std::vector<uint16_t>& img) {
+  img.assign(kFfW2 / 2, 0);
+  for (int co = 0; co < 32; ++co)
+    for (int ci = 0; ci < 32; ++ci) {
+      const int nn = 32 + co;
+      const size_t byte = static_cast<size_t>(kFfW2Tap) + (nn >> 3) * 512 + (ci >> 3) * 128 + (nn & 7) * 16 + (ci & 7) * 2;
+      img[byte / 2] = w[co * 32 + ci];
+    }
+}
+
 int launch_head(const TcParams& p, int sm_count, cudaStream_t stream) {
   static DeviceOnce attr_once;
   if (attr_once.first_time()) {

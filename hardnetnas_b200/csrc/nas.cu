@@ -562,6 +562,7 @@ struct NasState {
   uint16_t* w16 = nullptr;
   uint16_t* slot[3] = {nullptr, nullptr, nullptr};
   uint16_t* head_in = nullptr;       // [head_rows, head_k]
+  uint16_t* front_img = nullptr;     // op 1 as a fused-front weight image when stem + op 1 run as one kernel, else null
   size_t slot_elems = 0;             // per patch
   int chunk = 0;                     // patches per pass (<= handle chunk, capped so the three slots stay <= 4 GiB)
   int head_k = 0;
@@ -575,6 +576,7 @@ void nas_state_free(NasState* s) {
   cudaFree(s->w16);
   for (auto* p : s->slot) cudaFree(p);
   cudaFree(s->head_in);
+  cudaFree(s->front_img);
   delete s;
 }
 
@@ -626,6 +628,11 @@ static int launch_pw(const PwParams& p, int nt, int kcb, int sm_count, cudaStrea
 
 
 namespace hn {
+static bool nas_front_fused() {                // HN_NAS_FRONT=0 keeps stem and first pointwise conv as separate kernels
+  const char* e = std::getenv("HN_NAS_FRONT");
+  return !(e && e[0] == '0');
+}
+
 static bool dw_via_smem() {                    // HN_NAS_DW_SMEM=0 selects the register-strip kernel (A/B measurements, tests)
   const char* e = std::getenv("HN_NAS_DW_SMEM");
   return !(e && e[0] == '0');
@@ -636,7 +643,14 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
                        cudaStream_t s) {
   const int bf = st->act_bf16;
   {
-      for (int i = 0; i <= last_op; ++i) {
+      int first = 0;
+      if (st->front_img && last_op >= 1 && nas_front_fused()) {
+        const hn_nas_op &o0 = st->ops[0], &o1 = st->ops[1];
+        HN_TRY(launch_front_pw(src, in_dtype, st->slot[o1.dst], st->params + o0.w_off, st->params + o0.b_off, st->front_img,
+                               st->params + o1.b_off, n, bf, h->sm_count, s));
+        first = 2;
+      }
+      for (int i = first; i <= last_op; ++i) {
         const hn_nas_op& o = st->ops[i];
         switch (o.kind) {
           case OP_STEM: {
@@ -812,6 +826,22 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
   for (int k = 0; k < 3; ++k) {
     HN_CUDA_N(cudaMalloc(&st->slot[k], slot_bytes));
     HN_CUDA_N(cudaMemset(st->slot[k], 0, slot_bytes));
+  }
+  // stem -> pointwise 32 -> 32 + ReLU (the expansion conv of an expansion-1 block): one fused front-kernel launch
+  if (ops[1].kind == OP_PW && ops[1].cin == 32 && ops[1].cout == 32 && ops[1].hin == 32 && ops[1].relu && ops[1].res < 0 &&
+      ops[1].src == ops[0].dst) {
+    bool stem_reused = false;                  // nothing later may read the stem output, which no longer exists
+    for (int i = 2; i < n_ops && !stem_reused; ++i) {
+      if (ops[i].kind != OP_HEAD && ops[i].dst == ops[0].dst) break;   // slot overwritten: later readers see the new tensor
+      stem_reused = ops[i].src == ops[0].dst || (ops[i].kind == OP_PW && ops[i].res == ops[0].dst);
+    }
+    if (!stem_reused) {
+      std::vector<uint16_t> w16(32 * 32), img;
+      for (int j = 0; j < 32 * 32; ++j) w16[j] = f2h16(params[ops[1].w_off + j], bf);
+      front_pw_weight_image(w16.data(), img);
+      HN_CUDA_N(cudaMalloc(&st->front_img, img.size() * 2));
+      HN_CUDA_N(cudaMemcpy(st->front_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    }
   }
   HN_CUDA_N(cudaMalloc(&st->head_in, static_cast<size_t>(h->head_rows) * st->head_k * 2));
   HN_CUDA_N(cudaMemset(st->head_in, 0, static_cast<size_t>(h->head_rows) * st->head_k * 2));

@@ -63,6 +63,27 @@ def test_ragged_batches(batch):
     assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
 
 
+@pytest.mark.parametrize("front,dw", [("0", "1"), ("1", "0"), ("0", "0")])
+def test_unfused_kernels_agree(front, dw, monkeypatch):
+    """HN_NAS_FRONT=0 runs stem and first pointwise conv as two kernels instead of the fused front kernel; HN_NAS_DW_SMEM=0
+    runs the register-strip depthwise kernel instead of the shared-memory one. Every combination reproduces the oracle
+    (the defaults are covered by the tests above), also for a uint8 input and a ragged tail."""
+    monkeypatch.setenv("HN_NAS_FRONT", front)
+    monkeypatch.setenv("HN_NAS_DW_SMEM", dw)
+    for arch in ("wang2", "wang3"):
+        net, ops, sd = build(arch, chunk_patches=64, head_rows=256)
+        x = synth.make_patches(203, 6, edge_cases=False)
+        max_abs, cos = _cmp(net(x.cuda()), nas_oracle.nas_forward(x, ops, sd))
+        assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (arch, max_abs, cos)
+
+
+def test_uint8_patches_through_the_fused_front():
+    net, ops, sd = build("wang2", chunk_patches=64, head_rows=256)
+    x8 = (synth.make_patches(150, 8, edge_cases=False) * 255).round().to(torch.uint8)
+    max_abs, cos = _cmp(net(x8.cuda()), nas_oracle.nas_forward(x8.float(), ops, sd))
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+
+
 def test_config5_batch_64k_properties():
     """BASELINE config 5: wang2 at batch 65 536 — finite, unit norm, deterministic, equal to small-batch results."""
     net, ops, sd = build("wang2")
