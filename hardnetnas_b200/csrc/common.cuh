@@ -104,6 +104,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
+// Tensor-map shared -> global store (bulk group completion): the box at `src` (laid out in the map's swizzle) is written
+// to coordinates (c0, c1); parts outside the tensor are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // Bulk (non-tensor) shared -> global store through the async proxy: one thread moves a contiguous block.
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes)

@@ -33,6 +33,7 @@ enum : int { OP_STEM = 0, OP_PW = 1, OP_DW = 2, OP_MAXPOOL = 3, OP_SE = 4, OP_HE
 struct PwParams {
   CUtensorMap tmA;       // activations [rows, C_in]
   CUtensorMap tmB;       // weights [C_out, C_in] (BN scale folded)
+  CUtensorMap tmO;       // output [rows, C_out] as 32-row x min(NT, 64)-column swizzled store boxes
   const float* bias;     // [C_out]
   const uint16_t* res;   // optional residual [rows, C_out]
   uint16_t* out;         // [rows, C_out]
@@ -40,16 +41,48 @@ struct PwParams {
   int num_tiles;         // m_tiles * n_tiles
   int n_tiles;
   int num_kb;            // C_in / (KCB / 2)
-  int cout;
+  int cout;              // output row length as the kernel sees it (2 x C_out for row-paired ops)
+  int bias_n;            // length of `bias` (the kernel indexes it modulo this)
+  int nt, kcb;           // kernel configuration
+  int row_div;           // 2 when two consecutive rows are processed as one (C_in = 32), else 1
   int relu;
   int act_bf16;
 };
 
-constexpr int kPwStages = 4;
+// A 32-channel activation row is 64 bytes; TMA loads and stores of 64-byte rows ran these ops at ~3.8 TB/s where the
+// same kernel moves 128-byte rows at > 5 TB/s. Rows of a C_in = 32 op are therefore processed in PAIRS: [rows, 32] is
+// viewed as [rows / 2, 64] (the NHWC tensor is contiguous, rows per patch are even) and the weight becomes the block
+// diagonal [[W, 0], [0, W]], so the output [rows / 2, 2 C_out] is the same memory as [rows, C_out]. The extra zero MACs
+// are free (the tensor pipe idles in these HBM-bound ops).
+static bool pw_row_paired(const hn_nas_op& o) { return o.cin == 32 && o.cout <= 128; }
+
+// A pointwise stage is small (8-16 KB of activations + the weight tile), so the ring is DEEP: the bytes in flight per SM,
+// not the tensor pipe, set the rate of these HBM-bound GEMMs (4 stages left them at ~3.3 TB/s).
+// Warps: 0 TMA producer, 1 TMEM owner + UMMA issuer, then GROUPS epilogue groups of four warps that take tiles round
+// robin (one tile's TMEM -> bias/ReLU -> store chain is ~1000 cycles of mostly latency; a single group left these
+// HBM-bound kernels at ~3.5 TB/s). Four accumulators, tile `it` uses accumulator it % 4.
+template <int NT>
+constexpr int pw_groups() { return NT <= 64 ? 4 : 2; }
+template <int NT>
+constexpr int pw_threads() { return 64 + 128 * pw_groups<NT>(); }
+// Output staging for the swizzled TMA stores: one (32 rows x NT columns) buffer per epilogue warp; NT = 96 keeps the
+// direct stores (its rows do not split into equal power-of-two boxes).
+template <int NT>
+constexpr bool pw_tma_out() { return NT == 32 || NT == 64 || NT == 128; }
+template <int NT>
+constexpr uint32_t pw_staging_bytes() { return pw_tma_out<NT>() ? 4u * pw_groups<NT>() * 32u * NT * 2u : 0u; }
+template <int NT, int KCB>
+constexpr int pw_stages() {
+  constexpr int s = (220 * 1024 - static_cast<int>(pw_staging_bytes<NT>())) / (kTileM * KCB + NT * KCB);
+  return s > 16 ? 16 : s;
+}
+template <int NT, int KCB>
+constexpr uint32_t pw_bias_off() { return (8u * (2 * pw_stages<NT, KCB>() + 9) + 15u) & ~15u; }
 
 template <int NT, int KCB>
 constexpr size_t pw_smem_bytes() {
-  return size_t(kPwStages) * (size_t(kTileM) * KCB + size_t(NT) * KCB) + 1024 + 256 + 512 * 4;
+  return size_t(pw_stages<NT, KCB>()) * (size_t(kTileM) * KCB + size_t(NT) * KCB) + pw_staging_bytes<NT>() + 1024 +
+         pw_bias_off<NT, KCB>() + 512 * 4;
 }
 
 __device__ __forceinline__ float2 unpack16(uint32_t v, int bf16) {
@@ -60,26 +93,28 @@ __device__ __forceinline__ float2 unpack16(uint32_t v, int bf16) {
 }
 
 template <int NT, int KCB>
-__global__ void __launch_bounds__(kTcThreads, 1) pw_gemm_kernel(const __grid_constant__ PwParams p) {
-  constexpr int STAGES = kPwStages;
+__global__ void __launch_bounds__(pw_threads<NT>(), 1) pw_gemm_kernel(const __grid_constant__ PwParams p) {
+  constexpr int GROUPS = pw_groups<NT>();
+  constexpr int STAGES = pw_stages<NT, KCB>();
   constexpr uint32_t A_BYTES = kTileM * KCB;
   constexpr uint32_t B_BYTES = NT * KCB;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = tmem_cols_for(NT);
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(2 * NT);   // four NT-column accumulators
   constexpr int KC = KCB / 2;
   static_assert(B_BYTES % 1024 == 0, "weight tile must stay 1024B aligned");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+  const uint32_t staging_base = base + STAGES * STAGE_BYTES;            // 1024-byte aligned (stage sizes are multiples)
+  const uint32_t bar_base = staging_base + pw_staging_bytes<NT>();
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 8);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + pw_bias_off<NT, KCB>() - raw_addr));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,6 +122,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pw_gemm_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmO);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -94,7 +130,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pw_gemm_kernel(const __grid_con
         mbar_init(full_bar(s), 1);
         mbar_init(empty_bar(s), 1);
       }
-      for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < 4; ++a) {
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 4);
       }
@@ -105,7 +141,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) pw_gemm_kernel(const __grid_con
     tmem_relinquish();
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < p.cout; i += 128) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x - 64; i < p.cout; i += 128 * GROUPS) s_bias[i] = p.bias[i % p.bias_n];
   }
   tc_fence_before();
   __syncthreads();
@@ -136,8 +172,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) pw_gemm_kernel(const __grid_con
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it & 3;
+      const uint32_t acc_phase = (it >> 2) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * NT;
@@ -160,18 +196,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) pw_gemm_kernel(const __grid_con
     }
   } else {
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int row_in_tile = q * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+    int it = grp;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < p.num_tiles; tile += GROUPS * gridDim.x, it += GROUPS) {
+      const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int acc = it & 3;
+      const uint32_t acc_phase = (it >> 2) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT;
       const long long row = static_cast<long long>(mt) * kTileM + row_in_tile;
       const bool valid = row < p.total_rows;
       const long long off = row * p.cout + nt * NT;
+      // Output rows leave through swizzled TMA stores: a thread's 16-byte chunks go to the staging tile at
+      // chunk ^ f(row) (the 64B / 128B swizzle patterns), which makes the shared-memory writes conflict free and the
+      // global writes whole lines; direct 16-byte stores at a row stride touched 32 half-used sectors per request.
+      constexpr int BOXC = NT < 64 ? NT : 64;
+      constexpr uint32_t BOX_BYTES = 32u * BOXC * 2u;
+      const uint32_t stg = staging_base + static_cast<uint32_t>((warp - 2) * (NT / BOXC)) * BOX_BYTES;
+      const uint32_t swz = BOXC == 64 ? (lane & 7) : ((lane >> 1) & 3);
+      if constexpr (pw_tma_out<NT>()) {
+        if (lane == 0) bulk_wait_read<0>();     // this warp's previous store (two tiles ago) is done with the buffer
+        __syncwarp();
+      }
 #pragma unroll
       for (int c0 = 0; c0 < NT; c0 += 32) {
         uint32_t r[32];
@@ -198,7 +246,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) pw_gemm_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (valid) {
+        if constexpr (pw_tma_out<NT>()) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cc = c0 / 8 + j;                       // 16-byte chunk of the row (compile-time)
+            const uint32_t a = stg + (cc / (BOXC / 8)) * BOX_BYTES + lane * (BOXC * 2) + (((cc % (BOXC / 8)) ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack16(v[8 * j], v[8 * j + 1], p.act_bf16)),
+                         "r"(pack16(v[8 * j + 2], v[8 * j + 3], p.act_bf16)), "r"(pack16(v[8 * j + 4], v[8 * j + 5], p.act_bf16)),
+                         "r"(pack16(v[8 * j + 6], v[8 * j + 7], p.act_bf16))
+                         : "memory");
+          }
+        } else if (valid) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + off + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -209,9 +267,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) pw_gemm_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if constexpr (pw_tma_out<NT>()) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int bx = 0; bx < NT / BOXC; ++bx)
+            tma_store_2d(&p.tmO, stg + bx * BOX_BYTES, nt * NT + bx * BOXC, mt * kTileM + q * 32);
+          bulk_commit();
+        }
+      }
     }
   }
 
+  if (warp >= 2 && lane == 0) bulk_wait_all<0>();   // outstanding output stores read shared memory of this CTA
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -357,12 +426,14 @@ __global__ void __launch_bounds__(256) dw_conv_strip_kernel(const uint16_t* __re
 // every input byte crosses HBM -> L2 -> SM exactly once. A thread owns 8 channels x a VERTICAL strip of SH output rows
 // at one output column; consecutive threads walk (channel group, column), so a warp's 16-byte shared loads and its
 // 16-byte global stores are contiguous. Per kx the K weight vectors sit in registers and the (SH-1)*S+K input rows are
-// loaded once each. Out-of-image taps read a clamped address and are zeroed by select - no divergent branches.
-template <int K, int S, int SH>
+// loaded once each. Out-of-image taps load a 16-byte zero vector instead (one select on the address) - no divergent
+// branches; the activation type is a template parameter so the 16 -> 32 bit unpack is one instruction per value.
+template <int K, int S, int SH, bool BF16>
 __global__ void __launch_bounds__(256) dw_conv_smem_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                                                            const float* __restrict__ w /*[k*k][C]*/,
                                                            const float* __restrict__ bias, int patches, int C, int hin,
-                                                           int hout, int G, int relu, int bf16) {
+                                                           int hout, int G, int relu) {
+  constexpr int bf16 = BF16 ? 1 : 0;
   extern __shared__ __align__(128) uint8_t dw_smem[];
   constexpr int PAD = K >> 1;
   constexpr int NR = (SH - 1) * S + K;         // input rows a strip touches
@@ -373,6 +444,8 @@ __global__ void __launch_bounds__(256) dw_conv_smem_kernel(const uint16_t* __res
   const int w_floats = (K * K + 1) * C;
   const uint32_t buf_off = (static_cast<uint32_t>(w_floats) * 4 + 127) & ~127u;
   const uint32_t bar0 = smem_u32(dw_smem + buf_off + 2 * unit_bytes);
+  const uint16_t* s_zero = reinterpret_cast<const uint16_t*>(dw_smem + buf_off + 2 * unit_bytes + 16);
+  if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(dw_smem + buf_off + 2 * unit_bytes + 16)[threadIdx.x] = 0u;
   for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) s_w[i] = w[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) s_w[K * K * C + i] = bias[i];
   if (threadIdx.x == 0) {
@@ -429,7 +502,6 @@ __global__ void __launch_bounds__(256) dw_conv_smem_kernel(const uint16_t* __res
       for (int kx = 0; kx < K; ++kx) {
         const int ix = ox * S + kx - PAD;
         const bool x_ok = ix >= 0 && ix < hin;
-        const int ixc = min(max(ix, 0), hin - 1);
         float2 wk[K][4];
 #pragma unroll
         for (int ky = 0; ky < K; ++ky) {
@@ -443,9 +515,7 @@ __global__ void __launch_bounds__(256) dw_conv_smem_kernel(const uint16_t* __res
         for (int r = 0; r < NR; ++r) {
           const int iy = iy0 + r;
           const bool ok = x_ok && iy >= 0 && iy < hin;
-          const int iyc = min(max(iy, 0), hin - 1);
-          uint4 xv = *reinterpret_cast<const uint4*>(map + (iyc * hin + ixc) * C);
-          if (!ok) xv = make_uint4(0u, 0u, 0u, 0u);
+          const uint4 xv = *reinterpret_cast<const uint4*>(ok ? map + (iy * hin + ix) * C : s_zero);
           const float2 x[4] = {unpack16(xv.x, bf16), unpack16(xv.y, bf16), unpack16(xv.z, bf16), unpack16(xv.w, bf16)};
 #pragma unroll
           for (int j = 0; j < SH; ++j) {
@@ -606,7 +676,7 @@ static int launch_pw_cfg(const PwParams& p, int sm_count, cudaStream_t s) {
     HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   if (p.num_tiles <= 0) return HN_OK;
-  kern<<<std::min(p.num_tiles, sm_count), kTcThreads, smem, s>>>(p);
+  kern<<<std::min(p.num_tiles, sm_count), pw_threads<NT>(), smem, s>>>(p);
   HN_CUDA(cudaGetLastError());
   count_launch();
   return HN_OK;
@@ -659,9 +729,9 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
           }
           case OP_PW: {
             PwParams p = st->pw[i];
-            p.total_rows = static_cast<long long>(n) * o.hin * o.hin;
+            p.total_rows = static_cast<long long>(n) * o.hin * o.hin / p.row_div;
             p.num_tiles = static_cast<int>((p.total_rows + kTileM - 1) / kTileM) * p.n_tiles;
-            HN_TRY(launch_pw(p, o.cout / p.n_tiles, (o.cin % 64 == 0) ? 128 : 64, h->sm_count, s));
+            HN_TRY(launch_pw(p, p.nt, p.kcb, h->sm_count, s));
             break;
           }
           case OP_DW: {
@@ -679,23 +749,25 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
               const int items = (o.hout / 4) * o.hout * (o.cin / 8);
               int G = std::max(1, 256 / items);
               const size_t w_bytes = ((static_cast<size_t>(o.kernel) * o.kernel + 1) * o.cin * 4 + 127) & ~size_t(127);
-              while (G > 1 && w_bytes + 2 * G * map_bytes + 16 > 110 * 1024) G >>= 1;
-              const size_t smem = w_bytes + 2 * G * map_bytes + 16;
+              while (G > 1 && w_bytes + 2 * G * map_bytes + 32 > 110 * 1024) G >>= 1;
+              const size_t smem = w_bytes + 2 * G * map_bytes + 32;
               if (smem <= 227 * 1024) {
                 const int units = (n + G - 1) / G;
                 const int per_sm = std::max(1, std::min(4, static_cast<int>((227 * 1024) / (smem + 1024))));
                 const int sgrid = std::min(units, h->sm_count * per_sm);
-#define HN_DW_SMEM(KK, SS)                                                                                            \
+#define HN_DW_SMEM(KK, SS, BF)                                                                                        \
   do {                                                                                                                \
     static DeviceOnce once;                                                                                           \
     if (once.first_time())                                                                                            \
-      HN_CUDA(cudaFuncSetAttribute(dw_conv_smem_kernel<KK, SS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-    dw_conv_smem_kernel<KK, SS, 4><<<sgrid, 256, smem, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, G, o.relu, bf);   \
+      HN_CUDA(cudaFuncSetAttribute(dw_conv_smem_kernel<KK, SS, 4, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    dw_conv_smem_kernel<KK, SS, 4, BF><<<sgrid, 256, smem, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, G, o.relu);   \
   } while (0)
-                if (o.kernel == 3 && o.stride == 1) HN_DW_SMEM(3, 1);
-                else if (o.kernel == 3) HN_DW_SMEM(3, 2);
-                else if (o.stride == 1) HN_DW_SMEM(5, 1);
-                else HN_DW_SMEM(5, 2);
+#define HN_DW_SMEM_T(KK, SS) do { if (bf) HN_DW_SMEM(KK, SS, true); else HN_DW_SMEM(KK, SS, false); } while (0)
+                if (o.kernel == 3 && o.stride == 1) HN_DW_SMEM_T(3, 1);
+                else if (o.kernel == 3) HN_DW_SMEM_T(3, 2);
+                else if (o.stride == 1) HN_DW_SMEM_T(5, 1);
+                else HN_DW_SMEM_T(5, 2);
+#undef HN_DW_SMEM_T
 #undef HN_DW_SMEM
                 HN_CUDA(cudaGetLastError());
                 count_launch();
@@ -773,8 +845,9 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
       case OP_PW:
         ok = o.cin % 32 == 0 && o.cout % 32 == 0 && o.cin <= 512 && o.cout <= 512 && in_blob(o.w_off, 1LL * o.cin * o.cout) &&
              in_blob(o.b_off, o.cout) && o.res >= -1 && o.res <= 2 && o.res != o.dst && o.src != o.dst;
+        ok = ok && (o.hin * o.hin) % 2 == 0;
         st->w16_off[i] = w16_total;
-        w16_total += static_cast<size_t>(o.cin) * o.cout;
+        w16_total += static_cast<size_t>(o.cin) * o.cout * (pw_row_paired(o) ? 4 : 1);
         break;
       case OP_DW:
         ok = o.cin == o.cout && o.cin % 8 == 0 && (o.kernel == 3 || o.kernel == 5) && (o.stride == 1 || o.stride == 2) &&
@@ -812,6 +885,13 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
     std::vector<uint16_t> w16(w16_total);
     for (int i = 0; i < n_ops; ++i) {
       const hn_nas_op& o = ops[i];
+      if (o.kind == OP_PW && pw_row_paired(o)) {   // [[W, 0], [0, W]] as [2 C_out][64]; the vector is zero-initialised
+        for (int hh = 0; hh < 2; ++hh)
+          for (int co = 0; co < o.cout; ++co)
+            for (int ci = 0; ci < 32; ++ci)
+              w16[st->w16_off[i] + static_cast<size_t>(hh * o.cout + co) * 64 + hh * 32 + ci] = f2h16(params[o.w_off + co * 32 + ci], bf);
+        continue;
+      }
       const size_t n = o.kind == OP_PW ? static_cast<size_t>(o.cin) * o.cout : o.kind == OP_HEAD ? static_cast<size_t>(128) * st->head_k : 0;
       for (size_t j = 0; j < n; ++j) w16[st->w16_off[i] + j] = f2h16(params[o.w_off + j], bf);
     }
@@ -852,25 +932,39 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
     if (o.kind == OP_PW) {
       PwParams& p = st->pw[i];
       memset(&p, 0, sizeof(p));
-      const int kcb = (o.cin % 64 == 0) ? 128 : 64;
+      const int row_div = pw_row_paired(o) ? 2 : 1;
+      const int cin = o.cin * row_div, cout = o.cout * row_div;
+      const int kcb = (cin % 64 == 0) ? 128 : 64;
       const int kc = kcb / 2;
-      const int nt = pick_nt(o.cout);
-      const uint64_t rows_cap = static_cast<uint64_t>(st->chunk) * o.hin * o.hin;
-      const uint64_t dimsA[2] = {static_cast<uint64_t>(o.cin), rows_cap};
-      const uint64_t strA[1] = {static_cast<uint64_t>(o.cin) * 2};
+      const int nt = pick_nt(cout);
+      const uint64_t rows_cap = static_cast<uint64_t>(st->chunk) * o.hin * o.hin / row_div;
+      const uint64_t dimsA[2] = {static_cast<uint64_t>(cin), rows_cap};
+      const uint64_t strA[1] = {static_cast<uint64_t>(cin) * 2};
       const uint32_t boxA[2] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(kTileM)};
       int rc = make_tmap_16bit(&p.tmA, st->slot[o.src], 2, dimsA, strA, boxA, kcb);
       if (rc != HN_OK) return fail(rc);
-      const uint64_t dimsB[2] = {static_cast<uint64_t>(o.cin), static_cast<uint64_t>(o.cout)};
+      const uint64_t dimsB[2] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(cout)};
       const uint32_t boxB[2] = {static_cast<uint32_t>(kc), static_cast<uint32_t>(nt)};
       rc = make_tmap_16bit(&p.tmB, st->w16 + st->w16_off[i], 2, dimsB, strA, boxB, kcb);
       if (rc != HN_OK) return fail(rc);
+      if (nt == 32 || nt == 64 || nt == 128) {
+        const int boxc = std::min(nt, 64);
+        const uint64_t dimsO[2] = {static_cast<uint64_t>(cout), rows_cap};
+        const uint64_t strO[1] = {static_cast<uint64_t>(cout) * 2};
+        const uint32_t boxO[2] = {static_cast<uint32_t>(boxc), 32};
+        rc = make_tmap_16bit(&p.tmO, st->slot[o.dst], 2, dimsO, strO, boxO, boxc * 2);
+        if (rc != HN_OK) return fail(rc);
+      }
       p.bias = st->params + o.b_off;
       p.res = o.res >= 0 ? st->slot[o.res] : nullptr;
       p.out = st->slot[o.dst];
-      p.n_tiles = o.cout / nt;
-      p.num_kb = o.cin / kc;
-      p.cout = o.cout;
+      p.n_tiles = cout / nt;
+      p.num_kb = cin / kc;
+      p.cout = cout;
+      p.bias_n = o.cout;
+      p.nt = nt;
+      p.kcb = kcb;
+      p.row_div = row_div;
       p.relu = o.relu;
       p.act_bf16 = bf;
     } else if (o.kind == OP_HEAD) {
