@@ -443,6 +443,11 @@ def side_measurements(device, model, rank, world):
         res["config4_nas_wang2_algorithmic_GBps"] = 65536 * 4608 / (nas_ms / 1e3) / 1e9
         # layer-at-a-time NHWC 16-bit activations move ~562 KB/patch: the HBM fraction that implies
         res["config4_nas_wang2_layerwise_hbm_frac"] = 65536 * 562e3 / (nas_ms / 1e3) / 1e9 / load_peaks()["hbm_gbs"]
+        # bytes the 16 kernels of one pass actually move (ncu, profiles/roofline_traffic.json; stem + first 1x1 fused)
+        moved = load_traffic("nas_wang2_bytes_per_patch")
+        if moved:
+            res["config4_nas_wang2_moved_GBps"] = 65536 * moved / (nas_ms / 1e3) / 1e9
+            res["config4_nas_wang2_moved_hbm_frac"] = res["config4_nas_wang2_moved_GBps"] / load_peaks()["hbm_gbs"]
         del nas, xb, ob
     res["config3_match_65536x65536_ms"] = ms
     res["config3_match_pairs_per_sec"] = n * n / (ms / 1e3)

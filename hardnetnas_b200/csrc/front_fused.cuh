@@ -53,8 +53,12 @@ __device__ unsigned long long hn_ff_trace[32];
 #define HN_FF_T0() const long long t0__ = clock64()
 #define HN_FF_ACC(slot) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&hn_ff_trace[slot], static_cast<unsigned long long>(clock64() - t0__)); } while (0)
 #define HN_FF_WAIT(slot, bar, par) do { HN_FF_T0(); mbar_wait(bar, par); HN_FF_ACC(slot); } while (0)
+#define HN_FF_SECTION_BEGIN() const long long ts__ = clock64()
+#define HN_FF_SECTION_END(slot) do { if (blockIdx.x == 0 && lane == 0) atomicAdd(&hn_ff_trace[slot], static_cast<unsigned long long>(clock64() - ts__)); } while (0)
 #else
 #define HN_FF_WAIT(slot, bar, par) mbar_wait(bar, par)
+#define HN_FF_SECTION_BEGIN() do { } while (0)
+#define HN_FF_SECTION_END(slot) do { } while (0)
 #endif
 
 // PW2 = true is the NAS front (stem + the first block's 1x1 expansion, hardnetNAS fbnet_builder.py IRFBlock `pw`): the
@@ -156,7 +160,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   // 128 x 96 conv2 accumulators (columns [128, 512)): each epilogue group owns two, so the MMAs of its next tile are
   // already done when it finishes the current one.
   const uint32_t tm_l1 = tmem_base;
-  const uint32_t tm_c2 = tmem_base + 128;
+  const uint32_t tm_c2 = tmem_base + (PW2 ? 256 : 128);   // PW2: stage 1 holds a whole patch (8 x 32 columns)
+  constexpr uint32_t C2_STRIDE = PW2 ? 32 : 96;           // accumulator pitch of the second stage
 
   if (warp >= kFfLoader0) {
     // ============================== loaders: normalise + im2col of the input patch ==============================
@@ -266,6 +271,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     const uint32_t w2_lo = noswizzle_desc_lo(w2_addr, 128);
     const int n_local = (num_patches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     auto issue_l1_half = [&](int half) {
+      HN_FF_SECTION_BEGIN();
       if (elect_one()) {
 #pragma unroll
         for (int t = 0; t < 4; ++t)
@@ -274,7 +280,49 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         umma_commit(l1_full);
       }
       __syncwarp();
+      HN_FF_SECTION_END(11);
     };
+    if constexpr (PW2) {
+      // The pointwise second stage needs only 4 x 32 accumulator columns, so stage 1 of a WHOLE patch (8 tiles, 256
+      // columns) is issued at once and its epilogue drains all eight tiles without waiting for the issuer in between;
+      // the pointwise tiles of patch it - 1 are issued behind stage 1 of patch it.
+      for (int it = 0; it <= n_local; ++it) {
+        if (it < n_local) {
+          HN_FF_WAIT(2, a1_full, it & 1);
+          if (it > 0) HN_FF_WAIT(3, l1_empty, (it - 1) & 1);   // the epilogue has drained patch it - 1 from tensor memory
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) umma_f16_w(tm_l1 + t * 32, a1_lo + t * (4096 >> 4), L1A_HI, b1_lo, L1B_HI, idesc1, 0u);
+            umma_commit(a1_empty);
+            umma_commit(l1_full);
+          }
+          __syncwarp();
+        }
+        if (it > 0) {
+          const int b = (it - 1) & 1;
+          HN_FF_WAIT(4, act1_full(b), ((it - 1) >> 1) & 1);
+          tc_fence_after();
+          const uint32_t act_lo = act_lo0 + b * (kFfAct1 >> 4);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int a = t & 3;
+            HN_FF_WAIT(6, c2_empty(a), ((t >> 2) & 1) ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+              // centre tap only: A = the tile's own 128 slots (image row 4t -> slot (4t + 1) * 32), B = rows [32, 64) of ky = 1
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma_f16_w(tm_c2 + a * 32, act_lo + (((t * 128 + 32) * 16 + k * 2 * kFfPlane) >> 4), C2A_HI,
+                           w2_lo + ((kFfW2Tap + 4 * 512 + k * 256) >> 4), C2B_HI, idesc2, k != 0);
+              umma_commit(c2_full(a));
+              if (t == 7) umma_commit(act1_empty(b));
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else {
     if (n_local > 0) {
       mbar_wait(a1_full, 0);
       tc_fence_after();
@@ -306,20 +354,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         const int a = t & 3;             // 8 tiles per patch over 4 buffers: each buffer is used twice per patch
         HN_FF_WAIT(6, c2_empty(a), ((t >> 2) & 1) ^ 1u);
         tc_fence_after();
-        if constexpr (PW2) {
-          if (elect_one()) {
-            const uint32_t d = tm_c2 + a * 96;
-            // centre tap only: A = the tile's own 128 slots (image row 4t -> slot (4t + 1) * 32), B = rows [32, 64) of ky = 1
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              umma_f16_w(d, act_lo + (((t * 128 + 32) * 16 + k * 2 * kFfPlane) >> 4), C2A_HI,
-                         w2_lo + ((kFfW2Tap + 4 * 512 + k * 256) >> 4), C2B_HI, idesc2, k != 0);
-            umma_commit(c2_full(a));
-            if (t == 7) umma_commit(act1_empty(b));
-          }
-          __syncwarp();
-          continue;
-        }
+        HN_FF_SECTION_BEGIN();
         if (elect_one()) {
           const uint32_t d = tm_c2 + a * 96;
 #pragma unroll
@@ -334,6 +369,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
           umma_commit(mma_done(a));
         }
         __syncwarp();
+        HN_FF_SECTION_END(13);
         // D'2 (columns 64..95) is needed one pixel to the left: tcgen05.shift moves every 32-lane quarter (= one image
         // row) down by one lane, 8 columns per instruction (lane 31 keeps its value and is masked in the epilogue).
         // The shift is NOT ordered behind earlier MMAs by itself, so it is issued for the PREVIOUS tile once that tile's
@@ -358,6 +394,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         __syncwarp();
       }
     }
+    }   // !PW2
   } else if (warp < 4) {
     // ============================== stage-1 epilogue: TMEM -> bias, ReLU, pack -> act1 (smem) ==============================
     const int q = warp;
@@ -366,6 +403,31 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       const int b = it & 1;
       HN_FF_WAIT(8, act1_empty(b), ((it >> 1) & 1) ^ 1u);
       uint8_t* act = gbase + (act1_addr - base) + b * kFfAct1;
+      if constexpr (PW2) {
+        HN_FF_WAIT(9, l1_full, it & 1);
+        tc_fence_after();
+#pragma unroll 2
+        for (int t = 0; t < 8; ++t) {
+          uint32_t r[32];
+          tmem_ld32(tm_l1 + (static_cast<uint32_t>(q * 32) << 16) + t * 32, r);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = pack16_relu(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), act_bf16);
+          uint8_t* dst = act + (t * 128 + q * 32 + lane + 32) * 16;
+#pragma unroll
+          for (int pl = 0; pl < 4; ++pl)
+            *reinterpret_cast<uint4*>(dst + pl * kFfPlane) = make_uint4(o[4 * pl], o[4 * pl + 1], o[4 * pl + 2], o[4 * pl + 3]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(act1_full(b));
+          mbar_arrive(l1_empty);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         HN_FF_WAIT(9, l1_full, half);
@@ -407,7 +469,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       for (int tt = 0; tt < 4; ++tt) {
         const int t = 2 * tt + g;
         const int a = t & 3;
-        const uint32_t t_row = t_row0 + a * 96;
+        const uint32_t t_row = t_row0 + a * C2_STRIDE;
         HN_FF_WAIT(10, c2_full(a), (t >> 2) & 1);
         tc_fence_after();
         if constexpr (PW2) {
