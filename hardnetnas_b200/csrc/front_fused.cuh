@@ -16,8 +16,13 @@
 // and 10 are the constant 1 and the matching weight rows hold the shift split into a 16-bit hi + lo pair, so the tensor
 // core adds it in fp32 and the stage-1 epilogue is just TMEM -> ReLU/pack (one F2FP per two values) -> shared memory.
 //
-// Warps (17): 0-3 stage-1 epilogue (TMEM -> act1 in smem), 4-11 conv2 epilogue (two groups of four, one per
-// accumulator buffer), 12 TMEM owner + UMMA issuer, 13-16 loaders (normalise + im2col of the 1-channel input).
+// Warps (20): 0-3 stage-1 epilogue (TMEM -> act1 in smem), 4-11 conv2 epilogue (two groups of four, one per
+// accumulator pair), 12 TMEM owner + UMMA issuer A (stage 1 + even conv2 tiles), 13-16 loaders (normalise + im2col of
+// the 1-channel input), 17 UMMA issuer B (odd conv2 tiles), 18-19 shifters (tcgen05.shift of the even / odd tiles).
+// Why several issuing warps: an mbarrier.try_wait costs the polling warp ~180 cycles even when the barrier is already
+// complete (tools/issue_probe.cu), and one conv2 tile is only 336 cycles of tensor-pipe work. A single warp that polls
+// accumulator-free, issues, polls MMAs-retired and shifts leaves the pipe idle between tiles; with the tiles dealt to
+// two issuers and the shifts to two more warps those latencies overlap each other and the MMAs.
 #pragma once
 
 #include "common.cuh"
@@ -26,9 +31,11 @@
 
 namespace hn {
 
-constexpr int kFfThreads = 17 * 32;
+constexpr int kFfThreads = 20 * 32;
 constexpr int kFfIssuer = 12;
 constexpr int kFfLoader0 = 13;   // 4 loader warps: 13..16
+constexpr int kFfIssuerB = 17;
+constexpr int kFfShift0 = 18;    // 2 shifter warps: 18, 19
 constexpr uint32_t kFfPlane = 34 * 32 * 16;   // one 8-channel plane of the haloed stage-1 output
 constexpr uint32_t kFfAct1 = 4 * kFfPlane;    // 69 632 B per buffer
 constexpr uint32_t kFfA1 = 8 * 4096;          // eight 128 x 16 im2col tiles of the input patch
@@ -108,7 +115,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       mbar_init(l1_empty, 4);   // one arrive per stage-1 epilogue warp
       for (int b = 0; b < 2; ++b) {
         mbar_init(act1_full(b), 4);
-        mbar_init(act1_empty(b), 1);
+        mbar_init(act1_empty(b), PW2 ? 1 : 2);   // tcgen05.commit of every issuing warp
       }
       for (int a = 0; a < 4; ++a) {
         mbar_init(c2_full(a), 1);
@@ -163,7 +170,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   const uint32_t tm_c2 = tmem_base + (PW2 ? 256 : 128);   // PW2: stage 1 holds a whole patch (8 x 32 columns)
   constexpr uint32_t C2_STRIDE = PW2 ? 32 : 96;           // accumulator pitch of the second stage
 
-  if (warp >= kFfLoader0) {
+  if (warp >= kFfLoader0 && warp < kFfIssuerB) {
     // ============================== loaders: normalise + im2col of the input patch ==============================
     // Thread = image column x (lane) x 8 consecutive rows (warp): every global load is one coalesced 128 B row segment
     // and every im2col store phase touches 8 consecutive pixels = 8 distinct 16 B bank groups (conflict free).
@@ -258,8 +265,33 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       __syncwarp();
       if (lane == 0) mbar_arrive(a1_full);
     }
-  } else if (warp == kFfIssuer) {
-    // ============================== UMMA issuer ==============================
+  } else if (warp >= kFfShift0) {
+    // ============================== shifters (conv2 only) ==============================
+    // D'2 (columns 64..95 of an accumulator) is needed one pixel to the left: tcgen05.shift moves every 32-lane quarter
+    // (= one image row) down by one lane, 8 columns per instruction (lane 31 keeps its value and is masked in the
+    // epilogue). The shift is NOT ordered behind earlier MMAs by itself, so it waits for the tile's mma_done barrier.
+    if constexpr (!PW2) {
+      const int g = warp - kFfShift0;
+      const int n_local = (num_patches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      for (int it = 0; it < n_local; ++it) {
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+          const int t = 2 * tt + g;
+          const int a = t & 3;
+          HN_FF_WAIT(7, mma_done(a), (t >> 2) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t ds = tm_c2 + a * 96 + 64;
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(ds + c8 * 8) : "memory");
+            umma_commit(c2_full(a));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == kFfIssuer || warp == kFfIssuerB) {
+    // ============================== UMMA issuers ==============================
     // Descriptor hi words are constants; lo words are `buffer base + compile-time offset` (tile loop fully unrolled).
     const uint32_t idesc1 = make_idesc_f16(kTileM, 32, act_bf16);
     const uint32_t idesc2 = make_idesc_f16(kTileM, PW2 ? 32 : 96, act_bf16);
@@ -282,7 +314,9 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       __syncwarp();
       HN_FF_SECTION_END(11);
     };
+    const int iw = warp == kFfIssuer ? 0 : 1;
     if constexpr (PW2) {
+      if (iw == 0) {
       // The pointwise second stage needs only 4 x 32 accumulator columns, so stage 1 of a WHOLE patch (8 tiles, 256
       // columns) is issued at once and its epilogue drains all eight tiles without waiting for the issuer in between;
       // the pointwise tiles of patch it - 1 are issued behind stage 1 of patch it.
@@ -322,78 +356,60 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
           }
         }
       }
+      }
     } else {
-    if (n_local > 0) {
-      mbar_wait(a1_full, 0);
-      tc_fence_after();
-      issue_l1_half(0);
-      mbar_wait(l1_empty, 0);
-      tc_fence_after();
-      issue_l1_half(1);
-    }
-    for (int it = 0; it < n_local; ++it) {
-      const int b = it & 1;
-      const bool more = it + 1 < n_local;
-      if (more) {
-        // stage 1 of the NEXT patch is interleaved with the conv2 tiles of this one, so its epilogue overlaps them
-        HN_FF_WAIT(2, a1_full, (it + 1) & 1);
-        HN_FF_WAIT(3, l1_empty, 1);          // second half of patch `it` has been drained
+      // Issuer A (iw = 0) also runs stage 1: the first half of the NEXT patch before tile 0, the second half before
+      // tile 4, so the stage-1 epilogue overlaps the conv2 tiles of this patch. Issuer B only issues odd conv2 tiles.
+      if (iw == 0 && n_local > 0) {
+        mbar_wait(a1_full, 0);
         tc_fence_after();
         issue_l1_half(0);
-      }
-      HN_FF_WAIT(4, act1_full(b), (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t act_lo = act_lo0 + b * (kFfAct1 >> 4);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        if (t == 4 && more) {
-          HN_FF_WAIT(5, l1_empty, 0);        // first half of patch `it + 1` has been drained
-          tc_fence_after();
-          issue_l1_half(1);
-        }
-        const int a = t & 3;             // 8 tiles per patch over 4 buffers: each buffer is used twice per patch
-        HN_FF_WAIT(6, c2_empty(a), ((t >> 2) & 1) ^ 1u);
+        mbar_wait(l1_empty, 0);
         tc_fence_after();
-        HN_FF_SECTION_BEGIN();
-        if (elect_one()) {
-          const uint32_t d = tm_c2 + a * 96;
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              // A: 128 slots starting at image row 4t + ky - 1 (slot (4t + ky) * 32), channels 16k .. 16k + 15
-              umma_f16_w(d, act_lo + (((t * 128 + ky * 32) * 16 + k * 2 * kFfPlane) >> 4), C2A_HI,
-                         w2_lo + ((ky * kFfW2Tap + k * 256) >> 4), C2B_HI, idesc2, (ky | k) != 0);
-            }
-          }
-          umma_commit(mma_done(a));
-        }
-        __syncwarp();
-        HN_FF_SECTION_END(13);
-        // D'2 (columns 64..95) is needed one pixel to the left: tcgen05.shift moves every 32-lane quarter (= one image
-        // row) down by one lane, 8 columns per instruction (lane 31 keeps its value and is masked in the epilogue).
-        // The shift is NOT ordered behind earlier MMAs by itself, so it is issued for the PREVIOUS tile once that tile's
-        // MMAs have retired - by then this tile's MMAs are already queued and the tensor pipe stays busy.
-        const int sh = (t == 0) ? -1 : t - 1;
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const int ts = pass == 0 ? sh : (t == 7 ? 7 : -1);   // after the last tile also finish that tile itself
-          if (ts < 0) continue;
-          const int as = ts & 3;
-          HN_FF_WAIT(7, mma_done(as), (ts >> 2) & 1);
+        issue_l1_half(1);
+      }
+      for (int it = 0; it < n_local; ++it) {
+        const int b = it & 1;
+        const bool more = it + 1 < n_local;
+        if (iw == 0 && more) {
+          HN_FF_WAIT(2, a1_full, (it + 1) & 1);
+          HN_FF_WAIT(3, l1_empty, 1);          // second half of patch `it` has been drained
           tc_fence_after();
-          if (elect_one()) {
-            const uint32_t ds = tm_c2 + as * 96 + 64;
+          issue_l1_half(0);
+        }
+        HN_FF_WAIT(4, act1_full(b), (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t act_lo = act_lo0 + b * (kFfAct1 >> 4);
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(ds + c8 * 8) : "memory");
-            umma_commit(c2_full(as));
-            if (ts == 7) umma_commit(act1_empty(b));
+        for (int tt = 0; tt < 4; ++tt) {
+          const int t = 2 * tt + iw;
+          if (iw == 0 && tt == 2 && more) {
+            HN_FF_WAIT(5, l1_empty, 0);        // first half of patch `it + 1` has been drained
+            tc_fence_after();
+            issue_l1_half(1);
+          }
+          const int a = t & 3;             // 8 tiles per patch over 4 buffers: each buffer is used twice per patch
+          HN_FF_WAIT(6, c2_empty(a), ((t >> 2) & 1) ^ 1u);
+          tc_fence_after();
+          HN_FF_SECTION_BEGIN();
+          if (elect_one()) {
+            const uint32_t d = tm_c2 + a * 96;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                // A: 128 slots starting at image row 4t + ky - 1 (slot (4t + ky) * 32), channels 16k .. 16k + 15
+                umma_f16_w(d, act_lo + (((t * 128 + ky * 32) * 16 + k * 2 * kFfPlane) >> 4), C2A_HI,
+                           w2_lo + ((ky * kFfW2Tap + k * 256) >> 4), C2B_HI, idesc2, (ky | k) != 0);
+              }
+            }
+            umma_commit(mma_done(a));                  // -> shifter warp -> c2_full(a)
+            if (tt == 3) umma_commit(act1_empty(b));   // this issuer's MMAs no longer read act1[b]
           }
           __syncwarp();
+          HN_FF_SECTION_END(13);
         }
-        __syncwarp();
       }
-    }
     }   // !PW2
   } else if (warp < 4) {
     // ============================== stage-1 epilogue: TMEM -> bias, ReLU, pack -> act1 (smem) ==============================
