@@ -44,7 +44,8 @@ constexpr uint32_t kFfW2 = 3 * kFfW2Tap;      // 18 432 B
 constexpr uint32_t kFfW1 = 1024;
 constexpr int kFfRawDepth = 4;                 // raw input patches prefetched ahead of the loaders (bulk async copies)
 constexpr uint32_t kFfRaw = kFfRawDepth * 4096;
-constexpr size_t kFfSmem = kFfA1 + 2 * kFfAct1 + kFfW2 + kFfW1 + kFfRaw + 256 /*barriers*/ + 256 /*biases + reductions*/ + 1024 /*align*/;
+constexpr uint32_t kFfStage = 8 * 2048;       // PW2 only: one 32-pixel x 32-channel output staging tile per epilogue warp
+constexpr size_t kFfSmem = kFfA1 + 2 * kFfAct1 + kFfW2 + kFfW1 + kFfRaw + kFfStage + 256 /*barriers*/ + 256 /*biases + reductions*/ + 1024 /*align*/;
 static_assert(kFfSmem <= 227 * 1024, "smem budget");
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -77,7 +78,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
                    const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
                    const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
                    const float* __restrict__ bias2 /*[32]*/, int do_norm /*0: no input normalisation*/,
-                   int num_patches, int act_bf16) {
+                   int num_patches, int act_bf16,
+                   const __grid_constant__ CUtensorMap tm_out /*PW2: [n * 1024, 32] as 32 x 32 boxes, 64B swizzle*/) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -87,7 +89,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   const uint32_t w2_addr = act1_addr + 2 * kFfAct1;
   const uint32_t w1_addr = w2_addr + kFfW2;
   const uint32_t raw_addr0 = w1_addr + kFfW1;
-  const uint32_t bar_base = raw_addr0 + kFfRaw;
+  const uint32_t stage_addr = raw_addr0 + kFfRaw;
+  const uint32_t bar_base = stage_addr + kFfStage;
   const uint32_t a1_full = bar_base, a1_empty = bar_base + 8, l1_full = bar_base + 16, l1_empty = bar_base + 24;
   auto act1_full = [&](int b) { return bar_base + 32u + 8u * b; };
   auto act1_empty = [&](int b) { return bar_base + 48u + 8u * b; };
@@ -492,19 +495,35 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
           uint32_t r[32];
           tmem_ld32(t_row, r);
           tmem_ld_wait();
-          uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(patch) * 1024 + (4 * t + q) * 32 + lane) * 32);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(c2_empty(a));
+            bulk_wait_read<0>();                  // this warp's previous store is done reading the staging tile
+          }
+          __syncwarp();
+          // A warp's 32 pixels x 32 channels = 2 KB of contiguous NHWC output: staged in the 64B-swizzle pattern (16-byte
+          // chunk c of row r at chunk c ^ ((r >> 1) & 3): conflict-free) and written by ONE TMA store. Direct 16-byte
+          // stores at a 64-byte stride are 32 sectors per request and kept the L1 pipe of this kernel 79 % busy.
+          const uint32_t stg = stage_addr + (warp - 4) * 2048 + lane * 64;
+          const uint32_t swz = (lane >> 1) & 3;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float4 b0 = *reinterpret_cast<const float4*>(s_bias2 + c * 8), b1 = *reinterpret_cast<const float4*>(s_bias2 + c * 8 + 4);
             const uint32_t* rr = r + c * 8;
-            dst[c] = make_uint4(pack16_relu(__uint_as_float(rr[0]) + b0.x, __uint_as_float(rr[1]) + b0.y, act_bf16),
-                                pack16_relu(__uint_as_float(rr[2]) + b0.z, __uint_as_float(rr[3]) + b0.w, act_bf16),
-                                pack16_relu(__uint_as_float(rr[4]) + b1.x, __uint_as_float(rr[5]) + b1.y, act_bf16),
-                                pack16_relu(__uint_as_float(rr[6]) + b1.z, __uint_as_float(rr[7]) + b1.w, act_bf16));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + ((c ^ swz) << 4)),
+                         "r"(pack16_relu(__uint_as_float(rr[0]) + b0.x, __uint_as_float(rr[1]) + b0.y, act_bf16)),
+                         "r"(pack16_relu(__uint_as_float(rr[2]) + b0.z, __uint_as_float(rr[3]) + b0.w, act_bf16)),
+                         "r"(pack16_relu(__uint_as_float(rr[4]) + b1.x, __uint_as_float(rr[5]) + b1.y, act_bf16)),
+                         "r"(pack16_relu(__uint_as_float(rr[6]) + b1.z, __uint_as_float(rr[7]) + b1.w, act_bf16))
+                         : "memory");
           }
-          tc_fence_before();
+          fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(c2_empty(a));
+          if (lane == 0) {
+            tma_store_2d(&tm_out, stage_addr + (warp - 4) * 2048, 0, patch * 1024 + (4 * t + q) * 32);
+            bulk_commit();
+          }
           continue;
         }
         // channel-planar parity layout for the stride-2 conv3: [plane][ypar][xpar][16][16][8]
@@ -548,6 +567,9 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     }
   }
 
+  if constexpr (PW2) {
+    if (warp >= 4 && warp < kFfIssuer && lane == 0) bulk_wait_all<0>();   // output stores still read this CTA's smem
+  }
   tc_fence_before();
   __syncthreads();
 #ifdef HN_FF_TRACE

@@ -17,8 +17,9 @@ int launch_head(const TcParams& p, int sm_count, cudaStream_t stream);
 int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, float2* stats, int n,
               int act_bf16, int sm_count, cudaStream_t s);
 // NAS front: stem + pointwise 32 -> 32 conv in one launch of the fused front kernel (hardnet_forward.cu)
-int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const float* w1, const float* bias1,
-                    const uint16_t* w2img, const float* bias2, int n, int act_bf16, int sm_count, cudaStream_t s);
+int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUtensorMap& tm_out, const float* w1,
+                    const float* bias1, const uint16_t* w2img, const float* bias2, int n, int act_bf16, int sm_count,
+                    cudaStream_t s);
 void front_pw_weight_image(const uint16_t* w /*[32][32] 16-bit*/, std::vector<uint16_t>& img);
 }  // namespace hn
 

@@ -633,6 +633,7 @@ struct NasState {
   uint16_t* slot[3] = {nullptr, nullptr, nullptr};
   uint16_t* head_in = nullptr;       // [head_rows, head_k]
   uint16_t* front_img = nullptr;     // op 1 as a fused-front weight image when stem + op 1 run as one kernel, else null
+  CUtensorMap front_tm;              // its output ([chunk * 1024, 32] as 32 x 32 store boxes, 64B swizzle)
   size_t slot_elems = 0;             // per patch
   int chunk = 0;                     // patches per pass (<= handle chunk, capped so the three slots stay <= 4 GiB)
   int head_k = 0;
@@ -716,7 +717,7 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
       int first = 0;
       if (st->front_img && last_op >= 1 && nas_front_fused()) {
         const hn_nas_op &o0 = st->ops[0], &o1 = st->ops[1];
-        HN_TRY(launch_front_pw(src, in_dtype, st->slot[o1.dst], st->params + o0.w_off, st->params + o0.b_off, st->front_img,
+        HN_TRY(launch_front_pw(src, in_dtype, st->slot[o1.dst], st->front_tm, st->params + o0.w_off, st->params + o0.b_off, st->front_img,
                                st->params + o1.b_off, n, bf, h->sm_count, s));
         first = 2;
       }
@@ -985,6 +986,13 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
       p.l2_eps = 0.f;  // torch.norm without eps (model_supernet.py:84)
       p.act_bf16 = bf;
     }
+  }
+  if (st->front_img) {
+    const uint64_t dimsO[2] = {32, static_cast<uint64_t>(st->chunk) * 1024};
+    const uint64_t strO[1] = {64};
+    const uint32_t boxO[2] = {32, 32};
+    const int rc = make_tmap_16bit(&st->front_tm, st->slot[ops[1].dst], 2, dimsO, strO, boxO, 64);
+    if (rc != HN_OK) return fail(rc);
   }
   h->nas = st;
   return HN_OK;
