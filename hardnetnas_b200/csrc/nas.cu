@@ -704,6 +704,11 @@ static bool nas_front_fused() {                // HN_NAS_FRONT=0 keeps stem and 
   return !(e && e[0] == '0');
 }
 
+static bool dw_tall_strips() {                 // HN_NAS_DW_SH8=0: 4-row strips for every shape (A/B measurements)
+  const char* e = std::getenv("HN_NAS_DW_SH8");
+  return !(e && e[0] == '0');
+}
+
 static bool dw_via_smem() {                    // HN_NAS_DW_SMEM=0 selects the register-strip kernel (A/B measurements, tests)
   const char* e = std::getenv("HN_NAS_DW_SMEM");
   return !(e && e[0] == '0');
@@ -747,27 +752,32 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
             // with expansion 1); wider expansions fall through to the register-strip kernel below
             if (strip && dw_via_smem()) {
               const size_t map_bytes = static_cast<size_t>(o.hin) * o.hin * o.cin * 2;
-              const int items = (o.hout / 4) * o.hout * (o.cin / 8);
+              // 5x5 stride 1 is bound by the fp32 pipe + unpack instructions: strips of 8 rows re-use each loaded and
+              // unpacked input vector for more taps (12 rows for 8 outputs instead of 8 for 4)
+              const int sh = (o.kernel == 5 && o.stride == 1 && o.hout % 8 == 0 && dw_tall_strips()) ? 8 : 4;
+              const int items = (o.hout / sh) * o.hout * (o.cin / 8);
               int G = std::max(1, 256 / items);
               const size_t w_bytes = ((static_cast<size_t>(o.kernel) * o.kernel + 1) * o.cin * 4 + 127) & ~size_t(127);
               while (G > 1 && w_bytes + 2 * G * map_bytes + 32 > 110 * 1024) G >>= 1;
               const size_t smem = w_bytes + 2 * G * map_bytes + 32;
               if (smem <= 227 * 1024) {
                 const int units = (n + G - 1) / G;
-                const int per_sm = std::max(1, std::min(4, static_cast<int>((227 * 1024) / (smem + 1024))));
+                // resident CTAs per SM: shared memory, and registers for the 8-row variant (~176 per thread)
+                const int per_sm = sh == 8 ? 1 : std::max(1, std::min(4, static_cast<int>((227 * 1024) / (smem + 1024))));
                 const int sgrid = std::min(units, h->sm_count * per_sm);
-#define HN_DW_SMEM(KK, SS, BF)                                                                                        \
+#define HN_DW_SMEM(KK, SS, SHH, BF)                                                                                   \
   do {                                                                                                                \
     static DeviceOnce once;                                                                                           \
     if (once.first_time())                                                                                            \
-      HN_CUDA(cudaFuncSetAttribute(dw_conv_smem_kernel<KK, SS, 4, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-    dw_conv_smem_kernel<KK, SS, 4, BF><<<sgrid, 256, smem, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, G, o.relu);   \
+      HN_CUDA(cudaFuncSetAttribute(dw_conv_smem_kernel<KK, SS, SHH, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    dw_conv_smem_kernel<KK, SS, SHH, BF><<<sgrid, 256, smem, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, G, o.relu); \
   } while (0)
-#define HN_DW_SMEM_T(KK, SS) do { if (bf) HN_DW_SMEM(KK, SS, true); else HN_DW_SMEM(KK, SS, false); } while (0)
-                if (o.kernel == 3 && o.stride == 1) HN_DW_SMEM_T(3, 1);
-                else if (o.kernel == 3) HN_DW_SMEM_T(3, 2);
-                else if (o.stride == 1) HN_DW_SMEM_T(5, 1);
-                else HN_DW_SMEM_T(5, 2);
+#define HN_DW_SMEM_T(KK, SS, SHH) do { if (bf) HN_DW_SMEM(KK, SS, SHH, true); else HN_DW_SMEM(KK, SS, SHH, false); } while (0)
+                if (o.kernel == 3 && o.stride == 1) HN_DW_SMEM_T(3, 1, 4);
+                else if (o.kernel == 3) HN_DW_SMEM_T(3, 2, 4);
+                else if (o.stride == 1 && sh == 8) HN_DW_SMEM_T(5, 1, 8);
+                else if (o.stride == 1) HN_DW_SMEM_T(5, 1, 4);
+                else HN_DW_SMEM_T(5, 2, 4);
 #undef HN_DW_SMEM_T
 #undef HN_DW_SMEM
                 HN_CUDA(cudaGetLastError());
