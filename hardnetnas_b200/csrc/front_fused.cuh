@@ -72,12 +72,19 @@ __device__ unsigned long long hn_ff_trace[32];
 // PW2 = true is the NAS front (stem + the first block's 1x1 expansion, hardnetNAS fbnet_builder.py IRFBlock `pw`): the
 // second stage is a pointwise 32 -> 32 conv, i.e. only the centre tap of the same weight image, two N = 32 MMAs per
 // tile, no shift-and-add, and the output is plain NHWC ([n][32][32][32]) for the NAS op kernels.
+// Second-stage bias as a kernel parameter: parameters live in the constant bank, so `x + bias.v[c]` with a compile-time
+// c is one FADD with a constant operand. The former per-tile LDS.128 of the bias were 512 of the ~1400 shared-memory
+// data wavefronts per patch of a kernel bound by that pipe.
+struct FfBias {
+  float v[32];
+};
+
 template <typename TIn, bool PW2 = false>
 __global__ void __launch_bounds__(kFfThreads, 1)
 front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]; PW2: NHWC*/,
                    const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
                    const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
-                   const float* __restrict__ bias2 /*[32]*/, int do_norm /*0: no input normalisation*/,
+                   const __grid_constant__ FfBias bias2 /*[32]*/, int do_norm /*0: no input normalisation*/,
                    int num_patches, int act_bf16,
                    const __grid_constant__ CUtensorMap tm_out /*PW2: [n * 1024, 32] as 32 x 32 boxes, 64B swizzle*/) {
   extern __shared__ uint8_t smem_raw[];
@@ -101,7 +108,6 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   auto mma_done = [&](int a) { return bar_base + 200u + 8u * a; };
   const uint32_t tmem_slot = bar_base + 128;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + (tmem_slot - base));
-  float* s_bias2 = reinterpret_cast<float*>(gbase + (bar_base + 256 - base));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,7 +165,6 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       }
       W[((n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) >> 1] = to16bits(v, act_bf16);
     }
-    if (t < 32) s_bias2[t] = bias2[t];
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -509,7 +514,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
           const uint32_t swz = (lane >> 1) & 3;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias2 + c * 8), b1 = *reinterpret_cast<const float4*>(s_bias2 + c * 8 + 4);
+            const float4 b0 = make_float4(bias2.v[c * 8], bias2.v[c * 8 + 1], bias2.v[c * 8 + 2], bias2.v[c * 8 + 3]);
+            const float4 b1 = make_float4(bias2.v[c * 8 + 4], bias2.v[c * 8 + 5], bias2.v[c * 8 + 6], bias2.v[c * 8 + 7]);
             const uint32_t* rr = r + c * 8;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + ((c ^ swz) << 4)),
                          "r"(pack16_relu(__uint_as_float(rr[0]) + b0.x, __uint_as_float(rr[1]) + b0.y, act_bf16)),
@@ -542,8 +548,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int c = 2 * h2 + cc;
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias2 + c * 8), b1 = *reinterpret_cast<const float4*>(s_bias2 + c * 8 + 4);
-          const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float bias[8] = {bias2.v[c * 8], bias2.v[c * 8 + 1], bias2.v[c * 8 + 2], bias2.v[c * 8 + 3],
+                                 bias2.v[c * 8 + 4], bias2.v[c * 8 + 5], bias2.v[c * 8 + 6], bias2.v[c * 8 + 7]};
           // The left neighbour's partial sum crosses lanes as fp16 pairs: one shuffle moves two values (shuffles run on
           // the shared-memory pipe, the busiest unit of this kernel). |D'| stays far inside the fp16 range and the extra
           // rounding (2^-11 relative on one addend) is below the output's own 16-bit rounding. Sums are fp32.

@@ -18,7 +18,7 @@ int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, 
               int act_bf16, int sm_count, cudaStream_t s);
 // NAS front: stem + pointwise 32 -> 32 conv in one launch of the fused front kernel (hardnet_forward.cu)
 int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUtensorMap& tm_out, const float* w1,
-                    const float* bias1, const uint16_t* w2img, const float* bias2, int n, int act_bf16, int sm_count,
+                    const float* bias1, const uint16_t* w2img, const float* bias2_host /*[32], HOST memory*/, int n, int act_bf16, int sm_count,
                     cudaStream_t s);
 void front_pw_weight_image(const uint16_t* w /*[32][32] 16-bit*/, std::vector<uint16_t>& img);
 }  // namespace hn
@@ -37,6 +37,7 @@ struct hn_handle {
   float* w1 = nullptr;                                                 // [9][32]
   uint16_t* w2img = nullptr;  // conv2 weights as the fused front kernel's shared-memory image (front_fused.cuh)
   float* bias = nullptr;                                               // 7 x 128
+  float bias2_host[32] = {0};   // conv2's folded BN shift on the host: passed to the fused front kernel by value
   float2* stats = nullptr;                                             // per-patch (mean, 1/std), chunk entries
   hn::TcParams conv_params[5];
   hn::TcParams pair_params[5];   // same layers for the CTA-pair kernels (tc_conv_pair.cuh)

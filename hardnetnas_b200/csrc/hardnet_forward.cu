@@ -167,12 +167,14 @@ static int launch_front_fused(hn_handle* h, const void* patches, int in_dtype, u
   const int grid = std::min(n, h->sm_count);
   const uint4* w2 = reinterpret_cast<const uint4*>(h->w2img);
   static const CUtensorMap no_map = {};   // output tensor map: only the pointwise (NAS) variant stores through TMA
+  FfBias b2;
+  memcpy(b2.v, h->bias2_host, sizeof(b2.v));
   if (in_dtype == HN_F32) {
     const float* x = static_cast<const float*>(patches);
-    front_fused_kernel<float><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, h->bias + 128, 1, n, h->act_bf16, no_map);
+    front_fused_kernel<float><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, b2, 1, n, h->act_bf16, no_map);
   } else {
     const uint8_t* x = static_cast<const uint8_t*>(patches);
-    front_fused_kernel<uint8_t><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, h->bias + 128, 1, n, h->act_bf16, no_map);
+    front_fused_kernel<uint8_t><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, b2, 1, n, h->act_bf16, no_map);
   }
   HN_CUDA(cudaGetLastError());
   count_launch(1);
@@ -182,7 +184,7 @@ static int launch_front_fused(hn_handle* h, const void* patches, int in_dtype, u
 // NAS front: stem (1 -> 32, 3x3, folded BN, ReLU) + the first block's pointwise 32 -> 32 conv (folded BN, ReLU) in one
 // launch of the fused front kernel (PW2 variant); `w2img` is a front-kernel weight image whose centre tap is the 1x1 conv.
 int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUtensorMap& tm_out, const float* w1,
-                    const float* bias1, const uint16_t* w2img, const float* bias2, int n, int act_bf16, int sm_count,
+                    const float* bias1, const uint16_t* w2img, const float* bias2_host, int n, int act_bf16, int sm_count,
                     cudaStream_t s) {
   static DeviceOnce attr_once;
   if (attr_once.first_time()) {
@@ -192,6 +194,8 @@ int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUte
   if (n <= 0) return HN_OK;
   const int grid = std::min(n, sm_count);
   const uint4* w2 = reinterpret_cast<const uint4*>(w2img);
+  FfBias bias2;
+  memcpy(bias2.v, bias2_host, sizeof(bias2.v));
   if (in_dtype == HN_F32)
     front_fused_kernel<float, true><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const float*>(patches), out, w1, bias1, w2, bias2, 0, n, act_bf16, tm_out);
   else
@@ -485,6 +489,7 @@ extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const floa
   }
   (void)cout;
   HN_CUDA(cudaMemcpy(h->bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+  memcpy(h->bias2_host, bias.data() + 128, sizeof(h->bias2_host));
   h->act_bf16 = bf;
   h->packed = true;
   return HN_OK;

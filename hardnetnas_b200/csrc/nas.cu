@@ -634,6 +634,7 @@ struct NasState {
   uint16_t* head_in = nullptr;       // [head_rows, head_k]
   uint16_t* front_img = nullptr;     // op 1 as a fused-front weight image when stem + op 1 run as one kernel, else null
   CUtensorMap front_tm;              // its output ([chunk * 1024, 32] as 32 x 32 store boxes, 64B swizzle)
+  float front_bias2[32];             // op 1's folded BN shift (host copy: a by-value kernel parameter)
   size_t slot_elems = 0;             // per patch
   int chunk = 0;                     // patches per pass (<= handle chunk, capped so the three slots stay <= 4 GiB)
   int head_k = 0;
@@ -723,7 +724,7 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
       if (st->front_img && last_op >= 1 && nas_front_fused()) {
         const hn_nas_op &o0 = st->ops[0], &o1 = st->ops[1];
         HN_TRY(launch_front_pw(src, in_dtype, st->slot[o1.dst], st->front_tm, st->params + o0.w_off, st->params + o0.b_off, st->front_img,
-                               st->params + o1.b_off, n, bf, h->sm_count, s));
+                               st->front_bias2, n, bf, h->sm_count, s));
         first = 2;
       }
       for (int i = first; i <= last_op; ++i) {
@@ -930,6 +931,7 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
       std::vector<uint16_t> w16(32 * 32), img;
       for (int j = 0; j < 32 * 32; ++j) w16[j] = f2h16(params[ops[1].w_off + j], bf);
       front_pw_weight_image(w16.data(), img);
+      memcpy(st->front_bias2, params + ops[1].b_off, sizeof(st->front_bias2));
       HN_CUDA_N(cudaMalloc(&st->front_img, img.size() * 2));
       HN_CUDA_N(cudaMemcpy(st->front_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
     }
