@@ -405,8 +405,10 @@ def side_measurements(device, model, rank, world):
     else:
         import torch.distributed as dist
 
+        g_counts = [hd.shard_range(n, r, world)[1] - hd.shard_range(n, r, world)[0] for r in range(world)]
+
         def fn():
-            hd.match_sharded(q, gal)
+            hd.match_sharded(q, gal, g_counts=g_counts)
         for _ in range(2):
             fn()
         dist.barrier(); torch.cuda.synchronize()
