@@ -490,6 +490,10 @@ extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const floa
   (void)cout;
   HN_CUDA(cudaMemcpy(h->bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
   memcpy(h->bias2_host, bias.data() + 128, sizeof(h->bias2_host));
+  for (int li = 0; li < 5; ++li) {   // by-value copies for the conv kernels' epilogues
+    memcpy(h->conv_params[li].bias_v, bias.data() + 128 * (li + 1), sizeof(h->conv_params[li].bias_v));
+    memcpy(h->pair_params[li].bias_v, bias.data() + 128 * (li + 1), sizeof(h->pair_params[li].bias_v));
+  }
   h->act_bf16 = bf;
   h->packed = true;
   return HN_OK;

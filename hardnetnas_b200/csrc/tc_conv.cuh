@@ -36,6 +36,8 @@ struct TcParams {
   CUtensorMap tmA[4];      // conv stride 1 / gemm: [0]; conv stride 2: parity views [ypar * 2 + xpar]
   CUtensorMap tmB;         // weights, [C_out, K] K-major
   const float* bias;       // [N] folded BatchNorm shift
+  float bias_v[128];       // conv kernels: the same values BY VALUE - parameters sit in the constant bank, so the epilogue's
+                           // `acc + bias` is an FADD with a constant operand instead of shared-memory loads on the busy L1 pipe
   void* out;               // conv: 16-bit channel-planar (see above); head: f32/f16/bf16 [rows, N]
   long long total_rows;    // valid output rows (pixels or patches)
   int num_tiles;
@@ -156,7 +158,6 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
   const uint32_t w_bar = bar_base + 8u * (2 * STAGES + 4);
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -187,9 +188,6 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
     __syncwarp();
     tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < N; i += 128) s_bias[i] = p.bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -371,7 +369,7 @@ __global__ void __launch_bounds__(kTcThreads, MINB) conv3x3_kernel(const __grid_
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            o[j] = pack16_relu(__uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], __uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1],
+            o[j] = pack16_relu(__uint_as_float(r[2 * j]) + p.bias_v[c0 + 2 * j], __uint_as_float(r[2 * j + 1]) + p.bias_v[c0 + 2 * j + 1],
                                p.act_bf16);
           if (valid) {
 #pragma unroll

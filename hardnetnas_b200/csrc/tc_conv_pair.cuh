@@ -124,7 +124,6 @@ conv3x3_pair_kernel(const __grid_constant__ TcParams p) {
   const uint32_t w_bar = bar_base + 8u * (2 * STAGES + 4);
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 5);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -157,9 +156,6 @@ conv3x3_pair_kernel(const __grid_constant__ TcParams p) {
     __syncwarp();
     tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
     tmem_relinquish_pair();
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < N; i += 128) s_bias[i] = p.bias[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -299,7 +295,7 @@ conv3x3_pair_kernel(const __grid_constant__ TcParams p) {
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          o[j] = pack16_relu(__uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], __uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1],
+          o[j] = pack16_relu(__uint_as_float(r[2 * j]) + p.bias_v[c0 + 2 * j], __uint_as_float(r[2 * j + 1]) + p.bias_v[c0 + 2 * j + 1],
                              p.act_bf16);
         if (valid) {
 #pragma unroll
