@@ -391,6 +391,21 @@ def side_measurements(device, model, rank, world):
             da, dp = model(a), model(p)
             return loss_HardNet(da, dp, anchor_swap=True)
         res["config1_forward_loss_batch1024_ms"] = timeit(step, 20)
+        # the same step captured once into a CUDA graph (the calls are stream-ordered, no hidden synchronisation)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            res["config1_forward_loss_batch1024_cuda_graph_ms"] = timeit(graph.replay, 50)
+            del graph
+        except Exception as exc:   # a capture problem must not take the bench line down
+            res["config1_forward_loss_batch1024_cuda_graph_ms"] = None
+            print(f"[bench] CUDA graph capture of the config-1 step failed: {exc}", file=sys.stderr)
         da, dp = model(a), model(p)
         res["config1_loss_only_ms"] = timeit(lambda: loss_HardNet(da, dp, anchor_swap=True), 50)
     # matching: 65536 x 65536 overall, query rows and gallery rows sharded over the ranks

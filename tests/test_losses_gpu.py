@@ -167,3 +167,33 @@ def test_config2_forward_plus_loss():
                    - losses_oracle.loss_hardnet(ra, rp, swap).item()) <= LOSS_TOL
         # end to end (16-bit conv stack): stated bound 1e-3
         assert abs(loss_HardNet(da, dp, anchor_swap=swap).item() - losses_oracle.loss_hardnet(ra, rp, swap).item()) <= 1e-3
+
+
+def test_config2_step_is_cuda_graph_capturable():
+    """The hot calls are stream-ordered with no hidden synchronisation (all work is enqueued on the
+    passed stream): forward of anchors + positives and the fused loss capture into ONE CUDA graph, and a replay on new
+    inputs reproduces the eager result bit for bit."""
+    from hardnetnas_b200.hardnet import HardNet
+    from hardnetnas_b200.losses import loss_HardNet
+    torch.manual_seed(0)
+    model = HardNet().cuda().eval()
+    a = synth.make_patches(1024, 1234).cuda()
+    p = synth.make_positives(a.cpu(), 0.1, 7).cuda()
+    a2 = synth.make_patches(1024, 99).cuda()
+    p2 = synth.make_positives(a2.cpu(), 0.1, 8).cuda()
+    eager = loss_HardNet(model(a2), model(p2), anchor_swap=True).clone()
+    xa, xp = a.clone(), p.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):            # warm-up on the capture stream (attribute setting, workspace growth)
+        for _ in range(2):
+            loss_HardNet(model(xa), model(xp), anchor_swap=True)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss = loss_HardNet(model(xa), model(xp), anchor_swap=True)
+    xa.copy_(a2)
+    xp.copy_(p2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(loss, eager), (loss.item(), eager.item())
