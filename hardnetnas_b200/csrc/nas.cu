@@ -34,6 +34,7 @@ struct PwParams {
   CUtensorMap tmA;       // activations [rows, C_in]
   CUtensorMap tmB;       // weights [C_out, C_in] (BN scale folded)
   CUtensorMap tmO;       // output [rows, C_out] as 32-row x min(NT, 64)-column swizzled store boxes
+  CUtensorMap tmR;       // residual (same geometry as tmO), loaded into the output staging tile by the epilogue
   const float* bias;     // [C_out]
   const uint16_t* res;   // optional residual [rows, C_out]
   uint16_t* out;         // [rows, C_out]
@@ -77,7 +78,7 @@ constexpr int pw_stages() {
   return s > 16 ? 16 : s;
 }
 template <int NT, int KCB>
-constexpr uint32_t pw_bias_off() { return (8u * (2 * pw_stages<NT, KCB>() + 9) + 15u) & ~15u; }
+constexpr uint32_t pw_bias_off() { return (8u * (2 * pw_stages<NT, KCB>() + 9 + 16) + 15u) & ~15u; }   // + 16 residual barriers
 
 template <int NT, int KCB>
 constexpr size_t pw_smem_bytes() {
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(pw_threads<NT>(), 1) pw_gemm_kernel(const __gr
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 4 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 8);
+  auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 9 + w); };   // one per epilogue warp
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + pw_bias_off<NT, KCB>() - raw_addr));
 
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(pw_threads<NT>(), 1) pw_gemm_kernel(const __gr
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmO);
+    if (p.res != nullptr) tma_prefetch_desc(&p.tmR);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(pw_threads<NT>(), 1) pw_gemm_kernel(const __gr
         mbar_init(tfull_bar(a), 1);
         mbar_init(tempty_bar(a), 4);
       }
+      for (int w = 0; w < 4 * GROUPS; ++w) mbar_init(res_bar(w), 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -203,8 +207,29 @@ __global__ void __launch_bounds__(pw_threads<NT>(), 1) pw_gemm_kernel(const __gr
       const int mt = p.n_tiles == 1 ? tile : tile / p.n_tiles, nt = tile - mt * p.n_tiles;
       const int acc = it & 3;
       const uint32_t acc_phase = (it >> 2) & 1;
+      constexpr int BOXC = NT < 64 ? NT : 64;
+      constexpr uint32_t BOX_BYTES = 32u * BOXC * 2u;
+      const uint32_t stg = staging_base + static_cast<uint32_t>((warp - 2) * (NT / BOXC)) * BOX_BYTES;
+      const uint32_t swz = BOXC == 64 ? (lane & 7) : ((lane >> 1) & 3);
+      const bool tma_res = pw_tma_out<NT>() && p.res != nullptr;
+      if constexpr (pw_tma_out<NT>()) {
+        // The staging tile is free once this warp's previous store has read it. With a residual the tile is first
+        // FILLED with the residual rows by TMA (same box geometry and swizzle as the store), issued before the wait
+        // for the accumulator so its latency hides behind the MMAs; the epilogue then adds in place.
+        if (lane == 0) {
+          bulk_wait_read<0>();
+          if (tma_res) {
+            mbar_arrive_expect_tx(res_bar(warp - 2), 32u * NT * 2u);
+#pragma unroll
+            for (int bx = 0; bx < NT / BOXC; ++bx)
+              tma_load_2d(stg + bx * BOX_BYTES, &p.tmR, res_bar(warp - 2), nt * NT + bx * BOXC, mt * kTileM + q * 32);
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (tma_res) mbar_wait(res_bar(warp - 2), ((it - grp) / GROUPS) & 1);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT;
       const long long row = static_cast<long long>(mt) * kTileM + row_in_tile;
       const bool valid = row < p.total_rows;
@@ -212,14 +237,6 @@ __global__ void __launch_bounds__(pw_threads<NT>(), 1) pw_gemm_kernel(const __gr
       // Output rows leave through swizzled TMA stores: a thread's 16-byte chunks go to the staging tile at
       // chunk ^ f(row) (the 64B / 128B swizzle patterns), which makes the shared-memory writes conflict free and the
       // global writes whole lines; direct 16-byte stores at a row stride touched 32 half-used sectors per request.
-      constexpr int BOXC = NT < 64 ? NT : 64;
-      constexpr uint32_t BOX_BYTES = 32u * BOXC * 2u;
-      const uint32_t stg = staging_base + static_cast<uint32_t>((warp - 2) * (NT / BOXC)) * BOX_BYTES;
-      const uint32_t swz = BOXC == 64 ? (lane & 7) : ((lane >> 1) & 3);
-      if constexpr (pw_tma_out<NT>()) {
-        if (lane == 0) bulk_wait_read<0>();     // this warp's previous store (two tiles ago) is done with the buffer
-        __syncwarp();
-      }
 #pragma unroll
       for (int c0 = 0; c0 < NT; c0 += 32) {
         uint32_t r[32];
@@ -228,7 +245,22 @@ __global__ void __launch_bounds__(pw_threads<NT>(), 1) pw_gemm_kernel(const __gr
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[nt * NT + c0 + j];
-        if (p.res != nullptr && valid) {
+        if (tma_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cc = c0 / 8 + j;
+            const uint32_t a = stg + (cc / (BOXC / 8)) * BOX_BYTES + lane * (BOXC * 2) + (((cc % (BOXC / 8)) ^ swz) << 4);
+            uint4 rv;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv.x), "=r"(rv.y), "=r"(rv.z), "=r"(rv.w) : "r"(a) : "memory");
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = unpack16(w[t], p.act_bf16);
+              v[8 * j + 2 * t] += f.x;
+              v[8 * j + 2 * t + 1] += f.y;
+            }
+          }
+        } else if (p.res != nullptr && valid) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.res + off + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -967,6 +999,10 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
         const uint32_t boxO[2] = {static_cast<uint32_t>(boxc), 32};
         rc = make_tmap_16bit(&p.tmO, st->slot[o.dst], 2, dimsO, strO, boxO, boxc * 2);
         if (rc != HN_OK) return fail(rc);
+        if (o.res >= 0) {
+          rc = make_tmap_16bit(&p.tmR, st->slot[o.res], 2, dimsO, strO, boxO, boxc * 2);
+          if (rc != HN_OK) return fail(rc);
+        }
       }
       p.bias = st->params + o.b_off;
       p.res = o.res >= 0 ? st->slot[o.res] : nullptr;
