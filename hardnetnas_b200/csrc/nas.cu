@@ -575,6 +575,98 @@ __global__ void __launch_bounds__(256) dw_conv_smem_kernel(const uint16_t* __res
   }
 }
 
+// MaxPool2d(3, stride 2, padding 1) through the same bulk-copied shared-memory ring as the depthwise kernel: a thread
+// owns 8 channels x a vertical strip of 4 output rows and takes packed 16-bit maxima directly (max is exact in fp16 /
+// bf16, NaNs propagate like torch); out-of-image taps read a -inf vector.
+template <bool BF16>
+__global__ void __launch_bounds__(256) maxpool_smem_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                           int patches, int C, int hin, int hout, int G) {
+  extern __shared__ __align__(128) uint8_t dw_smem[];
+  constexpr int SH = 4, NR = (SH - 1) * 2 + 3;
+  const int cg = C >> 3;
+  const int map_elems = hin * hin * C;
+  const uint32_t unit_bytes = static_cast<uint32_t>(G) * map_elems * 2;
+  const uint32_t bar0 = smem_u32(dw_smem + 2 * unit_bytes);
+  const uint32_t ninf = BF16 ? 0xFF80FF80u : 0xFC00FC00u;
+  const uint16_t* s_ninf = reinterpret_cast<const uint16_t*>(dw_smem + 2 * unit_bytes + 16);
+  if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(dw_smem + 2 * unit_bytes + 16)[threadIdx.x] = ninf;
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int units = (patches + G - 1) / G;
+  auto issue = [&](int u, int slot) {
+    const int np = min(G, patches - u * G);
+    const uint32_t bytes = static_cast<uint32_t>(np) * map_elems * 2;
+    const uint32_t bar = bar0 + 8 * slot;
+    mbar_arrive_expect_tx(bar, bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + static_cast<size_t>(u) * unit_bytes;
+    const uint32_t dst = smem_u32(dw_smem + slot * unit_bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768) {
+      const uint32_t n = min(32768u, bytes - o);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + o),
+                   "l"(src + o), "r"(n), "r"(bar)
+                   : "memory");
+    }
+  };
+  auto vmax = [](uint32_t a, uint32_t b) -> uint32_t {
+    if constexpr (BF16) {
+      const __nv_bfloat162 r = __hmax2_nan(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+      return *reinterpret_cast<const uint32_t*>(&r);
+    } else {
+      const __half2 r = __hmax2_nan(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+      return *reinterpret_cast<const uint32_t*>(&r);
+    }
+  };
+  if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < units) issue(blockIdx.x, 0);
+  const int strips = hout / SH;
+  const int items_per_patch = strips * hout * cg;
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int slot = it & 1;
+    if (threadIdx.x == 0 && u + static_cast<int>(gridDim.x) < units) issue(u + gridDim.x, slot ^ 1);
+    mbar_wait(bar0 + 8 * slot, (it >> 1) & 1);
+    const uint16_t* buf = reinterpret_cast<const uint16_t*>(dw_smem + slot * unit_bytes);
+    const int np = min(G, patches - u * G);
+    for (int e = threadIdx.x; e < np * items_per_patch; e += blockDim.x) {
+      const int c8 = (e % cg) * 8;
+      int t = e / cg;
+      const int ox = t % hout;
+      t /= hout;
+      const int ys = t % strips;
+      const int pl = t / strips;
+      const uint16_t* map = buf + pl * map_elems + c8;
+      uint4 acc[SH];
+#pragma unroll
+      for (int j = 0; j < SH; ++j) acc[j] = make_uint4(ninf, ninf, ninf, ninf);
+      const int iy0 = ys * SH * 2 - 1;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 + kx - 1;
+        const bool x_ok = ix >= 0 && ix < hin;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int iy = iy0 + r;
+          const bool ok = x_ok && iy >= 0 && iy < hin;
+          const uint4 xv = *reinterpret_cast<const uint4*>(ok ? map + (iy * hin + ix) * C : s_ninf);
+#pragma unroll
+          for (int j = 0; j < SH; ++j) {
+            const int ky = r - j * 2;          // compile-time after unrolling
+            if (ky >= 0 && ky < 3)
+              acc[j] = make_uint4(vmax(acc[j].x, xv.x), vmax(acc[j].y, xv.y), vmax(acc[j].z, xv.z), vmax(acc[j].w, xv.w));
+          }
+        }
+      }
+      uint16_t* optr = out + ((static_cast<size_t>(u) * G + pl) * hout + ys * SH) * hout * C + ox * C + c8;
+#pragma unroll
+      for (int j = 0; j < SH; ++j) *reinterpret_cast<uint4*>(optr + static_cast<size_t>(j) * hout * C) = acc[j];
+    }
+    __syncthreads();
+  }
+}
+
 // MaxPool2d(kernel 3, stride 2, padding 1): padding never wins (implicit -inf), like torch
 __global__ void __launch_bounds__(256) maxpool_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                                                       long long patches, int C, int hin, int hout, int bf16) {
@@ -832,6 +924,28 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
           case OP_MAXPOOL: {
             const long long total = static_cast<long long>(n) * o.hout * o.hout * (o.cin / 8);
             const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->sm_count * 16LL));
+            {
+              const size_t map_bytes = static_cast<size_t>(o.hin) * o.hin * o.cin * 2;
+              const int items = (o.hout / 4) * o.hout * (o.cin / 8);
+              int G = items > 0 ? std::max(1, 256 / items) : 1;
+              while (G > 1 && 2 * G * map_bytes + 48 > 110 * 1024) G >>= 1;
+              const size_t smem = 2 * G * map_bytes + 48;
+              if (o.hout % 4 == 0 && smem <= 227 * 1024 && dw_via_smem()) {
+                const int units = (n + G - 1) / G;
+                const int per_sm = std::max(1, std::min(4, static_cast<int>((227 * 1024) / (smem + 1024))));
+                const int sgrid = std::min(units, h->sm_count * per_sm);
+                static DeviceOnce once;
+                if (once.first_time()) {
+                  HN_CUDA(cudaFuncSetAttribute(maxpool_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                  HN_CUDA(cudaFuncSetAttribute(maxpool_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                }
+                if (bf) maxpool_smem_kernel<true><<<sgrid, 256, smem, s>>>(st->slot[o.src], st->slot[o.dst], n, o.cin, o.hin, o.hout, G);
+                else maxpool_smem_kernel<false><<<sgrid, 256, smem, s>>>(st->slot[o.src], st->slot[o.dst], n, o.cin, o.hin, o.hout, G);
+                HN_CUDA(cudaGetLastError());
+                count_launch();
+                break;
+              }
+            }
             maxpool_kernel<<<grid, 256, 0, s>>>(st->slot[o.src], st->slot[o.dst], n, o.cin, o.hin, o.hout, bf);
             HN_CUDA(cudaGetLastError());
             count_launch();
