@@ -135,3 +135,70 @@ def loss_HardNet(anchor, positive, anchor_swap=False, anchor_ave=False, margin=1
 def loss_HardNet_nas(anchor, positive, margin=1.0):
     """hardnetNAS/general_functions/Losses.py:27-51 — same loss with anchor swap always on."""
     return loss_HardNet(anchor, positive, anchor_swap=True, margin=margin)
+
+
+# ---- the other loss helpers of hardnet/Losses.py -----------------------------------------------------------------
+# O(N * D) or small-N training utilities next to the hot path; hardnet/HardNet.py:36 imports them by name, so a module
+# swap needs them. Plain torch expressions on whatever device the inputs live on (no hard-coded .cuda()).
+
+def distance_vectors_pairwise(anchor, positive, negative=None):
+    """Row-wise L2 distances d(a_i, p_i) [and d(a_i, n_i), d(p_i, n_i)] with the reference's +1e-8 under the root
+    (hardnet/Losses.py:15-27)."""
+    eps = 1e-8
+    sq_a = (anchor * anchor).sum(dim=1)
+    sq_p = (positive * positive).sum(dim=1)
+
+    def dist(sq_x, sq_y, x, y):
+        return torch.sqrt(sq_x + sq_y - 2 * (x * y).sum(dim=1) + eps)
+
+    d_ap = dist(sq_a, sq_p, anchor, positive)
+    if negative is None:
+        return d_ap
+    sq_n = (negative * negative).sum(dim=1)
+    return d_ap, dist(sq_a, sq_n, anchor, negative), dist(sq_p, sq_n, positive, negative)
+
+
+def _reduce_triplet(pos, min_neg, margin, loss_type, eps=1e-8):
+    if loss_type == "triplet_margin":
+        return torch.clamp(margin + pos - min_neg, min=0.0)
+    if loss_type == "softmax":
+        e_pos = torch.exp(2.0 - pos)
+        return -torch.log(e_pos / (e_pos + torch.exp(2.0 - min_neg) + eps))
+    if loss_type == "contrastive":
+        return torch.clamp(margin - min_neg, min=0.0) + pos
+    print('Unknown loss type. Try triplet_margin, softmax or contrastive')
+    sys.exit(1)
+
+
+def loss_random_sampling(anchor, positive, negative, anchor_swap=False, margin=1.0, loss_type="triplet_margin"):
+    """Triplet-style loss with given (random) negatives instead of in-batch mining (hardnet/Losses.py:29-55)."""
+    assert anchor.size() == positive.size(), "Input sizes between positive and negative must be equal."
+    assert anchor.size() == negative.size(), "Input sizes between positive and negative must be equal."
+    assert anchor.dim() == 2, "Inputd must be a 2D matrix."
+    pos, d_an, d_pn = distance_vectors_pairwise(anchor, positive, negative)
+    min_neg = torch.min(d_an, d_pn) if anchor_swap else d_an
+    return torch.mean(_reduce_triplet(pos, min_neg, margin, loss_type))
+
+
+def loss_L2Net(anchor, positive, anchor_swap=False, margin=1.0, loss_type="triplet_margin"):
+    """L2Net sampling: the whole batch is the negative set; only the softmax form exists (hardnet/Losses.py:57-85).
+    The reference also builds the diagonal / duplicate masks here but never uses them in this branch."""
+    assert anchor.size() == positive.size(), "Input sizes between positive and negative must be equal."
+    assert anchor.dim() == 2, "Inputd must be a 2D matrix."
+    if loss_type != 'softmax':
+        print('Only softmax loss works with L2Net sampling')
+        sys.exit(1)
+    eps = 1e-8
+    d = distance_matrix_vector(anchor, positive)
+    e = torch.exp(2.0 - d)
+    e_pos = torch.exp(2.0 - torch.diag(d))
+    loss = -torch.log(e_pos / (e.sum(dim=1) + eps))
+    if anchor_swap:
+        loss = loss - torch.log(e_pos / (e.sum(dim=0) + eps))
+    return torch.mean(loss)
+
+
+def global_orthogonal_regularization(anchor, negative):
+    """GOR (hardnet/Losses.py:156-162): (mean a.n)^2 + max(mean (a.n)^2 - 1/d, 0)."""
+    dots = (anchor * negative).sum(dim=1)
+    return dots.mean() ** 2 + torch.clamp((dots * dots).mean() - 1.0 / anchor.size(1), min=0.0)

@@ -114,3 +114,24 @@ def test_mutual_nn_definition():
     for i, j in pairs.tolist():
         assert fwd[i] == j and bwd[j] == i
     assert pairs.size(0) == int((bwd[fwd] == torch.arange(300)).sum())
+
+
+def test_other_loss_helpers_match_reference_goldens(golden_dir):
+    """distance_vectors_pairwise / loss_random_sampling / loss_L2Net / global_orthogonal_regularization (hardnet/Losses.py:
+    15-85,156-162; imported by name at hardnet/HardNet.py:36) against values produced by the unmodified reference
+    (oracle/make_golden_losses_extra.py). Host-side torch expressions, so they are checked on CPU tensors."""
+    from oracle.make_golden_losses_extra import inputs
+    from hardnetnas_b200 import losses
+    g = _load(golden_dir, "losses_extra.npz")
+    a, p, n = inputs()
+    assert np.allclose(losses.distance_vectors_pairwise(a, p).numpy(), g["pair_ap"], atol=1e-6)
+    d_ap, d_an, d_pn = losses.distance_vectors_pairwise(a, p, n)
+    assert np.allclose(d_an.numpy(), g["pair_an"], atol=1e-6) and np.allclose(d_pn.numpy(), g["pair_pn"], atol=1e-6)
+    for lt in ("triplet_margin", "softmax", "contrastive"):
+        for swap in (False, True):
+            got = losses.loss_random_sampling(a, p, n, anchor_swap=swap, margin=1.0, loss_type=lt).item()
+            assert abs(got - float(g[f"random_{lt}_swap{int(swap)}"])) <= 1e-6, (lt, swap, got)
+    for swap in (False, True):
+        got = losses.loss_L2Net(a, p, anchor_swap=swap, loss_type="softmax").item()
+        assert abs(got - float(g[f"l2net_softmax_swap{int(swap)}"])) <= 1e-5, (swap, got)
+    assert abs(losses.global_orthogonal_regularization(a, n).item() - float(g["gor"])) <= 1e-9
