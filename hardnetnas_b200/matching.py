@@ -52,3 +52,42 @@ def mutual_nearest_neighbors(des1, des2):
     i = torch.arange(des1.size(0), device=fwd.device)
     keep = bwd[fwd] == i
     return torch.stack([i[keep], fwd[keep]], dim=1)
+
+
+# ---- match-score counters (FDLNet-master/utils/eval_utils.py:112-197) -----------------------------------------------
+# The callers right behind the hot path in the reference's evaluation: nearest neighbour (or ratio test) on the fused
+# kernel, then "is the matched keypoint within COO_THRSH pixels of the warped keypoint" and two counters. The reference
+# builds an Nq x Nq coordinate distance matrix and takes its diagonal; the same expression is evaluated row-wise here.
+
+def _keypoint_distance(kp1w, nn_kp2):
+    """diag(pairwise_distances(kp1w[:, 1:3], nn_kp2[:, 1:3])) of math_utils.py:22-40: sqrt(clamp(|x|^2 + |y|^2 - 2 x.y, 1e-8))."""
+    x, y = kp1w[:, 1:3].float(), nn_kp2[:, 1:3].float()
+    sq = (x * x).sum(1) + (y * y).sum(1) - 2.0 * (x * y).sum(1)
+    return torch.sqrt(sq.clamp(min=1e-8))
+
+
+def _score(predict_label, kp1w, nn_kp2, visible, coo_thrsh, predicted):
+    correspondences = _keypoint_distance(kp1w, nn_kp2).le(coo_thrsh) & visible.bool()
+    correct = (predict_label & correspondences).sum().item()
+    return correct, max(predicted.sum().item(), 1)
+
+
+def nearest_neighbor_match_score(des1, des2, kp1w, kp2, visible, COO_THRSH):
+    """eval_utils.py:112-127 -> (correct_matches, predict_matches = max(#visible, 1))."""
+    _, nn_idx = nearest_neighbor_match(des1, des2)
+    vis = visible.bool()
+    return _score(vis, kp1w, kp2.index_select(0, nn_idx), vis, COO_THRSH, vis)
+
+
+def nearest_neighbor_threshold_match_score(des1, des2, kp1w, kp2, visible, DES_THRSH, COO_THRSH):
+    """eval_utils.py:130-150 -> (correct_matches, predict_matches = max(#(nn_value < DES_THRSH and visible), 1))."""
+    label, nn_idx = nearest_neighbor_threshold_match(des1, des2, DES_THRSH)
+    predict = label & visible.bool()
+    return _score(predict, kp1w, kp2.index_select(0, nn_idx), visible, COO_THRSH, predict)
+
+
+def nearest_neighbor_distance_ratio_match_score(des1, des2, kp1w, kp2, visible, COO_THRSH, threshold=0.7):
+    """eval_utils.py:178-197 -> (correct_matches, predict_matches = max(#(Da / Db < threshold and visible), 1))."""
+    label, nn_kp2 = nearest_neighbor_distance_ratio_match(des1, des2, kp2, threshold)
+    predict = label & visible.bool()
+    return _score(predict, kp1w, nn_kp2, visible, COO_THRSH, predict)

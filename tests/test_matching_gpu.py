@@ -120,3 +120,17 @@ def test_config4_full_size_properties():
     ratio = (d1 / d2).cpu()
     assert (ratio[planted] < 0.7).float().mean().item() > 0.99
     assert (ratio[~planted] < 0.7).float().mean().item() < 0.01
+
+
+def test_match_score_counters_match_reference_goldens(golden_dir):
+    """nearest_neighbor_match_score / _threshold_match_score / _distance_ratio_match_score (FDLNet-master/utils/eval_utils.py:
+    112-197) on the fused matching kernel against the counters the unmodified reference produced
+    (oracle/make_golden_match_scores.py)."""
+    import numpy as np
+    from hardnetnas_b200 import matching
+    from oracle.make_golden_match_scores import COO_THRSH, DES_THRSH, inputs
+    g = np.load(golden_dir / "match_scores.npz")
+    q, gal, kp1w, kp2, visible = (t.cuda() for t in inputs())
+    assert list(matching.nearest_neighbor_match_score(q, gal, kp1w, kp2, visible, COO_THRSH)) == g["nn"].tolist()
+    assert list(matching.nearest_neighbor_threshold_match_score(q, gal, kp1w, kp2, visible, DES_THRSH, COO_THRSH)) == g["nn_thresh"].tolist()
+    assert list(matching.nearest_neighbor_distance_ratio_match_score(q, gal, kp1w, kp2, visible, COO_THRSH)) == g["nn_ratio"].tolist()
