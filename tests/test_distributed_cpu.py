@@ -70,7 +70,10 @@ def test_two_rank_matching_equals_single_process():
     dfull = losses_oracle.distance_matrix_vector_fdl(q, g)
     rows = torch.arange(nq)
     assert (dfull[rows, i1.long()] - dfull[rows, ri1.long()]).abs().max().item() <= 1e-6
-    assert torch.allclose(d1, rd1, atol=1e-6) and torch.allclose(d2, rd2, atol=1e-6)
+    # d = sqrt(2 - 2 a.p): a rounding difference of the fp32 dot product (MKL picks other kernels / summation orders for
+    # shard-shaped GEMMs) is amplified by 1 / d ~ 2.3 for matched pairs; 2e-5 is far below any plumbing error
+    err1, err2 = (d1 - rd1).abs().max().item(), (d2 - rd2).abs().max().item()
+    assert err1 <= 2e-5 and err2 <= 2e-5, (err1, err2)
     pairs = torch.cat([ret[r][3] for r in range(world)])
     ref_pairs = losses_oracle.mutual_nn(q, g)
     a = {tuple(r) for r in pairs.tolist()}
