@@ -22,6 +22,7 @@ SIGNATURES = {
     "hn_version": (C.c_int, []),
     "hn_last_error": (C.c_char_p, []),
     "hn_launch_count": (C.c_longlong, []),
+    "hn_set_hardnet_eps": (C.c_int, [_P, C.c_float, C.c_float]),
     "hn_profile_enable": (C.c_int, [_P, C.c_uint]),
     "hn_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "hn_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_longlong]),

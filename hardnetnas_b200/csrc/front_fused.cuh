@@ -85,7 +85,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
                    const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
                    const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
                    const __grid_constant__ FfBias bias2 /*[32]*/, int do_norm /*0: no input normalisation*/,
-                   int num_patches, int act_bf16,
+                   int num_patches, int act_bf16, float norm_eps /*added to the std: 1e-7 HardNet, 1e-8 HardNetNeiMask*/,
                    const __grid_constant__ CUtensorMap tm_out /*PW2: [n * 1024, 32] as 32 x 32 boxes, 64B swizzle*/) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -239,7 +239,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         if (lane == 0) red[8 + lw] = q8;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         const float var = ((red[8] + red[9]) + (red[10] + red[11])) * (1.f / 1023.f);   // torch.std is unbiased
-        inv = 1.f / (sqrtf(var) + 1e-7f);
+        inv = 1.f / (sqrtf(var) + norm_eps);
       }
 #pragma unroll
       for (int r = 0; r < 10; ++r) {

@@ -15,7 +15,7 @@ void nas_state_free(NasState* s);
 int launch_head(const TcParams& p, int sm_count, cudaStream_t stream);
 // input_norm (optional) + conv 1->32 k3 + BN + ReLU on the tensor core (hardnet_forward.cu); also the NAS stem
 int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, float2* stats, int n,
-              int act_bf16, int sm_count, cudaStream_t s);
+              int act_bf16, int sm_count, cudaStream_t s, float norm_eps = 1e-7f);
 // NAS front: stem + pointwise 32 -> 32 conv in one launch of the fused front kernel (hardnet_forward.cu)
 int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUtensorMap& tm_out, const float* w1,
                     const float* bias1, const uint16_t* w2img, const float* bias2_host /*[32], HOST memory*/, int n, int act_bf16, int sm_count,
@@ -37,6 +37,7 @@ struct hn_handle {
   float* w1 = nullptr;                                                 // [9][32]
   uint16_t* w2img = nullptr;  // conv2 weights as the fused front kernel's shared-memory image (front_fused.cuh)
   float* bias = nullptr;                                               // 7 x 128
+  float norm_eps = 1e-7f;       // added to the per-patch std in input_norm (hn_set_hardnet_eps)
   float bias2_host[32] = {0};   // conv2's folded BN shift on the host: passed to the fused front kernel by value
   float2* stats = nullptr;                                             // per-patch (mean, 1/std), chunk entries
   hn::TcParams conv_params[5];

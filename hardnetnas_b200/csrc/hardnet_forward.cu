@@ -133,7 +133,7 @@ static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) 
 
 // Stage 1 (input_norm + conv 1->32 + BN + ReLU) on the tensor core; do_norm = 0 gives the NAS stem.
 int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, const float* bias, float2* stats, int n,
-              int act_bf16, int sm_count, cudaStream_t s) {
+              int act_bf16, int sm_count, cudaStream_t s, float norm_eps) {
   static DeviceOnce attr_once;
   if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(l1_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kL1TcSmem)));
@@ -144,11 +144,11 @@ int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, 
   const int sgrid = std::min((n + 7) / 8, sm_count * 8);
   if (in_dtype == HN_F32) {
     const float* x = static_cast<const float*>(patches);
-    if (stats) patch_stats_kernel<float><<<sgrid, 256, 0, s>>>(x, stats, n);
+    if (stats) patch_stats_kernel<float><<<sgrid, 256, 0, s>>>(x, stats, n, norm_eps);
     l1_tc_kernel<float><<<grid, kL1TcThreads, kL1TcSmem, s>>>(x, out, w, bias, stats, n, act_bf16);
   } else {
     const uint8_t* x = static_cast<const uint8_t*>(patches);
-    if (stats) patch_stats_kernel<uint8_t><<<sgrid, 256, 0, s>>>(x, stats, n);
+    if (stats) patch_stats_kernel<uint8_t><<<sgrid, 256, 0, s>>>(x, stats, n, norm_eps);
     l1_tc_kernel<uint8_t><<<grid, kL1TcThreads, kL1TcSmem, s>>>(x, out, w, bias, stats, n, act_bf16);
   }
   HN_CUDA(cudaGetLastError());
@@ -171,10 +171,10 @@ static int launch_front_fused(hn_handle* h, const void* patches, int in_dtype, u
   memcpy(b2.v, h->bias2_host, sizeof(b2.v));
   if (in_dtype == HN_F32) {
     const float* x = static_cast<const float*>(patches);
-    front_fused_kernel<float><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, b2, 1, n, h->act_bf16, no_map);
+    front_fused_kernel<float><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, b2, 1, n, h->act_bf16, h->norm_eps, no_map);
   } else {
     const uint8_t* x = static_cast<const uint8_t*>(patches);
-    front_fused_kernel<uint8_t><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, b2, 1, n, h->act_bf16, no_map);
+    front_fused_kernel<uint8_t><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, b2, 1, n, h->act_bf16, h->norm_eps, no_map);
   }
   HN_CUDA(cudaGetLastError());
   count_launch(1);
@@ -197,9 +197,9 @@ int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUte
   FfBias bias2;
   memcpy(bias2.v, bias2_host, sizeof(bias2.v));
   if (in_dtype == HN_F32)
-    front_fused_kernel<float, true><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const float*>(patches), out, w1, bias1, w2, bias2, 0, n, act_bf16, tm_out);
+    front_fused_kernel<float, true><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const float*>(patches), out, w1, bias1, w2, bias2, 0, n, act_bf16, 0.f, tm_out);
   else
-    front_fused_kernel<uint8_t, true><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const uint8_t*>(patches), out, w1, bias1, w2, bias2, 0, n, act_bf16, tm_out);
+    front_fused_kernel<uint8_t, true><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const uint8_t*>(patches), out, w1, bias1, w2, bias2, 0, n, act_bf16, 0.f, tm_out);
   HN_CUDA(cudaGetLastError());
   count_launch(1);
   return HN_OK;
@@ -326,7 +326,7 @@ static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n
                           cudaStream_t s) {
   if (last_layer < 2) {
     StageTimer timer(h, 0, s);  // stage 1 alone (activation dump only), NHWC
-    return launch_l1(patches, in_dtype, h->act[0], h->w1, h->bias, h->stats, n, h->act_bf16, h->sm_count, s);
+    return launch_l1(patches, in_dtype, h->act[0], h->w1, h->bias, h->stats, n, h->act_bf16, h->sm_count, s, h->norm_eps);
   }
   // The 64 KB/patch conv2 output is the largest tensor of the stack. The front kernel and conv3 run in sub-passes of
   // `front_chunk` patches over the SAME head of act[1], so it is produced and consumed inside the 126 MB L2 instead of
@@ -426,6 +426,14 @@ extern "C" int hn_destroy(hn_handle* h) {
     for (cudaEvent_t e : v) cudaEventDestroy(e);
   nas_state_free(h->nas);
   delete h;
+  return HN_OK;
+}
+
+extern "C" int hn_set_hardnet_eps(hn_handle* h, float input_norm_eps, float l2_eps) {
+  HN_REQUIRE(h, "hn_set_hardnet_eps: NULL handle");
+  HN_REQUIRE(input_norm_eps >= 0.f && l2_eps >= 0.f, "hn_set_hardnet_eps: negative epsilon");
+  h->norm_eps = input_norm_eps;
+  h->head_params.l2_eps = l2_eps;
   return HN_OK;
 }
 

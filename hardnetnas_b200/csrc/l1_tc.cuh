@@ -41,7 +41,7 @@ __device__ __forceinline__ uint16_t to16bits(float v, int bf16) {
 // reference's 0 / 1e-7.
 template <typename TIn>
 __global__ void __launch_bounds__(256) patch_stats_kernel(const TIn* __restrict__ in, float2* __restrict__ stats,
-                                                          int num_patches) {
+                                                          int num_patches, float norm_eps) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int patch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; patch < num_patches; patch += warps) {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) patch_stats_kernel(const TIn* __restrict_
     float v = t[0];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) stats[patch] = make_float2(mean, 1.f / (sqrtf(v * (1.f / 1023.f)) + 1e-7f));  // torch.std is unbiased
+    if (lane == 0) stats[patch] = make_float2(mean, 1.f / (sqrtf(v * (1.f / 1023.f)) + norm_eps));  // torch.std is unbiased
   }
 }
 

@@ -102,10 +102,13 @@ class HardNet(nn.Module):
         self._packed_key = None
 
     # ---- reference surface -------------------------------------------------------------------------
+    INPUT_NORM_EPS = 1e-7    # hardnet/HardNet.py:309
+    L2_EPS = 1e-10           # hardnet/Utils.py:18 (under the root)
+
     def input_norm(self, x):
         flat = x.view(x.size(0), -1)
         mp = torch.mean(flat, dim=1)
-        sp = torch.std(flat, dim=1) + 1e-7
+        sp = torch.std(flat, dim=1) + self.INPUT_NORM_EPS
         return (x - mp.detach().view(-1, 1, 1, 1)) / sp.detach().view(-1, 1, 1, 1)
 
     def forward(self, input, out_dtype: torch.dtype = torch.float32, out: torch.Tensor | None = None):
@@ -147,6 +150,8 @@ class HardNet(nn.Module):
             _lib.check(eng.lib.hn_pack_hardnet(eng.handle, _lib.float_ptr_array(ws), _lib.float_ptr_array(means),
                                                _lib.float_ptr_array(vars_), C.c_float(bns[0].eps),
                                                _DTYPES[self.act_dtype]), "hn_pack_hardnet")
+            _lib.check(eng.lib.hn_set_hardnet_eps(eng.handle, C.c_float(self.INPUT_NORM_EPS), C.c_float(self.L2_EPS)),
+                       "hn_set_hardnet_eps")
         self._packed_key = key
 
     def _check_input(self, input):

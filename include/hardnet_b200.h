@@ -65,6 +65,12 @@ int hn_destroy(hn_handle* h);
 int hn_pack_hardnet(hn_handle* h, const float* const w[7], const float* const bn_mean[7],
                     const float* const bn_var[7], float bn_eps, int act_dtype);
 
+/* The two epsilons of the forward: `input_norm_eps` is added to the per-patch std (1e-7 in hardnet/HardNet.py:309, 1e-8 in
+ * HardNetNeiMask.input_norm, FDLNet-master/latency/rfnet/model/rf_des.py:41-49), `l2_eps` goes under the root of the final
+ * L2 normalisation (1e-10 in hardnet/Utils.py:18; 0 for HardNetNeiMask's x / torch.norm(x), rf_des.py:51-55).
+ * Defaults are HardNet's; the setting stays with the handle. */
+int hn_set_hardnet_eps(hn_handle* h, float input_norm_eps, float l2_eps);
+
 /* HardNet.forward in eval mode: input_norm -> 7 conv/BN/ReLU stages -> L2Norm.
  * patches: [B,1,32,32] (HN_F32 or HN_U8); desc_out: [B,128] (HN_F32 / HN_F16 / HN_BF16). */
 int hn_forward(hn_handle* h, const void* patches, int in_dtype, long long B, void* desc_out,

@@ -1,0 +1,77 @@
+"""HardNetNeiMask (FDLNet-master/latency/rfnet/model/rf_des.py:11-116): mirror class, oracle and CUDA path against
+descriptors / losses produced by the unmodified reference class (oracle/make_golden_neimask.py)."""
+import numpy as np
+import pytest
+import torch
+
+from hardnetnas_b200.rf_des import HardNetNeiMask
+from oracle import hardnet_oracle, synth
+from oracle.make_golden_neimask import keypoints
+
+
+def _model():
+    torch.manual_seed(0)
+    model = HardNetNeiMask(1.0, 8.0)
+    model.load_state_dict(synth.randomize_bn_stats(model.state_dict(), 3))
+    return model.eval()
+
+
+def _inputs(g):
+    x = synth.make_patches(64, 1234)
+    x[5] = torch.from_numpy(g["x5"])
+    return x
+
+
+def _wmv(model):
+    convs = [m for m in model.features if isinstance(m, torch.nn.Conv2d)]
+    bns = [m for m in model.features if isinstance(m, torch.nn.BatchNorm2d)]
+    return ([c.weight.detach() for c in convs], [b.running_mean for b in bns], [b.running_var for b in bns])
+
+
+def test_mirror_regenerates_reference_weights_and_state_dict_keys(golden_dir):
+    g = np.load(golden_dir / "neimask.npz")
+    model = _model()
+    w, m, v = _wmv(model)
+    assert np.array_equal(synth.weights_fingerprint(w), g["weights_fingerprint"])
+    assert np.array_equal(synth.weights_fingerprint(list(m) + list(v)), g["bn_fingerprint"])
+    keys = set(model.state_dict().keys())
+    assert "features.18.weight" in keys and "features.19.running_mean" in keys and not any(k.startswith("features.20") for k in keys)
+
+
+def test_oracle_and_train_mode_expressions_match_reference(golden_dir):
+    g = np.load(golden_dir / "neimask.npz")
+    model = _model()
+    x = _inputs(g)
+    ref = torch.from_numpy(g["desc"])
+    got = hardnet_oracle.hardnet_forward(x, *_wmv(model), norm_eps=1e-8, l2_eps=0.0)
+    assert (got - ref).abs().max().item() <= 2e-6
+    # the tiny-std patch tells the two epsilons apart: with HardNet's 1e-7 the descriptor moves by far more
+    other = hardnet_oracle.hardnet_forward(x[5:6], *_wmv(model))
+    assert (other - ref[5:6]).abs().max().item() > 2e-3
+    a, p = ref[:32], ref[32:]
+    assert abs(model.loss(a, p, keypoints(32, 1), keypoints(32, 2)).item() - float(g["loss_c8"])) <= 1e-6
+    model.C = 0.0
+    assert abs(model.loss(a, p, keypoints(32, 1), keypoints(32, 2)).item() - float(g["loss_c0"])) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_cuda_forward_matches_reference(golden_dir):
+    g = np.load(golden_dir / "neimask.npz")
+    model = _model().cuda()
+    x = _inputs(g)
+    ref = torch.from_numpy(g["desc"])
+    got = model(x.cuda()).float().cpu()
+    # 16-bit conv stack: the repo's stated bound (max-abs 1e-3, cosine 0.9999), including row 5 whose std (~3e-8) is of the
+    # order of the input_norm epsilon
+    assert (got - ref).abs().max().item() <= 1e-3
+    assert torch.nn.functional.cosine_similarity(got, ref, dim=1).min().item() >= 0.9999
+    # with HardNet's epsilons the same engine gives a clearly different row 5: the setting is really applied
+    from hardnetnas_b200.hardnet import HardNet
+    plain = HardNet()
+    sd = {}
+    for k, v in model.state_dict().items():
+        idx = int(k.split(".")[1])
+        sd[k.replace(f"features.{idx}.", f"features.{idx + 1 if idx >= 18 else idx}.")] = v   # HardNet has Dropout at 18
+    plain.load_state_dict(sd)
+    other = plain.cuda().eval()(x[5:6].cuda()).float().cpu()
+    assert (other - ref[5:6]).abs().max().item() > 2e-3
