@@ -61,6 +61,8 @@ def test_loss_matches_reference_goldens(golden_dir):
         got = loss_HardNet(ua.cuda(), up.cuda(), anchor_swap=swap).item()
         assert abs(got - float(g[f"loss_unit_swap{int(swap)}"])) <= LOSS_TOL
     assert abs(loss_HardNet_nas(ua.cuda(), up.cuda()).item() - float(g["loss_nas_unit"])) <= LOSS_TOL
+    import hardnetnas_b200.nas.losses as nas_losses   # module stand-in for general_functions/Losses.py (model_supernet.py:7)
+    assert abs(nas_losses.loss_HardNet(ua.cuda(), up.cuda(), 1.0).item() - float(g["loss_nas_unit"])) <= LOSS_TOL
     # descriptors of the reference model (fresh BN), incl. the duplicate-row (<0.008 -> +10) mask cases
     w, m, v = synth.hardnet_weights_from_seed(0, None)
     anchors = synth.make_patches(256, 1234)
