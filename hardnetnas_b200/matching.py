@@ -17,6 +17,15 @@ def distance_matrix_vector(anchor, positive):
     return torch.sqrt(m.clamp(min=1e-8, max=4.0))
 
 
+def pairwise_distances(x, y=None):
+    """L2 distances between the rows of x and y (y = x when omitted), FDLNet-master/utils/math_utils.py:22-40:
+    sqrt(clamp(|x|^2 + |y|^2 - 2 x.y, min=1e-8)). Small coordinate sets only (keypoints); descriptors go through the fused
+    matching kernel."""
+    y = x if y is None else y
+    d = (x * x).sum(1).view(-1, 1) + (y * y).sum(1).view(1, -1) - 2.0 * torch.mm(x, y.t())
+    return torch.sqrt(d.clamp(min=1e-8))
+
+
 def nearest_neighbor_match(des1, des2):
     """`des_dist_matrix.min(dim=-1)` of eval_utils.py:113-114 -> (nn_value [Nq] fp32, nn_idx [Nq] int64)."""
     d1, _, i1, _ = _ops.match_top2(des1, des2)

@@ -11,14 +11,7 @@ import torch
 import torch.nn as nn
 
 from .hardnet import HardNet
-from .matching import distance_matrix_vector
-
-
-def _pairwise_keypoint_distances(x):
-    """pairwise_distances(x, x) of FDLNet-master/utils/math_utils.py:22-40 (sqrt of the clamped squared distance)."""
-    sq = (x * x).sum(1)
-    d = sq.view(-1, 1) + sq.view(1, -1) - 2.0 * torch.mm(x, x.t())
-    return torch.sqrt(d.clamp(min=1e-8))
+from .matching import distance_matrix_vector, pairwise_distances
 
 
 class HardNetNeiMask(HardNet):
@@ -48,7 +41,7 @@ class HardNetNeiMask(HardNet):
         pos = d.diag()
         masked = d + torch.eye(d.size(1), device=d.device, dtype=d.dtype) * 10
         for kp in (anchor_kp, positive_kp):
-            near = _pairwise_keypoint_distances(kp[:, 1:3].to(torch.float)).lt(self.C)
+            near = pairwise_distances(kp[:, 1:3].to(torch.float)).lt(self.C)
             masked = masked + near.to(torch.float) * 10
         hardest = torch.min(masked.min(dim=1)[0], masked.min(dim=0)[0])
         return torch.clamp(self.MARGIN + pos - hardest, min=0.0).mean()

@@ -33,15 +33,17 @@ def inputs():
 
 def main():
     sys.path.insert(0, str(REF / "FDLNet-master"))
-    from utils import eval_utils
+    from utils import eval_utils, math_utils
     q, g, kp1w, kp2, visible = inputs()
     out = {
         "nn": np.array(eval_utils.nearest_neighbor_match_score(q, g, kp1w, kp2, visible, COO_THRSH)),
         "nn_thresh": np.array(eval_utils.nearest_neighbor_threshold_match_score(q, g, kp1w, kp2, visible, DES_THRSH, COO_THRSH)),
         "nn_ratio": np.array(eval_utils.nearest_neighbor_distance_ratio_match_score(q, g, kp1w, kp2, visible, COO_THRSH)),
     }
+    out["pairwise_16"] = math_utils.pairwise_distances(kp1w[:16, 1:3], kp2[:24, 1:3]).numpy()
+    out["pairwise_self_16"] = math_utils.pairwise_distances(kp1w[:16, 1:3]).numpy()
     np.savez_compressed(ROOT / "tests" / "golden" / "match_scores.npz", **out)
-    print({k: v.tolist() for k, v in out.items()})
+    print({k: (v.tolist() if v.size < 8 else v.shape) for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -38,6 +38,15 @@ def test_mirror_regenerates_reference_weights_and_state_dict_keys(golden_dir):
     assert "features.18.weight" in keys and "features.19.running_mean" in keys and not any(k.startswith("features.20") for k in keys)
 
 
+def test_pairwise_distances_match_reference(golden_dir):
+    from hardnetnas_b200.matching import pairwise_distances
+    from oracle.make_golden_match_scores import inputs
+    g = np.load(golden_dir / "match_scores.npz")
+    _, _, kp1w, kp2, _ = inputs()
+    assert np.allclose(pairwise_distances(kp1w[:16, 1:3], kp2[:24, 1:3]).numpy(), g["pairwise_16"], atol=1e-4)
+    assert np.allclose(pairwise_distances(kp1w[:16, 1:3]).numpy(), g["pairwise_self_16"], atol=1e-2)   # sqrt near 0 on the diagonal
+
+
 def test_oracle_and_train_mode_expressions_match_reference(golden_dir):
     g = np.load(golden_dir / "neimask.npz")
     model = _model()
