@@ -32,6 +32,7 @@ SIGNATURES = {
     "hn_forward_dump": (C.c_int, [_P, _P, C.c_int, C.c_longlong, C.c_int, _P, _P]),
     "hn_pack_nas": (C.c_int, [_P, _P, C.c_int, _P, C.c_longlong, C.c_int]),
     "hn_forward_nas": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P, C.c_int, _P]),
+    "hn_nas_plan": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int]),
     "hn_forward_nas_dump": (C.c_int, [_P, _P, C.c_int, C.c_longlong, C.c_int, _P, _P]),
     "hn_dist_workspace_bytes": (C.c_longlong, [C.c_longlong, C.c_longlong, C.c_int]),
     "hn_dist_min": (C.c_int, [_P, _P, C.c_longlong, C.c_longlong, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P,

@@ -11,10 +11,15 @@ _ws_cache: dict = {}
 
 
 def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Per-device scratch reused across calls (grown on demand), so the hot calls never allocate."""
-    key = (device.type, device.index)
+    """Scratch reused across calls (grown on demand), so the hot calls never allocate. One buffer per (device, stream):
+    calls on different streams may run concurrently and must not share packed operands or partial minima; a buffer that is
+    outgrown is handed back to the caching allocator only after the work queued on its stream (record_stream)."""
+    stream = torch.cuda.current_stream(device)
+    key = (device.type, device.index, stream.cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            ws.record_stream(stream)
         ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
         _ws_cache[key] = ws
     return ws

@@ -23,7 +23,21 @@ int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUte
 void front_pw_weight_image(const uint16_t* w /*[32][32] 16-bit*/, std::vector<uint16_t>& img);
 }  // namespace hn
 
+// Run-time switches (A/B measurements, tests), read from the environment ONCE in hn_create: the hot calls never call getenv.
+struct HnEnv {
+  bool nas_front = true;      // HN_NAS_FRONT=0: stem and first pointwise conv as separate kernels
+  bool nas_dw_smem = true;    // HN_NAS_DW_SMEM=0: register-strip depthwise / max-pool kernels
+  bool nas_dw_sh8 = true;     // HN_NAS_DW_SH8=0: 4-row strips for every depthwise shape
+  bool nas_resident = false;  // HN_NAS_RESIDENT=1: runs of NAS ops as patch-resident segment kernels (nas_resident.cuh). Off by
+                              // default: measured slower than one kernel per op (profiles/r2_nas_resident_*)
+  int nas_minb = 0;           // HN_NAS_MINB: CTAs per SM of the segment kernel (0 = choose)
+  int nas_cut_ratio = 4;      // HN_NAS_CUT_RATIO: start a new segment at a block boundary whose tensor is <= 1/ratio of the segment input
+  int nas_gmax = 8;           // HN_NAS_GMAX: cap on patches per group
+  char nas_split[128] = {0};  // HN_NAS_SPLIT="i,j,...": explicit op indices that start a new segment (overrides the heuristic)
+};
+
 struct hn_handle {
+  HnEnv env;
   int chunk = 0;            // patches per conv-stack pass
   int front_chunk = 0;      // patches per front-kernel + conv3 sub-pass (keeps the conv2 output L2 resident)
   long long head_rows = 0;  // capacity of the L6 output buffer (patches)

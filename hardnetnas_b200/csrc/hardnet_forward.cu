@@ -373,6 +373,18 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   h->chunk = chunk_patches;
   h->head_rows = head_rows;
   {
+    auto flag = [](const char* name, bool dflt) { const char* e = getenv(name); return e ? e[0] != '0' : dflt; };
+    auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    h->env.nas_front = flag("HN_NAS_FRONT", true);
+    h->env.nas_dw_smem = flag("HN_NAS_DW_SMEM", true);
+    h->env.nas_dw_sh8 = flag("HN_NAS_DW_SH8", true);
+    h->env.nas_resident = flag("HN_NAS_RESIDENT", false);
+    h->env.nas_minb = num("HN_NAS_MINB", 0);
+    h->env.nas_cut_ratio = std::max(1, num("HN_NAS_CUT_RATIO", 4));
+    h->env.nas_gmax = std::max(1, num("HN_NAS_GMAX", 8));
+    if (const char* e = getenv("HN_NAS_SPLIT")) snprintf(h->env.nas_split, sizeof(h->env.nas_split), "%s", e);
+  }
+  {
     const char* e = getenv("HN_FRONT_CHUNK");   // patches per front-kernel + conv3 sub-pass
     h->front_chunk = e ? std::max(2, atoi(e)) : chunk_patches;
   }

@@ -22,6 +22,7 @@
 #include "handle.h"
 #include "host_common.h"
 #include "tc_conv.cuh"
+#include "nas_resident.cuh"
 
 namespace hn {
 
@@ -748,7 +749,19 @@ __global__ void __launch_bounds__(256) se_kernel(uint16_t* __restrict__ x, long 
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
+// A run of consecutive ops executed by ONE launch of nas_seg_kernel (nas_resident.cuh) with the activations resident in
+// shared memory; `params` holds everything but the per-call pointers / patch count.
+struct NasSegment {
+  int first = 0, last = 0;   // op range [first, last]
+  int G = 1, minb = 1;
+  size_t smem = 0;
+  SegParams params;
+  uint8_t* blob = nullptr;   // device copy of the weight image
+};
+
 struct NasState {
+  std::vector<NasSegment> segs;
+  std::vector<int> seg_of_op;        // index into segs, or -1: the op runs as its own kernel
   std::vector<hn_nas_op> ops;
   std::vector<PwParams> pw;          // one per op (valid for OP_PW)
   std::vector<size_t> w16_off;       // 16-bit weight offset per op (PW / HEAD)
@@ -774,6 +787,7 @@ void nas_state_free(NasState* s) {
   for (auto* p : s->slot) cudaFree(p);
   cudaFree(s->head_in);
   cudaFree(s->front_img);
+  for (auto& sg : s->segs) cudaFree(sg.blob);
   delete s;
 }
 
@@ -825,19 +839,301 @@ static int launch_pw(const PwParams& p, int nt, int kcb, int sm_count, cudaStrea
 
 
 namespace hn {
-static bool nas_front_fused() {                // HN_NAS_FRONT=0 keeps stem and first pointwise conv as separate kernels
-  const char* e = std::getenv("HN_NAS_FRONT");
-  return !(e && e[0] == '0');
+
+// ------------------------------------------------------------------------------------------------------------
+// patch-resident segments (nas_resident.cuh)
+// ------------------------------------------------------------------------------------------------------------
+static bool seg_op_ok(const hn_nas_op& o) {
+  switch (o.kind) {
+    case OP_PW: return o.cin % 16 == 0 && o.cout % 32 == 0 && o.cin <= 512 && o.cout <= 512 && (o.hin * o.hin) % 8 == 0;
+    case OP_DW: return (o.kernel == 3 || o.kernel == 5) && (o.stride == 1 || o.stride == 2) && o.hout % 2 == 0 && o.cin % 8 == 0;
+    case OP_MAXPOOL: return o.hout % 4 == 0 && o.cin % 8 == 0;
+    case OP_SE: return o.cin <= 512 && o.mid <= 128 && o.cin % 8 == 0;
+    default: return false;
+  }
 }
 
-static bool dw_tall_strips() {                 // HN_NAS_DW_SH8=0: 4-row strips for every shape (A/B measurements)
-  const char* e = std::getenv("HN_NAS_DW_SH8");
-  return !(e && e[0] == '0');
+static int seg_pw_nt(int cout) {
+  if (cout <= 256) return cout;
+  if (cout % 128 == 0) return 128;
+  if (cout % 96 == 0) return 96;
+  return 32;
 }
 
-static bool dw_via_smem() {                    // HN_NAS_DW_SMEM=0 selects the register-strip kernel (A/B measurements, tests)
-  const char* e = std::getenv("HN_NAS_DW_SMEM");
-  return !(e && e[0] == '0');
+static size_t seg_align(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Shared-memory plan of ops [first, last]: per-patch bytes of the three slot buffers and the layout of the weight blob.
+struct SegPlan {
+  size_t slot_pp[3] = {0, 0, 0};
+  size_t act_pp = 0;
+  size_t blob_bytes = 0;
+  bool has_se = false;
+  std::vector<size_t> w_off, b_off, w2_off, b2_off;   // per op, relative to the blob start
+};
+
+static SegPlan seg_plan(const std::vector<hn_nas_op>& ops, int first, int last, int bf) {
+  const size_t dw_elem = bf ? 4 : 2;   // fp16 activations: fp16 depthwise weights / bias (packed HFMA2 arithmetic)
+  SegPlan pl;
+  const int n = last - first + 1;
+  pl.w_off.assign(n, 0); pl.b_off.assign(n, 0); pl.w2_off.assign(n, 0); pl.b2_off.assign(n, 0);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t r = off; off = seg_align(off + bytes, 128); return r; };
+  for (int i = first; i <= last; ++i) {
+    const hn_nas_op& o = ops[i];
+    const size_t in_b = static_cast<size_t>(o.cin) * o.hin * o.hin * 2, out_b = static_cast<size_t>(o.cout) * o.hout * o.hout * 2;
+    pl.slot_pp[o.src] = std::max(pl.slot_pp[o.src], in_b);
+    pl.slot_pp[o.dst] = std::max(pl.slot_pp[o.dst], out_b);
+    if (o.kind == OP_PW && o.res >= 0) pl.slot_pp[o.res] = std::max(pl.slot_pp[o.res], out_b);
+    const int k = i - first;
+    switch (o.kind) {
+      case OP_PW: pl.w_off[k] = take(static_cast<size_t>(o.cin) * o.cout * 2); pl.b_off[k] = take(o.cout * 4); break;
+      case OP_DW: pl.w_off[k] = take(static_cast<size_t>(o.kernel) * o.kernel * o.cin * dw_elem); pl.b_off[k] = take(o.cin * dw_elem); break;
+      case OP_SE:
+        pl.has_se = true;
+        pl.w_off[k] = take(static_cast<size_t>(o.mid) * o.cin * 4); pl.b_off[k] = take(o.mid * 4);
+        pl.w2_off[k] = take(static_cast<size_t>(o.mid) * o.cin * 4); pl.b2_off[k] = take(o.cin * 4);
+        break;
+      default: break;
+    }
+  }
+  pl.blob_bytes = off;
+  for (size_t b : pl.slot_pp) pl.act_pp += b;
+  return pl;
+}
+
+constexpr size_t kSegSlack = 2048;      // a partial accumulator tile reads up to 2 KB past the end of a source plane
+constexpr size_t kSegScratch = (512 + 128 + 512) * 4;
+
+// Largest group size that fits `minb` CTAs per SM (shared memory and tensor memory); 0 = does not fit.
+static int seg_fit(const std::vector<hn_nas_op>& ops, int first, int last, const SegPlan& pl, int minb, int gmax) {
+  const size_t budget = (228 * 1024) / minb - 1024 /*reserved per CTA*/ - 1024 /*alignment*/ - 1536 /*rounding of the offsets*/;
+  const size_t fixed = kSegSlack + pl.blob_bytes + (pl.has_se ? kSegScratch : 0) + 64 + 3 * 1024 /*buffer alignment*/;
+  if (fixed + pl.act_pp > budget) return 0;
+  int G = static_cast<int>(std::min<size_t>((budget - fixed) / pl.act_pp, gmax));
+  for (; G >= 1; --G) {
+    int cols = 0;
+    for (int i = first; i <= last; ++i)
+      if (ops[i].kind == OP_PW) cols = std::max(cols, ((G * ops[i].hin * ops[i].hin + kTileM - 1) / kTileM) * ops[i].cout);
+    if (cols <= 512 / minb) break;
+  }
+  return G;
+}
+
+// Finalises segment [first, last]: group size, shared-memory offsets, weight image on the device.
+static int seg_build(hn_handle* h, NasState* st, const float* params, int first, int last, NasSegment& sg) {
+  const SegPlan pl = seg_plan(st->ops, first, last, st->act_bf16);
+  int minb = 0, G = 0;
+  for (int mb : {2, 1}) {
+    if (h->env.nas_minb && h->env.nas_minb != mb) continue;
+    if (mb == 2 && st->act_bf16) continue;   // the fp32 depthwise path of bf16 nets needs > 64 registers per thread
+    G = seg_fit(st->ops, first, last, pl, mb, h->env.nas_gmax);
+    if (G >= 1) { minb = mb; break; }
+  }
+  if (G < 1) return HN_ERR_UNSUPPORTED;
+  sg.first = first; sg.last = last; sg.G = G; sg.minb = minb;
+  SegParams& p = sg.params;
+  memset(&p, 0, sizeof(p));
+  size_t off = 0;
+  size_t slot_off[3];
+  for (int k = 0; k < 3; ++k) { slot_off[k] = off; off = seg_align(off + pl.slot_pp[k] * G, 1024); }
+  off += kSegSlack;
+  p.blob_off = static_cast<int>(off);
+  p.blob_bytes = static_cast<int>(seg_align(pl.blob_bytes, 16));
+  off = seg_align(off + pl.blob_bytes, 128);
+  p.scratch_off = static_cast<int>(off);
+  if (pl.has_se) off += kSegScratch;
+  p.bar_off = static_cast<int>(off);
+  off += 64;
+  sg.smem = off + 1024;
+  p.G = G;
+  p.n_ops = last - first + 1;
+  p.op_base = first;
+  p.seg_id = static_cast<int>(st->segs.size()) & 7;
+  int cols = 32;
+  std::vector<uint8_t> blob(pl.blob_bytes, 0);
+  for (int i = first; i <= last; ++i) {
+    const hn_nas_op& o = st->ops[i];
+    const int k = i - first;
+    SegOp& so = p.ops[k];
+    so.kind = o.kind; so.cin = o.cin; so.cout = o.cout; so.kernel = o.kernel; so.stride = o.stride;
+    so.hin = o.hin; so.hout = o.hout; so.relu = o.relu; so.mid = o.mid;
+    so.src_off = static_cast<int>(slot_off[o.src]);
+    so.dst_off = static_cast<int>(slot_off[o.dst]);
+    so.res_off = (o.kind == OP_PW && o.res >= 0) ? static_cast<int>(slot_off[o.res]) : -1;
+    so.w_off = p.blob_off + static_cast<int>(pl.w_off[k]);
+    so.b_off = p.blob_off + static_cast<int>(pl.b_off[k]);
+    so.w2_off = p.blob_off + static_cast<int>(pl.w2_off[k]);
+    so.b2_off = p.blob_off + static_cast<int>(pl.b2_off[k]);
+    so.nt = o.kind == OP_PW ? seg_pw_nt(o.cout) : 0;
+    so.pitch = static_cast<uint32_t>(G) * o.hin * o.hin * 16;
+    if (o.kind == OP_PW) {
+      so.tiles = (G * o.hin * o.hin + kTileM - 1) / kTileM;
+      so.ksteps = o.cin / 16;
+      so.chunks = o.cout / so.nt;
+      so.idesc = make_idesc_f16(kTileM, so.nt, st->act_bf16);
+      so.b_hi = noswizzle_desc_hi(static_cast<uint32_t>(o.cin) * 16);
+    }
+    if (o.kind == OP_DW) so.sh = 2;
+    uint8_t* b = blob.data();
+    switch (o.kind) {
+      case OP_PW: {
+        // UMMA no-swizzle K-major image of W[cout][cin]: element (n, k) at (n / 8) * (cin * 16) + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+        uint16_t* w = reinterpret_cast<uint16_t*>(b + pl.w_off[k]);
+        for (int n = 0; n < o.cout; ++n)
+          for (int c = 0; c < o.cin; ++c)
+            w[((n >> 3) * o.cin * 16 + (c >> 3) * 128 + (n & 7) * 16 + (c & 7) * 2) >> 1] = f2h16(params[o.w_off + static_cast<size_t>(n) * o.cin + c], st->act_bf16);
+        memcpy(b + pl.b_off[k], params + o.b_off, o.cout * 4);
+        cols = std::max(cols, ((G * o.hin * o.hin + kTileM - 1) / kTileM) * o.cout);
+        break;
+      }
+      case OP_DW:
+        if (st->act_bf16) {
+          memcpy(b + pl.w_off[k], params + o.w_off, static_cast<size_t>(o.kernel) * o.kernel * o.cin * 4);
+          memcpy(b + pl.b_off[k], params + o.b_off, o.cin * 4);
+        } else {
+          uint16_t* w = reinterpret_cast<uint16_t*>(b + pl.w_off[k]);
+          for (int j = 0; j < o.kernel * o.kernel * o.cin; ++j) w[j] = f2h16(params[o.w_off + j], 0);
+          uint16_t* bb = reinterpret_cast<uint16_t*>(b + pl.b_off[k]);
+          for (int j = 0; j < o.cin; ++j) bb[j] = f2h16(params[o.b_off + j], 0);
+        }
+        break;
+      case OP_SE:
+        memcpy(b + pl.w_off[k], params + o.w_off, static_cast<size_t>(o.mid) * o.cin * 4);
+        memcpy(b + pl.b_off[k], params + o.b_off, o.mid * 4);
+        memcpy(b + pl.w2_off[k], params + o.w2_off, static_cast<size_t>(o.mid) * o.cin * 4);
+        memcpy(b + pl.b2_off[k], params + o.b2_off, o.cin * 4);
+        break;
+      default: break;
+    }
+  }
+  int tc = 32;
+  while (tc < cols) tc <<= 1;
+  p.tmem_cols = tc;
+  HN_CUDA(cudaMalloc(&sg.blob, std::max<size_t>(p.blob_bytes, 16)));
+  blob.resize(std::max<size_t>(p.blob_bytes, 16), 0);
+  HN_CUDA(cudaMemcpy(sg.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  p.blob = reinterpret_cast<const uint4*>(sg.blob);
+  return HN_OK;
+}
+
+// Partitions the ops behind the front kernel into patch-resident segments. A segment grows while it fits one CTA's shared
+// memory; it is cut at a block boundary (behind a linear pointwise conv, an SE or a max-pool) once the tensor there has
+// shrunk to <= 1 / cut_ratio of the segment's input, so that deeper, smaller stages run with larger groups.
+static int seg_partition(hn_handle* h, NasState* st, const float* params) {
+  const int n_ops = static_cast<int>(st->ops.size());
+  st->seg_of_op.assign(n_ops, -1);
+  st->segs.clear();
+  if (!h->env.nas_resident) return HN_OK;
+  std::vector<char> forced(n_ops, 0);
+  const bool explicit_split = h->env.nas_split[0] != 0;
+  if (explicit_split) {
+    for (const char* c = h->env.nas_split; *c;) {
+      const int v = atoi(c);
+      if (v > 0 && v < n_ops) forced[v] = 1;
+      while (*c && *c != ',') ++c;
+      if (*c == ',') ++c;
+    }
+  }
+  // every tensor an op of [a, b] reads must be the segment's input or produced inside it (a residual from before the
+  // segment that is not its input lives only in HBM)
+  auto reads_ok = [&](int a, int b) {
+    bool defined[3] = {false, false, false};
+    defined[st->ops[a].src] = true;
+    for (int i = a; i <= b; ++i) {
+      const hn_nas_op& o = st->ops[i];
+      if (!defined[o.src] || (o.kind == OP_PW && o.res >= 0 && !defined[o.res])) return false;
+      defined[o.dst] = true;
+    }
+    return true;
+  };
+  // only the last op's output reaches HBM: nothing behind the segment may read another tensor produced inside it
+  auto escapes_ok = [&](int a, int b) {
+    bool inside[3] = {false, false, false};
+    for (int i = a; i <= b; ++i) inside[st->ops[i].dst] = true;
+    inside[st->ops[b].dst] = false;
+    for (int j = b + 1; j < n_ops; ++j) {
+      const hn_nas_op& o = st->ops[j];
+      if (inside[o.src] || (o.kind == OP_PW && o.res >= 0 && inside[o.res])) return false;
+      if (o.kind != OP_HEAD) inside[o.dst] = false;
+    }
+    return true;
+  };
+  auto fits = [&](int a, int b) {
+    if (b - a + 1 > kSegMaxOps || !reads_ok(a, b)) return false;
+    const SegPlan pl = seg_plan(st->ops, a, b, st->act_bf16);
+    return seg_fit(st->ops, a, b, pl, 1, 1) >= 1;
+  };
+  auto close = [&](int a, int b) -> int {
+    while (a <= b) {
+      if (!fits(a, a)) { ++a; continue; }   // e.g. a residual conv cut off from its block input
+      int e = b;
+      while (e > a && !(fits(a, e) && escapes_ok(a, e))) --e;
+      // a lone depthwise / max-pool op gains nothing from residency (same bytes as its own bulk-copy kernel)
+      const bool lone = a == e && (st->ops[a].kind == OP_DW || st->ops[a].kind == OP_MAXPOOL);
+      if (!lone) {
+        NasSegment sg;
+        const int rc = seg_build(h, st, params, a, e, sg);
+        if (rc != HN_OK && rc != HN_ERR_UNSUPPORTED) return rc;
+        if (rc == HN_OK) {
+          for (int i = a; i <= e; ++i) st->seg_of_op[i] = static_cast<int>(st->segs.size());
+          st->segs.push_back(sg);
+        }
+      }
+      a = e + 1;
+    }
+    return HN_OK;
+  };
+  int start = -1;
+  for (int i = st->front_ops; i < n_ops - 1; ++i) {
+    const hn_nas_op& o = st->ops[i];
+    if (!seg_op_ok(o)) {
+      if (start >= 0) HN_TRY(close(start, i - 1));
+      start = -1;
+      continue;
+    }
+    if (start >= 0 && (forced[i] || !fits(start, i))) {
+      HN_TRY(close(start, i - 1));
+      start = -1;
+    }
+    if (start < 0) {
+      if (!fits(i, i)) continue;
+      start = i;
+    }
+    if (!explicit_split && i + 1 < n_ops - 1) {
+      const bool boundary = (o.kind == OP_PW && !o.relu && st->ops[i + 1].kind != OP_SE) || o.kind == OP_SE || o.kind == OP_MAXPOOL;
+      const hn_nas_op& f = st->ops[start];
+      const size_t in_b = static_cast<size_t>(f.cin) * f.hin * f.hin, cut_b = static_cast<size_t>(o.cout) * o.hout * o.hout;
+      if (boundary && cut_b * h->env.nas_cut_ratio <= in_b) {
+        HN_TRY(close(start, i));
+        start = -1;
+      }
+    }
+  }
+  if (start >= 0) HN_TRY(close(start, n_ops - 2));
+  return HN_OK;
+}
+
+template <int MINB, bool BF16>
+static int launch_seg_cfg(const SegParams& p, size_t smem, int sm_count, cudaStream_t s) {
+  auto kern = nas_seg_kernel<MINB, BF16>;
+  static DeviceOnce attr_once;
+  if (attr_once.first_time()) HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (228 * 1024) / MINB - 1024));
+  const int groups = (p.n + p.G - 1) / p.G;
+  if (groups <= 0) return HN_OK;
+  kern<<<std::min(groups, sm_count * MINB), kSegThreads, smem, s>>>(p);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
+static int launch_seg(const NasSegment& sg, const uint16_t* in, uint16_t* out, int n, int n_ops, int bf, int sm_count, cudaStream_t s) {
+  SegParams p = sg.params;
+  p.in = in;
+  p.out = out;
+  p.n = n;
+  p.n_ops = n_ops;
+  if (bf) return launch_seg_cfg<1, true>(p, sg.smem, sm_count, s);
+  return sg.minb == 2 ? launch_seg_cfg<2, false>(p, sg.smem, sm_count, s) : launch_seg_cfg<1, false>(p, sg.smem, sm_count, s);
 }
 
 // Runs ops [0, last_op] of the packed program for `n` patches (n <= chunk).
@@ -846,14 +1142,27 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
   const int bf = st->act_bf16;
   {
       int first = 0;
-      if (st->front_img && last_op >= st->front_ops - 1 && nas_front_fused()) {
+      if (st->front_img && last_op >= st->front_ops - 1 && h->env.nas_front) {
         const hn_nas_op &o0 = st->ops[0], &ol = st->ops[st->front_ops - 1];
         HN_TRY(launch_front_pw(src, in_dtype, st->slot[ol.dst], st->front_tm, st->params + o0.w_off, st->params + o0.b_off, st->front_img,
                                st->front_bias2, n, bf, h->sm_count, s));
         first = st->front_ops;
       }
+      const int n_total = static_cast<int>(st->ops.size());
       for (int i = first; i <= last_op; ++i) {
         const hn_nas_op& o = st->ops[i];
+        if (st->seg_of_op[i] >= 0) {
+          // patch-resident segment: ops [i, end] in one launch; a segment that ends right before the head writes the
+          // head GEMM's input rows directly
+          const NasSegment& sg = st->segs[st->seg_of_op[i]];
+          const int end = std::min(sg.last, last_op);
+          const hn_nas_op& ol = st->ops[end];
+          const bool to_head = end == n_total - 2 && last_op == n_total - 1;
+          uint16_t* dst = to_head ? st->head_in + static_cast<size_t>(off) * st->head_k : st->slot[ol.dst];
+          HN_TRY(launch_seg(sg, st->slot[st->ops[sg.first].src], dst, n, end - sg.first + 1, bf, h->sm_count, s));
+          i = to_head ? end + 1 : end;
+          continue;
+        }
         switch (o.kind) {
           case OP_STEM: {
             HN_TRY(launch_l1(src, in_dtype, st->slot[o.dst], st->params + o.w_off, st->params + o.b_off, nullptr, n, bf, h->sm_count, s));
@@ -876,11 +1185,11 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
             const float* bv = st->params + o.b_off;
             // shared-memory kernel whenever two units of whole maps fit next to the weights (every shape of SEARCH_SPACE2
             // with expansion 1); wider expansions fall through to the register-strip kernel below
-            if (strip && dw_via_smem()) {
+            if (strip && h->env.nas_dw_smem) {
               const size_t map_bytes = static_cast<size_t>(o.hin) * o.hin * o.cin * 2;
               // 5x5 stride 1 is bound by the fp32 pipe + unpack instructions: strips of 8 rows re-use each loaded and
               // unpacked input vector for more taps (12 rows for 8 outputs instead of 8 for 4)
-              const int sh = (o.kernel == 5 && o.stride == 1 && o.hout % 8 == 0 && dw_tall_strips()) ? 8 : 4;
+              const int sh = (o.kernel == 5 && o.stride == 1 && o.hout % 8 == 0 && h->env.nas_dw_sh8) ? 8 : 4;
               const int items = (o.hout / sh) * o.hout * (o.cin / 8);
               int G = std::max(1, 256 / items);
               const size_t w_bytes = ((static_cast<size_t>(o.kernel) * o.kernel + 1) * o.cin * 4 + 127) & ~size_t(127);
@@ -931,7 +1240,7 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
               int G = items > 0 ? std::max(1, 256 / items) : 1;
               while (G > 1 && 2 * G * map_bytes + 48 > 110 * 1024) G >>= 1;
               const size_t smem = 2 * G * map_bytes + 48;
-              if (o.hout % 4 == 0 && smem <= 227 * 1024 && dw_via_smem()) {
+              if (o.hout % 4 == 0 && smem <= 227 * 1024 && h->env.nas_dw_smem) {
                 const int units = (n + G - 1) / G;
                 const int per_sm = std::max(1, std::min(4, static_cast<int>((227 * 1024) / (smem + 1024))));
                 const int sgrid = std::min(units, h->sm_count * per_sm);
@@ -1170,6 +1479,10 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
     const int rc = make_tmap_16bit(&st->front_tm, st->slot[ops[st->front_ops - 1].dst], 2, dimsO, strO, boxO, 64);
     if (rc != HN_OK) return fail(rc);
   }
+  {
+    const int rc = seg_partition(h, st, params);
+    if (rc != HN_OK) return fail(rc);
+  }
   h->nas = st;
   return HN_OK;
 }
@@ -1206,6 +1519,32 @@ extern "C" int hn_forward_nas(hn_handle* h, const void* patches, int in_dtype, l
     HN_TRY(launch_head(p, h->sm_count, s));
   }
   return HN_OK;
+}
+
+#ifdef HN_SEG_TRACE
+extern "C" int hn_debug_seg_trace(unsigned long long* out256, int reset) {
+  HN_CUDA(cudaDeviceSynchronize());
+  HN_CUDA(cudaMemcpyFromSymbol(out256, hn::hn_seg_trace, 256 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[256] = {0};
+    HN_CUDA(cudaMemcpyToSymbol(hn::hn_seg_trace, z, sizeof(z)));
+  }
+  return HN_OK;
+}
+#endif
+
+extern "C" int hn_nas_plan(hn_handle* h, int* out, int cap) {
+  HN_REQUIRE(h, "hn_nas_plan: NULL handle");
+  if (!h->nas) {
+    set_error("hn_nas_plan: no NAS net packed");
+    return HN_ERR_STATE;
+  }
+  const int n = static_cast<int>(h->nas->segs.size());
+  for (int i = 0; i < n && i < cap && out; ++i) {
+    const NasSegment& sg = h->nas->segs[i];
+    out[4 * i] = sg.first; out[4 * i + 1] = sg.last; out[4 * i + 2] = sg.G; out[4 * i + 3] = sg.minb;
+  }
+  return n;
 }
 
 extern "C" int hn_forward_nas_dump(hn_handle* h, const void* patches, int in_dtype, long long B, int op_index, void* act_out,

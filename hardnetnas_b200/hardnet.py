@@ -64,7 +64,33 @@ class _Engine:
             pass
 
 
-class HardNet(nn.Module):
+class _EngineOwner:
+    """Mixin of the modules that own an `_Engine` (a ctypes handle: neither picklable nor shareable).
+
+    Copies made by copy.deepcopy / pickle / torch.save(model) / EMA-SWA wrappers and nn.DataParallel replicas drop the
+    engine and re-create their own lazily on their first eval forward. `repack()` forces a fresh weight pack: the pack
+    is keyed on the tensors' version counters and storage pointers, which in-place edits through `.data` (as the
+    reference's weights_init does, hardnet/HardNet.py:317-324) do not change."""
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        state["_packed_key"] = None
+        return state
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica._engine = None
+        replica._packed_key = None
+        return replica
+
+    def repack(self):
+        """Invalidate the packed weights (call after editing parameters or BatchNorm buffers through `.data`)."""
+        self._packed_key = None
+        return self
+
+
+class HardNet(_EngineOwner, nn.Module):
     """HardNet model definition (same constructor contract as the reference: no required arguments)."""
 
     def __init__(self, act_dtype: str = "fp16", chunk_patches: int = 0, head_rows: int = 0):

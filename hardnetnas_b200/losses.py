@@ -94,42 +94,22 @@ def loss_HardNet(anchor, positive, anchor_swap=False, anchor_ave=False, margin=1
         if torch.is_grad_enabled() and (anchor.requires_grad or positive.requires_grad):
             return _FusedHardestInBatch.apply(anchor, positive, float(margin), bool(anchor_swap))
         return _ops.loss_hardnet(anchor, positive, float(margin), bool(anchor_swap))
-    # ---- modes outside the accelerated path: same expression sequence as the reference ----------------
-    eps = 1e-8
-    pos1, d = _masked_matrix(anchor, positive)
+    # ---- modes outside the accelerated path (hardnet/Losses.py:109-152): which negatives enter, then the shared reduction ----
+    pos, d = _masked_matrix(anchor, positive)
+    n = anchor.size(0)
     if batch_reduce == 'min':
-        min_neg = torch.min(d, 1)[0]
-        if anchor_swap:
-            min_neg = torch.min(min_neg, torch.min(d, 0)[0])
-        pos = pos1
+        neg, neg_t = d.min(dim=1)[0], d.min(dim=0)[0]
     elif batch_reduce == 'average':
-        pos = pos1.repeat(anchor.size(0)).view(-1, 1).squeeze(0)
-        min_neg = d.view(-1, 1)
-        if anchor_swap:
-            min_neg = torch.min(min_neg, torch.t(d).contiguous().view(-1, 1))
-        min_neg = min_neg.squeeze(0)
+        pos = pos.repeat(n)                                  # every (row, column) pair is a term
+        neg, neg_t = d.reshape(-1), d.t().reshape(-1)
     elif batch_reduce == 'random':
-        idxs = torch.randperm(anchor.size(0), device=anchor.device).long()
-        min_neg = d.gather(1, idxs.view(-1, 1))
-        if anchor_swap:
-            min_neg = torch.min(min_neg, torch.t(d).gather(1, idxs.view(-1, 1)))
-        min_neg = torch.t(min_neg).squeeze(0)
-        pos = pos1
+        idxs = torch.randperm(n, device=anchor.device).view(-1, 1)
+        neg, neg_t = d.gather(1, idxs).view(-1), d.t().gather(1, idxs).view(-1)
     else:
         print('Unknown batch reduce mode. Try min, average or random')
         sys.exit(1)
-    if loss_type == "triplet_margin":
-        loss = torch.clamp(margin + pos - min_neg, min=0.0)
-    elif loss_type == 'softmax':
-        exp_pos = torch.exp(2.0 - pos)
-        exp_den = exp_pos + torch.exp(2.0 - min_neg) + eps
-        loss = -torch.log(exp_pos / exp_den)
-    elif loss_type == 'contrastive':
-        loss = torch.clamp(margin - min_neg, min=0.0) + pos
-    else:
-        print('Unknown loss type. Try triplet_margin, softmax or contrastive')
-        sys.exit(1)
-    return torch.mean(loss)
+    min_neg = torch.min(neg, neg_t) if anchor_swap else neg
+    return torch.mean(_reduce_triplet(pos, min_neg, margin, loss_type))
 
 
 def loss_HardNet_nas(anchor, positive, margin=1.0):

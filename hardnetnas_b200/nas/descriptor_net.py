@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..hardnet import _Engine, _OUT_DTYPES
+from ..hardnet import _Engine, _EngineOwner, _OUT_DTYPES
 from .fbnet_builder import PRIMITIVES, ConvBNRelu, Flatten, IRFBlock, Identity
 from .fbnet_modeldef import MODEL_ARCH, arch_ops
 from .lookup_table import LookUpTable
@@ -95,7 +95,7 @@ class _Program:
         return op
 
 
-class SampledDescriptorNet(nn.Module):
+class SampledDescriptorNet(_EngineOwner, nn.Module):
     def __init__(self, ops, act_dtype: str = "fp16", chunk_patches: int = 0, head_rows: int = 0):
         super().__init__()
         if isinstance(ops, str):
@@ -235,6 +235,17 @@ class SampledDescriptorNet(nn.Module):
             _lib.check(eng.lib.hn_pack_nas(eng.handle, ops, len(prog.ops), C.c_void_p(blob.data_ptr()), blob.numel(),
                                            _lib.HN_F16 if self.act_dtype == "fp16" else _lib.HN_BF16), "hn_pack_nas")
         self._packed_key = key
+
+    def resident_plan(self, device=None):
+        """[(first_op, last_op, patches_per_group, ctas_per_sm)] of the runs of ops that execute patch-resident (one launch,
+        activations in shared memory) on `device`; ops outside every run are one kernel each."""
+        device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._ensure_packed(device)
+        buf = (C.c_int * (4 * 32))()
+        n = self._engine.lib.hn_nas_plan(self._engine.handle, buf, 32)
+        if n < 0:
+            _lib.check(n, "hn_nas_plan")
+        return [tuple(buf[4 * i:4 * i + 4]) for i in range(n)]
 
     def forward_op(self, x, op_index: int):
         """Test hook: NHWC 16-bit output of op `op_index` of the compiled program, [B,H,W,C]."""

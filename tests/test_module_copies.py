@@ -1,0 +1,40 @@
+"""The drop-in modules hold a ctypes engine handle; copies (deepcopy, pickle, torch.save(model), DataParallel replicas)
+must drop it and re-create their own lazily instead of failing or sharing it (CPU-only checks with a stand-in engine)."""
+import copy
+import ctypes
+import io
+import pickle
+
+import pytest
+import torch
+
+from hardnetnas_b200.hardnet import HardNet
+from hardnetnas_b200.nas import SampledDescriptorNet
+
+
+class _FakeEngine:
+    def __init__(self):
+        self.handle = ctypes.c_void_p(1)   # ctypes pointers cannot be pickled
+        self.device = None
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize("make", [HardNet, lambda: SampledDescriptorNet("wang2")])
+def test_copies_drop_the_engine(make):
+    m = make()
+    m._engine, m._packed_key = _FakeEngine(), ("stale",)
+    c = copy.deepcopy(m)
+    assert c._engine is None and c._packed_key is None
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), c.state_dict().values()))
+    pickle.loads(pickle.dumps(m))
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    assert r._engine is None and set(r.state_dict()) == set(m.state_dict())
+    rep = m._replicate_for_data_parallel()
+    assert rep._engine is None and m._engine is not None
+    assert m.repack() is m and m._packed_key is None
+    m._engine = None
