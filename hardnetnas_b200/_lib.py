@@ -39,6 +39,10 @@ SIGNATURES = {
                               C.c_longlong, _P]),
     "hn_loss_hardnet": (C.c_int, [_P, _P, C.c_longlong, C.c_float, C.c_int, _P, _P, C.c_longlong, _P]),
     "hn_match": (C.c_int, [_P, _P, C.c_longlong, C.c_longlong, C.c_longlong, _P, _P, _P, _P, _P, C.c_longlong, _P]),
+    "hn_pack_descriptors": (C.c_int, [_P, C.c_longlong, _P, _P]),
+    "hn_match_ex": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_longlong, C.c_longlong, _P, _P, _P, _P, _P, C.c_longlong, _P, _P]),
+    "hn_match_profile_enable": (C.c_int, [C.c_int]),
+    "hn_match_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "hn_clip_patches": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, _P, _P, _P, _P, C.c_longlong, C.c_int, _P, _P]),
 }
 

@@ -79,12 +79,29 @@ def loss_hardnet(anchor: torch.Tensor, positive: torch.Tensor, margin: float, an
     return out
 
 
-def match_top2(q: torch.Tensor, g: torch.Tensor, g_offset: int = 0):
-    """(d1, d2, i1, i2): nearest / second-nearest gallery row per query in the FDLNet distance form."""
+def pack_descriptors(x: torch.Tensor) -> torch.Tensor:
+    """[n,128] fp32 unit rows -> the fp16 operand rows of the matching GEMM (x * 2^8), see hn_pack_descriptors."""
+    lib = _lib.load()
+    x = _require_cuda_f32("pack_descriptors", x)
+    out = torch.empty((x.size(0), 128), dtype=torch.float16, device=x.device)
+    if x.size(0):
+        with torch.cuda.device(x.device):
+            _lib.check(lib.hn_pack_descriptors(_ptr(x), x.size(0), _ptr(out), _stream_ptr()), "hn_pack_descriptors")
+    return out
+
+
+def match_top2(q: torch.Tensor, g: torch.Tensor, g_offset: int = 0, q16: torch.Tensor | None = None,
+               g16: torch.Tensor | None = None, g_ready_event: torch.cuda.Event | None = None):
+    """(d1, d2, i1, i2): nearest / second-nearest gallery row per query in the FDLNet distance form.
+    q16 / g16: operands already packed by `pack_descriptors` (skips the packing kernels); g_ready_event: the exact re-rank
+    (the only reader of the fp32 gallery `g`) waits for it, so `g` may still be arriving while the GEMM runs."""
     lib = _lib.load()
     q = _require_cuda_f32("match", q)
     g = _require_cuda_f32("match", g)
     nq, ng = q.size(0), g.size(0)
+    for t, n in ((q16, nq), (g16, ng)):
+        if t is not None and not (t.is_cuda and t.dtype == torch.float16 and tuple(t.shape) == (n, 128) and t.is_contiguous()):
+            raise ValueError("match: packed operands must be contiguous CUDA fp16 [n,128] tensors from pack_descriptors")
     dev = q.device
     with torch.cuda.device(dev):
         ws = _workspace(dev, lib.hn_dist_workspace_bytes(nq, ng, 0))
@@ -92,6 +109,7 @@ def match_top2(q: torch.Tensor, g: torch.Tensor, g_offset: int = 0):
         d2 = torch.empty(nq, dtype=torch.float32, device=dev)
         i1 = torch.empty(nq, dtype=torch.int32, device=dev)
         i2 = torch.empty(nq, dtype=torch.int32, device=dev)
-        _lib.check(lib.hn_match(_ptr(q), _ptr(g), nq, ng, g_offset, _ptr(d1), _ptr(d2), _ptr(i1), _ptr(i2), _ptr(ws),
-                                ws.numel(), _stream_ptr()), "hn_match")
+        ev = C.c_void_p(g_ready_event.cuda_event) if g_ready_event is not None else C.c_void_p(0)
+        _lib.check(lib.hn_match_ex(_ptr(q), _ptr(g), _ptr(q16), _ptr(g16), nq, ng, g_offset, _ptr(d1), _ptr(d2), _ptr(i1),
+                                   _ptr(i2), _ptr(ws), ws.numel(), ev, _stream_ptr()), "hn_match")
     return d1, d2, i1, i2

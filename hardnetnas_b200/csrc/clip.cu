@@ -17,7 +17,7 @@ __device__ __forceinline__ float linspace_pm1(int i, int steps) {
   return i < steps / 2 ? -1.0f + step * static_cast<float>(i) : 1.0f - step * static_cast<float>(steps - i - 1);
 }
 
-__global__ void __launch_bounds__(256) clip_patch_kernel(const float* __restrict__ images, int H, int W,
+__global__ void __launch_bounds__(256) clip_patch_kernel(const float* __restrict__ images, long long B, int H, int W,
                                                          const long long* __restrict__ kpts_byxc,
                                                          const float* __restrict__ kpts_scale,
                                                          const float* __restrict__ kpts_ori, const float* __restrict__ im_info,
@@ -51,7 +51,14 @@ __global__ void __launch_bounds__(256) clip_patch_kernel(const float* __restrict
     const long long max_x = W - 1, max_y = H - 1;
     const long long x0 = min(max(x0u, 0LL), max_x), x1 = min(max(x0u + 1, 0LL), max_x);
     const long long y0 = min(max(y0u, 0LL), max_y), y1 = min(max(y0u + 1, 0LL), max_y);
-    const float* img = images + kpts_byxc[n * 4] * (static_cast<long long>(H) * W);
+    // The reference gathers from the flattened image stack and raises on a batch index outside [0, B); a kernel cannot
+    // raise, so such a keypoint yields a NaN patch instead of an out-of-bounds read.
+    const long long b = kpts_byxc[n * 4];
+    if (b < 0 || b >= B) {
+      out[i] = __int_as_float(0x7fc00000);
+      continue;
+    }
+    const float* img = images + b * (static_cast<long long>(H) * W);
     const float Ia = __ldg(img + y0 * W + x0), Ib = __ldg(img + y1 * W + x0);
     const float Ic = __ldg(img + y0 * W + x1), Id = __ldg(img + y1 * W + x1);
     const float x0f = static_cast<float>(x0), x1f = static_cast<float>(x1);
@@ -77,7 +84,7 @@ extern "C" int hn_clip_patches(const float* images, long long B, int H, int W, c
   HN_TRY(device_sm_count(&sm));
   const long long total = N * psize * psize;
   const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, static_cast<long long>(sm) * 16));
-  clip_patch_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(images, H, W, kpts_byxc, kpts_scale, kpts_ori, im_info, N,
+  clip_patch_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(images, B, H, W, kpts_byxc, kpts_scale, kpts_ori, im_info, N,
                                                                         N / B, psize, out);
   HN_CUDA(cudaGetLastError());
   count_launch();

@@ -1,6 +1,7 @@
 // C ABI for the distance / hardest-in-batch / matching path: operand packing, the fused tcgen05
 // distance kernels (tc_dist.cuh), fp32 re-ranking of shortlisted candidates and the small finalisers.
 #include <algorithm>
+#include <vector>
 
 #include "host_common.h"
 #include "tc_dist.cuh"
@@ -161,6 +162,32 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q
   }
 }
 
+// Optional per-stage CUDA-event timing of hn_match (bench.py: the roofline of the matching GEMM is computed from the kernel's
+// own in-run time): stage 0 = operand packing, 1 = GEMM + shortlist, 2 = exact re-rank.
+struct MatchProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev[3];
+  size_t used[3] = {0, 0, 0};
+};
+static MatchProfile g_match_profile;
+struct MatchTimer {
+  int stage;
+  cudaStream_t s;
+  bool on;
+  MatchTimer(int stage_, cudaStream_t s_) : stage(stage_), s(s_), on(g_match_profile.on) { if (on) record(); }
+  ~MatchTimer() { if (on) record(); }
+  void record() {
+    auto& v = g_match_profile.ev[stage];
+    size_t& u = g_match_profile.used[stage];
+    if (u == v.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+      v.push_back(e);
+    }
+    cudaEventRecord(v[u++], s);
+  }
+};
+
 static int make_desc_map(CUtensorMap* tm, const uint16_t* base, long long rows, int K, int box_rows = kDistTile) {
   const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows)};
   const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
@@ -313,13 +340,27 @@ extern "C" int hn_loss_hardnet(const float* anchor, const float* positive, long 
   return HN_OK;
 }
 
-extern "C" int hn_match(const float* q, const float* g, long long Nq, long long Ng, long long g_offset, float* d1,
-                        float* d2, int32_t* i1, int32_t* i2, void* workspace, long long workspace_bytes, void* stream) {
+extern "C" int hn_pack_descriptors(const float* x, long long n, void* out16, void* stream) {
+  HN_REQUIRE(x && out16, "hn_pack_descriptors: NULL argument");
+  HN_REQUIRE(n >= 1 && n < (1LL << 31), "hn_pack_descriptors: n out of range (%lld)", n);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  pack_desc_kernel<<<static_cast<unsigned>((n * 32 + threads - 1) / threads), threads, 0, s>>>(x, n, static_cast<uint16_t*>(out16), 0, 0, nullptr);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
+extern "C" int hn_match_ex(const float* q, const float* g, const void* q16_in, const void* g16_in, long long Nq, long long Ng,
+                           long long g_offset, float* d1, float* d2, int32_t* i1, int32_t* i2, void* workspace,
+                           long long workspace_bytes, void* g_ready_event, void* stream) {
   HN_REQUIRE(q && g && workspace, "hn_match: NULL argument");
   HN_REQUIRE(Nq >= 1 && Ng >= 1, "hn_match: empty input (Nq=%lld, Ng=%lld)", Nq, Ng);
   HN_REQUIRE(Nq < (1LL << 31) && Ng + g_offset < (1LL << 31), "hn_match: more than 2^31 rows");
   HN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "hn_match: workspace must be 256-byte aligned");
   HN_REQUIRE(workspace_bytes >= hn_dist_workspace_bytes(Nq, Ng, 0), "hn_match: workspace too small");
+  HN_REQUIRE((reinterpret_cast<uintptr_t>(q16_in) & 15) == 0 && (reinterpret_cast<uintptr_t>(g16_in) & 15) == 0,
+             "hn_match: packed operands must be 16-byte aligned");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int sm = 0;
   HN_TRY(device_sm_count(&sm));
@@ -329,14 +370,20 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   int* cand = reinterpret_cast<int*>(b + align256(static_cast<size_t>(Nq) * 256) + align256(static_cast<size_t>(Ng) * 256));
   float* cand_val = reinterpret_cast<float*>(reinterpret_cast<char*>(cand) + align256(static_cast<size_t>(Nq) * 32 * kTopC * 4));
   const int threads = 256;
-  pack_desc_kernel<<<static_cast<unsigned>((Nq * 32 + threads - 1) / threads), threads, 0, s>>>(q, Nq, q16, 0, 0, nullptr);
-  pack_desc_kernel<<<static_cast<unsigned>((Ng * 32 + threads - 1) / threads), threads, 0, s>>>(g, Ng, g16, 0, 1, nullptr);
-  HN_CUDA(cudaGetLastError());
+  {
+    MatchTimer timer(0, s);
+    if (q16_in) q16 = const_cast<uint16_t*>(static_cast<const uint16_t*>(q16_in));
+    else pack_desc_kernel<<<static_cast<unsigned>((Nq * 32 + threads - 1) / threads), threads, 0, s>>>(q, Nq, q16, 0, 0, nullptr);
+    if (g16_in) g16 = const_cast<uint16_t*>(static_cast<const uint16_t*>(g16_in));
+    else pack_desc_kernel<<<static_cast<unsigned>((Ng * 32 + threads - 1) / threads), threads, 0, s>>>(g, Ng, g16, 0, 1, nullptr);
+    HN_CUDA(cudaGetLastError());
+    count_launch((q16_in ? 0 : 1) + (g16_in ? 0 : 1));
+  }
   DistParams dp;
   memset(&dp, 0, sizeof(dp));
   // CTA pairs (tc_dist_pair.cuh) once the problem is large enough to fill the machine with 512-row query blocks
-  const char* pe = getenv("HN_MATCH_PAIR");   // 0 / 1 force the single-CTA / CTA-pair kernel (tests), default: by size
-  const int pair_env = pe ? atoi(pe) : -1;
+  // HN_MATCH_PAIR = 0 / 1 forces the single-CTA / CTA-pair kernel (tests), default: by size. Read once per process.
+  static const int pair_env = [] { const char* pe = getenv("HN_MATCH_PAIR"); return pe ? atoi(pe) : -1; }();
   const bool use_pair = pair_env >= 0 ? pair_env != 0 : (Nq >= 8192 && Ng >= 1024);
   HN_TRY(make_desc_map(&dp.side[0].tmA, q16, Nq, 128));
   HN_TRY(make_desc_map(&dp.side[0].tmB, g16, Ng, 128, use_pair ? 64 : kDistTile));
@@ -347,29 +394,67 @@ extern "C" int hn_match(const float* q, const float* g, long long Nq, long long 
   dp.k_blocks = 2;
   dp.form = HN_FORM_FDL;
   dp.dot_scale = kDotScale;
-  if (use_pair) {
-    const int pairs = std::max(sm / 2, 1);
-    dp.segments = pick_segments(Nq, 4 * kDistTile, Ng, pairs, 16);
-    const long long items = ((Nq + 4 * kDistTile - 1) / (4 * kDistTile)) * dp.segments;
-    static DeviceOnce attr_once;
-    if (attr_once.first_time()) {
-      HN_CUDA(cudaFuncSetAttribute(match_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMpSmem)));
+  {
+    MatchTimer timer(1, s);
+    if (use_pair) {
+      const int pairs = std::max(sm / 2, 1);
+      dp.segments = pick_segments(Nq, 4 * kDistTile, Ng, pairs, 16);
+      const long long items = ((Nq + 4 * kDistTile - 1) / (4 * kDistTile)) * dp.segments;
+      static DeviceOnce attr_once;
+      if (attr_once.first_time()) {
+        HN_CUDA(cudaFuncSetAttribute(match_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMpSmem)));
+      }
+      match_pair_kernel<<<2 * static_cast<int>(std::min<long long>(items, pairs)), kMpThreads, kMpSmem, s>>>(dp);
+      HN_CUDA(cudaGetLastError());
+      count_launch();
+    } else {
+      dp.segments = pick_segments(Nq, 2 * kDistTile, Ng, sm, 16);
+      const long long items = ((Nq + 2 * kDistTile - 1) / (2 * kDistTile)) * dp.segments;
+      HN_TRY((launch_dist<2, EPI_SHORTLIST>(dp, static_cast<int>(std::min<long long>(items, sm)), 1, s)));
     }
-    match_pair_kernel<<<2 * static_cast<int>(std::min<long long>(items, pairs)), kMpThreads, kMpSmem, s>>>(dp);
-    HN_CUDA(cudaGetLastError());
-    count_launch();
-  } else {
-    dp.segments = pick_segments(Nq, 2 * kDistTile, Ng, sm, 16);
-    const long long items = ((Nq + 2 * kDistTile - 1) / (2 * kDistTile)) * dp.segments;
-    HN_TRY((launch_dist<2, EPI_SHORTLIST>(dp, static_cast<int>(std::min<long long>(items, sm)), 1, s)));
   }
+  // The re-rank reads the fp32 gallery rows of the shortlisted columns; a caller that gathered the packed gallery first
+  // (half the bytes) passes the event that marks the fp32 rows' arrival, so that transfer hides behind the GEMM.
+  if (g_ready_event) HN_CUDA(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(g_ready_event), 0));
   // |fp16-operand dot - exact dot| <= 2^-10 for rows of norm <= 1 (L2-normalised descriptors, the only input this path
   // is defined for: FDLNet-master/utils/math_utils.py:15-18 clamps 2 - 2ab to [1e-8, 4]); keep 4x that as the margin.
   const float margin = 4.0f * (1.0f / 1024.0f) / kDotScale;
-  // the CTA-pair kernel keeps two top-kTopC lists per row and segment (one per 64-column half of its tiles)
-  rerank_kernel<<<static_cast<unsigned>((Nq + 3) / 4), 128, 0, s>>>(q, g, cand, cand_val, margin, Nq, Ng,
-                                                                   dp.segments * kTopC * (use_pair ? 2 : 1), g_offset, d1, d2, i1, i2);
-  HN_CUDA(cudaGetLastError());
-  count_launch(3);
+  {
+    MatchTimer timer(2, s);
+    // the CTA-pair kernel keeps two top-kTopC lists per row and segment (one per 64-column half of its tiles)
+    rerank_kernel<<<static_cast<unsigned>((Nq + 3) / 4), 128, 0, s>>>(q, g, cand, cand_val, margin, Nq, Ng,
+                                                                     dp.segments * kTopC * (use_pair ? 2 : 1), g_offset, d1, d2, i1, i2);
+    HN_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return HN_OK;
+}
+
+extern "C" int hn_match(const float* q, const float* g, long long Nq, long long Ng, long long g_offset, float* d1,
+                        float* d2, int32_t* i1, int32_t* i2, void* workspace, long long workspace_bytes, void* stream) {
+  return hn_match_ex(q, g, nullptr, nullptr, Nq, Ng, g_offset, d1, d2, i1, i2, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int hn_match_profile_enable(int on) {
+  g_match_profile.on = on != 0;
+  for (size_t& u : g_match_profile.used) u = 0;
+  return HN_OK;
+}
+
+extern "C" int hn_match_profile_read(double ms_out[3], long long launches_out[3]) {
+  HN_REQUIRE(ms_out && launches_out, "hn_match_profile_read: NULL argument");
+  for (int st = 0; st < 3; ++st) {
+    double total = 0.0;
+    const size_t pairs = g_match_profile.used[st] / 2;
+    for (size_t i = 0; i < pairs; ++i) {
+      HN_CUDA(cudaEventSynchronize(g_match_profile.ev[st][2 * i + 1]));
+      float ms = 0.f;
+      HN_CUDA(cudaEventElapsedTime(&ms, g_match_profile.ev[st][2 * i], g_match_profile.ev[st][2 * i + 1]));
+      total += ms;
+    }
+    ms_out[st] = total;
+    launches_out[st] = static_cast<long long>(pairs);
+    g_match_profile.used[st] = 0;
+  }
   return HN_OK;
 }

@@ -455,6 +455,9 @@ extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const floa
   HN_REQUIRE(act_dtype == HN_F16 || act_dtype == HN_BF16, "hn_pack_hardnet: act_dtype must be HN_F16 or HN_BF16");
   for (int i = 0; i < 7; ++i) HN_REQUIRE(w[i] && bn_mean[i] && bn_var[i], "hn_pack_hardnet: NULL tensor %d", i);
   const int bf = act_dtype == HN_BF16;
+  // Packing is rare and synchronous: forwards still queued on any stream (PyTorch's side streams are non-blocking, i.e. not
+  // ordered against the legacy stream these copies use) must finish reading the old weights first ...
+  HN_CUDA(cudaDeviceSynchronize());
   static const int cout[7] = {32, 32, 64, 64, 128, 128, 128};
   std::vector<float> bias(7 * 128, 0.f);
   std::vector<float> scale(128);
@@ -514,6 +517,9 @@ extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const floa
     memcpy(h->conv_params[li].bias_v, bias.data() + 128 * (li + 1), sizeof(h->conv_params[li].bias_v));
     memcpy(h->pair_params[li].bias_v, bias.data() + 128 * (li + 1), sizeof(h->pair_params[li].bias_v));
   }
+  // ... and every copy (small pageable H2D copies return once staged, before their DMA lands) must be complete before a
+  // forward on another stream can read the new weights.
+  HN_CUDA(cudaDeviceSynchronize());
   h->act_bf16 = bf;
   h->packed = true;
   return HN_OK;

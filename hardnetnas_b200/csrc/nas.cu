@@ -1290,6 +1290,8 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
   HN_REQUIRE(ops[0].kind == OP_STEM && ops[0].cout == 32 && ops[0].hin == 32, "hn_pack_nas: first op must be the 1->32 stem");
   HN_REQUIRE(ops[n_ops - 1].kind == OP_HEAD && ops[n_ops - 1].cout == 128, "hn_pack_nas: last op must be the 128-d head");
   const int bf = act_dtype == HN_BF16;
+  // same ordering rule as hn_pack_hardnet: drain every stream before the old net is freed, and again once the copies landed
+  HN_CUDA(cudaDeviceSynchronize());
   nas_state_free(h->nas);
   h->nas = nullptr;
   NasState* st = new NasState();
@@ -1482,6 +1484,10 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
   {
     const int rc = seg_partition(h, st, params);
     if (rc != HN_OK) return fail(rc);
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("hn_pack_nas: cudaDeviceSynchronize failed");
+    return fail(HN_ERR_CUDA);
   }
   h->nas = st;
   return HN_OK;

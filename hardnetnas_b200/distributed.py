@@ -57,28 +57,90 @@ def _default_matcher():
     return _ops.match_top2
 
 
+def _counts_or_exchange(local_rows: int, counts: list[int] | None, device) -> list[int]:
+    rank, world = _world()
+    if counts is not None or world == 1:
+        return counts if counts is not None else [local_rows]
+    c = torch.tensor([local_rows], dtype=torch.long, device=device)
+    cl = [torch.zeros_like(c) for _ in range(world)]
+    dist.all_gather(cl, c)
+    return [int(t.item()) for t in cl]
+
+
+def _gather_packed_then_rows(local: torch.Tensor, counts: list[int]):
+    """Gallery exchange of the B200 path: ONE all_gather of the packed fp16 rows (what the GEMM reads: half the NVLink bytes,
+    each rank packs only its own shard), then the fp32 rows (what the exact re-rank reads) as a second, asynchronous
+    all_gather whose completion is an event - it finishes behind the GEMM. Returns (rows_fp32, rows_fp16, ready_event)."""
+    from . import _ops
+    world = len(counts)
+    packed_local = _ops.pack_descriptors(local)
+    packed = torch.empty((world * counts[0], 128), dtype=torch.float16, device=local.device)
+    dist.all_gather_into_tensor(packed, packed_local)
+    rows = torch.empty((world * counts[0], 128), dtype=torch.float32, device=local.device)
+    work = dist.all_gather_into_tensor(rows, local.contiguous(), async_op=True)
+    side = _side_stream(local.device)
+    ready = torch.cuda.Event()
+    with torch.cuda.stream(side):
+        work.wait()            # the side stream (not the compute stream) waits for the collective
+        ready.record(side)
+    return rows, packed, ready
+
+
+_side_streams: dict = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 def match_sharded(q_local: torch.Tensor, g_local: torch.Tensor, matcher: Callable | None = None,
                   g_counts: list[int] | None = None):
     """(d1, d2, i1, i2) for this rank's query rows against the gallery of ALL ranks; indices are global
     gallery rows in rank order. `g_counts` = gallery rows held by every rank when the caller knows them (e.g. from
     `shard_range`): it saves the small count exchange and its host synchronisation, which is a visible share of a
-    sub-millisecond matching call."""
+    sub-millisecond matching call.
+    With the default (B200) matcher and equal shards the packed gallery is gathered first and the fp32 rows arrive behind the
+    GEMM (`_gather_packed_then_rows`); an injected matcher (CPU tests) or ragged shards use one plain gather."""
+    rank, world = _world()
+    if matcher is None and world > 1 and q_local.is_cuda:
+        counts = _counts_or_exchange(g_local.size(0), g_counts, g_local.device)
+        if len(set(counts)) == 1:
+            from . import _ops
+            g_full, g16_full, ready = _gather_packed_then_rows(g_local, counts)
+            return _ops.match_top2(q_local, g_full, g16=g16_full, g_ready_event=ready)
+        g_counts = counts
     matcher = matcher or _default_matcher()
     g_full = all_gather_rows(g_local, g_counts)
     return matcher(q_local, g_full)
 
 
-def mutual_nn_sharded(q_local: torch.Tensor, g_local: torch.Tensor, matcher: Callable | None = None) -> torch.Tensor:
-    """Mutual-NN pairs (global query row, global gallery row) whose query row lives on this rank."""
-    matcher = matcher or _default_matcher()
+def mutual_nn_sharded(q_local: torch.Tensor, g_local: torch.Tensor, matcher: Callable | None = None,
+                      q_counts: list[int] | None = None, g_counts: list[int] | None = None) -> torch.Tensor:
+    """Mutual-NN pairs (global query row, global gallery row) whose query row lives on this rank. The forward direction
+    shards the query rows (gallery gathered), the backward direction shards the gallery rows (queries gathered); only the
+    backward index vector is exchanged afterwards. With `q_counts` / `g_counts` given no count exchange happens."""
     rank, world = _world()
-    g_full = all_gather_rows(g_local)
-    q_full = all_gather_rows(q_local)
-    fwd_local = matcher(q_local, g_full)[2].long()   # nearest gallery row of my queries
-    bwd_local = matcher(g_local, q_full)[2].long()   # nearest query row of my gallery rows
-    bwd_full = all_gather_rows(bwd_local)
-    q_counts = all_gather_rows(torch.tensor([q_local.size(0)], dtype=torch.long, device=q_local.device))
-    q_off = int(q_counts[:rank].sum().item()) if world > 1 else 0
+    qc = _counts_or_exchange(q_local.size(0), q_counts, q_local.device)
+    gc = _counts_or_exchange(g_local.size(0), g_counts, g_local.device)
+    if matcher is None and world > 1 and q_local.is_cuda and len(set(qc)) == 1 and len(set(gc)) == 1:
+        from . import _ops
+        g_full, g16_full, g_ready = _gather_packed_then_rows(g_local, gc)
+        q_full, q16_full, q_ready = _gather_packed_then_rows(q_local, qc)
+        lo = rank * qc[0]
+        fwd_local = _ops.match_top2(q_local, g_full, q16=q16_full[lo:lo + qc[0]], g16=g16_full, g_ready_event=g_ready)[2].long()
+        glo = rank * gc[0]
+        bwd_local = _ops.match_top2(g_local, q_full, q16=g16_full[glo:glo + gc[0]], g16=q16_full, g_ready_event=q_ready)[2]
+    else:
+        matcher = matcher or _default_matcher()
+        g_full = all_gather_rows(g_local, gc)
+        q_full = all_gather_rows(q_local, qc)
+        fwd_local = matcher(q_local, g_full)[2].long()   # nearest gallery row of my queries
+        bwd_local = matcher(g_local, q_full)[2]          # nearest query row of my gallery rows
+    bwd_full = all_gather_rows(bwd_local.contiguous(), gc).long()
+    q_off = sum(qc[:rank])
     i = torch.arange(q_local.size(0), device=q_local.device) + q_off
     keep = bwd_full[fwd_local] == i
     return torch.stack([i[keep], fwd_local[keep]], dim=1)

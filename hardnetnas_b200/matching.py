@@ -52,15 +52,27 @@ def match_top2(des1, des2):
     return d1, d2, i1.long(), i2.long()
 
 
-def mutual_nearest_neighbors(des1, des2):
-    """Mutual NN pairs [M,2]: (i, j) with j = argmin_j D[i,:] and i = argmin_i D[:,j]. Not in the reference;
-    composed from its row / column minima (hardnet/Losses.py:105-108, eval_utils.py:24-32)."""
-    _, _, fwd, _ = _ops.match_top2(des1, des2)
-    _, _, bwd, _ = _ops.match_top2(des2, des1)
+def mutual_nn_ratio(des1, des2, threshold=0.7, return_pairs=True):
+    """Mutual nearest neighbours AND the ratio test of BASELINE config 4 in one call:
+    (pairs [M,2] int64 or None, mutual bool[Nq], ratio_label bool[Nq], Ia int64[Nq], Da, Db).
+    (i, j) is mutual iff j = argmin_j D[i,:] and i = argmin_i D[:,j] - not in the reference; composed from its row / column
+    minima (hardnet/Losses.py:105-108, eval_utils.py:24-32); ratio_label = Da / Db < threshold (eval_utils.py:168-175).
+    Both operand sets are packed to fp16 once and feed the forward (queries x gallery) and the backward (gallery x queries)
+    GEMM. The masks come without any host synchronisation; compacting them into the `pairs` list needs its length on the host
+    (return_pairs=False skips it)."""
+    q16, g16 = _ops.pack_descriptors(des1), _ops.pack_descriptors(des2)
+    d1, d2, fwd, _ = _ops.match_top2(des1, des2, q16=q16, g16=g16)
+    _, _, bwd, _ = _ops.match_top2(des2, des1, q16=g16, g16=q16)
     fwd, bwd = fwd.long(), bwd.long()
     i = torch.arange(des1.size(0), device=fwd.device)
-    keep = bwd[fwd] == i
-    return torch.stack([i[keep], fwd[keep]], dim=1)
+    mutual = bwd[fwd] == i
+    pairs = torch.stack([i[mutual], fwd[mutual]], dim=1) if return_pairs else None
+    return pairs, mutual, (d1 / d2).lt(threshold), fwd, d1, d2
+
+
+def mutual_nearest_neighbors(des1, des2):
+    """Mutual NN pairs [M,2]: (i, j) with j = argmin_j D[i,:] and i = argmin_i D[:,j] (see mutual_nn_ratio)."""
+    return mutual_nn_ratio(des1, des2)[0]
 
 
 # ---- match-score counters (FDLNet-master/utils/eval_utils.py:112-197) -----------------------------------------------

@@ -124,10 +124,10 @@ class SampledDescriptorNet(_EngineOwner, nn.Module):
         y = self.last_stages(y)
         return y / torch.norm(y, p=2, dim=-1, keepdim=True)
 
-    def forward(self, x, out_dtype: torch.dtype = torch.float32):
+    def forward(self, x, out_dtype: torch.dtype = torch.float32, out: torch.Tensor | None = None):
         if self.training:
             return self.forward_torch(x)
-        return self._forward_b200(x, out_dtype)
+        return self._forward_b200(x, out_dtype, out)
 
     def load_from_supernet(self, state_dict: dict, candidate_names: list[str]):
         """Copy the selected ops' weights out of an FBNet_Stochastic_SuperNet state_dict
@@ -260,7 +260,7 @@ class SampledDescriptorNet(_EngineOwner, nn.Module):
                                                    out.data_ptr(), C.c_void_p(stream)), "hn_forward_nas_dump")
         return out
 
-    def _forward_b200(self, x, out_dtype=torch.float32):
+    def _forward_b200(self, x, out_dtype=torch.float32, out=None):
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise _lib.HardnetB200Error("SampledDescriptorNet eval forward runs on B200 CUDA tensors only (no CPU fallback)")
         if x.dim() != 4 or tuple(x.shape[1:]) != (1, 32, 32):
@@ -268,10 +268,13 @@ class SampledDescriptorNet(_EngineOwner, nn.Module):
         in_dt = _lib.HN_U8 if x.dtype == torch.uint8 else _lib.HN_F32
         x = x.contiguous() if x.dtype in (torch.uint8, torch.float32) else x.float().contiguous()
         self._ensure_packed(x.device)
-        out = torch.empty((x.size(0), 128), dtype=out_dtype, device=x.device)
+        if out is None:
+            out = torch.empty((x.size(0), 128), dtype=out_dtype, device=x.device)
+        elif not (out.is_cuda and out.is_contiguous() and tuple(out.shape) == (x.size(0), 128) and out.dtype in _OUT_DTYPES):
+            raise ValueError("out must be a contiguous CUDA [B,128] tensor of dtype float32 / float16 / bfloat16")
         eng = self._engine
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(eng.lib.hn_forward_nas(eng.handle, x.data_ptr(), in_dt, x.size(0), out.data_ptr(),
-                                              _OUT_DTYPES[out_dtype], C.c_void_p(stream)), "hn_forward_nas")
+                                              _OUT_DTYPES[out.dtype], C.c_void_p(stream)), "hn_forward_nas")
         return out

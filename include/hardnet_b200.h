@@ -146,10 +146,31 @@ int hn_loss_hardnet(const float* anchor, const float* positive, long long N, flo
 
 /* Brute-force matching in the FDLNet distance form: for every query row the nearest and second nearest
  * gallery rows (D.min(dim=-1) of eval_utils.py:113-114 and sorted[:,0:2] of :168-175).
- * q:[Nq,128], g:[Ng,128] fp32. Outputs: d1[Nq], d2[Nq] distances, i1[Nq] gallery index (+g_offset). */
+ * q:[Nq,128], g:[Ng,128] fp32. Outputs: d1[Nq], d2[Nq] distances, i1[Nq] gallery index (+g_offset).
+ * Precondition: L2-normalised rows (|x| <= 1 up to rounding), the only input the FDLNet distance form is defined for
+ * (math_utils.py:15-18 clamps 2 - 2ab to [1e-8, 4]): the exactness guarantee of the shortlist + fp32 re-rank rests on the
+ * 2^-10 error bound of the fp16-operand dot product of unit vectors, and |x| >= 256 would overflow the packed operands. */
 int hn_match(const float* q, const float* g, long long Nq, long long Ng, long long g_offset, float* d1,
              float* d2, int32_t* i1, int32_t* i2, void* workspace, long long workspace_bytes,
              void* stream);
+
+/* The fp16 operand rows hn_match feeds to the tensor core (x * 2^8, K = 128), for callers that exchange the PACKED gallery
+ * between GPUs (half the NVLink bytes of the fp32 rows) or match one set several times. x:[n,128] fp32 -> out16:[n,128]. */
+int hn_pack_descriptors(const float* x, long long n, void* out16, void* stream);
+
+/* hn_match with optional pre-packed operands (q16 / g16 from hn_pack_descriptors, NULL = pack here) and an optional
+ * cudaEvent_t the exact re-rank waits for: the GEMM reads only the packed rows, the re-rank reads the fp32 gallery rows of
+ * the shortlisted columns, so a sharded caller gathers the packed gallery first and lets the fp32 gather finish behind the
+ * GEMM (hardnetnas_b200/distributed.py). Preconditions as hn_match: unit-norm rows (|x| <= 1). */
+int hn_match_ex(const float* q, const float* g, const void* q16, const void* g16, long long Nq, long long Ng,
+                long long g_offset, float* d1, float* d2, int32_t* i1, int32_t* i2, void* workspace,
+                long long workspace_bytes, void* g_ready_event, void* stream);
+
+/* Measurement hooks (process-wide): bracket the three stages of every hn_match call (0 = operand packing, 1 = GEMM +
+ * shortlist, 2 = exact re-rank) with CUDA events; hn_match_profile_read waits for them, returns the summed milliseconds and
+ * launch counts per stage and resets the counters. */
+int hn_match_profile_enable(int on);
+int hn_match_profile_read(double ms_out[3], long long launches_out[3]);
 
 /* ---- patch extraction (FDLNet-master/utils/image_utils.py:11-158, clip_patch) ------------------------ */
 /* Crops a psize x psize patch around every keypoint with the reference's similarity transform
