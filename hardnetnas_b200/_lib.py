@@ -13,7 +13,7 @@ LIB_PATH = _HERE / "libhardnet_b200.so"
 
 HN_F32, HN_F16, HN_BF16, HN_U8 = 0, 1, 2, 3
 HN_FORM_HARDNET, HN_FORM_FDL = 0, 1
-HN_FLAG_LOSS_MASK, HN_FLAG_SWAP = 1, 2
+HN_FLAG_LOSS_MASK, HN_FLAG_SWAP, HN_FLAG_NEI_MASK = 1, 2, 4
 
 # name -> (restype, argtypes); kept in sync with include/hardnet_b200.h (tests/test_abi.py checks it)
 _P = C.c_void_p
@@ -37,6 +37,8 @@ SIGNATURES = {
     "hn_dist_workspace_bytes": (C.c_longlong, [C.c_longlong, C.c_longlong, C.c_int]),
     "hn_dist_min": (C.c_int, [_P, _P, C.c_longlong, C.c_longlong, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P,
                               C.c_longlong, _P]),
+    "hn_dist_min_ex": (C.c_int, [_P, _P, C.c_longlong, C.c_longlong, C.c_int, C.c_int, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P,
+                                 C.c_longlong, _P]),
     "hn_loss_hardnet": (C.c_int, [_P, _P, C.c_longlong, C.c_float, C.c_int, _P, _P, C.c_longlong, _P]),
     "hn_match": (C.c_int, [_P, _P, C.c_longlong, C.c_longlong, C.c_longlong, _P, _P, _P, _P, _P, C.c_longlong, _P]),
     "hn_pack_descriptors": (C.c_int, [_P, C.c_longlong, _P, _P]),

@@ -42,26 +42,34 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def dist_min(a: torch.Tensor, p: torch.Tensor, form: int, loss_mask: bool, swap: bool):
-    """Returns dict(pos, row_min, row_arg[, col_min, col_arg]) — see hn_dist_min in include/hardnet_b200.h."""
+def dist_min(a: torch.Tensor, p: torch.Tensor, form: int, loss_mask: bool, swap: bool, a_xy: torch.Tensor | None = None,
+             p_xy: torch.Tensor | None = None, nei_c: float = 0.0):
+    """Returns dict(pos, row_min, row_arg[, col_min, col_arg]) — see hn_dist_min / hn_dist_min_ex in include/hardnet_b200.h.
+    a_xy / p_xy ([N,2] keypoint coordinates) switch on the neighbour mask of HardNetNeiMask.loss."""
     lib = _lib.load()
     a = _require_cuda_f32("dist_min", a)
     p = _require_cuda_f32("dist_min", p)
     na, npos = a.size(0), p.size(0)
     dev = a.device
+    nei = a_xy is not None
+    if nei:
+        a_xy = a_xy.detach().to(dev, torch.float32).contiguous()
+        p_xy = p_xy.detach().to(dev, torch.float32).contiguous()
+        assert tuple(a_xy.shape) == (na, 2) and tuple(p_xy.shape) == (npos, 2), "keypoint coordinates must be [N,2]"
     with torch.cuda.device(dev):
         ws = _workspace(dev, lib.hn_dist_workspace_bytes(na, npos, 1))
+        has_pos = loss_mask or nei
         out = {
-            "pos": torch.empty(min(na, npos), dtype=torch.float32, device=dev) if loss_mask else None,
+            "pos": torch.empty(min(na, npos), dtype=torch.float32, device=dev) if has_pos else None,
             "row_min": torch.empty(na, dtype=torch.float32, device=dev),
             "row_arg": torch.empty(na, dtype=torch.int32, device=dev),
             "col_min": torch.empty(npos, dtype=torch.float32, device=dev) if swap else None,
             "col_arg": torch.empty(npos, dtype=torch.int32, device=dev) if swap else None,
         }
-        flags = (_lib.HN_FLAG_LOSS_MASK if loss_mask else 0) | (_lib.HN_FLAG_SWAP if swap else 0)
-        _lib.check(lib.hn_dist_min(_ptr(a), _ptr(p), na, npos, form, flags, _ptr(out["pos"]), _ptr(out["row_min"]),
-                                   _ptr(out["row_arg"]), _ptr(out["col_min"]), _ptr(out["col_arg"]), _ptr(ws),
-                                   ws.numel(), _stream_ptr()), "hn_dist_min")
+        flags = (_lib.HN_FLAG_LOSS_MASK if loss_mask else 0) | (_lib.HN_FLAG_SWAP if swap else 0) | (_lib.HN_FLAG_NEI_MASK if nei else 0)
+        _lib.check(lib.hn_dist_min_ex(_ptr(a), _ptr(p), na, npos, form, flags, _ptr(a_xy), _ptr(p_xy), C.c_float(nei_c),
+                                      _ptr(out["pos"]), _ptr(out["row_min"]), _ptr(out["row_arg"]), _ptr(out["col_min"]),
+                                      _ptr(out["col_arg"]), _ptr(ws), ws.numel(), _stream_ptr()), "hn_dist_min")
     return out
 
 

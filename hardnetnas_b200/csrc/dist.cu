@@ -242,7 +242,7 @@ static int pick_segments(long long rows, int rows_per_block, long long cols, int
 
 // Shared body of hn_dist_min / hn_loss_hardnet. Leaves packed minima and pos in the workspace.
 static int run_exact(const float* a, const float* p, long long Na, long long Np, int form, int flags, ExactWs& w,
-                     cudaStream_t s) {
+                     cudaStream_t s, const float* a_xy = nullptr, const float* p_xy = nullptr, float nei_c = 0.f) {
   int sm = 0;
   HN_TRY(device_sm_count(&sm));
   const int threads = 256;
@@ -275,6 +275,12 @@ static int run_exact(const float* a, const float* p, long long Na, long long Np,
   dp.k_blocks = 6;
   dp.form = form;
   dp.loss_mask = (flags & HN_FLAG_LOSS_MASK) ? 1 : 0;
+  dp.nei_mask = (flags & HN_FLAG_NEI_MASK) ? 1 : 0;
+  dp.nei_c = nei_c;
+  for (int sd = 0; sd < 2; ++sd) {   // the mask is symmetric in (row, column): both directions index the same two arrays
+    dp.side[sd].xy_a_rows = dp.side[sd].xy_a_cols = reinterpret_cast<const float2*>(a_xy);
+    dp.side[sd].xy_p_rows = dp.side[sd].xy_p_cols = reinterpret_cast<const float2*>(p_xy);
+  }
   dp.dot_scale = kDotScale;
   const long long rows = swap ? std::max(Na, Np) : Na;
   const long long cols = swap ? std::min(Na, Np) : Np;
@@ -298,9 +304,9 @@ extern "C" long long hn_dist_workspace_bytes(long long Na, long long Np, int spl
   return static_cast<long long>(std::max(w.bytes, shortlist) + 256);
 }
 
-extern "C" int hn_dist_min(const float* a, const float* p, long long Na, long long Np, int form, int flags, float* pos,
-                           float* row_min, int32_t* row_arg, float* col_min, int32_t* col_arg, void* workspace,
-                           long long workspace_bytes, void* stream) {
+extern "C" int hn_dist_min_ex(const float* a, const float* p, long long Na, long long Np, int form, int flags, const float* a_xy,
+                              const float* p_xy, float nei_c, float* pos, float* row_min, int32_t* row_arg, float* col_min,
+                              int32_t* col_arg, void* workspace, long long workspace_bytes, void* stream) {
   HN_REQUIRE(a && p && workspace, "hn_dist_min: NULL argument");
   HN_REQUIRE(Na >= 1 && Np >= 1, "hn_dist_min: empty input (Na=%lld, Np=%lld)", Na, Np);
   HN_REQUIRE(Na < (1LL << 31) && Np < (1LL << 31), "hn_dist_min: more than 2^31 rows");
@@ -311,18 +317,31 @@ extern "C" int hn_dist_min(const float* a, const float* p, long long Na, long lo
     set_error("hn_dist_min: column outputs need HN_FLAG_SWAP");
     return HN_ERR_INVALID;
   }
+  if (flags & HN_FLAG_NEI_MASK) {
+    HN_REQUIRE(a_xy && p_xy && Na == Np, "hn_dist_min: the neighbour mask needs both keypoint arrays and a square problem");
+    HN_REQUIRE(!(flags & HN_FLAG_LOSS_MASK), "hn_dist_min: HN_FLAG_LOSS_MASK and HN_FLAG_NEI_MASK are different losses");
+    HN_REQUIRE((reinterpret_cast<uintptr_t>(a_xy) & 7) == 0 && (reinterpret_cast<uintptr_t>(p_xy) & 7) == 0,
+               "hn_dist_min: keypoint arrays must be 8-byte aligned");
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   ExactWs w = carve_exact(workspace, Na, Np);
-  HN_TRY(run_exact(a, p, Na, Np, form, flags, w, s));
+  HN_TRY(run_exact(a, p, Na, Np, form, flags, w, s, a_xy, p_xy, nei_c));
   const int threads = 256;
   if (row_min || row_arg)
     unpack_min_kernel<<<static_cast<unsigned>((Na + threads - 1) / threads), threads, 0, s>>>(w.row_pack, Na, row_min, row_arg);
   if (col_min || col_arg)
     unpack_min_kernel<<<static_cast<unsigned>((Np + threads - 1) / threads), threads, 0, s>>>(w.col_pack, Np, col_min, col_arg);
-  if (pos && (flags & HN_FLAG_LOSS_MASK))
+  if (pos && (flags & (HN_FLAG_LOSS_MASK | HN_FLAG_NEI_MASK)))
     HN_CUDA(cudaMemcpyAsync(pos, w.pos, static_cast<size_t>(std::min(Na, Np)) * 4, cudaMemcpyDeviceToDevice, s));
   HN_CUDA(cudaGetLastError());
   return HN_OK;
+}
+
+extern "C" int hn_dist_min(const float* a, const float* p, long long Na, long long Np, int form, int flags, float* pos,
+                           float* row_min, int32_t* row_arg, float* col_min, int32_t* col_arg, void* workspace,
+                           long long workspace_bytes, void* stream) {
+  return hn_dist_min_ex(a, p, Na, Np, form, flags, nullptr, nullptr, 0.f, pos, row_min, row_arg, col_min, col_arg, workspace,
+                        workspace_bytes, stream);
 }
 
 extern "C" int hn_loss_hardnet(const float* anchor, const float* positive, long long N, float margin, int anchor_swap,

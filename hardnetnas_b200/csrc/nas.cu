@@ -576,6 +576,122 @@ __global__ void __launch_bounds__(256) dw_conv_smem_kernel(const uint16_t* __res
   }
 }
 
+// The same kernel in packed half2 arithmetic for fp16 activations: fp16 weights (converted while they are staged in shared
+// memory), fp16 accumulators, no unpacking - HFMA2 issues at twice the FP32 FMA rate and a thread needs 40 instead of ~100
+// registers. The 9 / 25-term fp16 accumulation costs ~1e-4 of descriptor error against the 1e-3 gate (CPU emulation of the
+// whole net: wang2 8.4e-5 -> 1.5e-4, wang3 1.2e-4 -> 1.8e-4, wang4 1.9e-4 -> 2.2e-4 max-abs); HN_NAS_DW_F32=1 keeps the
+// fp32 kernel. bf16 activations always use fp32 arithmetic (8-bit mantissa accumulators would not hold the gate).
+template <int K, int S, int SH>
+__global__ void __launch_bounds__(256) dw_conv_smem_h2_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                              const float* __restrict__ w /*[k*k][C]*/,
+                                                              const float* __restrict__ bias, int patches, int C, int hin,
+                                                              int hout, int G, int relu) {
+  extern __shared__ __align__(128) uint8_t dw_smem[];
+  constexpr int PAD = K >> 1;
+  constexpr int NR = (SH - 1) * S + K;
+  const int cg = C >> 3;
+  const int map_elems = hin * hin * C;
+  const uint32_t unit_bytes = static_cast<uint32_t>(G) * map_elems * 2;
+  __half* s_w = reinterpret_cast<__half*>(dw_smem);                  // [K*K][C] weights, then [C] bias (fp16)
+  const int w_halfs = (K * K + 1) * C;
+  const uint32_t buf_off = (static_cast<uint32_t>(w_halfs) * 2 + 127) & ~127u;
+  const uint32_t bar0 = smem_u32(dw_smem + buf_off + 2 * unit_bytes);
+  const uint16_t* s_zero = reinterpret_cast<const uint16_t*>(dw_smem + buf_off + 2 * unit_bytes + 16);
+  if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(dw_smem + buf_off + 2 * unit_bytes + 16)[threadIdx.x] = 0u;
+  for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) s_w[i] = __float2half_rn(w[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_w[K * K * C + i] = __float2half_rn(bias[i]);
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int units = (patches + G - 1) / G;
+  auto issue = [&](int u, int slot) {
+    const int np = min(G, patches - u * G);
+    const uint32_t bytes = static_cast<uint32_t>(np) * map_elems * 2;
+    const uint32_t bar = bar0 + 8 * slot;
+    mbar_arrive_expect_tx(bar, bytes);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + static_cast<size_t>(u) * unit_bytes;
+    const uint32_t dst = smem_u32(dw_smem + buf_off + slot * unit_bytes);
+    for (uint32_t o = 0; o < bytes; o += 32768) {
+      const uint32_t n = min(32768u, bytes - o);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + o),
+                   "l"(src + o), "r"(n), "r"(bar)
+                   : "memory");
+    }
+  };
+  if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < units) issue(blockIdx.x, 0);
+  const int strips = hout / SH;
+  const int items_per_patch = strips * hout * cg;
+  const __half2 hzero = __float2half2_rn(0.f);
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int slot = it & 1;
+    if (threadIdx.x == 0 && u + static_cast<int>(gridDim.x) < units) issue(u + gridDim.x, slot ^ 1);
+    mbar_wait(bar0 + 8 * slot, (it >> 1) & 1);
+    const uint16_t* buf = reinterpret_cast<const uint16_t*>(dw_smem + buf_off + slot * unit_bytes);
+    const int np = min(G, patches - u * G);
+    for (int e = threadIdx.x; e < np * items_per_patch; e += blockDim.x) {
+      const int c8 = (e % cg) * 8;
+      int t = e / cg;
+      const int ox = t % hout;
+      t /= hout;
+      const int ys = t % strips;
+      const int pl = t / strips;
+      const uint16_t* map = buf + pl * map_elems + c8;
+      __half2 acc[SH][4];
+      {
+        const uint4 b = *reinterpret_cast<const uint4*>(s_w + K * K * C + c8);
+#pragma unroll
+        for (int j = 0; j < SH; ++j) {
+          acc[j][0] = *reinterpret_cast<const __half2*>(&b.x); acc[j][1] = *reinterpret_cast<const __half2*>(&b.y);
+          acc[j][2] = *reinterpret_cast<const __half2*>(&b.z); acc[j][3] = *reinterpret_cast<const __half2*>(&b.w);
+        }
+      }
+      const int iy0 = ys * SH * S - PAD;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int ix = ox * S + kx - PAD;
+        const bool x_ok = ix >= 0 && ix < hin;
+        uint4 wk[K];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) wk[ky] = *reinterpret_cast<const uint4*>(s_w + (ky * K + kx) * C + c8);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int iy = iy0 + r;
+          const bool ok = x_ok && iy >= 0 && iy < hin;
+          const uint4 xv = *reinterpret_cast<const uint4*>(ok ? map + (iy * hin + ix) * C : s_zero);
+          const __half2 x[4] = {*reinterpret_cast<const __half2*>(&xv.x), *reinterpret_cast<const __half2*>(&xv.y),
+                                *reinterpret_cast<const __half2*>(&xv.z), *reinterpret_cast<const __half2*>(&xv.w)};
+#pragma unroll
+          for (int j = 0; j < SH; ++j) {
+            const int ky = r - j * S;          // compile-time after unrolling
+            if (ky >= 0 && ky < K) {
+              const __half2 wv[4] = {*reinterpret_cast<const __half2*>(&wk[ky].x), *reinterpret_cast<const __half2*>(&wk[ky].y),
+                                     *reinterpret_cast<const __half2*>(&wk[ky].z), *reinterpret_cast<const __half2*>(&wk[ky].w)};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[j][q] = __hfma2(x[q], wv[q], acc[j][q]);
+            }
+          }
+        }
+      }
+      uint16_t* optr = out + ((static_cast<size_t>(u) * G + pl) * hout + ys * SH) * hout * C + ox * C + c8;
+#pragma unroll
+      for (int j = 0; j < SH; ++j) {
+        if (relu) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[j][q] = __hmax2(acc[j][q], hzero);
+        }
+        *reinterpret_cast<uint4*>(optr + static_cast<size_t>(j) * hout * C) =
+            make_uint4(*reinterpret_cast<const uint32_t*>(&acc[j][0]), *reinterpret_cast<const uint32_t*>(&acc[j][1]),
+                       *reinterpret_cast<const uint32_t*>(&acc[j][2]), *reinterpret_cast<const uint32_t*>(&acc[j][3]));
+      }
+    }
+    __syncthreads();                           // every thread is done with this slot before it is refilled
+  }
+}
+
 // MaxPool2d(3, stride 2, padding 1) through the same bulk-copied shared-memory ring as the depthwise kernel: a thread
 // owns 8 channels x a vertical strip of 4 output rows and takes packed 16-bit maxima directly (max is exact in fp16 /
 // bf16, NaNs propagate like torch); out-of-image taps read a -inf vector.
@@ -1198,7 +1314,8 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
               if (smem <= 227 * 1024) {
                 const int units = (n + G - 1) / G;
                 // resident CTAs per SM: shared memory, and registers for the 8-row variant (~176 per thread)
-                const int per_sm = sh == 8 ? 1 : std::max(1, std::min(4, static_cast<int>((227 * 1024) / (smem + 1024))));
+                const bool f32_math = bf || h->env.nas_dw_f32;   // the 8-row fp32 variant needs ~176 registers per thread, the half2 one ~110
+                const int per_sm = (sh == 8 && f32_math) ? 1 : std::max(1, std::min(sh == 8 ? 2 : 4, static_cast<int>((227 * 1024) / (smem + 1024))));
                 const int sgrid = std::min(units, h->sm_count * per_sm);
 #define HN_DW_SMEM(KK, SS, SHH, BF)                                                                                   \
   do {                                                                                                                \
@@ -1207,13 +1324,21 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
       HN_CUDA(cudaFuncSetAttribute(dw_conv_smem_kernel<KK, SS, SHH, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
     dw_conv_smem_kernel<KK, SS, SHH, BF><<<sgrid, 256, smem, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, G, o.relu); \
   } while (0)
-#define HN_DW_SMEM_T(KK, SS, SHH) do { if (bf) HN_DW_SMEM(KK, SS, SHH, true); else HN_DW_SMEM(KK, SS, SHH, false); } while (0)
+#define HN_DW_SMEM_H2(KK, SS, SHH)                                                                                    \
+  do {                                                                                                                \
+    static DeviceOnce once;                                                                                           \
+    if (once.first_time())                                                                                            \
+      HN_CUDA(cudaFuncSetAttribute(dw_conv_smem_h2_kernel<KK, SS, SHH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    dw_conv_smem_h2_kernel<KK, SS, SHH><<<sgrid, 256, smem, s>>>(src, dst, wv, bv, n, o.cin, o.hin, o.hout, G, o.relu); \
+  } while (0)
+#define HN_DW_SMEM_T(KK, SS, SHH) do { if (bf) HN_DW_SMEM(KK, SS, SHH, true); else if (h->env.nas_dw_f32) HN_DW_SMEM(KK, SS, SHH, false); else HN_DW_SMEM_H2(KK, SS, SHH); } while (0)
                 if (o.kernel == 3 && o.stride == 1) HN_DW_SMEM_T(3, 1, 4);
                 else if (o.kernel == 3) HN_DW_SMEM_T(3, 2, 4);
                 else if (o.stride == 1 && sh == 8) HN_DW_SMEM_T(5, 1, 8);
                 else if (o.stride == 1) HN_DW_SMEM_T(5, 1, 4);
                 else HN_DW_SMEM_T(5, 2, 4);
 #undef HN_DW_SMEM_T
+#undef HN_DW_SMEM_H2
 #undef HN_DW_SMEM
                 HN_CUDA(cudaGetLastError());
                 count_launch();

@@ -35,6 +35,10 @@ struct DistSide {
   float* pos;                  // EXACT: diagonal distance before masking (may be null)
   int* cand;                   // SHORTLIST: [Na, segments, kTopC] chunk ids
   float* cand_val;             // SHORTLIST: the chunks' approximate (fp16-operand, scaled) dot-product maxima
+  // neighbour mask (FDLNet-master/latency/rfnet/model/rf_des.py:72-86): (x, y) keypoint coordinates of the row / column items
+  // in the anchor image (xy_a*) and in the positive image (xy_p*); a pair closer than nei_c pixels in either gets +10 each
+  const float2* xy_a_rows; const float2* xy_a_cols;
+  const float2* xy_p_rows; const float2* xy_p_cols;
   long long Na, Nb;
 };
 
@@ -44,12 +48,15 @@ struct DistParams {
   int segments;
   int form;                    // HN_FORM_*
   int loss_mask;               // apply +1e-8, diagonal +10, (<0.008) +10
+  int nei_mask;                // diagonal +10 and the neighbour masks (no +1e-8, no duplicate mask): HardNetNeiMask.loss
+  float nei_c;                 // neighbour radius C in pixels
   float dot_scale;             // undoes the power-of-two operand scaling
 };
 
 template <int MB>
 constexpr size_t dist_smem_bytes(int k_blocks) {
-  return size_t(MB) * k_blocks * (kDistTile * 128) + size_t(kDistStages) * (kDistTile * 128) + 1024 + 256 + 2 * kDistTile * 4;
+  return size_t(MB) * k_blocks * (kDistTile * 128) + size_t(kDistStages) * (kDistTile * 128) + 1024 + 256 + 2 * kDistTile * 4 +
+         2 * kDistTile * 16 /* column keypoints of the neighbour mask */;
 }
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -75,6 +82,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
   const uint32_t tmem_slot = bar_base + 8u * (2 * kDistStages + 6);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
   float* s_nb = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));  // [2][128]
+  float4* s_xy = reinterpret_cast<float4*>(smem_raw + (bar_base + 256u + 2 * kDistTile * 4 - raw_addr));  // [2][128] (ax, ay, px, py)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -211,8 +219,10 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
       float na = 0.f;
       float tb[kTopC];
       int tc[kTopC];
+      float2 r_axy = make_float2(0.f, 0.f), r_pxy = make_float2(0.f, 0.f);
       if (EPI == EPI_EXACT) {
         if (p.form == HN_FORM_HARDNET && row_ok) na = sd.norm_a[row];
+        if (p.nei_mask && row_ok) { r_axy = sd.xy_a_rows[row]; r_pxy = sd.xy_p_rows[row]; }
       } else {
 #pragma unroll
         for (int i = 0; i < kTopC; ++i) { tb[i] = -__int_as_float(0x7f800000); tc[i] = 0; }
@@ -227,6 +237,15 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
           if (ep_tid < kDistTile) {
             const long long c = col0 + ep_tid;
             s_nb[acc * kDistTile + ep_tid] = c < sd.Nb ? sd.norm_b[c] : 0.f;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * MB) : "memory");
+        }
+        if (EPI == EPI_EXACT && p.nei_mask) {
+          if (ep_tid < kDistTile) {
+            const long long c = col0 + ep_tid;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < sd.Nb) { const float2 a = sd.xy_a_cols[c], b = sd.xy_p_cols[c]; v = make_float4(a.x, a.y, b.x, b.y); }
+            s_xy[acc * kDistTile + ep_tid] = v;
           }
           asm volatile("bar.sync 1, %0;" ::"n"(128 * MB) : "memory");
         }
@@ -293,6 +312,18 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
                   d += 10.0f;                                 // Losses.py:100
                 }
                 if (d < 0.008f) d += 10.0f;                   // Losses.py:101-103
+              }
+              if (p.nei_mask) {
+                if (col == row) {
+                  if (sd.pos && row_ok) sd.pos[row] = d;      // rf_des.py:70 (before masking)
+                  d += 10.0f;                                 // rf_des.py:71
+                }
+                // pairwise_distances(kp, kp).lt(C), math_utils.py:22-40: sqrt(clamp(|x|^2 + |y|^2 - 2 x.y, 1e-8)) < C
+                const float4 cxy = s_xy[acc * kDistTile + c0 + j];
+                const float da = (r_axy.x * r_axy.x + r_axy.y * r_axy.y) + (cxy.x * cxy.x + cxy.y * cxy.y) - 2.0f * (r_axy.x * cxy.x + r_axy.y * cxy.y);
+                const float dp = (r_pxy.x * r_pxy.x + r_pxy.y * r_pxy.y) + (cxy.z * cxy.z + cxy.w * cxy.w) - 2.0f * (r_pxy.x * cxy.z + r_pxy.y * cxy.w);
+                if (sqrtf(fmaxf(da, 1e-8f)) < p.nei_c) d += 10.0f;   // rf_des.py:74-79
+                if (sqrtf(fmaxf(dp, 1e-8f)) < p.nei_c) d += 10.0f;   // rf_des.py:80-85
               }
               if (col < sd.Nb && d < best) { best = d; best_col = static_cast<int>(col); }
             }

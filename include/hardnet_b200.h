@@ -44,6 +44,8 @@ typedef enum hn_dtype { HN_F32 = 0, HN_F16 = 1, HN_BF16 = 2, HN_U8 = 3 } hn_dtyp
 /* hn_dist_min flags */
 #define HN_FLAG_LOSS_MASK 1 /* +1e-8, diagonal +10, (<0.008) +10        hardnet/Losses.py:95-103          */
 #define HN_FLAG_SWAP 2      /* also produce column minima (anchor swap) hardnet/Losses.py:106-108         */
+#define HN_FLAG_NEI_MASK 4  /* diagonal +10 and +10 per keypoint set whose two keypoints lie closer than C pixels
+                               (HardNetNeiMask.loss, FDLNet-master/latency/rfnet/model/rf_des.py:66-86)      */
 
 int hn_version(void);
 const char* hn_last_error(void);
@@ -137,6 +139,14 @@ long long hn_dist_workspace_bytes(long long Na, long long Np, int split);
 int hn_dist_min(const float* a, const float* p, long long Na, long long Np, int form, int flags,
                 float* pos, float* row_min, int32_t* row_arg, float* col_min, int32_t* col_arg,
                 void* workspace, long long workspace_bytes, void* stream);
+
+/* hn_dist_min with the neighbour mask of HardNetNeiMask.loss as an input of the fused epilogue (HN_FLAG_NEI_MASK, Na == Np):
+ * a_xy / p_xy are the [N,2] fp32 (x, y) keypoint coordinates of the items in the anchor / positive image
+ * (anchor_kp[:, 1:3], positive_kp[:, 1:3]); element (i, j) gets +10 if i == j, +10 if |a_xy[i] - a_xy[j]| < nei_c and +10 if
+ * |p_xy[i] - p_xy[j]| < nei_c, with the reference's distance arithmetic (math_utils.py:22-40). pos = diagonal before masking. */
+int hn_dist_min_ex(const float* a, const float* p, long long Na, long long Np, int form, int flags, const float* a_xy,
+                   const float* p_xy, float nei_c, float* pos, float* row_min, int32_t* row_arg, float* col_min,
+                   int32_t* col_arg, void* workspace, long long workspace_bytes, void* stream);
 
 /* loss_HardNet, batch_reduce='min', loss_type='triplet_margin' (hardnet/Losses.py:87-108,142-143,153;
  * hardnetNAS/general_functions/Losses.py:27-51 is the anchor_swap=1 case). loss_out: 1 float (device). */
