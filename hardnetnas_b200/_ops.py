@@ -99,10 +99,13 @@ def pack_descriptors(x: torch.Tensor) -> torch.Tensor:
 
 
 def match_top2(q: torch.Tensor, g: torch.Tensor, g_offset: int = 0, q16: torch.Tensor | None = None,
-               g16: torch.Tensor | None = None, g_ready_event: torch.cuda.Event | None = None):
+               g16: torch.Tensor | None = None, g_ready_event: torch.cuda.Event | None = None,
+               block_max: torch.Tensor | None = None):
     """(d1, d2, i1, i2): nearest / second-nearest gallery row per query in the FDLNet distance form.
     q16 / g16: operands already packed by `pack_descriptors` (skips the packing kernels); g_ready_event: the exact re-rank
-    (the only reader of the fp32 gallery `g`) waits for it, so `g` may still be arriving while the GEMM runs."""
+    (the only reader of the fp32 gallery `g`) waits for it, so `g` may still be arriving while the GEMM runs.
+    block_max: optional fp32 tensor of `block_max_elems(nq, ng)` elements that receives the GEMM's per-cell maxima (column side
+    of mutual NN, see hn_match_mutual)."""
     lib = _lib.load()
     q = _require_cuda_f32("match", q)
     g = _require_cuda_f32("match", g)
@@ -119,5 +122,45 @@ def match_top2(q: torch.Tensor, g: torch.Tensor, g_offset: int = 0, q16: torch.T
         i2 = torch.empty(nq, dtype=torch.int32, device=dev)
         ev = C.c_void_p(g_ready_event.cuda_event) if g_ready_event is not None else C.c_void_p(0)
         _lib.check(lib.hn_match_ex(_ptr(q), _ptr(g), _ptr(q16), _ptr(g16), nq, ng, g_offset, _ptr(d1), _ptr(d2), _ptr(i1),
-                                   _ptr(i2), _ptr(ws), ws.numel(), ev, _stream_ptr()), "hn_match")
+                                   _ptr(i2), _ptr(block_max), _ptr(ws), ws.numel(), ev, _stream_ptr()), "hn_match")
     return d1, d2, i1, i2
+
+
+def block_max_elems(nq: int, ng: int) -> int:
+    return int(_lib.load().hn_block_max_elems(nq, ng))
+
+
+def match_mutual(q: torch.Tensor, g: torch.Tensor, q16: torch.Tensor | None = None, g16: torch.Tensor | None = None):
+    """(d1, d2, i1, i2, mutual bool[Nq]) from ONE matching GEMM: hn_match_mutual."""
+    lib = _lib.load()
+    q = _require_cuda_f32("match_mutual", q)
+    g = _require_cuda_f32("match_mutual", g)
+    nq, ng = q.size(0), g.size(0)
+    dev = q.device
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.hn_mutual_workspace_bytes(nq, ng))
+        d1 = torch.empty(nq, dtype=torch.float32, device=dev)
+        d2 = torch.empty(nq, dtype=torch.float32, device=dev)
+        i1 = torch.empty(nq, dtype=torch.int32, device=dev)
+        i2 = torch.empty(nq, dtype=torch.int32, device=dev)
+        mutual = torch.empty(nq, dtype=torch.bool, device=dev)
+        _lib.check(lib.hn_match_mutual(_ptr(q), _ptr(g), _ptr(q16), _ptr(g16), nq, ng, _ptr(d1), _ptr(d2), _ptr(i1), _ptr(i2),
+                                       _ptr(mutual), _ptr(ws), ws.numel(), _stream_ptr()), "hn_match_mutual")
+    return d1, d2, i1, i2, mutual
+
+
+def mutual_claims(i1: torch.Tensor, d1: torch.Tensor, q_offset: int, claim: torch.Tensor):
+    """atomicMin of (distance, global row) into claim[int64, Ng] (pre-filled with INT64_MAX = unclaimed)."""
+    lib = _lib.load()
+    with torch.cuda.device(i1.device):
+        _lib.check(lib.hn_mutual_claims(_ptr(i1), _ptr(d1), i1.numel(), q_offset, _ptr(claim), claim.numel(), _stream_ptr()),
+                   "hn_mutual_claims")
+
+
+def mutual_verify(q: torch.Tensor, q_offset: int, g: torch.Tensor, claim: torch.Tensor, block_max: torch.Tensor,
+                  beaten: torch.Tensor):
+    """beaten[uint8, Ng] |= some local query row is nearer to g_j than the claimant of column j."""
+    lib = _lib.load()
+    with torch.cuda.device(q.device):
+        _lib.check(lib.hn_mutual_verify(_ptr(q), q.size(0), q_offset, _ptr(g), g.size(0), _ptr(claim), _ptr(block_max), _ptr(beaten),
+                                        _stream_ptr()), "hn_mutual_verify")

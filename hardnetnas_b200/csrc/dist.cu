@@ -188,6 +188,142 @@ struct MatchTimer {
   }
 };
 
+
+// ------------------------------------------------------------------------------------------------------------
+// mutual nearest neighbours from ONE GEMM (column side: claims + verification against the block maxima)
+// ------------------------------------------------------------------------------------------------------------
+// claim[j] = min over the queries i whose nearest gallery row is j of (distance bits << 32 | global query row): only the best
+// claimant of a column can be its mutual partner. `claim` must be initialised to an "unclaimed" value: any word whose upper
+// half is >= 0x7F000000 (no real distance has such bits): bytes of 0x7F, or INT64_MAX - positive as a signed integer too, so
+// that an all_reduce(MIN) over int64 orders claims like the unsigned atomicMin does.
+__global__ void mutual_claim_kernel(const int* __restrict__ i1, const float* __restrict__ d1, long long nq, long long q_offset,
+                                    unsigned long long* __restrict__ claim, long long ng) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const long long j = i1[i];
+  if (j < 0 || j >= ng) return;
+  atomicMin(claim + j, (static_cast<unsigned long long>(__float_as_uint(d1[i])) << 32) | static_cast<unsigned int>(i + q_offset));
+}
+
+// Is the claimant of column j really the nearest query of g_j (lowest row wins ties, like torch.min)? Some query row k beats
+// it only if dot(q_k, g_j) >= dot(claimant) and then the GEMM's (32-row block, 8-column chunk) maximum of k's cell is at least
+// that dot product minus the error bound of the fp16-operand product. One warp per chunk: scan the chunk's block maxima
+// (contiguous), evaluate the exact fp32 distances of the few cells that can hold such a row - the cell with the largest
+// maximum first, which settles most beaten claims at once - and stop as soon as every claimed column is decided.
+// The dot product is summed in the order of rerank_kernel, so a distance computed here is bit-identical to the one a second
+// (gallery x queries) matching pass would produce.
+__global__ void __launch_bounds__(256) mutual_verify_kernel(const float* __restrict__ q, long long nq, long long q_offset,
+                                                            const float* __restrict__ g, long long ng,
+                                                            const unsigned long long* __restrict__ claim,
+                                                            const float* __restrict__ block_max, int n_row_blocks,
+                                                            float margin_scaled, float inv_dot_scale,
+                                                            unsigned char* __restrict__ beaten) {
+  __shared__ float4 s_g[8][kChunk][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long cb = static_cast<long long>(blockIdx.x) * 8 + w;
+  if (cb * kChunk >= ng) return;
+  unsigned long long cl = 0x7FFFFFFFFFFFFFFFull;   // unclaimed
+  if (lane < kChunk && cb * kChunk + lane < ng) cl = claim[cb * kChunk + lane];
+  float dcl[kChunk], thr[kChunk];
+  unsigned int icl[kChunk];
+  unsigned undecided = 0, lost = 0;
+  const float ninf = -__int_as_float(0x7f800000);
+#pragma unroll
+  for (int c = 0; c < kChunk; ++c) {
+    const unsigned long long cc = __shfl_sync(0xffffffffu, cl, c);
+    dcl[c] = __uint_as_float(static_cast<unsigned int>(cc >> 32));
+    icl[c] = static_cast<unsigned int>(cc & 0xffffffffu);
+    thr[c] = __int_as_float(0x7f800000);
+    if ((cc >> 32) < 0x7F000000ull) {
+      undecided |= 1u << c;
+      thr[c] = (1.0f - 0.5f * dcl[c] * dcl[c]) * inv_dot_scale - margin_scaled;
+      s_g[w][c][lane] = __ldg(reinterpret_cast<const float4*>(g + (cb * kChunk + c) * 128) + lane);
+    }
+  }
+  if (!undecided) return;
+  __syncwarp();
+  const float* bm_row = block_max + cb * n_row_blocks;
+
+  auto evaluate = [&](int rb, float vb) {
+    const long long k = static_cast<long long>(rb) * 32 + lane;
+    const bool valid = k < nq;
+    const unsigned int gk = static_cast<unsigned int>(k + q_offset);
+    const float4* qrow = reinterpret_cast<const float4*>(q + (valid ? k : 0) * 128);
+#pragma unroll 1
+    for (int c = 0; c < kChunk; ++c) {
+      if (!((undecided >> c) & 1u) || thr[c] > vb) continue;   // warp-uniform
+      float p[32];
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        const float4 qv = __ldg(qrow + l);
+        const float4 gv = s_g[w][c][l];
+        p[l] = fmaf(qv.x, gv.x, fmaf(qv.y, gv.y, fmaf(qv.z, gv.z, qv.w * gv.w)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int l = 0; l < o; ++l) p[l] += p[l + o];
+      }
+      const float d = sqrtf(fminf(fmaxf(2.0f - 2.0f * p[0], 1e-8f), 4.0f));
+      const bool beats = valid && gk != icl[c] && (d < dcl[c] || (d == dcl[c] && gk < icl[c]));
+      if (__any_sync(0xffffffffu, beats)) {
+        undecided &= ~(1u << c);
+        lost |= 1u << c;
+      }
+    }
+  };
+
+  // pass 1: the cell with the largest maximum
+  float best = ninf;
+  int best_rb = 0x7fffffff;
+  for (int rb = lane; rb < n_row_blocks; rb += 32) {
+    const float v = bm_row[rb];
+    if (v > best) { best = v; best_rb = rb; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int orb = __shfl_xor_sync(0xffffffffu, best_rb, o);
+    if (ob > best || (ob == best && orb < best_rb)) { best = ob; best_rb = orb; }
+  }
+  if (best_rb != 0x7fffffff) evaluate(best_rb, best);
+  // pass 2: every other cell that can still hold a better row for an undecided column
+  for (int base = 0; base < n_row_blocks && undecided; base += 32) {
+    const int rb = base + lane;
+    const float v = rb < n_row_blocks ? bm_row[rb] : ninf;
+    float min_thr = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int c = 0; c < kChunk; ++c)
+      if ((undecided >> c) & 1u) min_thr = fminf(min_thr, thr[c]);
+    unsigned cand = __ballot_sync(0xffffffffu, v >= min_thr && rb != best_rb);
+    while (cand && undecided) {
+      const int b = __ffs(cand) - 1;
+      cand &= cand - 1;
+      evaluate(base + b, __shfl_sync(0xffffffffu, v, b));
+    }
+  }
+  if (lane < kChunk && ((lost >> lane) & 1u)) beaten[cb * kChunk + lane] = 1;
+}
+
+// mutual[i] = the best claimant of my nearest column is me, and nobody beat it
+__global__ void mutual_final_kernel(const int* __restrict__ i1, long long nq, long long q_offset,
+                                    const unsigned long long* __restrict__ claim, const unsigned char* __restrict__ beaten,
+                                    long long ng, unsigned char* __restrict__ mutual) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const long long j = i1[i];
+  bool m = false;
+  if (j >= 0 && j < ng) m = static_cast<unsigned int>(claim[j] & 0xffffffffu) == static_cast<unsigned int>(i + q_offset) && !beaten[j];
+  mutual[i] = m ? 1 : 0;
+}
+
+// Which matching GEMM runs: -1 = by problem size, 0 = single-CTA kernel, 1 = CTA-pair kernel. The initial value comes from
+// HN_MATCH_PAIR, read ONCE when first needed; tests switch it through hn_match_force_kernel instead of the environment.
+static int& match_kernel_mode() {
+  static int mode = [] { const char* pe = getenv("HN_MATCH_PAIR"); return pe ? atoi(pe) : -1; }();
+  return mode;
+}
+
 static int make_desc_map(CUtensorMap* tm, const uint16_t* base, long long rows, int K, int box_rows = kDistTile) {
   const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows)};
   const uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
@@ -371,7 +507,7 @@ extern "C" int hn_pack_descriptors(const float* x, long long n, void* out16, voi
 }
 
 extern "C" int hn_match_ex(const float* q, const float* g, const void* q16_in, const void* g16_in, long long Nq, long long Ng,
-                           long long g_offset, float* d1, float* d2, int32_t* i1, int32_t* i2, void* workspace,
+                           long long g_offset, float* d1, float* d2, int32_t* i1, int32_t* i2, float* block_max, void* workspace,
                            long long workspace_bytes, void* g_ready_event, void* stream) {
   HN_REQUIRE(q && g && workspace, "hn_match: NULL argument");
   HN_REQUIRE(Nq >= 1 && Ng >= 1, "hn_match: empty input (Nq=%lld, Ng=%lld)", Nq, Ng);
@@ -401,13 +537,14 @@ extern "C" int hn_match_ex(const float* q, const float* g, const void* q16_in, c
   DistParams dp;
   memset(&dp, 0, sizeof(dp));
   // CTA pairs (tc_dist_pair.cuh) once the problem is large enough to fill the machine with 512-row query blocks
-  // HN_MATCH_PAIR = 0 / 1 forces the single-CTA / CTA-pair kernel (tests), default: by size. Read once per process.
-  static const int pair_env = [] { const char* pe = getenv("HN_MATCH_PAIR"); return pe ? atoi(pe) : -1; }();
-  const bool use_pair = pair_env >= 0 ? pair_env != 0 : (Nq >= 8192 && Ng >= 1024);
+  const int pair_mode = match_kernel_mode();
+  const bool use_pair = pair_mode >= 0 ? pair_mode != 0 : (Nq >= 8192 && Ng >= 1024);
   HN_TRY(make_desc_map(&dp.side[0].tmA, q16, Nq, 128));
   HN_TRY(make_desc_map(&dp.side[0].tmB, g16, Ng, 128, use_pair ? 64 : kDistTile));
   dp.side[0].cand = cand;
   dp.side[0].cand_val = cand_val;
+  dp.side[0].block_max = block_max;
+  dp.side[0].n_row_blocks = static_cast<int>((Nq + 31) / 32);
   dp.side[0].Na = Nq;
   dp.side[0].Nb = Ng;
   dp.k_blocks = 2;
@@ -451,7 +588,72 @@ extern "C" int hn_match_ex(const float* q, const float* g, const void* q16_in, c
 
 extern "C" int hn_match(const float* q, const float* g, long long Nq, long long Ng, long long g_offset, float* d1,
                         float* d2, int32_t* i1, int32_t* i2, void* workspace, long long workspace_bytes, void* stream) {
-  return hn_match_ex(q, g, nullptr, nullptr, Nq, Ng, g_offset, d1, d2, i1, i2, workspace, workspace_bytes, nullptr, stream);
+  return hn_match_ex(q, g, nullptr, nullptr, Nq, Ng, g_offset, d1, d2, i1, i2, nullptr, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" long long hn_block_max_elems(long long Nq, long long Ng) {
+  if (Nq < 0 || Ng < 0) return 0;
+  return ((Ng + kChunk - 1) / kChunk) * ((Nq + 31) / 32);
+}
+
+extern "C" int hn_mutual_claims(const int32_t* i1, const float* d1, long long Nq, long long q_offset, unsigned long long* claim,
+                                long long Ng, void* stream) {
+  HN_REQUIRE(i1 && d1 && claim, "hn_mutual_claims: NULL argument");
+  HN_REQUIRE(Nq >= 1 && Ng >= 1 && Nq + q_offset < (1LL << 32), "hn_mutual_claims: size out of range");
+  mutual_claim_kernel<<<static_cast<unsigned>((Nq + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(i1, d1, Nq, q_offset, claim, Ng);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
+extern "C" int hn_mutual_verify(const float* q, long long Nq, long long q_offset, const float* g, long long Ng,
+                                const unsigned long long* claim, const float* block_max, unsigned char* beaten, void* stream) {
+  HN_REQUIRE(q && g && claim && block_max && beaten, "hn_mutual_verify: NULL argument");
+  HN_REQUIRE(Nq >= 1 && Ng >= 1 && Nq + q_offset < (1LL << 32), "hn_mutual_verify: size out of range");
+  const long long chunks = (Ng + kChunk - 1) / kChunk;
+  // twice the 2^-10 error bound of the fp16-operand dot product of unit vectors, in the GEMM's scaled units
+  const float margin = 2.0f * (1.0f / 1024.0f) / kDotScale;
+  mutual_verify_kernel<<<static_cast<unsigned>((chunks + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      q, Nq, q_offset, g, Ng, claim, block_max, static_cast<int>((Nq + 31) / 32), margin, 1.0f / kDotScale, beaten);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
+extern "C" long long hn_mutual_workspace_bytes(long long Nq, long long Ng) {
+  if (Nq < 0 || Ng < 0) return 0;
+  return hn_dist_workspace_bytes(Nq, Ng, 0) + static_cast<long long>(align256(static_cast<size_t>(hn_block_max_elems(Nq, Ng)) * 4) +
+                                                                         align256(static_cast<size_t>(Ng) * 8) + align256(static_cast<size_t>(Ng)) + 256);
+}
+
+extern "C" int hn_match_mutual(const float* q, const float* g, const void* q16, const void* g16, long long Nq, long long Ng,
+                               float* d1, float* d2, int32_t* i1, int32_t* i2, unsigned char* mutual, void* workspace,
+                               long long workspace_bytes, void* stream) {
+  HN_REQUIRE(q && g && d1 && i1 && mutual && workspace, "hn_match_mutual: NULL argument (d1, i1 and mutual are required outputs)");
+  HN_REQUIRE(workspace_bytes >= hn_mutual_workspace_bytes(Nq, Ng), "hn_match_mutual: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long base = hn_dist_workspace_bytes(Nq, Ng, 0);
+  char* b = static_cast<char*>(workspace) + align256(static_cast<size_t>(base));
+  float* bm = reinterpret_cast<float*>(b);
+  b += align256(static_cast<size_t>(hn_block_max_elems(Nq, Ng)) * 4);
+  unsigned long long* claim = reinterpret_cast<unsigned long long*>(b);
+  b += align256(static_cast<size_t>(Ng) * 8);
+  unsigned char* beaten = reinterpret_cast<unsigned char*>(b);
+  HN_TRY(hn_match_ex(q, g, q16, g16, Nq, Ng, 0, d1, d2, i1, i2, bm, workspace, base, nullptr, stream));
+  HN_CUDA(cudaMemsetAsync(claim, 0x7f, static_cast<size_t>(Ng) * 8, s));   // "unclaimed"
+  HN_CUDA(cudaMemsetAsync(beaten, 0, static_cast<size_t>(Ng), s));
+  HN_TRY(hn_mutual_claims(i1, d1, Nq, 0, claim, Ng, stream));
+  HN_TRY(hn_mutual_verify(q, Nq, 0, g, Ng, claim, bm, beaten, stream));
+  mutual_final_kernel<<<static_cast<unsigned>((Nq + 255) / 256), 256, 0, s>>>(i1, Nq, 0, claim, beaten, Ng, mutual);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
+extern "C" int hn_match_force_kernel(int mode) {
+  HN_REQUIRE(mode >= -1 && mode <= 1, "hn_match_force_kernel: mode must be -1 (by size), 0 (single CTA) or 1 (CTA pair)");
+  match_kernel_mode() = mode;
+  return HN_OK;
 }
 
 extern "C" int hn_match_profile_enable(int on) {

@@ -35,6 +35,9 @@ struct DistSide {
   float* pos;                  // EXACT: diagonal distance before masking (may be null)
   int* cand;                   // SHORTLIST: [Na, segments, kTopC] chunk ids
   float* cand_val;             // SHORTLIST: the chunks' approximate (fp16-operand, scaled) dot-product maxima
+  float* block_max;            // SHORTLIST, optional: [ceil(Nb / 8)][ceil(Na / 32)] maxima of the approximate dot products over
+                               // (32-row block, 8-column chunk) cells: what the column side of mutual NN needs from this GEMM
+  int n_row_blocks;            // ceil(Na / 32)
   // neighbour mask (FDLNet-master/latency/rfnet/model/rf_des.py:72-86): (x, y) keypoint coordinates of the row / column items
   // in the anchor image (xy_a*) and in the positive image (xy_p*); a pair closer than nei_c pixels in either gets +10 each
   const float2* xy_a_rows; const float2* xy_a_cols;
@@ -60,6 +63,30 @@ constexpr size_t dist_smem_bytes(int k_blocks) {
 }
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// c[0..7]: this lane's (= this row's) maxima over eight consecutive 8-column chunks. Returns, in every lane, the maximum over
+// the warp's 32 rows of chunk (lane >> 2): a halving butterfly - each exchange keeps half of the chunks and sends the other
+// half, so the 8 x 32 values cost 4 + 2 + 1 + 1 + 1 = 9 shuffles instead of 40.
+__device__ __forceinline__ float warp_chunk_max8(const float (&c)[8], int lane) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+  float a[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float keep = b4 ? c[t + 4] : c[t], send = b4 ? c[t] : c[t + 4];
+    a[t] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+  float b[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const float keep = b3 ? a[t + 2] : a[t], send = b3 ? a[t] : a[t + 2];
+    b[t] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+  const float keep = b2 ? b[1] : b[0], send = b2 ? b[0] : b[1];
+  float v = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return v;
+}
 
 template <int MB, int EPI>
 __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_constant__ DistParams p) {
@@ -259,6 +286,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) tmem_ld32(t_row + gq * 32, r[gq]);
           tmem_ld_wait();
+          float cm[16];   // this row's maxima of the tile's sixteen chunks
 #pragma unroll
           for (int gq = 0; gq < 4; ++gq) {
             const int c0 = gq * 32;
@@ -274,6 +302,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
             for (int s = 0; s < 32 / kChunk; ++s) {
               const float* w = v + s * kChunk;
               const float m = fmaxf(max3(w[0], w[1], w[2]), max3(max3(w[3], w[4], w[5]), w[6], w[7]));
+              cm[gq * 4 + s] = m;
               if (m > tb[kTopC - 1]) {
                 const int id = static_cast<int>((col0 + c0) / kChunk) + s;
                 // sorted insert (descending); strict '>' keeps the earlier chunk on ties
@@ -283,6 +312,17 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
                 tb[1] = g1 ? (g0 ? tb[0] : m) : tb[1]; tc[1] = g1 ? (g0 ? tc[0] : id) : tc[1];
                 tb[0] = g0 ? m : tb[0];               tc[0] = g0 ? id : tc[0];
               }
+            }
+          }
+          if (sd.block_max != nullptr) {   // warp-uniform: column side of mutual NN (hn_match_mutual)
+            const long long rb = row >> 5;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const float half8[8] = {cm[hf * 8], cm[hf * 8 + 1], cm[hf * 8 + 2], cm[hf * 8 + 3],
+                                      cm[hf * 8 + 4], cm[hf * 8 + 5], cm[hf * 8 + 6], cm[hf * 8 + 7]};
+              const float bm = warp_chunk_max8(half8, lane);
+              const long long cb = col0 / kChunk + hf * 8 + (lane >> 2);
+              if ((lane & 3) == 0 && cb * kChunk < sd.Nb && rb < sd.n_row_blocks) sd.block_max[cb * sd.n_row_blocks + rb] = bm;
             }
           }
         } else {

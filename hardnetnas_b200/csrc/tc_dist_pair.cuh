@@ -191,6 +191,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMpThreads, 1) match
 #pragma unroll
         for (int gq = 0; gq < 2; ++gq) tmem_ld32(t_row + gq * 32, r[gq]);
         tmem_ld_wait();
+        float cm[8];   // this row's maxima of the eight chunks of this 64-column half
 #pragma unroll
         for (int gq = 0; gq < 2; ++gq) {
           const int c0 = gq * 32;
@@ -206,6 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMpThreads, 1) match
           for (int s = 0; s < 32 / kChunk; ++s) {
             const float* w = v + s * kChunk;
             const float m = fmaxf(max3(w[0], w[1], w[2]), max3(max3(w[3], w[4], w[5]), w[6], w[7]));
+            cm[gq * 4 + s] = m;
             if (m > tb[kTopC - 1]) {
               const int id = static_cast<int>((col0 + c0) / kChunk) + s;
               const bool g0 = m > tb[0], g1 = m > tb[1], g2 = m > tb[2];
@@ -219,6 +221,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMpThreads, 1) match
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(acc ? lead_tempty1 : lead_tempty0);
+        if (sd.block_max != nullptr) {   // warp-uniform: column side of mutual NN (hn_match_mutual)
+          const float bm = warp_chunk_max8(cm, lane);
+          const long long cb = col0 / kChunk + (lane >> 2);
+          const long long rb = row >> 5;
+          if ((lane & 3) == 0 && cb * kChunk < sd.Nb && rb < sd.n_row_blocks) sd.block_max[cb * sd.n_row_blocks + rb] = bm;
+        }
       }
       if (row_ok) {
         int4* dst = reinterpret_cast<int4*>(sd.cand + ((row * p.segments + seg) * 2 + half) * kTopC);

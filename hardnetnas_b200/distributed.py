@@ -117,28 +117,52 @@ def match_sharded(q_local: torch.Tensor, g_local: torch.Tensor, matcher: Callabl
     return matcher(q_local, g_full)
 
 
+def mutual_nn_ratio_sharded(q_local: torch.Tensor, g_local: torch.Tensor, q_counts: list[int], g_counts: list[int],
+                            threshold: float = 0.7):
+    """BASELINE config 4 on R GPUs, as masks over this rank's query rows (no host synchronisation):
+    (mutual bool[nq], ratio_label bool[nq], Ia int64[nq] global gallery rows, Da, Db). Equal gallery shards required.
+    ONE GEMM per rank (my query rows x the whole gallery, packed gallery gathered first, fp32 rows behind the GEMM). Column
+    side: every rank claims the nearest columns of its rows, all_reduce(MIN) of the packed (distance, row) claims (8 B per
+    gallery row), every rank checks the global claims against its own rows with the block maxima of its GEMM,
+    all_reduce(MAX) of the 1-byte "beaten" flags (hn_mutual_claims / hn_mutual_verify)."""
+    from . import _ops
+    rank, world = _world()
+    dev = q_local.device
+    g_full, g16_full, g_ready = _gather_packed_then_rows(g_local, g_counts)
+    ng, nq = g_full.size(0), q_local.size(0)
+    q_off = sum(q_counts[:rank])
+    bm = torch.empty(_ops.block_max_elems(nq, ng), dtype=torch.float32, device=dev)
+    d1, d2, fwd, _ = _ops.match_top2(q_local, g_full, g16=g16_full, g_ready_event=g_ready, block_max=bm)
+    claim = torch.full((ng,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)   # unclaimed
+    _ops.mutual_claims(fwd, d1, q_off, claim)
+    dist.all_reduce(claim, op=dist.ReduceOp.MIN)     # distances are positive: signed order = unsigned order of the packing
+    beaten = torch.zeros(ng, dtype=torch.uint8, device=dev)
+    _ops.mutual_verify(q_local, q_off, g_full, claim, bm, beaten)
+    dist.all_reduce(beaten, op=dist.ReduceOp.MAX)
+    fwd = fwd.long()
+    i = torch.arange(nq, device=dev) + q_off
+    mutual = ((claim[fwd] & 0xFFFFFFFF) == i) & (beaten[fwd] == 0)
+    return mutual, (d1 / d2).lt(threshold), fwd, d1, d2
+
+
 def mutual_nn_sharded(q_local: torch.Tensor, g_local: torch.Tensor, matcher: Callable | None = None,
                       q_counts: list[int] | None = None, g_counts: list[int] | None = None) -> torch.Tensor:
-    """Mutual-NN pairs (global query row, global gallery row) whose query row lives on this rank. The forward direction
-    shards the query rows (gallery gathered), the backward direction shards the gallery rows (queries gathered); only the
-    backward index vector is exchanged afterwards. With `q_counts` / `g_counts` given no count exchange happens."""
+    """Mutual-NN pairs (global query row, global gallery row) whose query row lives on this rank.
+    B200 path: one GEMM per rank plus two small all_reduces (see the body). Injected matcher (CPU tests) / ragged gallery
+    shards: forward direction over the gathered gallery, backward direction over the gathered queries, backward index vector
+    exchanged. With `q_counts` / `g_counts` given no count exchange happens."""
     rank, world = _world()
     qc = _counts_or_exchange(q_local.size(0), q_counts, q_local.device)
     gc = _counts_or_exchange(g_local.size(0), g_counts, g_local.device)
-    if matcher is None and world > 1 and q_local.is_cuda and len(set(qc)) == 1 and len(set(gc)) == 1:
-        from . import _ops
-        g_full, g16_full, g_ready = _gather_packed_then_rows(g_local, gc)
-        q_full, q16_full, q_ready = _gather_packed_then_rows(q_local, qc)
-        lo = rank * qc[0]
-        fwd_local = _ops.match_top2(q_local, g_full, q16=q16_full[lo:lo + qc[0]], g16=g16_full, g_ready_event=g_ready)[2].long()
-        glo = rank * gc[0]
-        bwd_local = _ops.match_top2(g_local, q_full, q16=g16_full[glo:glo + gc[0]], g16=q16_full, g_ready_event=q_ready)[2]
-    else:
-        matcher = matcher or _default_matcher()
-        g_full = all_gather_rows(g_local, gc)
-        q_full = all_gather_rows(q_local, qc)
-        fwd_local = matcher(q_local, g_full)[2].long()   # nearest gallery row of my queries
-        bwd_local = matcher(g_local, q_full)[2]          # nearest query row of my gallery rows
+    if matcher is None and world > 1 and q_local.is_cuda and len(set(gc)) == 1:
+        mutual, _, fwd, _, _ = mutual_nn_ratio_sharded(q_local, g_local, qc, gc)
+        i = torch.arange(q_local.size(0), device=q_local.device) + sum(qc[:rank])
+        return torch.stack([i[mutual], fwd[mutual]], dim=1)
+    matcher = matcher or _default_matcher()
+    g_full = all_gather_rows(g_local, gc)
+    q_full = all_gather_rows(q_local, qc)
+    fwd_local = matcher(q_local, g_full)[2].long()   # nearest gallery row of my queries
+    bwd_local = matcher(g_local, q_full)[2]          # nearest query row of my gallery rows
     bwd_full = all_gather_rows(bwd_local.contiguous(), gc).long()
     q_off = sum(qc[:rank])
     i = torch.arange(q_local.size(0), device=q_local.device) + q_off

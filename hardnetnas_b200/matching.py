@@ -57,9 +57,21 @@ def mutual_nn_ratio(des1, des2, threshold=0.7, return_pairs=True):
     (pairs [M,2] int64 or None, mutual bool[Nq], ratio_label bool[Nq], Ia int64[Nq], Da, Db).
     (i, j) is mutual iff j = argmin_j D[i,:] and i = argmin_i D[:,j] - not in the reference; composed from its row / column
     minima (hardnet/Losses.py:105-108, eval_utils.py:24-32); ratio_label = Da / Db < threshold (eval_utils.py:168-175).
-    Both operand sets are packed to fp16 once and feed the forward (queries x gallery) and the backward (gallery x queries)
-    GEMM. The masks come without any host synchronisation; compacting them into the `pairs` list needs its length on the host
-    (return_pairs=False skips it)."""
+    ONE matching GEMM serves both directions (hn_match_mutual: the epilogue's per-cell maxima bound the column side, a small
+    exact kernel verifies each column's best claimant). The masks come without any host synchronisation; compacting them into
+    the `pairs` list needs its length on the host (return_pairs=False skips it)."""
+    d1, d2, fwd, _, mutual = _ops.match_mutual(des1, des2)
+    fwd = fwd.long()
+    pairs = None
+    if return_pairs:
+        i = torch.arange(des1.size(0), device=fwd.device)
+        pairs = torch.stack([i[mutual], fwd[mutual]], dim=1)
+    return pairs, mutual, (d1 / d2).lt(threshold), fwd, d1, d2
+
+
+def mutual_nn_ratio_two_pass(des1, des2, threshold=0.7, return_pairs=True):
+    """The same result from two matching passes (queries x gallery, gallery x queries), operands packed once. Kept as the
+    cross-check of the single-GEMM path (tests) and for A/B timing (bench.py)."""
     q16, g16 = _ops.pack_descriptors(des1), _ops.pack_descriptors(des2)
     d1, d2, fwd, _ = _ops.match_top2(des1, des2, q16=q16, g16=g16)
     _, _, bwd, _ = _ops.match_top2(des2, des1, q16=g16, g16=q16)

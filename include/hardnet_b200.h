@@ -168,13 +168,42 @@ int hn_match(const float* q, const float* g, long long Nq, long long Ng, long lo
  * between GPUs (half the NVLink bytes of the fp32 rows) or match one set several times. x:[n,128] fp32 -> out16:[n,128]. */
 int hn_pack_descriptors(const float* x, long long n, void* out16, void* stream);
 
-/* hn_match with optional pre-packed operands (q16 / g16 from hn_pack_descriptors, NULL = pack here) and an optional
- * cudaEvent_t the exact re-rank waits for: the GEMM reads only the packed rows, the re-rank reads the fp32 gallery rows of
- * the shortlisted columns, so a sharded caller gathers the packed gallery first and lets the fp32 gather finish behind the
- * GEMM (hardnetnas_b200/distributed.py). Preconditions as hn_match: unit-norm rows (|x| <= 1). */
+/* hn_match with optional pre-packed operands (q16 / g16 from hn_pack_descriptors, NULL = pack here), an optional output of
+ * the GEMM's block maxima (see hn_match_mutual; NULL = not computed) and an optional cudaEvent_t the exact re-rank waits for:
+ * the GEMM reads only the packed rows, the re-rank reads the fp32 gallery rows of the shortlisted columns, so a sharded
+ * caller gathers the packed gallery first and lets the fp32 gather finish behind the GEMM (hardnetnas_b200/distributed.py).
+ * Preconditions as hn_match: unit-norm rows (|x| <= 1). */
 int hn_match_ex(const float* q, const float* g, const void* q16, const void* g16, long long Nq, long long Ng,
-                long long g_offset, float* d1, float* d2, int32_t* i1, int32_t* i2, void* workspace,
+                long long g_offset, float* d1, float* d2, int32_t* i1, int32_t* i2, float* block_max, void* workspace,
                 long long workspace_bytes, void* g_ready_event, void* stream);
+
+/* Mutual nearest neighbours from ONE matching GEMM (a16; composition of the reference's row / column minima,
+ * hardnet/Losses.py:105-108, FDLNet-master/utils/eval_utils.py:24-32): mutual[i] = 1 iff i1[i] = argmin_j D[i,:] and
+ * i = argmin_i D[:, i1[i]] (lowest index wins ties in both directions, like torch.min).
+ * The row side is hn_match. For the column side the GEMM epilogue also emits `block_max`
+ * [ceil(Ng/8)][ceil(Nq/32)]: the maximum approximate dot product of every (32-query block, 8-gallery-column chunk) cell.
+ * Then (1) every query claims its nearest column (packed (distance, row) atomicMin: only the best claimant can be mutual),
+ * (2) one warp per column chunk checks in exact fp32 the few cells whose maximum can still hold a closer query than the
+ * claimant (the cell with the largest maximum first; stop at the first closer row), (3) mutual[i] = I hold the claim and it
+ * was not beaten. Distances are summed in the re-rank's order, so the result equals two hn_match passes bit for bit
+ * wherever both shortlists are exact. d1 / d2 / i1 / i2 as hn_match (d1, i1, mutual required). */
+long long hn_mutual_workspace_bytes(long long Nq, long long Ng);
+int hn_match_mutual(const float* q, const float* g, const void* q16, const void* g16, long long Nq, long long Ng, float* d1,
+                    float* d2, int32_t* i1, int32_t* i2, unsigned char* mutual, void* workspace, long long workspace_bytes,
+                    void* stream);
+/* The column-side steps on their own, for the sharded form (each rank holds a block of query rows starting at global row
+ * q_offset and the whole gallery): claims of the local rows into `claim` [Ng] (initialised to INT64_MAX = unclaimed;
+ * all_reduce(MIN) as int64 across ranks afterwards), then verification of the GLOBAL claims against the local rows with the block maxima of the
+ * local hn_match_ex call into `beaten` [Ng] (initialised to 0; all_reduce(MAX) afterwards). */
+long long hn_block_max_elems(long long Nq, long long Ng);
+int hn_mutual_claims(const int32_t* i1, const float* d1, long long Nq, long long q_offset, unsigned long long* claim,
+                     long long Ng, void* stream);
+int hn_mutual_verify(const float* q, long long Nq, long long q_offset, const float* g, long long Ng,
+                     const unsigned long long* claim, const float* block_max, unsigned char* beaten, void* stream);
+
+/* Test / measurement switch (process-wide): which matching GEMM hn_match runs: -1 = chosen by problem size (default; the
+ * initial value is read once from HN_MATCH_PAIR), 0 = single-CTA kernel, 1 = CTA-pair (cta_group::2) kernel. */
+int hn_match_force_kernel(int mode);
 
 /* Measurement hooks (process-wide): bracket the three stages of every hn_match call (0 = operand packing, 1 = GEMM +
  * shortlist, 2 = exact re-rank) with CUDA events; hn_match_profile_read waits for them, returns the summed milliseconds and

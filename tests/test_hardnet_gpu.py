@@ -200,3 +200,15 @@ def test_second_gpu_in_the_same_process():
     b = [t.cpu() for t in match_top2(q.to("cuda:1"), g.to("cuda:1"))]
     for s, t in zip(a, b):
         assert torch.equal(s, t)
+
+
+def test_direct_parity_at_a_full_default_pass_65536_patches():
+    """One direct comparison at bulk size: 65 536 patches through the default 18 944-patch passes
+    (three full passes + a ragged one, full head batches) against the CPU oracle on every row - not a sample, not a
+    small-chunk engine."""
+    model, (w, m, v) = _model(3)
+    x = synth.make_patches(65536, 77)
+    desc = model(x.cuda()).float().cpu()
+    ref = torch.cat([hardnet_oracle.hardnet_forward(x[i:i + 8192], w, m, v) for i in range(0, 65536, 8192)])
+    max_abs, cos = _cmp(desc, ref)
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)

@@ -11,6 +11,15 @@ TIE_TAU = 1e-5
 DIST_TOL = 2e-6
 
 
+@pytest.fixture
+def force_kernel():
+    """hn_match_force_kernel(mode): -1 by size, 0 single-CTA GEMM, 1 CTA-pair GEMM; restored afterwards."""
+    from hardnetnas_b200 import _lib
+    lib = _lib.load()
+    yield lambda mode: _lib.check(lib.hn_match_force_kernel(int(mode)), "hn_match_force_kernel")
+    lib.hn_match_force_kernel(-1)
+
+
 def _check(q, g, chunk=1024):
     from hardnetnas_b200.matching import match_top2
     d1, d2, i1, i2 = [t.cpu() for t in match_top2(q.cuda(), g.cuda())]
@@ -53,19 +62,19 @@ def test_ragged_sizes(nq, ng):
 
 
 @pytest.mark.parametrize("nq,ng", [(1, 1), (5, 7), (257, 129), (511, 64), (513, 4097), (1000, 130), (4096, 8192), (9000, 20000)])
-def test_ragged_sizes_cta_pair_kernel(nq, ng, monkeypatch):
+def test_ragged_sizes_cta_pair_kernel(nq, ng, force_kernel):
     """Same checks with the CTA-pair (cta_group::2) matching kernel forced on (by default it is used from 8192 queries)."""
-    monkeypatch.setenv("HN_MATCH_PAIR", "1")
+    force_kernel(1)
     q, g, _ = synth.make_match_set(nq, ng, seed=3 + nq)
     _check(q, g)
 
 
-def test_single_and_pair_kernels_agree(monkeypatch):
+def test_single_and_pair_kernels_agree(force_kernel):
     from hardnetnas_b200.matching import match_top2
     q, g, _ = synth.make_match_set(3000, 9000, seed=8)
     outs = []
-    for mode in ("0", "1"):
-        monkeypatch.setenv("HN_MATCH_PAIR", mode)
+    for mode in (0, 1):
+        force_kernel(mode)
         outs.append([t.cpu() for t in match_top2(q.cuda(), g.cuda())])
     for a, b in zip(*outs):
         assert torch.equal(a, b)
@@ -85,6 +94,35 @@ def test_duplicate_gallery_rows_pick_first_index():
     q[0] = g[20]
     d1, d2, i1, i2 = _check(q, g)
     assert i1[0].item() == 20 and i2[0].item() == 40
+
+
+@pytest.mark.parametrize("nq,ng,pair", [(3000, 5000, -1), (5000, 3000, 1), (777, 1234, 0), (9000, 9000, -1), (33, 8, -1), (4100, 2050, 1)])
+def test_mutual_nn_single_gemm_matches_oracle_and_two_pass(nq, ng, pair, force_kernel):
+    """hn_match_mutual (one GEMM: block maxima -> claims -> exact verification) against the CPU oracle and against the
+    two-pass composition, on both matching kernels and ragged sizes."""
+    from hardnetnas_b200.matching import mutual_nn_ratio, mutual_nn_ratio_two_pass
+    force_kernel(pair)
+    q, g, _ = synth.make_match_set(nq, ng, seed=21)
+    pairs, mutual, ratio, fwd, d1, d2 = mutual_nn_ratio(q.cuda(), g.cuda())
+    ref = losses_oracle.mutual_nn(q, g)
+    assert torch.equal(pairs.cpu(), ref), (nq, ng)
+    p2, m2, r2, f2, a2, b2 = mutual_nn_ratio_two_pass(q.cuda(), g.cuda())
+    assert torch.equal(mutual, m2) and torch.equal(ratio, r2) and torch.equal(fwd, f2) and torch.equal(d1, a2)
+
+
+def test_mutual_nn_duplicate_rows_and_unstructured_sets():
+    """Tie rule (lowest index wins in both directions) and a set without planted structure (many weak claims)."""
+    from hardnetnas_b200.matching import mutual_nn_ratio, mutual_nn_ratio_two_pass
+    g = synth.unit_vectors(4096, 128, 5)
+    q = synth.unit_vectors(2048, 128, 6)
+    q[10] = g[100]; q[11] = g[100]          # two identical queries claim the same column: the lower row is mutual
+    g[200] = g[300]                          # duplicate gallery rows: the query picks the lower column
+    q[12] = g[300]
+    pairs, mutual, _, fwd, _, _ = mutual_nn_ratio(q.cuda(), g.cuda())
+    assert mutual[10].item() and not mutual[11].item() and fwd[10].item() == 100 and fwd[11].item() == 100
+    assert fwd[12].item() == 200 and mutual[12].item()
+    assert torch.equal(pairs.cpu(), losses_oracle.mutual_nn(q, g))
+    assert torch.equal(mutual, mutual_nn_ratio_two_pass(q.cuda(), g.cuda())[1])
 
 
 def test_mutual_nn_matches_oracle():
@@ -120,6 +158,12 @@ def test_config4_full_size_properties():
     ratio = (d1 / d2).cpu()
     assert (ratio[planted] < 0.7).float().mean().item() > 0.99
     assert (ratio[~planted] < 0.7).float().mean().item() < 0.01
+    # mutual NN at full size from the single GEMM: equal to the two-pass composition, planted pairs are mutual
+    from hardnetnas_b200.matching import mutual_nn_ratio, mutual_nn_ratio_two_pass
+    _, mutual, _, fwd, _, _ = mutual_nn_ratio(qc, gc, return_pairs=False)
+    _, m2, _, f2, _, _ = mutual_nn_ratio_two_pass(qc, gc, return_pairs=False)
+    assert torch.equal(fwd, f2) and torch.equal(mutual, m2)
+    assert mutual.cpu()[planted].float().mean().item() > 0.999
 
 
 def test_match_score_counters_match_reference_goldens(golden_dir):
