@@ -210,17 +210,26 @@ __global__ void mutual_claim_kernel(const int* __restrict__ i1, const float* __r
 // that dot product minus the error bound of the fp16-operand product. One warp per chunk: scan the chunk's block maxima
 // (contiguous), evaluate the exact fp32 distances of the few cells that can hold such a row - the cell with the largest
 // maximum first, which settles most beaten claims at once - and stop as soon as every claimed column is decided.
-// The dot product is summed in the order of rerank_kernel, so a distance computed here is bit-identical to the one a second
-// (gallery x queries) matching pass would produce.
-__global__ void __launch_bounds__(256) mutual_verify_kernel(const float* __restrict__ q, long long nq, long long q_offset,
-                                                            const float* __restrict__ g, long long ng,
-                                                            const unsigned long long* __restrict__ claim,
-                                                            const float* __restrict__ block_max, int n_row_blocks,
-                                                            float margin_scaled, float inv_dot_scale,
-                                                            unsigned char* __restrict__ beaten) {
-  __shared__ float4 s_g[8][kChunk][32];
+// A cell's 32 query rows are staged ONCE in shared memory with coalesced loads (row pitch 132 floats: the per-row reads below
+// are bank-conflict free; per-lane global reads at a 512-byte stride cost 32 L1 wavefronts per instruction and made this
+// kernel slower than a whole second GEMM) and serve every column of the chunk that needs the cell, two columns per sweep.
+// The dot product is summed in the order of rerank_kernel (32 float4 partials, then the xor-butterfly tree), so a distance
+// computed here is bit-identical to the one a second (gallery x queries) matching pass would produce.
+constexpr int kVerifyWarps = 8;
+constexpr int kVerifyPitch = 132;   // floats per staged query row
+constexpr size_t kVerifySmem = static_cast<size_t>(kVerifyWarps) * (32 * kVerifyPitch * 4 + kChunk * 32 * 16);
+
+__global__ void __launch_bounds__(kVerifyWarps * 32) mutual_verify_kernel(const float* __restrict__ q, long long nq, long long q_offset,
+                                                                         const float* __restrict__ g, long long ng,
+                                                                         const unsigned long long* __restrict__ claim,
+                                                                         const float* __restrict__ block_max, int n_row_blocks,
+                                                                         float margin_scaled, float inv_dot_scale,
+                                                                         unsigned char* __restrict__ beaten) {
+  extern __shared__ __align__(16) uint8_t vsm[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long cb = static_cast<long long>(blockIdx.x) * 8 + w;
+  float* s_q = reinterpret_cast<float*>(vsm) + static_cast<size_t>(w) * 32 * kVerifyPitch;                       // [32][132]
+  float4* s_g = reinterpret_cast<float4*>(vsm + static_cast<size_t>(kVerifyWarps) * 32 * kVerifyPitch * 4) + w * kChunk * 32;   // [8][32]
+  const long long cb = static_cast<long long>(blockIdx.x) * kVerifyWarps + w;
   if (cb * kChunk >= ng) return;
   unsigned long long cl = 0x7FFFFFFFFFFFFFFFull;   // unclaimed
   if (lane < kChunk && cb * kChunk + lane < ng) cl = claim[cb * kChunk + lane];
@@ -237,40 +246,60 @@ __global__ void __launch_bounds__(256) mutual_verify_kernel(const float* __restr
     if ((cc >> 32) < 0x7F000000ull) {
       undecided |= 1u << c;
       thr[c] = (1.0f - 0.5f * dcl[c] * dcl[c]) * inv_dot_scale - margin_scaled;
-      s_g[w][c][lane] = __ldg(reinterpret_cast<const float4*>(g + (cb * kChunk + c) * 128) + lane);
+      s_g[c * 32 + lane] = __ldg(reinterpret_cast<const float4*>(g + (cb * kChunk + c) * 128) + lane);
     }
   }
   if (!undecided) return;
   __syncwarp();
   const float* bm_row = block_max + cb * n_row_blocks;
 
+  // distance of this lane's staged row to column c (arithmetic of rerank_kernel)
+  auto row_distance = [&](int c) {
+    float p[32];
+    const float* qr = s_q + lane * kVerifyPitch;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const float4 qv = *reinterpret_cast<const float4*>(qr + 4 * l);
+      const float4 gv = s_g[c * 32 + l];
+      p[l] = fmaf(qv.x, gv.x, fmaf(qv.y, gv.y, fmaf(qv.z, gv.z, qv.w * gv.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int l = 0; l < o; ++l) p[l] += p[l + o];
+    }
+    return sqrtf(fminf(fmaxf(2.0f - 2.0f * p[0], 1e-8f), 4.0f));
+  };
+
   auto evaluate = [&](int rb, float vb) {
-    const long long k = static_cast<long long>(rb) * 32 + lane;
+    unsigned need = 0;
+#pragma unroll
+    for (int c = 0; c < kChunk; ++c)
+      if (((undecided >> c) & 1u) && thr[c] <= vb) need |= 1u << c;
+    if (!need) return;
+    // stage the cell's 32 rows: one coalesced 512-byte row per iteration
+    const long long k0 = static_cast<long long>(rb) * 32;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < nq) v = __ldg(reinterpret_cast<const float4*>(q + (k0 + r) * 128) + lane);
+      *reinterpret_cast<float4*>(s_q + r * kVerifyPitch + 4 * lane) = v;
+    }
+    __syncwarp();
+    const long long k = k0 + lane;
     const bool valid = k < nq;
     const unsigned int gk = static_cast<unsigned int>(k + q_offset);
-    const float4* qrow = reinterpret_cast<const float4*>(q + (valid ? k : 0) * 128);
 #pragma unroll 1
     for (int c = 0; c < kChunk; ++c) {
-      if (!((undecided >> c) & 1u) || thr[c] > vb) continue;   // warp-uniform
-      float p[32];
-#pragma unroll
-      for (int l = 0; l < 32; ++l) {
-        const float4 qv = __ldg(qrow + l);
-        const float4 gv = s_g[w][c][l];
-        p[l] = fmaf(qv.x, gv.x, fmaf(qv.y, gv.y, fmaf(qv.z, gv.z, qv.w * gv.w)));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int l = 0; l < o; ++l) p[l] += p[l + o];
-      }
-      const float d = sqrtf(fminf(fmaxf(2.0f - 2.0f * p[0], 1e-8f), 4.0f));
+      if (!((need >> c) & 1u)) continue;   // warp-uniform
+      const float d = row_distance(c);
       const bool beats = valid && gk != icl[c] && (d < dcl[c] || (d == dcl[c] && gk < icl[c]));
       if (__any_sync(0xffffffffu, beats)) {
         undecided &= ~(1u << c);
         lost |= 1u << c;
       }
     }
+    __syncwarp();   // the staging tile is reused by the next cell
   };
 
   // pass 1: the cell with the largest maximum
@@ -613,7 +642,10 @@ extern "C" int hn_mutual_verify(const float* q, long long Nq, long long q_offset
   const long long chunks = (Ng + kChunk - 1) / kChunk;
   // twice the 2^-10 error bound of the fp16-operand dot product of unit vectors, in the GEMM's scaled units
   const float margin = 2.0f * (1.0f / 1024.0f) / kDotScale;
-  mutual_verify_kernel<<<static_cast<unsigned>((chunks + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  static DeviceOnce attr_once;
+  if (attr_once.first_time())
+    HN_CUDA(cudaFuncSetAttribute(mutual_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kVerifySmem)));
+  mutual_verify_kernel<<<static_cast<unsigned>((chunks + kVerifyWarps - 1) / kVerifyWarps), kVerifyWarps * 32, kVerifySmem, static_cast<cudaStream_t>(stream)>>>(
       q, Nq, q_offset, g, Ng, claim, block_max, static_cast<int>((Nq + 31) / 32), margin, 1.0f / kDotScale, beaten);
   HN_CUDA(cudaGetLastError());
   count_launch();

@@ -211,6 +211,16 @@ int hn_match_force_kernel(int mode);
 int hn_match_profile_enable(int on);
 int hn_match_profile_read(double ms_out[3], long long launches_out[3]);
 
+/* ---- evaluation metrics of the test loop (hardnet/HardNet.py:443-477) -------------------------------------------------- */
+/* Row-wise descriptor distance torch.sqrt(torch.sum((out_a - out_p) ** 2, 1)) (HardNet.py:458). a, p: [n,128] fp32; out: [n]. */
+int hn_pair_distances(const float* a, const float* p, long long n, float* out, void* stream);
+/* ErrorRateAt95Recall(labels, scores) (hardnet/EvalMetrics.py:6-19) without the host-side sort: the threshold element (the
+ * ceil(0.95 * #positives)-th positive in ascending 1 / (scores + 1e-8) order, equal distances in input order like a stable
+ * sort) is found by radix selection and the negatives in front of it are counted. scores: [n] fp32 = 1 / (distance + 1e-8)
+ * as in HardNet.py:472; labels: [n] uint8 (non-zero = matching pair); out4 (DEVICE int64[4]) = FP, TN, #positives,
+ * threshold_index. FPR95 = FP / (FP + TN). */
+int hn_fpr95(const float* scores, const unsigned char* labels, long long n, long long* out4, void* stream);
+
 /* ---- patch extraction (FDLNet-master/utils/image_utils.py:11-158, clip_patch) ------------------------ */
 /* Crops a psize x psize patch around every keypoint with the reference's similarity transform
  * (scale / im_info[b][0] / 2, optional rotation (cos, sin)) and bilinear interpolation with clamped taps.

@@ -156,6 +156,31 @@ def test_fpr95_agrees_with_reference_path():
     assert metrics.ErrorRateAt95Recall(labels, torch.from_numpy(1.0 / (rdist + 1e-8))) == fpr_ref
 
 
+@pytest.mark.parametrize("n,pos_frac,ties", [(1, 1.0, False), (7, 0.0, False), (1000, 0.5, False), (100003, 0.3, False), (50000, 0.5, True),
+                                             (4096, 1.0, True), (2049, 0.02, True)])
+def test_fpr95_selection_kernel_equals_the_sorted_reference(n, pos_frac, ties):
+    """hn_fpr95 (radix selection of the threshold element, no sort) against hardnet/EvalMetrics.py:6-19 evaluated with a STABLE
+    sort on identical inputs: FP, TN and the threshold index must be equal, including heavy ties (quantised distances), all /
+    no positives and tiny inputs."""
+    import numpy as np
+    from hardnetnas_b200 import metrics
+    rng = np.random.RandomState(n)
+    labels = (rng.rand(n) < pos_frac).astype(np.int64)
+    dist = rng.rand(n).astype(np.float32) * 2.0
+    dist[labels == 1] *= 0.6                                  # positives tend to be closer
+    if ties:
+        dist = np.round(dist * 16).astype(np.float32) / 16    # 33 distinct values: long runs of equal distances
+    scores = (1.0 / (dist + np.float32(1e-8))).astype(np.float32)
+    d2 = (1.0 / (scores + np.float32(1e-8))).astype(np.float32)
+    lab_sorted = labels[np.argsort(d2, kind="stable")]
+    thr = int(np.argmax(np.cumsum(lab_sorted) >= 0.95 * np.sum(lab_sorted)))
+    fp, tn = int(np.sum(lab_sorted[:thr] == 0)), int(np.sum(lab_sorted[thr:] == 0))
+    got = metrics.fpr95_counts(torch.from_numpy(labels).cuda(), torch.from_numpy(scores).cuda()).tolist()
+    assert got == [fp, tn, int(labels.sum()), thr], (got, fp, tn, thr)
+    if fp + tn:
+        assert metrics.ErrorRateAt95Recall(torch.from_numpy(labels).cuda(), torch.from_numpy(scores).cuda()) == float(fp) / float(fp + tn)
+
+
 def test_host_pipeline_matches_direct_forward():
     """extract_descriptors (pinned host in / out, H2D + forward + D2H pipelined) returns what forward() returns."""
     from hardnetnas_b200.extract import DescriptorExtractor, extract_descriptors
