@@ -149,18 +149,21 @@ def match_mutual(q: torch.Tensor, g: torch.Tensor, q16: torch.Tensor | None = No
     return d1, d2, i1, i2, mutual
 
 
-def mutual_claims(i1: torch.Tensor, d1: torch.Tensor, q_offset: int, claim: torch.Tensor):
-    """atomicMin of (distance, global row) into claim[int64, Ng] (pre-filled with INT64_MAX = unclaimed)."""
+def mutual_claims(i1: torch.Tensor, d1: torch.Tensor, d2: torch.Tensor, q_offset: int, claim: torch.Tensor) -> torch.Tensor:
+    """atomicMin of (distance, global row) into claim[int64, Ng] (pre-filled with INT64_MAX = unclaimed); returns the per
+    32-row-block minimum of d2 the verification needs."""
     lib = _lib.load()
+    rbmin = torch.empty((i1.numel() + 31) // 32, dtype=torch.float32, device=i1.device)
     with torch.cuda.device(i1.device):
-        _lib.check(lib.hn_mutual_claims(_ptr(i1), _ptr(d1), i1.numel(), q_offset, _ptr(claim), claim.numel(), _stream_ptr()),
-                   "hn_mutual_claims")
+        _lib.check(lib.hn_mutual_claims(_ptr(i1), _ptr(d1), _ptr(d2), i1.numel(), q_offset, _ptr(claim), claim.numel(), _ptr(rbmin),
+                                        _stream_ptr()), "hn_mutual_claims")
+    return rbmin
 
 
 def mutual_verify(q: torch.Tensor, q_offset: int, g: torch.Tensor, claim: torch.Tensor, block_max: torch.Tensor,
-                  beaten: torch.Tensor):
+                  rb_min_d2: torch.Tensor, beaten: torch.Tensor):
     """beaten[uint8, Ng] |= some local query row is nearer to g_j than the claimant of column j."""
     lib = _lib.load()
     with torch.cuda.device(q.device):
-        _lib.check(lib.hn_mutual_verify(_ptr(q), q.size(0), q_offset, _ptr(g), g.size(0), _ptr(claim), _ptr(block_max), _ptr(beaten),
-                                        _stream_ptr()), "hn_mutual_verify")
+        _lib.check(lib.hn_mutual_verify(_ptr(q), q.size(0), q_offset, _ptr(g), g.size(0), _ptr(claim), _ptr(block_max),
+                                        _ptr(rb_min_d2), _ptr(beaten), _stream_ptr()), "hn_mutual_verify")

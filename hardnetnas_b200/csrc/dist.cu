@@ -196,33 +196,43 @@ struct MatchTimer {
 // claimant of a column can be its mutual partner. `claim` must be initialised to an "unclaimed" value: any word whose upper
 // half is >= 0x7F000000 (no real distance has such bits): bytes of 0x7F, or INT64_MAX - positive as a signed integer too, so
 // that an all_reduce(MIN) over int64 orders claims like the unsigned atomicMin does.
-__global__ void mutual_claim_kernel(const int* __restrict__ i1, const float* __restrict__ d1, long long nq, long long q_offset,
-                                    unsigned long long* __restrict__ claim, long long ng) {
+__global__ void mutual_claim_kernel(const int* __restrict__ i1, const float* __restrict__ d1, const float* __restrict__ d2,
+                                    long long nq, long long q_offset, unsigned long long* __restrict__ claim, long long ng,
+                                    float* __restrict__ rb_min_d2) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // a warp is one 32-row block: its smallest second-nearest distance bounds every d(k, j) with j not the nearest column of k
+  float m = i < nq ? d2[i] : __int_as_float(0x7f800000);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && i < nq) rb_min_d2[i >> 5] = m;
   if (i >= nq) return;
   const long long j = i1[i];
   if (j < 0 || j >= ng) return;
   atomicMin(claim + j, (static_cast<unsigned long long>(__float_as_uint(d1[i])) << 32) | static_cast<unsigned int>(i + q_offset));
 }
 
-// Is the claimant of column j really the nearest query of g_j (lowest row wins ties, like torch.min)? Some query row k beats
-// it only if dot(q_k, g_j) >= dot(claimant) and then the GEMM's (32-row block, 8-column chunk) maximum of k's cell is at least
-// that dot product minus the error bound of the fp16-operand product. One warp per chunk: scan the chunk's block maxima
-// (contiguous), evaluate the exact fp32 distances of the few cells that can hold such a row - the cell with the largest
-// maximum first, which settles most beaten claims at once - and stop as soon as every claimed column is decided.
+// Is the claimant of column j really the nearest query of g_j (lowest row wins ties, like torch.min)? A query row k can beat
+// it only if BOTH hold: (1) dot(q_k, g_j) >= dot(claimant), and then the GEMM's (32-row block, 8-column chunk) maximum of k's
+// cell is at least that dot product minus the error bound of the fp16-operand product; (2) k's own second-nearest distance
+// d2[k] <= d(claimant, j): j is not k's nearest column (else k is a claimant itself and lost the atomicMin), so d(k, j) is at
+// least k's second-smallest distance. (2) is what makes confident matches free: a claim at distance 0.4 is never challenged
+// by rows whose second-nearest gallery row is 1.1 away, whatever their cell maximum says. One warp per chunk: scan the chunk's
+// block maxima and the row blocks' minimum d2 (both contiguous), evaluate the exact fp32 distances of the cells passing both
+// tests, stop as soon as every claimed column is decided.
 // A cell's 32 query rows are staged ONCE in shared memory with coalesced loads (row pitch 132 floats: the per-row reads below
 // are bank-conflict free; per-lane global reads at a 512-byte stride cost 32 L1 wavefronts per instruction and made this
 // kernel slower than a whole second GEMM) and serve every column of the chunk that needs the cell, two columns per sweep.
 // The dot product is summed in the order of rerank_kernel (32 float4 partials, then the xor-butterfly tree), so a distance
 // computed here is bit-identical to the one a second (gallery x queries) matching pass would produce.
-constexpr int kVerifyWarps = 8;
+constexpr int kVerifyWarps = 1;   // one warp per CTA: a chunk with a weakly claimed column evaluates ~20 cells one after the other (~70 us), so CTAs must be small and many (10 per SM by shared memory) for the hardware to balance them
 constexpr int kVerifyPitch = 132;   // floats per staged query row
 constexpr size_t kVerifySmem = static_cast<size_t>(kVerifyWarps) * (32 * kVerifyPitch * 4 + kChunk * 32 * 16);
 
 __global__ void __launch_bounds__(kVerifyWarps * 32) mutual_verify_kernel(const float* __restrict__ q, long long nq, long long q_offset,
                                                                          const float* __restrict__ g, long long ng,
                                                                          const unsigned long long* __restrict__ claim,
-                                                                         const float* __restrict__ block_max, int n_row_blocks,
+                                                                         const float* __restrict__ block_max,
+                                                                         const float* __restrict__ rb_min_d2, int n_row_blocks,
                                                                          float margin_scaled, float inv_dot_scale,
                                                                          unsigned char* __restrict__ beaten) {
   extern __shared__ __align__(16) uint8_t vsm[];
@@ -271,19 +281,24 @@ __global__ void __launch_bounds__(kVerifyWarps * 32) mutual_verify_kernel(const 
     return sqrtf(fminf(fmaxf(2.0f - 2.0f * p[0], 1e-8f), 4.0f));
   };
 
-  auto evaluate = [&](int rb, float vb) {
+  auto evaluate = [&](int rb, float vb, float min_d2) {
     unsigned need = 0;
 #pragma unroll
     for (int c = 0; c < kChunk; ++c)
-      if (((undecided >> c) & 1u) && thr[c] <= vb) need |= 1u << c;
+      if (((undecided >> c) & 1u) && thr[c] <= vb && min_d2 <= dcl[c]) need |= 1u << c;
     if (!need) return;
     // stage the cell's 32 rows: one coalesced 512-byte row per iteration
     const long long k0 = static_cast<long long>(rb) * 32;
-#pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + r < nq) v = __ldg(reinterpret_cast<const float4*>(q + (k0 + r) * 128) + lane);
-      *reinterpret_cast<float4*>(s_q + r * kVerifyPitch + 4 * lane) = v;
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 8) {   // eight row loads in flight
+      float4 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + r0 + r < nq) v[r] = __ldg(reinterpret_cast<const float4*>(q + (k0 + r0 + r) * 128) + lane);
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) *reinterpret_cast<float4*>(s_q + (r0 + r) * kVerifyPitch + 4 * lane) = v[r];
     }
     __syncwarp();
     const long long k = k0 + lane;
@@ -302,33 +317,18 @@ __global__ void __launch_bounds__(kVerifyWarps * 32) mutual_verify_kernel(const 
     __syncwarp();   // the staging tile is reused by the next cell
   };
 
-  // pass 1: the cell with the largest maximum
-  float best = ninf;
-  int best_rb = 0x7fffffff;
-  for (int rb = lane; rb < n_row_blocks; rb += 32) {
-    const float v = bm_row[rb];
-    if (v > best) { best = v; best_rb = rb; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int orb = __shfl_xor_sync(0xffffffffu, best_rb, o);
-    if (ob > best || (ob == best && orb < best_rb)) { best = ob; best_rb = orb; }
-  }
-  if (best_rb != 0x7fffffff) evaluate(best_rb, best);
-  // pass 2: every other cell that can still hold a better row for an undecided column
   for (int base = 0; base < n_row_blocks && undecided; base += 32) {
     const int rb = base + lane;
     const float v = rb < n_row_blocks ? bm_row[rb] : ninf;
-    float min_thr = __int_as_float(0x7f800000);
+    const float md2 = rb < n_row_blocks ? rb_min_d2[rb] : __int_as_float(0x7f800000);
+    bool mine = false;
 #pragma unroll
-    for (int c = 0; c < kChunk; ++c)
-      if ((undecided >> c) & 1u) min_thr = fminf(min_thr, thr[c]);
-    unsigned cand = __ballot_sync(0xffffffffu, v >= min_thr && rb != best_rb);
+    for (int c = 0; c < kChunk; ++c) mine |= ((undecided >> c) & 1u) && thr[c] <= v && md2 <= dcl[c];
+    unsigned cand = __ballot_sync(0xffffffffu, mine);
     while (cand && undecided) {
       const int b = __ffs(cand) - 1;
       cand &= cand - 1;
-      evaluate(base + b, __shfl_sync(0xffffffffu, v, b));
+      evaluate(base + b, __shfl_sync(0xffffffffu, v, b), __shfl_sync(0xffffffffu, md2, b));
     }
   }
   if (lane < kChunk && ((lost >> lane) & 1u)) beaten[cb * kChunk + lane] = 1;
@@ -397,12 +397,23 @@ static ExactWs carve_exact(void* ws, long long Na, long long Np) {
   return w;
 }
 
-static int pick_segments(long long rows, int rows_per_block, long long cols, int sm_count, int max_seg) {
+// Number of gallery segments a block of query rows is split into: work items = row blocks x segments are dealt round robin to
+// `workers` persistent CTAs (or CTA pairs), so the count is chosen for the best fill of the last round (64k x 64k on 74 CTA
+// pairs: 2 segments = 256 items = 3.46 rounds, i.e. 14 % of the machine idles in the last one; 15 segments = 25.9 rounds).
+// Fewer segments win ties (every segment adds a shortlist per row for the re-rank to scan); a segment keeps >= 4 gallery tiles.
+static int pick_segments(long long rows, int rows_per_block, long long cols, int workers, int max_seg) {
   const long long m_blocks = (rows + rows_per_block - 1) / rows_per_block;
   const long long n_tiles = (cols + kDistTile - 1) / kDistTile;
-  long long s = (2LL * sm_count + m_blocks - 1) / m_blocks;
-  s = std::min<long long>(s, std::min<long long>(n_tiles, max_seg));
-  return static_cast<int>(std::max<long long>(s, 1));
+  const long long cap = std::max<long long>(1, std::min<long long>(max_seg, n_tiles / 4));
+  int best = 1;
+  double best_eff = -1.0;
+  for (long long sgm = 1; sgm <= cap; ++sgm) {
+    const long long items = m_blocks * sgm;
+    const long long rounds = (items + workers - 1) / workers;
+    const double eff = static_cast<double>(items) / static_cast<double>(rounds * workers);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = static_cast<int>(sgm); }
+  }
+  return best;
 }
 
 // Shared body of hn_dist_min / hn_loss_hardnet. Leaves packed minima and pos in the workspace.
@@ -625,19 +636,20 @@ extern "C" long long hn_block_max_elems(long long Nq, long long Ng) {
   return ((Ng + kChunk - 1) / kChunk) * ((Nq + 31) / 32);
 }
 
-extern "C" int hn_mutual_claims(const int32_t* i1, const float* d1, long long Nq, long long q_offset, unsigned long long* claim,
-                                long long Ng, void* stream) {
-  HN_REQUIRE(i1 && d1 && claim, "hn_mutual_claims: NULL argument");
+extern "C" int hn_mutual_claims(const int32_t* i1, const float* d1, const float* d2, long long Nq, long long q_offset,
+                                unsigned long long* claim, long long Ng, float* rb_min_d2, void* stream) {
+  HN_REQUIRE(i1 && d1 && d2 && claim && rb_min_d2, "hn_mutual_claims: NULL argument");
   HN_REQUIRE(Nq >= 1 && Ng >= 1 && Nq + q_offset < (1LL << 32), "hn_mutual_claims: size out of range");
-  mutual_claim_kernel<<<static_cast<unsigned>((Nq + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(i1, d1, Nq, q_offset, claim, Ng);
+  mutual_claim_kernel<<<static_cast<unsigned>((Nq + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(i1, d1, d2, Nq, q_offset, claim, Ng, rb_min_d2);
   HN_CUDA(cudaGetLastError());
   count_launch();
   return HN_OK;
 }
 
 extern "C" int hn_mutual_verify(const float* q, long long Nq, long long q_offset, const float* g, long long Ng,
-                                const unsigned long long* claim, const float* block_max, unsigned char* beaten, void* stream) {
-  HN_REQUIRE(q && g && claim && block_max && beaten, "hn_mutual_verify: NULL argument");
+                                const unsigned long long* claim, const float* block_max, const float* rb_min_d2,
+                                unsigned char* beaten, void* stream) {
+  HN_REQUIRE(q && g && claim && block_max && rb_min_d2 && beaten, "hn_mutual_verify: NULL argument");
   HN_REQUIRE(Nq >= 1 && Ng >= 1 && Nq + q_offset < (1LL << 32), "hn_mutual_verify: size out of range");
   const long long chunks = (Ng + kChunk - 1) / kChunk;
   // twice the 2^-10 error bound of the fp16-operand dot product of unit vectors, in the GEMM's scaled units
@@ -646,7 +658,7 @@ extern "C" int hn_mutual_verify(const float* q, long long Nq, long long q_offset
   if (attr_once.first_time())
     HN_CUDA(cudaFuncSetAttribute(mutual_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kVerifySmem)));
   mutual_verify_kernel<<<static_cast<unsigned>((chunks + kVerifyWarps - 1) / kVerifyWarps), kVerifyWarps * 32, kVerifySmem, static_cast<cudaStream_t>(stream)>>>(
-      q, Nq, q_offset, g, Ng, claim, block_max, static_cast<int>((Nq + 31) / 32), margin, 1.0f / kDotScale, beaten);
+      q, Nq, q_offset, g, Ng, claim, block_max, rb_min_d2, static_cast<int>((Nq + 31) / 32), margin, 1.0f / kDotScale, beaten);
   HN_CUDA(cudaGetLastError());
   count_launch();
   return HN_OK;
@@ -655,13 +667,14 @@ extern "C" int hn_mutual_verify(const float* q, long long Nq, long long q_offset
 extern "C" long long hn_mutual_workspace_bytes(long long Nq, long long Ng) {
   if (Nq < 0 || Ng < 0) return 0;
   return hn_dist_workspace_bytes(Nq, Ng, 0) + static_cast<long long>(align256(static_cast<size_t>(hn_block_max_elems(Nq, Ng)) * 4) +
-                                                                         align256(static_cast<size_t>(Ng) * 8) + align256(static_cast<size_t>(Ng)) + 256);
+                                                                         align256(static_cast<size_t>(Ng) * 8) + align256(static_cast<size_t>(Ng)) +
+                                                                         align256(static_cast<size_t>((Nq + 31) / 32) * 4) + 256);
 }
 
 extern "C" int hn_match_mutual(const float* q, const float* g, const void* q16, const void* g16, long long Nq, long long Ng,
                                float* d1, float* d2, int32_t* i1, int32_t* i2, unsigned char* mutual, void* workspace,
                                long long workspace_bytes, void* stream) {
-  HN_REQUIRE(q && g && d1 && i1 && mutual && workspace, "hn_match_mutual: NULL argument (d1, i1 and mutual are required outputs)");
+  HN_REQUIRE(q && g && d1 && d2 && i1 && mutual && workspace, "hn_match_mutual: NULL argument (d1, d2, i1 and mutual are required outputs)");
   HN_REQUIRE(workspace_bytes >= hn_mutual_workspace_bytes(Nq, Ng), "hn_match_mutual: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const long long base = hn_dist_workspace_bytes(Nq, Ng, 0);
@@ -671,11 +684,13 @@ extern "C" int hn_match_mutual(const float* q, const float* g, const void* q16, 
   unsigned long long* claim = reinterpret_cast<unsigned long long*>(b);
   b += align256(static_cast<size_t>(Ng) * 8);
   unsigned char* beaten = reinterpret_cast<unsigned char*>(b);
+  b += align256(static_cast<size_t>(Ng));
+  float* rbmin = reinterpret_cast<float*>(b);
   HN_TRY(hn_match_ex(q, g, q16, g16, Nq, Ng, 0, d1, d2, i1, i2, bm, workspace, base, nullptr, stream));
   HN_CUDA(cudaMemsetAsync(claim, 0x7f, static_cast<size_t>(Ng) * 8, s));   // "unclaimed"
   HN_CUDA(cudaMemsetAsync(beaten, 0, static_cast<size_t>(Ng), s));
-  HN_TRY(hn_mutual_claims(i1, d1, Nq, 0, claim, Ng, stream));
-  HN_TRY(hn_mutual_verify(q, Nq, 0, g, Ng, claim, bm, beaten, stream));
+  HN_TRY(hn_mutual_claims(i1, d1, d2, Nq, 0, claim, Ng, rbmin, stream));
+  HN_TRY(hn_mutual_verify(q, Nq, 0, g, Ng, claim, bm, rbmin, beaten, stream));
   mutual_final_kernel<<<static_cast<unsigned>((Nq + 255) / 256), 256, 0, s>>>(i1, Nq, 0, claim, beaten, Ng, mutual);
   HN_CUDA(cudaGetLastError());
   count_launch();

@@ -134,10 +134,10 @@ def mutual_nn_ratio_sharded(q_local: torch.Tensor, g_local: torch.Tensor, q_coun
     bm = torch.empty(_ops.block_max_elems(nq, ng), dtype=torch.float32, device=dev)
     d1, d2, fwd, _ = _ops.match_top2(q_local, g_full, g16=g16_full, g_ready_event=g_ready, block_max=bm)
     claim = torch.full((ng,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)   # unclaimed
-    _ops.mutual_claims(fwd, d1, q_off, claim)
+    rbmin = _ops.mutual_claims(fwd, d1, d2, q_off, claim)
     dist.all_reduce(claim, op=dist.ReduceOp.MIN)     # distances are positive: signed order = unsigned order of the packing
     beaten = torch.zeros(ng, dtype=torch.uint8, device=dev)
-    _ops.mutual_verify(q_local, q_off, g_full, claim, bm, beaten)
+    _ops.mutual_verify(q_local, q_off, g_full, claim, bm, rbmin, beaten)
     dist.all_reduce(beaten, op=dist.ReduceOp.MAX)
     fwd = fwd.long()
     i = torch.arange(nq, device=dev) + q_off

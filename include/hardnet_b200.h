@@ -183,9 +183,10 @@ int hn_match_ex(const float* q, const float* g, const void* q16, const void* g16
  * The row side is hn_match. For the column side the GEMM epilogue also emits `block_max`
  * [ceil(Ng/8)][ceil(Nq/32)]: the maximum approximate dot product of every (32-query block, 8-gallery-column chunk) cell.
  * Then (1) every query claims its nearest column (packed (distance, row) atomicMin: only the best claimant can be mutual),
- * (2) one warp per column chunk checks in exact fp32 the few cells whose maximum can still hold a closer query than the
- * claimant (the cell with the largest maximum first; stop at the first closer row), (3) mutual[i] = I hold the claim and it
- * was not beaten. Distances are summed in the re-rank's order, so the result equals two hn_match passes bit for bit
+ * (2) one warp per column chunk checks in exact fp32 the few cells that can still hold a closer query than the claimant: the
+ * cell's maximum must reach the claimant's dot product AND some row of the cell must have its own second-nearest distance
+ * d2 <= the claimant's distance (any other column of that row is at least d2 away) - confident matches are never challenged,
+ * (3) mutual[i] = I hold the claim and it was not beaten. Distances are summed in the re-rank's order, so the result equals two hn_match passes bit for bit
  * wherever both shortlists are exact. d1 / d2 / i1 / i2 as hn_match (d1, i1, mutual required). */
 long long hn_mutual_workspace_bytes(long long Nq, long long Ng);
 int hn_match_mutual(const float* q, const float* g, const void* q16, const void* g16, long long Nq, long long Ng, float* d1,
@@ -196,10 +197,11 @@ int hn_match_mutual(const float* q, const float* g, const void* q16, const void*
  * all_reduce(MIN) as int64 across ranks afterwards), then verification of the GLOBAL claims against the local rows with the block maxima of the
  * local hn_match_ex call into `beaten` [Ng] (initialised to 0; all_reduce(MAX) afterwards). */
 long long hn_block_max_elems(long long Nq, long long Ng);
-int hn_mutual_claims(const int32_t* i1, const float* d1, long long Nq, long long q_offset, unsigned long long* claim,
-                     long long Ng, void* stream);
+int hn_mutual_claims(const int32_t* i1, const float* d1, const float* d2, long long Nq, long long q_offset,
+                     unsigned long long* claim, long long Ng, float* rb_min_d2 /*[ceil(Nq/32)] out*/, void* stream);
 int hn_mutual_verify(const float* q, long long Nq, long long q_offset, const float* g, long long Ng,
-                     const unsigned long long* claim, const float* block_max, unsigned char* beaten, void* stream);
+                     const unsigned long long* claim, const float* block_max, const float* rb_min_d2, unsigned char* beaten,
+                     void* stream);
 
 /* Test / measurement switch (process-wide): which matching GEMM hn_match runs: -1 = chosen by problem size (default; the
  * initial value is read once from HN_MATCH_PAIR), 0 = single-CTA kernel, 1 = CTA-pair (cta_group::2) kernel. */
