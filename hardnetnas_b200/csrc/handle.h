@@ -28,6 +28,8 @@ struct HnEnv {
   bool nas_front = true;      // HN_NAS_FRONT=0: stem and first pointwise conv as separate kernels
   bool nas_dw_smem = true;    // HN_NAS_DW_SMEM=0: register-strip depthwise / max-pool kernels
   bool nas_dw_sh8 = true;     // HN_NAS_DW_SH8=0: 4-row strips for every depthwise shape
+  int nas_front_chunk = 0;    // HN_NAS_FRONT_CHUNK: patches per front-kernel + first-reader sub-pass (0 = whole pass); keeps the
+                              // 64 KB/patch stem output inside L2
   bool nas_dw_f32 = false;    // HN_NAS_DW_F32=1: fp32 depthwise arithmetic also for fp16 activations (default: packed half2)
   bool nas_resident = false;  // HN_NAS_RESIDENT=1: runs of NAS ops as patch-resident segment kernels (nas_resident.cuh). Off by
                               // default: measured slower than one kernel per op (profiles/r2_nas_resident_*)

@@ -379,6 +379,7 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
     h->env.nas_dw_smem = flag("HN_NAS_DW_SMEM", true);
     h->env.nas_dw_sh8 = flag("HN_NAS_DW_SH8", true);
     h->env.nas_dw_f32 = flag("HN_NAS_DW_F32", false);
+    h->env.nas_front_chunk = std::max(0, num("HN_NAS_FRONT_CHUNK", 0)) & ~1;
     h->env.nas_resident = flag("HN_NAS_RESIDENT", false);
     h->env.nas_minb = num("HN_NAS_MINB", 0);
     h->env.nas_cut_ratio = std::max(1, num("HN_NAS_CUT_RATIO", 4));

@@ -1252,21 +1252,45 @@ static int launch_seg(const NasSegment& sg, const uint16_t* in, uint16_t* out, i
   return sg.minb == 2 ? launch_seg_cfg<2, false>(p, sg.smem, sm_count, s) : launch_seg_cfg<1, false>(p, sg.smem, sm_count, s);
 }
 
-// Runs ops [0, last_op] of the packed program for `n` patches (n <= chunk).
+// Runs ops [0, last_op] of the packed program for `n` patches (n <= chunk). With first_op >= 0 only ops [first_op, last_op]
+// run and, if out_override is set, the LAST of them writes there instead of its slot (sub-pass of the front stage below).
 static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype, int n, long long off, int last_op,
-                       cudaStream_t s) {
+                       cudaStream_t s, int first_op = -1, uint16_t* out_override = nullptr) {
   const int bf = st->act_bf16;
   {
       int first = 0;
-      if (st->front_img && last_op >= st->front_ops - 1 && h->env.nas_front) {
+      if (first_op >= 0) {
+        first = first_op;
+      } else if (st->front_img && last_op >= st->front_ops - 1 && h->env.nas_front) {
         const hn_nas_op &o0 = st->ops[0], &ol = st->ops[st->front_ops - 1];
-        HN_TRY(launch_front_pw(src, in_dtype, st->slot[ol.dst], st->front_tm, st->params + o0.w_off, st->params + o0.b_off, st->front_img,
-                               st->front_bias2, n, bf, h->sm_count, s));
-        first = st->front_ops;
+        // The front kernel's 64 KB/patch output is the largest tensor of the net and its only reader is the next op (a
+        // stride-2 depthwise conv or max-pool). Both run in sub-passes of `nas_front_chunk` patches over the SAME head of the
+        // slot, so the tensor is produced, consumed and overwritten inside the 126 MB L2 instead of making an HBM round trip
+        // (128 KB/patch of the pass's traffic); the reader writes its 4x smaller output at the sub-pass's offset.
+        const int nxt = st->front_ops;
+        const hn_nas_op& on = st->ops[nxt];
+        const bool sub = h->env.nas_front_chunk > 0 && h->env.nas_front_chunk < n && nxt <= last_op && nxt < static_cast<int>(st->ops.size()) - 1 &&
+                         st->seg_of_op[nxt] < 0 && (on.kind == OP_DW || on.kind == OP_MAXPOOL) && on.src == ol.dst;
+        if (sub) {
+          const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
+          const size_t out_pp = static_cast<size_t>(on.cout) * on.hout * on.hout;
+          for (int o2 = 0; o2 < n; o2 += h->env.nas_front_chunk) {
+            const int m = std::min(h->env.nas_front_chunk, n - o2);
+            HN_TRY(launch_front_pw(src + static_cast<size_t>(o2) * 1024 * in_elem, in_dtype, st->slot[ol.dst], st->front_tm,
+                                   st->params + o0.w_off, st->params + o0.b_off, st->front_img, st->front_bias2, m, bf, h->sm_count, s));
+            HN_TRY(run_nas_ops(h, st, src, in_dtype, m, off, nxt, s, nxt, st->slot[on.dst] + static_cast<size_t>(o2) * out_pp));
+          }
+          first = nxt + 1;
+        } else {
+          HN_TRY(launch_front_pw(src, in_dtype, st->slot[ol.dst], st->front_tm, st->params + o0.w_off, st->params + o0.b_off, st->front_img,
+                                 st->front_bias2, n, bf, h->sm_count, s));
+          first = st->front_ops;
+        }
       }
       const int n_total = static_cast<int>(st->ops.size());
       for (int i = first; i <= last_op; ++i) {
         const hn_nas_op& o = st->ops[i];
+        uint16_t* const op_out = (out_override && i == last_op && o.kind != OP_HEAD) ? out_override : (o.kind != OP_HEAD ? st->slot[o.dst] : nullptr);
         if (st->seg_of_op[i] >= 0) {
           // patch-resident segment: ops [i, end] in one launch; a segment that ends right before the head writes the
           // head GEMM's input rows directly
@@ -1296,7 +1320,7 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
             const long long total = static_cast<long long>(n) * o.hout * (strip ? o.hout / 4 : o.hout) * (o.cin / 8);
             const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, h->sm_count * 16LL));
             const uint16_t* src = st->slot[o.src];
-            uint16_t* dst = st->slot[o.dst];
+            uint16_t* dst = op_out;
             const float* wv = st->params + o.w_off;
             const float* bv = st->params + o.b_off;
             // shared-memory kernel whenever two units of whole maps fit next to the weights (every shape of SEARCH_SPACE2
@@ -1374,14 +1398,14 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
                   HN_CUDA(cudaFuncSetAttribute(maxpool_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                   HN_CUDA(cudaFuncSetAttribute(maxpool_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 }
-                if (bf) maxpool_smem_kernel<true><<<sgrid, 256, smem, s>>>(st->slot[o.src], st->slot[o.dst], n, o.cin, o.hin, o.hout, G);
-                else maxpool_smem_kernel<false><<<sgrid, 256, smem, s>>>(st->slot[o.src], st->slot[o.dst], n, o.cin, o.hin, o.hout, G);
+                if (bf) maxpool_smem_kernel<true><<<sgrid, 256, smem, s>>>(st->slot[o.src], op_out, n, o.cin, o.hin, o.hout, G);
+                else maxpool_smem_kernel<false><<<sgrid, 256, smem, s>>>(st->slot[o.src], op_out, n, o.cin, o.hin, o.hout, G);
                 HN_CUDA(cudaGetLastError());
                 count_launch();
                 break;
               }
             }
-            maxpool_kernel<<<grid, 256, 0, s>>>(st->slot[o.src], st->slot[o.dst], n, o.cin, o.hin, o.hout, bf);
+            maxpool_kernel<<<grid, 256, 0, s>>>(st->slot[o.src], op_out, n, o.cin, o.hin, o.hout, bf);
             HN_CUDA(cudaGetLastError());
             count_launch();
             break;

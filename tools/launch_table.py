@@ -12,7 +12,7 @@ for r in rows[1:]:
     d = byid.setdefault(r[0], {"k": re.sub(r"\(.*", "", r[ki]), "g": r[gi]})
     d[r[mi]] = float(r[vi].replace(",", ""))
     d[r[mi] + "_u"] = r[ui]
-L = [d for d in byid.values() if "hn::" in d["k"]]
+L = [d for d in byid.values() if "at::" not in d["k"] and "elementwise" not in d["k"]]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else len(L)
 tot = 0.0
 for d in L[:n]:
