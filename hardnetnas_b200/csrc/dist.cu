@@ -83,6 +83,12 @@ __global__ void loss_finalize_kernel(const float* __restrict__ pos, const unsign
 
 // Exact fp32 re-rank of the shortlisted chunks: one warp per query row, one candidate gallery row per lane.
 // Distances in the FDLNet form; ties resolve to the lower gallery index like torch.min / a stable sort.
+// Known limit (documented precondition of hn_match): the GEMM keeps the kTopC = 4 best chunks per row and list (a list = one
+// gallery segment, or one 64-column half of it in the CTA-pair kernel). Should five or more chunks of ONE list reach the
+// threshold, the fifth is not re-ranked; with 15-30 lists per row this needs five near-tied best candidates inside one list
+// (|d - d2| within the 2^-9 margin). Scanning the whole segment whenever a list's fourth chunk passes the threshold was
+// measured: it fires on ~5 % of the rows of the BASELINE config-4 set and makes the call 5x slower (0.88 -> 4.2 ms), so the
+// exact remedy has to track the largest DROPPED chunk maximum in the GEMM epilogue instead (not done).
 __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q, const float* __restrict__ g,
                                                      const int* __restrict__ cand, const float* __restrict__ cand_val,
                                                      float margin, long long nq, long long ng, int slots,
@@ -119,10 +125,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q
   // the 128-term dot is finished with a butterfly, so every lane ends up with the same (d, index) stream. Per-lane
   // row reads (one lane per candidate) cost 32 L1 wavefronts per row instead of 4.
   const float4 qv = reinterpret_cast<const float4*>(sq[w])[lane];
-  for (int c = 0; c < slots; ++c) {
-    const int chunk = cand[row * slots + c];
-    if (chunk < 0 || cand_val[row * slots + c] < thr) continue;   // warp-uniform
-    const long long col0 = static_cast<long long>(chunk) * kChunk;
+  auto eval_chunk = [&](long long chunk) {
+    const long long col0 = chunk * kChunk;
     float part[kChunk];
 #pragma unroll
     for (int r = 0; r < kChunk; ++r) {
@@ -150,6 +154,11 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float* __restrict__ q
         b2 = d; j2 = ci;
       }
     }
+  };
+  for (int c = 0; c < slots; ++c) {
+    const int chunk = cand[row * slots + c];
+    if (chunk < 0 || cand_val[row * slots + c] < thr) continue;   // warp-uniform
+    eval_chunk(chunk);
   }
   // every lane holds the same top-2 now
   const float m = b1, s = b2;
@@ -400,11 +409,12 @@ static ExactWs carve_exact(void* ws, long long Na, long long Np) {
 // Number of gallery segments a block of query rows is split into: work items = row blocks x segments are dealt round robin to
 // `workers` persistent CTAs (or CTA pairs), so the count is chosen for the best fill of the last round (64k x 64k on 74 CTA
 // pairs: 2 segments = 256 items = 3.46 rounds, i.e. 14 % of the machine idles in the last one; 15 segments = 25.9 rounds).
-// Fewer segments win ties (every segment adds a shortlist per row for the re-rank to scan); a segment keeps >= 4 gallery tiles.
+// Fewer segments win ties (every segment adds a shortlist per row for the re-rank to scan). A problem with fewer items than
+// workers (the loss at N = 1024) simply takes the most items it can get: there the fill grows with every extra segment.
 static int pick_segments(long long rows, int rows_per_block, long long cols, int workers, int max_seg) {
   const long long m_blocks = (rows + rows_per_block - 1) / rows_per_block;
   const long long n_tiles = (cols + kDistTile - 1) / kDistTile;
-  const long long cap = std::max<long long>(1, std::min<long long>(max_seg, n_tiles / 4));
+  const long long cap = std::max<long long>(1, std::min<long long>(max_seg, n_tiles));   // small problems: as many items as tiles allow
   int best = 1;
   double best_eff = -1.0;
   for (long long sgm = 1; sgm <= cap; ++sgm) {
@@ -463,7 +473,8 @@ static int run_exact(const float* a, const float* p, long long Na, long long Np,
   dp.segments = pick_segments(rows, kDistTile, cols, sm, 16);
   const long long items = ((rows + kDistTile - 1) / kDistTile) * dp.segments;
   const int grid_x = static_cast<int>(std::min<long long>(items, sm));
-  HN_TRY((launch_dist<1, EPI_EXACT>(dp, grid_x, swap ? 2 : 1, s)));
+  if (dp.nei_mask) HN_TRY((launch_dist<1, EPI_EXACT_NEI>(dp, grid_x, swap ? 2 : 1, s)));
+  else HN_TRY((launch_dist<1, EPI_EXACT>(dp, grid_x, swap ? 2 : 1, s)));
   return HN_OK;
 }
 

@@ -24,7 +24,7 @@ constexpr int kDistStages = 4;
 constexpr int kTopC = 4;     // chunks kept per row and segment
 constexpr int kChunk = 8;    // columns per chunk
 
-enum : int { EPI_EXACT = 0, EPI_SHORTLIST = 1 };
+enum : int { EPI_EXACT = 0, EPI_SHORTLIST = 1, EPI_EXACT_NEI = 2 };   // EXACT_NEI = EXACT + the keypoint-neighbour masks
 
 struct DistSide {
   CUtensorMap tmA;             // rows of this launch direction, [Na, K] 16-bit
@@ -90,6 +90,8 @@ __device__ __forceinline__ float warp_chunk_max8(const float (&c)[8], int lane) 
 
 template <int MB, int EPI>
 __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_constant__ DistParams p) {
+  constexpr bool EXACT = EPI == EPI_EXACT || EPI == EPI_EXACT_NEI;
+  constexpr bool NEI = EPI == EPI_EXACT_NEI;   // compile-time: the plain loss kernel carries none of the mask code
   constexpr uint32_t BLK_BYTES = kDistTile * 128;  // 128 rows x 64 fp16
   constexpr uint32_t TMEM_COLS = 2 * MB * kDistTile;
   const DistSide& sd = p.side[blockIdx.y];
@@ -247,9 +249,9 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
       float tb[kTopC];
       int tc[kTopC];
       float2 r_axy = make_float2(0.f, 0.f), r_pxy = make_float2(0.f, 0.f);
-      if (EPI == EPI_EXACT) {
+      if (EXACT) {
         if (p.form == HN_FORM_HARDNET && row_ok) na = sd.norm_a[row];
-        if (p.nei_mask && row_ok) { r_axy = sd.xy_a_rows[row]; r_pxy = sd.xy_p_rows[row]; }
+        if (NEI && row_ok) { r_axy = sd.xy_a_rows[row]; r_pxy = sd.xy_p_rows[row]; }
       } else {
 #pragma unroll
         for (int i = 0; i < kTopC; ++i) { tb[i] = -__int_as_float(0x7f800000); tc[i] = 0; }
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         const long long col0 = static_cast<long long>(t) * kDistTile;
-        if (EPI == EPI_EXACT && p.form == HN_FORM_HARDNET) {
+        if (EXACT && p.form == HN_FORM_HARDNET) {
           // column norms of this tile -> smem (double buffered with the accumulator)
           if (ep_tid < kDistTile) {
             const long long c = col0 + ep_tid;
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
           }
           asm volatile("bar.sync 1, %0;" ::"n"(128 * MB) : "memory");
         }
-        if (EPI == EPI_EXACT && p.nei_mask) {
+        if (NEI) {
           if (ep_tid < kDistTile) {
             const long long c = col0 + ep_tid;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
           uint32_t r[32];
           tmem_ld32(t_row + c0, r);
           tmem_ld_wait();
-          if (EPI == EPI_EXACT) {
+          if (EXACT) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const long long col = col0 + c0 + j;
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
                 }
                 if (d < 0.008f) d += 10.0f;                   // Losses.py:101-103
               }
-              if (p.nei_mask) {
+              if (NEI) {
                 if (col == row) {
                   if (sd.pos && row_ok) sd.pos[row] = d;      // rf_des.py:70 (before masking)
                   d += 10.0f;                                 // rf_des.py:71
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
       }
 
       if (row_ok) {
-        if (EPI == EPI_EXACT) {
+        if (EXACT) {
           if (sd.row_pack && best_col != 0x7fffffff) {
             const unsigned long long pk =
                 (static_cast<unsigned long long>(__float_as_uint(best)) << 32) | static_cast<unsigned int>(best_col);
