@@ -45,6 +45,12 @@ constexpr uint32_t kFfW1 = 1024;
 constexpr int kFfRawDepth = 4;                 // raw input patches prefetched ahead of the loaders (bulk async copies)
 constexpr uint32_t kFfRaw = kFfRawDepth * 4096;
 constexpr uint32_t kFfStage = 8 * 2048;       // PW2 only: one 32-pixel x 32-channel output staging tile per epilogue warp
+// FDW (PW2 + the block's stride-2 depthwise conv / max-pool in the same kernel): the pointwise output of a whole patch stays
+// in shared memory (4 planes x 1024 pixels x 16 B, row/column parity sub-planes so the stride-2 taps of consecutive output
+// columns are consecutive 16-byte slots) and only the 16 x 16 x 32 result (16 KB/patch instead of 64 KB) is written. The
+// 64 KB tile takes the place of the second stage-1 buffer: stage 1 is single-buffered in this variant.
+constexpr uint32_t kFfAct2 = 4 * 1024 * 16;
+constexpr uint32_t kFfDwW = 26 * 32 * 2;      // fp16 depthwise weights [k * k <= 25][32] + bias [32]
 constexpr size_t kFfSmem = kFfA1 + 2 * kFfAct1 + kFfW2 + kFfW1 + kFfRaw + kFfStage + 256 /*barriers*/ + 256 /*biases + reductions*/ + 1024 /*align*/;
 static_assert(kFfSmem <= 227 * 1024, "smem budget");
 
@@ -79,25 +85,32 @@ struct FfBias {
   float v[32];
 };
 
-template <typename TIn, bool PW2 = false>
+// FDW: 0 = none; 3 / 5 = depthwise 3x3 / 5x5 stride 2 (+ bias, optional ReLU) behind the pointwise stage; 1 = MaxPool 3x3
+// stride 2 pad 1 (hardnetNAS fbnet_builder.py:455-570 IRFBlock `dw`, :202-228 Identity). fp16 activations only.
+template <typename TIn, bool PW2 = false, int FDW = 0>
 __global__ void __launch_bounds__(kFfThreads, 1)
-front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]; PW2: NHWC*/,
+front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]; PW2: NHWC; FDW: NHWC [n][16][16][32]*/,
                    const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
                    const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
                    const __grid_constant__ FfBias bias2 /*[32]*/, int do_norm /*0: no input normalisation*/,
                    int num_patches, int act_bf16, float norm_eps /*added to the std: 1e-7 HardNet, 1e-8 HardNetNeiMask*/,
-                   const __grid_constant__ CUtensorMap tm_out /*PW2: [n * 1024, 32] as 32 x 32 boxes, 64B swizzle*/) {
+                   const __grid_constant__ CUtensorMap tm_out /*PW2: [n * 1024, 32] as 32 x 32 boxes, 64B swizzle*/,
+                   const float* __restrict__ dw_w = nullptr /*FDW 3 | 5: [k * k][32] folded*/, const float* __restrict__ dw_b = nullptr /*[32]*/,
+                   int dw_relu = 0) {
+  static_assert(FDW == 0 || PW2, "the fused depthwise stage sits behind the pointwise variant");
+  constexpr int NACT1 = FDW ? 1 : 2;   // stage-1 activation buffers
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw_addr);
   const uint32_t a1_addr = base;
   const uint32_t act1_addr = a1_addr + kFfA1;
-  const uint32_t w2_addr = act1_addr + 2 * kFfAct1;
+  const uint32_t w2_addr = act1_addr + NACT1 * kFfAct1;
   const uint32_t w1_addr = w2_addr + kFfW2;
   const uint32_t raw_addr0 = w1_addr + kFfW1;
-  const uint32_t stage_addr = raw_addr0 + kFfRaw;
-  const uint32_t bar_base = stage_addr + kFfStage;
+  const uint32_t stage_addr = raw_addr0 + kFfRaw;                 // FDW: the pointwise output tile (kFfAct2) + depthwise weights
+  const uint32_t dww_addr = stage_addr + kFfAct2;
+  const uint32_t bar_base = FDW ? dww_addr + kFfDwW + 128 : stage_addr + kFfStage;
   const uint32_t a1_full = bar_base, a1_empty = bar_base + 8, l1_full = bar_base + 16, l1_empty = bar_base + 24;
   auto act1_full = [&](int b) { return bar_base + 32u + 8u * b; };
   auto act1_empty = [&](int b) { return bar_base + 48u + 8u * b; };
@@ -146,7 +159,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     for (int i = t; i < static_cast<int>(kFfW2 / 16); i += kFfThreads - 32)
       *reinterpret_cast<uint4*>(gbase + (w2_addr - base) + i * 16) = __ldg(w2img + i);
     // halo rows of both act1 buffers (slots [0, 32) and [33 * 32, 34 * 32) of every plane) are zero and stay zero
-    for (int i = t; i < 2 * 4 * 2 * 32; i += kFfThreads - 32) {
+    for (int i = t; i < NACT1 * 4 * 2 * 32; i += kFfThreads - 32) {
       const int slot = i & 31, top = (i >> 5) & 1, plane = (i >> 6) & 3, b = i >> 8;
       *reinterpret_cast<uint4*>(gbase + (act1_addr - base) + b * kFfAct1 + plane * kFfPlane +
                                 (top ? 33 * 32 + slot : slot) * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -164,6 +177,11 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         v = k == 9 ? hif : bsh - hif;
       }
       W[((n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) >> 1] = to16bits(v, act_bf16);
+    }
+    if constexpr (FDW == 3 || FDW == 5) {
+      __half* dw16 = reinterpret_cast<__half*>(gbase + (dww_addr - base));
+      for (int i = t; i < FDW * FDW * 32; i += kFfThreads - 32) dw16[i] = __float2half_rn(dw_w[i]);
+      for (int i = t; i < 32; i += kFfThreads - 32) dw16[FDW * FDW * 32 + i] = __float2half_rn(dw_b[i]);
     }
     fence_proxy_async_smem();
   }
@@ -342,8 +360,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
           __syncwarp();
         }
         if (it > 0) {
-          const int b = (it - 1) & 1;
-          HN_FF_WAIT(4, act1_full(b), ((it - 1) >> 1) & 1);
+          const int b = FDW ? 0 : (it - 1) & 1;
+          HN_FF_WAIT(4, act1_full(b), FDW ? ((it - 1) & 1) : (((it - 1) >> 1) & 1));
           tc_fence_after();
           const uint32_t act_lo = act_lo0 + b * (kFfAct1 >> 4);
 #pragma unroll
@@ -424,8 +442,8 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     const int q = warp;
     int it = 0;
     for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
-      const int b = it & 1;
-      HN_FF_WAIT(8, act1_empty(b), ((it >> 1) & 1) ^ 1u);
+      const int b = FDW ? 0 : it & 1;
+      HN_FF_WAIT(8, act1_empty(b), (FDW ? (it & 1) : ((it >> 1) & 1)) ^ 1u);
       uint8_t* act = gbase + (act1_addr - base) + b * kFfAct1;
       if constexpr (PW2) {
         HN_FF_WAIT(9, l1_full, it & 1);
@@ -496,6 +514,28 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         const uint32_t t_row = t_row0 + a * C2_STRIDE;
         HN_FF_WAIT(10, c2_full(a), (t >> 2) & 1);
         tc_fence_after();
+        if constexpr (FDW != 0) {
+          // pointwise tile -> bias, ReLU, fp16 -> the patch-resident parity-planar tile (pixel (y, x) of plane c at slot
+          // ((y & 1) * 2 + (x & 1)) * 256 + (y >> 1) * 16 + (x >> 1)): even / odd lanes write two contiguous 256-byte runs
+          uint32_t r[32];
+          tmem_ld32(t_row, r);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(c2_empty(a));
+          const uint32_t slot = static_cast<uint32_t>(planar_pixel_slot<32, true>(4 * t + q, lane));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t* rr = r + c * 8;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage_addr + c * 16384u + slot * 16u),
+                         "r"(pack16_relu(__uint_as_float(rr[0]) + bias2.v[c * 8], __uint_as_float(rr[1]) + bias2.v[c * 8 + 1], 0)),
+                         "r"(pack16_relu(__uint_as_float(rr[2]) + bias2.v[c * 8 + 2], __uint_as_float(rr[3]) + bias2.v[c * 8 + 3], 0)),
+                         "r"(pack16_relu(__uint_as_float(rr[4]) + bias2.v[c * 8 + 4], __uint_as_float(rr[5]) + bias2.v[c * 8 + 5], 0)),
+                         "r"(pack16_relu(__uint_as_float(rr[6]) + bias2.v[c * 8 + 6], __uint_as_float(rr[7]) + bias2.v[c * 8 + 7], 0))
+                         : "memory");
+          }
+          continue;
+        }
         if constexpr (PW2) {
           uint32_t r[32];
           tmem_ld32(t_row, r);
@@ -570,10 +610,85 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         __syncwarp();
         if (lane == 0) mbar_arrive(c2_empty(a));
       }
+      if constexpr (FDW != 0) {
+        // ---- stride-2 depthwise conv / max-pool of the patch-resident tile by the same eight warps: a thread owns 8
+        // channels x one output column x a strip of 4 output rows (4 planes x 16 columns x 4 strips = 256 items) ----
+        asm volatile("bar.sync 2, 256;" ::: "memory");            // all eight tiles of this patch are in the tile
+        {
+          constexpr int K = FDW == 1 ? 3 : FDW, PAD = K >> 1, SH = 4, NR = (SH - 1) * 2 + K;
+          const int item = static_cast<int>(threadIdx.x) - 128;   // warps 4..11
+          const int ox = item & 15, ys = (item >> 4) & 3, plane = item >> 6;
+          const uint8_t* tile = gbase + (stage_addr - base) + plane * 16384;
+          const __half* s_dw = reinterpret_cast<const __half*>(gbase + (dww_addr - base));
+          const uint32_t ninf = 0xFC00FC00u;
+          __half2 acc[SH][4];
+          if constexpr (FDW == 1) {
+#pragma unroll
+            for (int j = 0; j < SH; ++j)
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) acc[j][qq] = *reinterpret_cast<const __half2*>(&ninf);
+          } else {
+            const uint4 b = *reinterpret_cast<const uint4*>(s_dw + K * K * 32 + plane * 8);
+#pragma unroll
+            for (int j = 0; j < SH; ++j) {
+              acc[j][0] = *reinterpret_cast<const __half2*>(&b.x); acc[j][1] = *reinterpret_cast<const __half2*>(&b.y);
+              acc[j][2] = *reinterpret_cast<const __half2*>(&b.z); acc[j][3] = *reinterpret_cast<const __half2*>(&b.w);
+            }
+          }
+          const int iy0 = ys * SH * 2 - PAD;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const int ix = ox * 2 + kx - PAD;
+            const bool x_ok = ix >= 0 && ix < 32;
+            uint4 wk[K];
+            if constexpr (FDW != 1) {
+#pragma unroll
+              for (int ky = 0; ky < K; ++ky) wk[ky] = *reinterpret_cast<const uint4*>(s_dw + (ky * K + kx) * 32 + plane * 8);
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              const int iy = iy0 + r;
+              const bool ok = x_ok && iy >= 0 && iy < 32;
+              uint4 xv = FDW == 1 ? make_uint4(ninf, ninf, ninf, ninf) : make_uint4(0u, 0u, 0u, 0u);
+              if (ok) xv = *reinterpret_cast<const uint4*>(tile + planar_pixel_slot<32, true>(iy, ix) * 16);
+              const __half2 x[4] = {*reinterpret_cast<const __half2*>(&xv.x), *reinterpret_cast<const __half2*>(&xv.y),
+                                    *reinterpret_cast<const __half2*>(&xv.z), *reinterpret_cast<const __half2*>(&xv.w)};
+#pragma unroll
+              for (int j = 0; j < SH; ++j) {
+                const int ky = r - j * 2;          // compile-time after unrolling
+                if (ky >= 0 && ky < K) {
+                  if constexpr (FDW == 1) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) acc[j][qq] = __hmax2_nan(acc[j][qq], x[qq]);
+                  } else {
+                    const __half2 wv[4] = {*reinterpret_cast<const __half2*>(&wk[ky].x), *reinterpret_cast<const __half2*>(&wk[ky].y),
+                                           *reinterpret_cast<const __half2*>(&wk[ky].z), *reinterpret_cast<const __half2*>(&wk[ky].w)};
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) acc[j][qq] = __hfma2(x[qq], wv[qq], acc[j][qq]);
+                  }
+                }
+              }
+            }
+          }
+          uint16_t* optr = out + (static_cast<size_t>(patch) * 256 + (ys * SH) * 16 + ox) * 32 + plane * 8;
+          const __half2 hzero = __float2half2_rn(0.f);
+#pragma unroll
+          for (int j = 0; j < SH; ++j) {
+            if (FDW != 1 && dw_relu) {
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) acc[j][qq] = __hmax2(acc[j][qq], hzero);
+            }
+            *reinterpret_cast<uint4*>(optr + static_cast<size_t>(j) * 16 * 32) =
+                make_uint4(*reinterpret_cast<const uint32_t*>(&acc[j][0]), *reinterpret_cast<const uint32_t*>(&acc[j][1]),
+                           *reinterpret_cast<const uint32_t*>(&acc[j][2]), *reinterpret_cast<const uint32_t*>(&acc[j][3]));
+          }
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");            // the tile may be overwritten by the next patch
+      }
     }
   }
 
-  if constexpr (PW2) {
+  if constexpr (PW2 && FDW == 0) {
     if (warp >= 4 && warp < kFfIssuer && lane == 0) bulk_wait_all<0>();   // output stores still read this CTA's smem
   }
   tc_fence_before();

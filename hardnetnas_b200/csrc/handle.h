@@ -20,6 +20,10 @@ int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, 
 int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUtensorMap& tm_out, const float* w1,
                     const float* bias1, const uint16_t* w2img, const float* bias2_host /*[32], HOST memory*/, int n, int act_bf16, int sm_count,
                     cudaStream_t s);
+// the same with the stride-2 depthwise conv (fdw = 3 | 5) or max-pool (fdw = 1) behind it: output [n][16][16][32] NHWC fp16
+int launch_front_pw_dw(const void* patches, int in_dtype, uint16_t* out, const float* w1, const float* bias1, const uint16_t* w2img,
+                       const float* bias2_host, int fdw, const float* dw_w, const float* dw_b, int dw_relu, int n, int sm_count,
+                       cudaStream_t s);
 void front_pw_weight_image(const uint16_t* w /*[32][32] 16-bit*/, std::vector<uint16_t>& img);
 }  // namespace hn
 
@@ -30,6 +34,7 @@ struct HnEnv {
   bool nas_dw_sh8 = true;     // HN_NAS_DW_SH8=0: 4-row strips for every depthwise shape
   int nas_front_chunk = 0;    // HN_NAS_FRONT_CHUNK: patches per front-kernel + first-reader sub-pass (0 = whole pass); keeps the
                               // 64 KB/patch stem output inside L2
+  bool nas_front_dw = true;   // HN_NAS_FRONT_DW=0: the stride-2 depthwise conv / max-pool behind the stem as its own kernel
   bool nas_dw_f32 = false;    // HN_NAS_DW_F32=1: fp32 depthwise arithmetic also for fp16 activations (default: packed half2)
   bool nas_resident = false;  // HN_NAS_RESIDENT=1: runs of NAS ops as patch-resident segment kernels (nas_resident.cuh). Off by
                               // default: measured slower than one kernel per op (profiles/r2_nas_resident_*)

@@ -205,6 +205,36 @@ int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUte
   return HN_OK;
 }
 
+// NAS front with the block's stride-2 depthwise conv (fdw = 3 | 5) or max-pool (fdw = 1) fused behind the pointwise stage
+// (FDW variant of the front kernel): patches -> [n][16][16][32] NHWC fp16; the 64 KB/patch pointwise output stays on chip.
+int launch_front_pw_dw(const void* patches, int in_dtype, uint16_t* out, const float* w1, const float* bias1, const uint16_t* w2img,
+                       const float* bias2_host, int fdw, const float* dw_w, const float* dw_b, int dw_relu, int n, int sm_count,
+                       cudaStream_t s) {
+  static DeviceOnce attr_once;
+  if (attr_once.first_time()) {
+#define HN_FDW_ATTR(T, F) HN_CUDA(cudaFuncSetAttribute(front_fused_kernel<T, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFfSmem)))
+    HN_FDW_ATTR(float, 1); HN_FDW_ATTR(float, 3); HN_FDW_ATTR(float, 5);
+    HN_FDW_ATTR(uint8_t, 1); HN_FDW_ATTR(uint8_t, 3); HN_FDW_ATTR(uint8_t, 5);
+#undef HN_FDW_ATTR
+  }
+  if (n <= 0) return HN_OK;
+  const int grid = std::min(n, sm_count);
+  const uint4* w2 = reinterpret_cast<const uint4*>(w2img);
+  static const CUtensorMap no_map = {};
+  FfBias bias2;
+  memcpy(bias2.v, bias2_host, sizeof(bias2.v));
+#define HN_FDW_LAUNCH(T, F) front_fused_kernel<T, true, F><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const T*>(patches), out, w1, bias1, w2, bias2, 0, n, 0, 0.f, no_map, dw_w, dw_b, dw_relu)
+  if (in_dtype == HN_F32) {
+    if (fdw == 1) HN_FDW_LAUNCH(float, 1); else if (fdw == 3) HN_FDW_LAUNCH(float, 3); else HN_FDW_LAUNCH(float, 5);
+  } else {
+    if (fdw == 1) HN_FDW_LAUNCH(uint8_t, 1); else if (fdw == 3) HN_FDW_LAUNCH(uint8_t, 3); else HN_FDW_LAUNCH(uint8_t, 5);
+  }
+#undef HN_FDW_LAUNCH
+  HN_CUDA(cudaGetLastError());
+  count_launch(1);
+  return HN_OK;
+}
+
 // Front-kernel weight image (front_fused.cuh) of a pointwise 32 -> 32 conv: [co][ci] 16-bit weights at the centre tap.
 void front_pw_weight_image(const uint16_t* w /*[32][32]*/, std::vector<uint16_t>& img) {
   img.assign(kFfW2 / 2, 0);
@@ -379,6 +409,7 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
     h->env.nas_dw_smem = flag("HN_NAS_DW_SMEM", true);
     h->env.nas_dw_sh8 = flag("HN_NAS_DW_SH8", true);
     h->env.nas_dw_f32 = flag("HN_NAS_DW_F32", false);
+    h->env.nas_front_dw = flag("HN_NAS_FRONT_DW", true);
     h->env.nas_front_chunk = std::max(0, num("HN_NAS_FRONT_CHUNK", 0)) & ~1;
     h->env.nas_resident = flag("HN_NAS_RESIDENT", false);
     h->env.nas_minb = num("HN_NAS_MINB", 0);

@@ -889,6 +889,7 @@ struct NasState {
   CUtensorMap front_tm;              // its output ([chunk * 1024, 32] as 32 x 32 store boxes, 64B swizzle)
   float front_bias2[32];             // op 1's folded BN shift (host copy: a by-value kernel parameter)
   int front_ops = 0;                 // ops the front kernel covers: 2 = stem + pointwise, 1 = stem alone (identity pointwise)
+  int front_fdw = 0;                 // != 0: op `front_ops` (depthwise 3 | 5 stride 2, or max-pool = 1) also runs inside the front kernel
   size_t slot_elems = 0;             // per patch
   int chunk = 0;                     // patches per pass (<= handle chunk, capped so the three slots stay <= 4 GiB)
   int head_k = 0;
@@ -1269,6 +1270,12 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
         // (128 KB/patch of the pass's traffic); the reader writes its 4x smaller output at the sub-pass's offset.
         const int nxt = st->front_ops;
         const hn_nas_op& on = st->ops[nxt];
+        if (st->front_fdw && nxt <= last_op) {
+          HN_TRY(launch_front_pw_dw(src, in_dtype, st->slot[on.dst], st->params + o0.w_off, st->params + o0.b_off, st->front_img,
+                                    st->front_bias2, st->front_fdw, on.kind == OP_DW ? st->params + on.w_off : nullptr,
+                                    on.kind == OP_DW ? st->params + on.b_off : nullptr, on.relu, n, h->sm_count, s));
+          first = nxt + 1;
+        } else {
         const bool sub = h->env.nas_front_chunk > 0 && h->env.nas_front_chunk < n && nxt <= last_op && nxt < static_cast<int>(st->ops.size()) - 1 &&
                          st->seg_of_op[nxt] < 0 && (on.kind == OP_DW || on.kind == OP_MAXPOOL) && on.src == ol.dst;
         if (sub) {
@@ -1285,6 +1292,7 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
           HN_TRY(launch_front_pw(src, in_dtype, st->slot[ol.dst], st->front_tm, st->params + o0.w_off, st->params + o0.b_off, st->front_img,
                                  st->front_bias2, n, bf, h->sm_count, s));
           first = st->front_ops;
+        }
         }
       }
       const int n_total = static_cast<int>(st->ops.size());
@@ -1555,6 +1563,20 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
     HN_CUDA_N(cudaMalloc(&st->front_img, img.size() * 2));
     HN_CUDA_N(cudaMemcpy(st->front_img, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
     st->front_ops = 1;
+  }
+  // the op behind the front stage, if it is the block's stride-2 depthwise conv (or the Identity's max-pool) on the
+  // 32 x 32 x 32 tensor, runs inside the front kernel too (fp16 activations): 64 KB/patch never reach HBM
+  if (!bf && h->env.nas_front_dw && h->env.nas_front && !h->env.nas_resident && st->front_ops < n_ops - 1) {
+    const hn_nas_op& o = ops[st->front_ops];
+    const hn_nas_op& prev = ops[st->front_ops - 1];
+    const bool shape_ok = o.cin == 32 && o.cout == 32 && o.hin == 32 && o.hout == 16 && o.stride == 2 && o.src == prev.dst;
+    const int fdw = (o.kind == OP_DW && (o.kernel == 3 || o.kernel == 5)) ? o.kernel : (o.kind == OP_MAXPOOL ? 1 : 0);
+    bool reused = false;               // nothing later may read the pointwise output, which no longer exists
+    for (int i = st->front_ops + 1; i < n_ops && !reused; ++i) {
+      if (ops[i].kind != OP_HEAD && ops[i].dst == prev.dst) break;
+      reused = ops[i].src == prev.dst || (ops[i].kind == OP_PW && ops[i].res == prev.dst);
+    }
+    if (shape_ok && fdw && !reused) st->front_fdw = fdw;
   }
   HN_CUDA_N(cudaMalloc(&st->head_in, static_cast<size_t>(h->head_rows) * st->head_k * 2));
   HN_CUDA_N(cudaMemset(st->head_in, 0, static_cast<size_t>(h->head_rows) * st->head_k * 2));

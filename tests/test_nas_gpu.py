@@ -142,6 +142,32 @@ def test_patch_resident_segments(arch, env, monkeypatch):
         assert (got - r).abs().max().item() <= 6e-3 * r.abs().max().item() + 1e-5, (arch, stage, op_index)
 
 
+@pytest.mark.parametrize("arch", ["wang2", "wang3", "wang4"])
+def test_front_kernel_with_and_without_the_fused_depthwise_stage(arch, monkeypatch):
+    """Default: the stride-2 depthwise conv (wang2: 3x3, wang3: 5x5) or max-pool (wang4) behind the stem runs inside the front
+    kernel (the 64 KB/patch pointwise output stays in shared memory). HN_NAS_FRONT_DW=0 runs it as its own kernel. Both must
+    reproduce the oracle at every stage, for fp32 and uint8 input and a ragged batch; bf16 nets never fuse it."""
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("HN_NAS_FRONT_DW", flag)
+        net, ops, sd = build(arch, chunk_patches=64, head_rows=256)
+        x = synth.make_patches(203, 6, edge_cases=False)
+        ref, feats = nas_oracle.nas_forward(x, ops, sd, return_features=True)
+        got = net(x.cuda())
+        max_abs, cos = _cmp(got, ref)
+        assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (arch, flag, max_abs, cos)
+        prog = net.compile_program()
+        for stage, op_index in enumerate(prog.stage_end[:3]):
+            g = net.forward_op(x[:37].cuda(), op_index).float().cpu().permute(0, 3, 1, 2)
+            r = feats[stage][:37]
+            assert (g - r).abs().max().item() <= 6e-3 * r.abs().max().item() + 1e-5, (arch, flag, stage)
+        x8 = (synth.make_patches(150, 8, edge_cases=False) * 255).round().to(torch.uint8)
+        max_abs, cos = _cmp(net(x8.cuda()), nas_oracle.nas_forward(x8.float(), ops, sd))
+        assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (arch, flag, "u8", max_abs, cos)
+        outs.append(got)
+    assert (outs[0].float() - outs[1].float()).abs().max().item() <= 5e-4
+
+
 def test_default_plan_is_one_kernel_per_op():
     net, _, _ = build("wang2")
     assert net.resident_plan() == []
