@@ -613,8 +613,13 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       if constexpr (FDW != 0) {
         // ---- stride-2 depthwise conv / max-pool of the patch-resident tile by the same eight warps: a thread owns 8
         // channels x one output column x a strip of 4 output rows (4 planes x 16 columns x 4 strips = 256 items) ----
-        asm volatile("bar.sync 2, 256;" ::: "memory");            // all eight tiles of this patch are in the tile
         {
+          HN_FF_SECTION_BEGIN();
+          asm volatile("bar.sync 2, 256;" ::: "memory");          // all eight tiles of this patch are in the tile
+          HN_FF_SECTION_END(17);
+        }
+        {
+          HN_FF_SECTION_BEGIN();
           constexpr int K = FDW == 1 ? 3 : FDW, PAD = K >> 1, SH = 4, NR = (SH - 1) * 2 + K;
           const int item = static_cast<int>(threadIdx.x) - 128;   // warps 4..11
           const int ox = item & 15, ys = (item >> 4) & 3, plane = item >> 6;
@@ -682,8 +687,13 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
                 make_uint4(*reinterpret_cast<const uint32_t*>(&acc[j][0]), *reinterpret_cast<const uint32_t*>(&acc[j][1]),
                            *reinterpret_cast<const uint32_t*>(&acc[j][2]), *reinterpret_cast<const uint32_t*>(&acc[j][3]));
           }
+          HN_FF_SECTION_END(14);
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");            // the tile may be overwritten by the next patch
+        {
+          HN_FF_SECTION_BEGIN();
+          asm volatile("bar.sync 2, 256;" ::: "memory");          // the tile may be overwritten by the next patch
+          HN_FF_SECTION_END(18);
+        }
       }
     }
   }

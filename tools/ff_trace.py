@@ -32,7 +32,8 @@ names = {0: "loader: raw_full (x4 warps)", 1: "loader: a1_empty (x4)", 2: "issue
          4: "issuer: act1_full", 5: "issuer: l1_empty (1st half)", 6: "issuer: c2_empty (8 tiles)", 7: "issuer: mma_done (8 tiles)",
          8: "L1 epi: act1_empty (x4 warps)", 9: "L1 epi: l1_full (x4, 2 halves)", 10: "conv2 epi: c2_full (x16 warps... per group tiles)",
          11: "issuer: stage-1 MMA issue sections", 12: "issuer: PW2 conv2 MMA issue sections",
-         13: "issuer: conv2 MMA issue sections (8 tiles)"}
+         13: "issuer: conv2 MMA issue sections (8 tiles)", 14: "FDW: depthwise phase (x8 warps)",
+         17: "FDW: barrier before the depthwise phase (x8)", 18: "FDW: barrier behind it (x8)"}
 print(f"CTA 0: {v[15] / patches:.0f} cycles per patch over {patches} patches")
 for k, n in names.items():
     print(f"  {n:50s} {v[k] / patches:9.0f} cycles/patch")
