@@ -42,6 +42,7 @@ SIGNATURES = {
     "hn_loss_hardnet": (C.c_int, [_P, _P, C.c_longlong, C.c_float, C.c_int, _P, _P, C.c_longlong, _P]),
     "hn_match": (C.c_int, [_P, _P, C.c_longlong, C.c_longlong, C.c_longlong, _P, _P, _P, _P, _P, C.c_longlong, _P]),
     "hn_pack_descriptors": (C.c_int, [_P, C.c_longlong, _P, _P]),
+    "hn_pack_descriptors_multicast": (C.c_int, [_P, C.c_longlong, _P, _P, _P]),
     "hn_match_ex": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_longlong, C.c_longlong, _P, _P, _P, _P, _P, _P, C.c_longlong, _P, _P]),
     "hn_mutual_workspace_bytes": (C.c_longlong, [C.c_longlong, C.c_longlong]),
     "hn_match_mutual": (C.c_int, [_P, _P, _P, _P, C.c_longlong, C.c_longlong, _P, _P, _P, _P, _P, _P, C.c_longlong, _P]),

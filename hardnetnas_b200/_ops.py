@@ -87,15 +87,28 @@ def loss_hardnet(anchor: torch.Tensor, positive: torch.Tensor, margin: float, an
     return out
 
 
-def pack_descriptors(x: torch.Tensor) -> torch.Tensor:
-    """[n,128] fp32 unit rows -> the fp16 operand rows of the matching GEMM (x * 2^8), see hn_pack_descriptors."""
+def pack_descriptors(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """[n,128] fp32 unit rows -> the fp16 operand rows of the matching GEMM (x * 2^8), see hn_pack_descriptors.
+    `out`: optional destination (e.g. a symmetric-memory exchange buffer)."""
     lib = _lib.load()
     x = _require_cuda_f32("pack_descriptors", x)
-    out = torch.empty((x.size(0), 128), dtype=torch.float16, device=x.device)
+    if out is None:
+        out = torch.empty((x.size(0), 128), dtype=torch.float16, device=x.device)
+    elif not (out.is_cuda and out.dtype == torch.float16 and tuple(out.shape) == (x.size(0), 128) and out.is_contiguous()):
+        raise ValueError("pack_descriptors: out must be a contiguous CUDA fp16 [n,128] tensor")
     if x.size(0):
         with torch.cuda.device(x.device):
             _lib.check(lib.hn_pack_descriptors(_ptr(x), x.size(0), _ptr(out), _stream_ptr()), "hn_pack_descriptors")
     return out
+
+
+def pack_descriptors_multicast(x: torch.Tensor, mc16_ptr: int, mc32_ptr: int) -> None:
+    """Pack x:[n,128] and push the fp16 and the fp32 rows to multicast addresses (hn_pack_descriptors_multicast)."""
+    lib = _lib.load()
+    x = _require_cuda_f32("pack_descriptors_multicast", x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hn_pack_descriptors_multicast(_ptr(x), x.size(0), C.c_void_p(mc16_ptr), C.c_void_p(mc32_ptr), _stream_ptr()),
+                   "hn_pack_descriptors_multicast")
 
 
 def match_top2(q: torch.Tensor, g: torch.Tensor, g_offset: int = 0, q16: torch.Tensor | None = None,

@@ -48,6 +48,41 @@ __global__ void pack_desc_kernel(const float* __restrict__ x, long long n, uint1
   }
 }
 
+// Push all-gather over NVSwitch multicast: a rank packs its shard and writes BOTH forms (fp16 operand rows for the GEMM, fp32
+// rows for the exact re-rank) to multicast addresses (multimem.st): the switch replicates every 16-byte store into the
+// symmetric buffer of every GPU of the group, so after one cross-GPU barrier each GPU holds the whole gallery without a
+// gather kernel, a copy engine or a second pass over the data. Half a warp per row: a lane owns 8 consecutive floats.
+__global__ void pack_desc_multicast_kernel(const float* __restrict__ x, long long n, uint16_t* __restrict__ mc16,
+                                           float* __restrict__ mc32) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long row = gid >> 4;
+  const int l = static_cast<int>(gid & 15);
+  if (row >= n) return;
+  const float4 a = reinterpret_cast<const float4*>(x + row * 128)[2 * l];
+  const float4 b = reinterpret_cast<const float4*>(x + row * 128)[2 * l + 1];
+  const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 v = __floats2half2_rn(f[2 * j] * kOperandScale, f[2 * j + 1] * kOperandScale);
+    h[j] = *reinterpret_cast<const uint32_t*>(&v);
+  }
+  if (mc16 != nullptr)
+    asm volatile("multimem.st.weak.global.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(mc16 + row * 128 + l * 8), "r"(h[0]), "r"(h[1]),
+                 "r"(h[2]), "r"(h[3])
+                 : "memory");
+  if (mc32 != nullptr) {
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc32 + row * 128 + l * 8), "f"(a.x), "f"(a.y),
+                 "f"(a.z), "f"(a.w)
+                 : "memory");
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc32 + row * 128 + l * 8 + 4), "f"(b.x), "f"(b.y),
+                 "f"(b.z), "f"(b.w)
+                 : "memory");
+  }
+  // no per-thread fence: the stores are complete when the kernel retires, and the cross-GPU barrier that follows on the same
+  // stream publishes them (release / acquire at system scope); a __threadfence_system() here cost 0.1 ms per 24 MiB
+}
+
 __global__ void unpack_min_kernel(const unsigned long long* __restrict__ pack, long long n, float* __restrict__ val,
                                   int* __restrict__ arg) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -552,6 +587,19 @@ extern "C" int hn_pack_descriptors(const float* x, long long n, void* out16, voi
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int threads = 256;
   pack_desc_kernel<<<static_cast<unsigned>((n * 32 + threads - 1) / threads), threads, 0, s>>>(x, n, static_cast<uint16_t*>(out16), 0, 0, nullptr);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
+extern "C" int hn_pack_descriptors_multicast(const float* x, long long n, void* mc16, void* mc32, void* stream) {
+  HN_REQUIRE(x && (mc16 || mc32), "hn_pack_descriptors_multicast: NULL argument (either destination may be NULL, not both)");
+  HN_REQUIRE(n >= 1 && n < (1LL << 31), "hn_pack_descriptors_multicast: n out of range (%lld)", n);
+  HN_REQUIRE((reinterpret_cast<uintptr_t>(mc16) & 15) == 0 && (reinterpret_cast<uintptr_t>(mc32) & 15) == 0,
+             "hn_pack_descriptors_multicast: multicast addresses must be 16-byte aligned");
+  const int threads = 256;
+  pack_desc_multicast_kernel<<<static_cast<unsigned>((n * 16 + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, static_cast<uint16_t*>(mc16), static_cast<float*>(mc32));
   HN_CUDA(cudaGetLastError());
   count_launch();
   return HN_OK;

@@ -68,11 +68,17 @@ def _counts_or_exchange(local_rows: int, counts: list[int] | None, device) -> li
 
 
 def _gather_packed_then_rows(local: torch.Tensor, counts: list[int]):
-    """Gallery exchange of the B200 path: ONE all_gather of the packed fp16 rows (what the GEMM reads: half the NVLink bytes,
-    each rank packs only its own shard), then the fp32 rows (what the exact re-rank reads) as a second, asynchronous
-    all_gather whose completion is an event - it finishes behind the GEMM. Returns (rows_fp32, rows_fp16, ready_event)."""
+    """Gallery exchange of the B200 path. Returns (rows_fp32, rows_fp16, ready_event): the packed fp16 rows (what the GEMM
+    reads: half the bytes, each rank packs only its shard) are complete on the current stream, the fp32 rows (what the exact
+    re-rank reads) when `ready_event` fires - they arrive behind the GEMM.
+    Preferred transport: PEER COPIES over NVLink out of symmetric-memory send buffers (`_PeerExchange`): the copy engines
+    move the shards, no SM is taken from the persistent matching GEMM (NCCL's gather kernels running next to it cost more
+    than the transfer itself at 8 GPUs). Fallback: two NCCL all_gathers, the second one asynchronous."""
     from . import _ops
     world = len(counts)
+    xchg = _PeerExchange.get(local.device, counts[0]) if _peer_exchange_enabled() else None
+    if xchg is not None:
+        return xchg.gather(local)
     packed_local = _ops.pack_descriptors(local)
     packed = torch.empty((world * counts[0], 128), dtype=torch.float16, device=local.device)
     dist.all_gather_into_tensor(packed, packed_local)
@@ -84,6 +90,67 @@ def _gather_packed_then_rows(local: torch.Tensor, counts: list[int]):
         work.wait()            # the side stream (not the compute stream) waits for the collective
         ready.record(side)
     return rows, packed, ready
+
+
+def _peer_exchange_enabled() -> bool:
+    import os
+    return os.environ.get("HN_P2P_GATHER", "1") != "0"
+
+
+class _PeerExchange:
+    """Gallery exchange through symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into every
+    rank of the group, with an NVSwitch MULTICAST mapping on NVLS-capable systems). Per call every rank packs its shard and
+    PUSHES it - the fp16 operand rows and the fp32 rows - to the multicast address of its slice of the symmetric gallery
+    buffers (`hn_pack_descriptors_multicast`, multimem.st): the switch replicates the stores into every GPU's copy, so one
+    device-side barrier (~7 us) later each GPU holds the whole gallery. No gather kernel shares the SMs with the persistent
+    matching GEMM, no copy engine is programmed 2(R-1) times, the data crosses each GPU's NVLink once.
+    The buffers are double-buffered by call parity: a rank passes barrier k + 1 only after every rank has finished reading
+    the buffers of call k (their barrier sits behind their re-rank in stream order), so the pushes of call k + 2 are safe."""
+    _cache: dict = {}
+    _failed = False
+
+    @classmethod
+    def get(cls, device, rows: int):
+        if cls._failed:
+            return None
+        key = (device.index, rows)
+        if key not in cls._cache:
+            try:
+                cls._cache[key] = cls(device, rows)
+            except Exception as exc:   # no symmetric memory / multicast on this system or build: NCCL path
+                import sys
+                print(f"[hardnetnas_b200] multicast exchange unavailable ({exc!r}); using NCCL all_gather", file=sys.stderr)
+                cls._failed = True
+                return None
+        return cls._cache[key]
+
+    def __init__(self, device, rows: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.rank, self.world = _world()
+        self.rows, self.device = rows, device
+        group = dist.group.WORLD
+        n = self.world * rows
+        self.full16 = [symm_mem.empty((n, 128), dtype=torch.float16, device=device) for _ in range(2)]
+        self.full32 = [symm_mem.empty((n, 128), dtype=torch.float32, device=device) for _ in range(2)]
+        self.h16 = [symm_mem.rendezvous(t, group) for t in self.full16]
+        self.h32 = [symm_mem.rendezvous(t, group) for t in self.full32]
+        if any(int(h.multicast_ptr) == 0 for h in self.h16 + self.h32):
+            raise RuntimeError("no multicast mapping (NVLS) for the symmetric buffers")
+        self.mc16 = [int(h.multicast_ptr) + self.rank * rows * 128 * 2 for h in self.h16]
+        self.mc32 = [int(h.multicast_ptr) + self.rank * rows * 128 * 4 for h in self.h32]
+        self.calls = 0
+
+    def gather(self, local: torch.Tensor):
+        from . import _ops
+        par = self.calls & 1
+        self.calls += 1
+        # One kernel pushes both forms, one barrier publishes them. Measured alternatives at 8 GPUs (tools/match_scale3.py,
+        # 64k x 64k, compute-only 0.153 ms): this 0.239 ms; fp16 first and the fp32 rows on a side stream behind the GEMM
+        # 0.253 ms (whatever runs next to the persistent GEMM slows it by more than the transfer it hides); peer copies by the
+        # copy engines 0.35 ms (2 R small copies per call); two NCCL all_gathers 0.276 ms.
+        _ops.pack_descriptors_multicast(local, self.mc16[par], self.mc32[par])
+        self.h16[par].barrier(channel=0)      # every rank's pushes of this call have landed (and call k - 2 is fully read)
+        return self.full32[par], self.full16[par], None
 
 
 _side_streams: dict = {}

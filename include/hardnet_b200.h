@@ -168,6 +168,14 @@ int hn_match(const float* q, const float* g, long long Nq, long long Ng, long lo
  * between GPUs (half the NVLink bytes of the fp32 rows) or match one set several times. x:[n,128] fp32 -> out16:[n,128]. */
 int hn_pack_descriptors(const float* x, long long n, void* out16, void* stream);
 
+/* Push all-gather of a gallery shard over NVSwitch multicast: packs x:[n,128] like hn_pack_descriptors and writes the packed
+ * fp16 rows to mc16 and the fp32 rows to mc32, which must be MULTICAST addresses of symmetric buffers mapped on every GPU
+ * of the group (e.g. torch.distributed._symmetric_memory: handle.multicast_ptr + this rank's row offset). The switch
+ * replicates each store to all GPUs; after a cross-GPU barrier every GPU's local view of the buffers holds all shards.
+ * Either destination may be NULL: the packed rows go first (the GEMM waits for them), the fp32 rows follow on a side stream
+ * and land behind the GEMM (only the re-rank reads them). */
+int hn_pack_descriptors_multicast(const float* x, long long n, void* mc16, void* mc32, void* stream);
+
 /* hn_match with optional pre-packed operands (q16 / g16 from hn_pack_descriptors, NULL = pack here), an optional output of
  * the GEMM's block maxima (see hn_match_mutual; NULL = not computed) and an optional cudaEvent_t the exact re-rank waits for:
  * the GEMM reads only the packed rows, the re-rank reads the fp32 gallery rows of the shortlisted columns, so a sharded
