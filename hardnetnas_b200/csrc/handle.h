@@ -61,6 +61,7 @@ struct hn_handle {
   float* bias = nullptr;                                               // 7 x 128
   float norm_eps = 1e-7f;       // added to the per-patch std in input_norm (hn_set_hardnet_eps)
   float bias2_host[32] = {0};   // conv2's folded BN shift on the host: passed to the fused front kernel by value
+  float* head_partial = nullptr;  // split-K partial sums of the head GEMM at small batches ([#SM][128][128] fp32)
   float2* stats = nullptr;                                             // per-patch (mean, 1/std), chunk entries
   hn::TcParams conv_params[5];
   hn::TcParams pair_params[5];   // same layers for the CTA-pair kernels (tc_conv_pair.cuh)

@@ -246,16 +246,34 @@ void front_pw_weight_image(const uint16_t* w /*[32][32]*/, std::vector<uint16_t>
     }
 }
 
-int launch_head(const TcParams& p, int sm_count, cudaStream_t stream) {
+int launch_head(const TcParams& p_in, int sm_count, cudaStream_t stream) {
   static DeviceOnce attr_once;
   if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(gemm_l2norm_kernel<kHeadN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(kHeadSmem)));
   }
-  if (p.num_tiles <= 0) return HN_OK;
-  gemm_l2norm_kernel<kHeadN><<<std::min(p.num_tiles, sm_count), kTcThreads, kHeadSmem, stream>>>(p);
+  if (p_in.num_tiles <= 0) return HN_OK;
+  TcParams p = p_in;
+  // Small batches: a 128-row tile streams the whole K x 128 weight matrix (2 MB for HardNet's 8 x 8 head) through ONE SM, so a
+  // 1024-patch head took 41 us on 8 CTAs against 4 us at the bulk rate. Split K over up to 16 CTAs per tile (raw fp32
+  // partials, summed with the bias and normalised by head_finalize_kernel) whenever the tiles alone fill less than half of the
+  // machine. (Changes the last bit of a descriptor relative to the unsplit head: a different fp32 summation order.)
+  int splits = 1;
+  if (p.partial != nullptr && p.num_tiles * 2 <= sm_count) {
+    while (splits * 2 <= 16 && p.num_tiles * splits * 2 <= sm_count && p.num_k_stages % (splits * 2) == 0) splits *= 2;
+  }
+  p.k_splits = splits;
+  const int items = p.num_tiles * splits;
+  gemm_l2norm_kernel<kHeadN><<<std::min(items, sm_count), kTcThreads, kHeadSmem, stream>>>(p);
   HN_CUDA(cudaGetLastError());
   count_launch();
+  if (splits > 1) {
+    const int threads = 256;
+    head_finalize_kernel<<<static_cast<unsigned>((p.total_rows * 32 + threads - 1) / threads), threads, 0, stream>>>(
+        p.partial, splits, static_cast<long long>(p.num_tiles) * kTileM, p.total_rows, p.bias, p.l2_eps, p.out, p.out_dtype);
+    HN_CUDA(cudaGetLastError());
+    count_launch();
+  }
   return HN_OK;
 }
 
@@ -449,6 +467,8 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   HN_CUDA_H(cudaMalloc(&h->w2img, kFfW2));
   HN_CUDA_H(cudaMalloc(&h->bias, 7 * 128 * sizeof(float)));
   HN_CUDA_H(cudaMalloc(&h->stats, static_cast<size_t>(chunk_patches) * sizeof(float2)));
+  // split-K partials of the head at small batches: tiles x splits <= #SM work items of 128 x 128 fp32 each
+  HN_CUDA_H(cudaMalloc(&h->head_partial, static_cast<size_t>(h->sm_count) * kTileM * kHeadN * sizeof(float)));
 #undef HN_CUDA_H
   st = build_params(h);
   if (st != HN_OK) return fail(st);
@@ -467,6 +487,7 @@ extern "C" int hn_destroy(hn_handle* h) {
   cudaFree(h->w2img);
   cudaFree(h->bias);
   cudaFree(h->stats);
+  cudaFree(h->head_partial);
   for (auto& v : h->ev)
     for (cudaEvent_t e : v) cudaEventDestroy(e);
   nas_state_free(h->nas);
@@ -586,6 +607,7 @@ extern "C" int hn_forward(hn_handle* h, const void* patches, int in_dtype, long 
     p.act_bf16 = h->act_bf16;
     p.out_dtype = out_dtype;
     p.out = static_cast<char*>(desc_out) + static_cast<size_t>(base) * 128 * out_elem;
+    p.partial = h->head_partial;
     StageTimer timer(h, 6, s);
     HN_TRY(launch_head(p, h->sm_count, s));
   }

@@ -1693,6 +1693,7 @@ extern "C" int hn_forward_nas(hn_handle* h, const void* patches, int in_dtype, l
     p.num_tiles = static_cast<int>((nb + kTileM - 1) / kTileM);
     p.out_dtype = out_dtype;
     p.out = static_cast<char*>(desc_out) + static_cast<size_t>(base) * 128 * out_elem;
+    p.partial = h->head_partial;
     HN_TRY(launch_head(p, h->sm_count, s));
   }
   return HN_OK;

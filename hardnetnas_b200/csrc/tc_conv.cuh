@@ -45,6 +45,9 @@ struct TcParams {
   int act_bf16;            // 16-bit activation flavour: 0 = fp16, 1 = bf16
   int out_dtype;           // head only: DT_F32 / DT_F16 / DT_BF16
   float l2_eps;            // head only: 1e-10 (Utils.py:18); 0 for the NAS head
+  int k_splits;            // head only: > 1 = split-K (small batches): a CTA reduces num_k_stages / k_splits stages of one row tile
+                           // and writes raw fp32 partial sums to `partial`; head_finalize_kernel adds them, the bias and the norm
+  float* partial;          // [k_splits][num_tiles * 128][128] fp32
 };
 
 __device__ __forceinline__ uint32_t pack16(float lo, float hi, int bf16) {
@@ -452,9 +455,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int splits = p.k_splits > 1 ? p.k_splits : 1;
+    const int nks = p.num_k_stages / splits;                 // k-stages per work item
+    for (int item = blockIdx.x; item < p.num_tiles * splits; item += gridDim.x) {
+      const int tile = item / splits, ks0 = (item - tile * splits) * nks;
 #pragma unroll 1
-      for (int ks = 0; ks < p.num_k_stages; ++ks) {
+      for (int ksi = 0; ksi < nks; ++ksi) {
+        const int ks = ks0 + ksi;
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (elect_one()) {
           const uint32_t st_base = base + stage * STAGE_BYTES;
@@ -476,14 +483,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const int splits = p.k_splits > 1 ? p.k_splits : 1;
+    const int nks = p.num_k_stages / splits;
+    for (int item = blockIdx.x; item < p.num_tiles * splits; item += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * N;
 #pragma unroll 1
-      for (int ks = 0; ks < p.num_k_stages; ++ks) {
+      for (int ks = 0; ks < nks; ++ks) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
@@ -496,7 +505,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
                          (ks | g | k) != 0);
           }
           umma_commit(empty_bar(stage));
-          if (ks == p.num_k_stages - 1) umma_commit(tfull_bar(acc));
+          if (ks == nks - 1) umma_commit(tfull_bar(acc));
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -506,7 +515,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const int splits = p.k_splits > 1 ? p.k_splits : 1;
+    for (int item = blockIdx.x; item < p.num_tiles * splits; item += gridDim.x, ++it) {
+      const int tile = item / splits, split = item - tile * splits;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -514,6 +525,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * N;
       const long long row = static_cast<long long>(tile) * kTileM + row_in_tile;
       const bool valid = row < p.total_rows;
+      if (splits > 1) {
+        // split-K: raw partial sums of this K range; bias, norm and the output type belong to head_finalize_kernel
+        float* dstp = p.partial + (static_cast<long long>(split) * p.num_tiles * kTileM + row) * N;
+#pragma unroll
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(t_row + c0, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(dstp + c0)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                    __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        continue;
+      }
       // bias, then x / sqrt(sum(x*x) + eps) over the N columns of the row (Utils.py:19-22)
       float ss = 0.f;
 #pragma unroll
@@ -562,6 +593,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Second half of the split-K head: sum the K-range partials in split order, add the bias, L2-normalise, store.
+// One warp per descriptor row, a lane owns 4 of the 128 columns.
+static __global__ void __launch_bounds__(256) head_finalize_kernel(const float* __restrict__ partial, int k_splits, long long rows_padded,
+                                                            long long total_rows, const float* __restrict__ bias, float l2_eps,
+                                                            void* __restrict__ out, int out_dtype) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= total_rows) return;
+  float4 v = *reinterpret_cast<const float4*>(bias + lane * 4);
+  for (int s = 0; s < k_splits; ++s) {
+    const float4 a = *reinterpret_cast<const float4*>(partial + (static_cast<long long>(s) * rows_padded + row) * 128 + lane * 4);
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  float ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.0f / sqrtf(ss + l2_eps);
+  v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+  if (out_dtype == DT_F32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(out) + row * 128 + lane * 4) = v;
+  } else {
+    const int bf = out_dtype == DT_BF16;
+    *reinterpret_cast<uint2*>(static_cast<uint16_t*>(out) + row * 128 + lane * 4) = make_uint2(pack16(v.x, v.y, bf), pack16(v.z, v.w, bf));
   }
 }
 

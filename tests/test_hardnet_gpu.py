@@ -129,7 +129,11 @@ def test_full_size_properties():
     assert (d1.norm(dim=1) - 1).abs().max().item() < 1e-4
     small, _ = _model(None, chunk_patches=32, head_rows=128)
     d3 = small(x[:1000])
-    assert torch.equal(d3, d1[:1000])
+    # the conv stack is chunking-invariant bit for bit; the head of a small batch runs split-K (another fp32 summation order
+    # than the bulk head), which may move the last bit of a descriptor component
+    assert (d3 - d1[:1000]).abs().max().item() <= 1e-6
+    d4 = small(x[:1000])
+    assert torch.equal(d3, d4)
 
 
 def test_fpr95_agrees_with_reference_path():
