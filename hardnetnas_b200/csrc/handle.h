@@ -41,6 +41,10 @@ struct HnEnv {
   int nas_minb = 0;           // HN_NAS_MINB: CTAs per SM of the segment kernel (0 = choose)
   int nas_cut_ratio = 4;      // HN_NAS_CUT_RATIO: start a new segment at a block boundary whose tensor is <= 1/ratio of the segment input
   int nas_gmax = 8;           // HN_NAS_GMAX: cap on patches per group
+  bool nas_tail = true;       // HN_NAS_TAIL=0: no warpgroup-per-patch tail kernel (nas_tail.cuh) behind the fused front stage
+  int nas_tail_cut = 2;       // HN_NAS_TAIL_CUT: start a new tail launch at a block boundary whose tensor is <= 1/cut of the launch's
+                              // input (smaller maps -> smaller buffers -> more warpgroups per SM); 0 = one launch for the whole tail
+  int nas_tail_wg = 4;        // HN_NAS_TAIL_WG: cap on warpgroups (patches in flight) per CTA
   char nas_split[128] = {0};  // HN_NAS_SPLIT="i,j,...": explicit op indices that start a new segment (overrides the heuristic)
 };
 

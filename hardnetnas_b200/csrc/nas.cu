@@ -23,6 +23,7 @@
 #include "host_common.h"
 #include "tc_conv.cuh"
 #include "nas_resident.cuh"
+#include "nas_tail.cuh"
 
 namespace hn {
 
@@ -875,7 +876,19 @@ struct NasSegment {
   uint8_t* blob = nullptr;   // device copy of the weight image
 };
 
+// A run of consecutive ops behind the front stage executed by ONE launch of nas_tail_kernel (nas_tail.cuh), a warpgroup per patch.
+struct NasTail {
+  int first = 0, last = 0;   // op range [first, last]
+  int nwg = 0;               // warpgroups (= patches in flight) per CTA
+  size_t smem = 0;
+  int slot_off[3] = {0, 0, 0};   // byte offsets of the three program slots inside a warpgroup's region
+  TailParams params;
+  uint8_t* blob = nullptr;   // device copy of the weight image
+};
+
 struct NasState {
+  std::vector<NasTail> tails;
+  std::vector<int> tail_of_op;       // index into tails, or -1
   std::vector<NasSegment> segs;
   std::vector<int> seg_of_op;        // index into segs, or -1: the op runs as its own kernel
   std::vector<hn_nas_op> ops;
@@ -905,6 +918,7 @@ void nas_state_free(NasState* s) {
   cudaFree(s->head_in);
   cudaFree(s->front_img);
   for (auto& sg : s->segs) cudaFree(sg.blob);
+  for (auto& tl : s->tails) cudaFree(tl.blob);
   delete s;
 }
 
@@ -1230,6 +1244,204 @@ static int seg_partition(hn_handle* h, NasState* st, const float* params) {
   return HN_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// warpgroup-per-patch tail launches (nas_tail.cuh)
+// ------------------------------------------------------------------------------------------------------------
+static int tail_pw_shape(const hn_nas_op& o) {
+  const int rows = o.hin * o.hin;
+  if (o.cin == 32 && o.cout == 32 && rows == 256) return 0;
+  if (o.cin == 32 && o.cout == 64 && rows == 64) return 1;
+  if (o.cin == 64 && o.cout == 64 && rows == 64) return 2;
+  if (o.cin == 64 && o.cout == 128 && rows == 16) return 3;
+  if (o.cin == 128 && o.cout == 128 && rows == 16) return 4;
+  return -1;
+}
+static int tail_dw_shape(const hn_nas_op& o) {
+  if (o.cin != o.cout || o.hout * o.stride != o.hin) return -1;
+  if (o.cin == 32 && o.hout == 16 && o.stride == 1) return 0;
+  if (o.cin == 32 && o.hout == 8 && o.stride == 2) return 1;
+  if (o.cin == 64 && o.hout == 8 && o.stride == 1) return 2;
+  if (o.cin == 64 && o.hout == 4 && o.stride == 2) return 3;
+  if (o.cin == 128 && o.hout == 4 && o.stride == 1) return 4;
+  return -1;
+}
+static int tail_op_shape(const hn_nas_op& o) {
+  switch (o.kind) {
+    case OP_PW: return tail_pw_shape(o);
+    case OP_DW: return (o.kernel == 3 || o.kernel == 5) ? tail_dw_shape(o) : -1;
+    case OP_MAXPOOL: { const int sh = tail_dw_shape(o); return (sh == 1 || sh == 3) ? sh : -1; }
+    default: return -1;
+  }
+}
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// Finalises tail launch [first, last]: buffer offsets, warpgroups per CTA, weight image on the device.
+static int tail_build(hn_handle* h, NasState* st, const float* params, int first, int last, NasTail& tl) {
+  size_t slot_bytes[3] = {0, 0, 0};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t r = off; off = seg_align(off + bytes, 128); return r; };
+  const int n = last - first + 1;
+  if (n > kTailMaxOps) return HN_ERR_UNSUPPORTED;
+  std::vector<size_t> w_off(n, 0), b_off(n, 0);
+  for (int i = first; i <= last; ++i) {
+    const hn_nas_op& o = st->ops[i];
+    const size_t in_b = static_cast<size_t>(o.cin) * o.hin * o.hin * 2, out_b = static_cast<size_t>(o.cout) * o.hout * o.hout * 2;
+    slot_bytes[o.src] = std::max(slot_bytes[o.src], in_b);
+    slot_bytes[o.dst] = std::max(slot_bytes[o.dst], out_b);
+    if (o.kind == OP_PW && o.res >= 0) slot_bytes[o.res] = std::max(slot_bytes[o.res], out_b);
+    const int k = i - first;
+    if (o.kind == OP_PW) { w_off[k] = take(static_cast<size_t>(o.cin) * o.cout * 2); b_off[k] = take(o.cout * 4); }
+    if (o.kind == OP_DW) { w_off[k] = take(static_cast<size_t>(o.kernel) * o.kernel * o.cin * 2); b_off[k] = take(o.cin * 2); }
+  }
+  const size_t blob_bytes = seg_align(off, 16);
+  size_t wg_stride = 0;
+  for (int k = 0; k < 3; ++k) { tl.slot_off[k] = static_cast<int>(wg_stride); wg_stride += seg_align(slot_bytes[k], 1024); }
+  // a partial accumulator tile reads up to 2 KB past the end of a source plane: the blob sits behind the last region, so
+  // those reads stay inside the CTA's shared memory
+  const size_t fixed = seg_align(std::max<size_t>(blob_bytes, 2048), 128) + 64 + 1024 /*alignment of the base*/;
+  int nwg = h->env.nas_tail_wg;
+  while (nwg >= 1 && nwg * wg_stride + fixed > 227 * 1024) --nwg;
+  if (nwg < 1) return HN_ERR_UNSUPPORTED;
+  tl.first = first; tl.last = last; tl.nwg = nwg;
+  TailParams& p = tl.params;
+  memset(&p, 0, sizeof(p));
+  p.wg_stride = static_cast<int>(wg_stride);
+  p.blob_off = static_cast<int>(nwg * wg_stride);
+  p.blob_bytes = static_cast<int>(blob_bytes);
+  p.bar_off = static_cast<int>(seg_align(p.blob_off + std::max<size_t>(blob_bytes, 2048), 128));
+  tl.smem = p.bar_off + 64 + 1024;
+  std::vector<uint8_t> blob(std::max<size_t>(blob_bytes, 16), 0);
+  for (int i = first; i <= last; ++i) {
+    const hn_nas_op& o = st->ops[i];
+    const int k = i - first;
+    TailOp& to = p.ops[k];
+    to.kind = o.kind == OP_PW ? TAIL_PW : (o.kind == OP_DW ? TAIL_DW : TAIL_POOL);
+    to.shape = tail_op_shape(o);
+    to.kernel = o.kernel; to.relu = o.relu;
+    to.src_off = tl.slot_off[o.src];
+    to.dst_off = tl.slot_off[o.dst];
+    to.res_off = (o.kind == OP_PW && o.res >= 0) ? tl.slot_off[o.res] : -1;
+    to.w_off = p.blob_off + static_cast<int>(w_off[k]);
+    to.b_off = p.blob_off + static_cast<int>(b_off[k]);
+    uint8_t* b = blob.data();
+    if (o.kind == OP_PW) {
+      // UMMA no-swizzle K-major image of W[cout][cin]: element (n, k) at (n / 8) * (cin * 16) + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+      uint16_t* w = reinterpret_cast<uint16_t*>(b + w_off[k]);
+      for (int nn = 0; nn < o.cout; ++nn)
+        for (int c = 0; c < o.cin; ++c)
+          w[((nn >> 3) * o.cin * 16 + (c >> 3) * 128 + (nn & 7) * 16 + (c & 7) * 2) >> 1] = f2h16(params[o.w_off + static_cast<size_t>(nn) * o.cin + c], 0);
+      memcpy(b + b_off[k], params + o.b_off, o.cout * 4);
+    } else if (o.kind == OP_DW) {
+      uint16_t* w = reinterpret_cast<uint16_t*>(b + w_off[k]);
+      for (int j = 0; j < o.kernel * o.kernel * o.cin; ++j) w[j] = f2h16(params[o.w_off + j], 0);
+      uint16_t* bb = reinterpret_cast<uint16_t*>(b + b_off[k]);
+      for (int j = 0; j < o.cin; ++j) bb[j] = f2h16(params[o.b_off + j], 0);
+    }
+  }
+  const hn_nas_op& of = st->ops[first];
+  p.in_off = tl.slot_off[of.src];
+  p.in_pix = of.hin * of.hin;
+  p.in_planes_log2 = ilog2(of.cin / 8);
+  HN_CUDA(cudaMalloc(&tl.blob, blob.size()));
+  HN_CUDA(cudaMemcpy(tl.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  p.blob = reinterpret_cast<const uint4*>(tl.blob);
+  return HN_OK;
+}
+
+// Covers every op between the front stage and the head with tail launches, or none at all (any unsupported op, bf16
+// activations, no fused depthwise front stage: the one-kernel-per-op path stays).
+static int tail_partition(hn_handle* h, NasState* st, const float* params) {
+  const int n_ops = static_cast<int>(st->ops.size());
+  st->tail_of_op.assign(n_ops, -1);
+  st->tails.clear();
+  if (!h->env.nas_tail || st->act_bf16 || !st->front_fdw || !h->env.nas_front) return HN_OK;
+  const int first = st->front_ops + 1, last = n_ops - 2;
+  if (first > last) return HN_OK;
+  for (int i = first; i <= last; ++i)
+    if (tail_op_shape(st->ops[i]) < 0) return HN_OK;
+  // every tensor an op of [a, b] reads must be the run's input or produced inside it, and only the last op's output may
+  // be read behind the run
+  auto closed = [&](int a, int b) {
+    bool defined[3] = {false, false, false};
+    defined[st->ops[a].src] = true;
+    for (int i = a; i <= b; ++i) {
+      const hn_nas_op& o = st->ops[i];
+      if (!defined[o.src] || (o.kind == OP_PW && o.res >= 0 && !defined[o.res])) return false;
+      defined[o.dst] = true;
+    }
+    bool inside[3] = {false, false, false};
+    for (int i = a; i <= b; ++i) inside[st->ops[i].dst] = true;
+    inside[st->ops[b].dst] = false;
+    for (int j = b + 1; j < n_ops; ++j) {
+      const hn_nas_op& o = st->ops[j];
+      if (inside[o.src] || (o.kind == OP_PW && o.res >= 0 && inside[o.res])) return false;
+      if (o.kind != OP_HEAD) inside[o.dst] = false;
+    }
+    return true;
+  };
+  std::vector<std::pair<int, int>> runs;
+  int start = first;
+  for (int i = first; i <= last; ++i) {
+    bool cut = i == last;
+    if (!cut && h->env.nas_tail_cut > 0) {
+      const hn_nas_op& o = st->ops[i];
+      const hn_nas_op& f = st->ops[start];
+      const bool boundary = (o.kind == OP_PW && !o.relu) || o.kind == OP_MAXPOOL || (o.kind == OP_PW && st->ops[i + 1].kind != OP_DW);
+      const size_t in_b = static_cast<size_t>(f.cin) * f.hin * f.hin, cut_b = static_cast<size_t>(o.cout) * o.hout * o.hout;
+      cut = boundary && cut_b * h->env.nas_tail_cut <= in_b && closed(start, i) && closed(i + 1, last);
+    }
+    if (cut) { runs.emplace_back(start, i); start = i + 1; }
+  }
+  for (auto& r : runs)
+    if (!closed(r.first, r.second)) return HN_OK;
+  for (auto& r : runs) {
+    NasTail tl;
+    const int rc = tail_build(h, st, params, r.first, r.second, tl);
+    if (rc != HN_OK) {
+      for (auto& t2 : st->tails) cudaFree(t2.blob);
+      st->tails.clear();
+      st->tail_of_op.assign(n_ops, -1);
+      return rc == HN_ERR_UNSUPPORTED ? HN_OK : rc;
+    }
+    for (int i = r.first; i <= r.second; ++i) st->tail_of_op[i] = static_cast<int>(st->tails.size());
+    st->tails.push_back(tl);
+  }
+  return HN_OK;
+}
+
+template <int NWG>
+static int launch_tail_cfg(const TailParams& p, size_t smem, int sm_count, cudaStream_t s) {
+  auto kern = nas_tail_kernel<NWG>;
+  static DeviceOnce attr_once;
+  if (attr_once.first_time()) HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (p.n <= 0) return HN_OK;
+  kern<<<std::min((p.n + NWG - 1) / NWG, sm_count), NWG * 128, smem, s>>>(p);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
+// ops [tl.first, end] of the run for n patches; `out` receives the NHWC output of op `end`
+static int launch_tail(const NasState* st, const NasTail& tl, const uint16_t* in, uint16_t* out, int n, int end, int sm_count, cudaStream_t s) {
+  TailParams p = tl.params;
+  const hn_nas_op& ol = st->ops[end];
+  p.in = in;
+  p.out = out;
+  p.n = n;
+  p.n_ops = end - tl.first + 1;
+  p.out_off = tl.slot_off[ol.dst];
+  p.out_pix = ol.hout * ol.hout;
+  p.out_planes_log2 = ilog2(ol.cout / 8);
+  switch (tl.nwg) {
+    case 1: return launch_tail_cfg<1>(p, tl.smem, sm_count, s);
+    case 2: return launch_tail_cfg<2>(p, tl.smem, sm_count, s);
+    case 3: return launch_tail_cfg<3>(p, tl.smem, sm_count, s);
+    default: return launch_tail_cfg<4>(p, tl.smem, sm_count, s);
+  }
+}
+
 template <int MINB, bool BF16>
 static int launch_seg_cfg(const SegParams& p, size_t smem, int sm_count, cudaStream_t s) {
   auto kern = nas_seg_kernel<MINB, BF16>;
@@ -1299,6 +1511,16 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
       for (int i = first; i <= last_op; ++i) {
         const hn_nas_op& o = st->ops[i];
         uint16_t* const op_out = (out_override && i == last_op && o.kind != OP_HEAD) ? out_override : (o.kind != OP_HEAD ? st->slot[o.dst] : nullptr);
+        if (st->tail_of_op[i] >= 0) {
+          // warpgroup-per-patch tail launch: ops [i, end]; a run that ends right before the head writes the head GEMM's rows
+          const NasTail& tl = st->tails[st->tail_of_op[i]];
+          const int end = std::min(tl.last, last_op);
+          const bool to_head = end == n_total - 2 && last_op == n_total - 1;
+          uint16_t* dst = to_head ? st->head_in + static_cast<size_t>(off) * st->head_k : ((out_override && end == last_op) ? out_override : st->slot[st->ops[end].dst]);
+          HN_TRY(launch_tail(st, tl, st->slot[st->ops[tl.first].src], dst, n, end, h->sm_count, s));
+          i = to_head ? end + 1 : end;
+          continue;
+        }
         if (st->seg_of_op[i] >= 0) {
           // patch-resident segment: ops [i, end] in one launch; a segment that ends right before the head writes the
           // head GEMM's input rows directly
@@ -1653,7 +1875,9 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
     if (rc != HN_OK) return fail(rc);
   }
   {
-    const int rc = seg_partition(h, st, params);
+    int rc = seg_partition(h, st, params);
+    if (rc != HN_OK) return fail(rc);
+    rc = tail_partition(h, st, params);
     if (rc != HN_OK) return fail(rc);
   }
   if (cudaDeviceSynchronize() != cudaSuccess) {
@@ -1717,10 +1941,15 @@ extern "C" int hn_nas_plan(hn_handle* h, int* out, int cap) {
     set_error("hn_nas_plan: no NAS net packed");
     return HN_ERR_STATE;
   }
-  const int n = static_cast<int>(h->nas->segs.size());
+  int n = static_cast<int>(h->nas->segs.size());
   for (int i = 0; i < n && i < cap && out; ++i) {
     const NasSegment& sg = h->nas->segs[i];
     out[4 * i] = sg.first; out[4 * i + 1] = sg.last; out[4 * i + 2] = sg.G; out[4 * i + 3] = sg.minb;
+  }
+  // warpgroup-per-patch tail launches: (first, last, patches in flight per CTA, 0)
+  for (const NasTail& tl : h->nas->tails) {
+    if (n < cap && out) { out[4 * n] = tl.first; out[4 * n + 1] = tl.last; out[4 * n + 2] = tl.nwg; out[4 * n + 3] = 0; }
+    ++n;
   }
   return n;
 }

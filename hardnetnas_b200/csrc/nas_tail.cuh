@@ -1,0 +1,352 @@
+// NAS descriptor net behind the fused front kernel as ONE launch per run of blocks ("tail"): every op between the
+// front stage (stem + first pointwise conv + stride-2 depthwise conv / max-pool, front_fused.cuh) and the head GEMM —
+// hardnetNAS/fbnet_building_blocks/fbnet_builder.py:455-570 (IRFBlock: pw -> dw -> pwl [+ x]) and :202-228 (Identity:
+// max-pool / 1x1 conv), stacked as in hardnetNAS/supernet_functions/model_supernet.py:70-85 — runs with the patch's
+// activations resident in shared memory.
+//
+// Unlike nas_seg_kernel (nas_resident.cuh: the whole CTA steps through the ops of a group of patches, every step pays a
+// CTA-wide issue -> commit -> wait -> tcgen05.ld -> store -> barrier latency) the unit of execution here is a WARPGROUP:
+// four warps own ONE patch from its load to its store, synchronise only among themselves (named barrier, own mbarrier,
+// own 128 tensor-memory columns) and the 3-4 warpgroups of a CTA run independently, so one warpgroup's latency-bound
+// tensor-core phase overlaps the others' CUDA-core depthwise phases without any hand-written pipeline. All shapes are
+// compile-time (the search space SEARCH_SPACE2 has five stage shapes behind the front kernel, lookup_table_builder.py:18-45),
+// so the per-thread work split needs no integer division and every thread of a warpgroup has exactly one depthwise item.
+//   PW    1x1 conv: tcgen05 GEMM on the activation IN PLACE (channel-planar [c / 8][pixel][c % 8] = UMMA no-swizzle
+//         K-major, SBO 128 B, LBO = plane pitch) against the resident weight image; epilogue TMEM -> bias (+ residual)
+//         (+ ReLU) -> fp16 -> planar destination. Maps with fewer than 128 pixels issue a full M = 128 tile and ignore the
+//         surplus accumulator rows.
+//   DW    depthwise k x k (3 | 5, stride 1 | 2) in packed half2 arithmetic, the summation order of dw_conv_smem_h2_kernel
+//         (nas.cu); a thread = 8 channels x one output column x a strip of SH rows, SH = C * hout^2 / 1024.
+//   POOL  MaxPool2d(3, 2, 1) with packed fp16 maxima.
+// fp16 activations, expansion-1 blocks without SE (every recorded architecture: wang2 / wang3 / wang4); anything else
+// keeps the one-kernel-per-op path (nas.cu).
+#pragma once
+
+#include "common.cuh"
+#include "nas_resident.cuh"
+#include "tc_conv.cuh"
+
+namespace hn {
+
+constexpr int kTailMaxOps = 24;
+constexpr int kTailMaxWG = 4;
+constexpr int kTailCols = 128;   // tensor-memory columns per warpgroup
+enum : int { TAIL_PW = 1, TAIL_DW = 2, TAIL_POOL = 3 };
+
+struct TailOp {
+  int kind;
+  int shape;                       // PW: 0..4 = (cin, cout, pixels) below; DW / POOL: 0..4 = (C, hout, stride) below
+  int kernel, relu;
+  int src_off, dst_off, res_off;   // byte offsets inside the warpgroup's buffer region (res: -1 = none)
+  int w_off, b_off;                // byte offsets from the aligned shared-memory base (weight blob)
+};
+
+struct TailParams {
+  const uint16_t* in;     // [n][in_pix][in_planes * 8] NHWC fp16 (input of ops[0])
+  uint16_t* out;          // [n][out_pix][out_planes * 8] NHWC fp16 (output of ops[n_ops - 1])
+  const uint4* blob;      // weight image in global memory (copied once per CTA)
+  int blob_off, blob_bytes;
+  int n, n_ops;
+  int wg_stride;          // bytes of one warpgroup's buffer region (region w starts at w * wg_stride)
+  int bar_off;            // kTailMaxWG mbarriers + tensor-memory slot
+  int in_off, in_pix, in_planes_log2;
+  int out_off, out_pix, out_planes_log2;
+  TailOp ops[kTailMaxOps];
+};
+
+#ifdef HN_TAIL_TRACE
+// Diagnostic build only: cycles thread 0 of warpgroup 0 of CTA 0 spends per op ([op]), load [32], store [33], total [34], patches [35]
+__device__ unsigned long long hn_tail_trace[64];
+#define HN_TAIL_T(var) const long long var = clock64()
+#define HN_TAIL_ACC(slot, t0) do { if (blockIdx.x == 0 && threadIdx.x == 0) hn_tail_trace[slot] += static_cast<unsigned long long>(clock64() - (t0)); } while (0)
+#else
+#define HN_TAIL_T(var) do { } while (0)
+#define HN_TAIL_ACC(slot, t0) do { } while (0)
+#endif
+
+__device__ __forceinline__ void tail_wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+// ---- depthwise conv / max-pool of one patch by the 128 threads of a warpgroup -------------------------------------------
+template <int K, int S, int C, int HOUT, bool POOL>
+__device__ __forceinline__ void tail_dw(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const uint8_t* __restrict__ s_w /*[K * K][C] fp16*/,
+                                        const uint8_t* __restrict__ s_b /*[C] fp16*/, int relu, int t) {
+  constexpr int HIN = HOUT * S, PLANES = C / 8, PAD = K >> 1;
+  constexpr int SH = PLANES * HOUT * HOUT / 128;
+  static_assert(SH >= 1 && SH * 128 == PLANES * HOUT * HOUT && HOUT % SH == 0, "one item per thread");
+  constexpr int STRIPS = HOUT / SH, NR = (SH - 1) * S + K;
+  const int ox = t % HOUT, ys = (t / HOUT) % STRIPS, plane = t / (HOUT * STRIPS);
+  const uint8_t* map = src + plane * (HIN * HIN * 16);
+  constexpr uint32_t kNinf = 0xFC00FC00u;
+  __half2 acc[SH][4];
+  if constexpr (POOL) {
+#pragma unroll
+    for (int j = 0; j < SH; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] = *reinterpret_cast<const __half2*>(&kNinf);
+  } else {
+    const uint4 b = *reinterpret_cast<const uint4*>(s_b + plane * 16);
+#pragma unroll
+    for (int j = 0; j < SH; ++j) {
+      acc[j][0] = *reinterpret_cast<const __half2*>(&b.x); acc[j][1] = *reinterpret_cast<const __half2*>(&b.y);
+      acc[j][2] = *reinterpret_cast<const __half2*>(&b.z); acc[j][3] = *reinterpret_cast<const __half2*>(&b.w);
+    }
+  }
+  const int iy0 = ys * SH * S - PAD;
+#pragma unroll 1
+  for (int kx = 0; kx < K; ++kx) {
+    const int ix = ox * S + kx - PAD;
+    const bool x_ok = ix >= 0 && ix < HIN;
+    uint4 wk[K];
+    if constexpr (!POOL) {
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) wk[ky] = *reinterpret_cast<const uint4*>(s_w + ((ky * K + kx) * C + plane * 8) * 2);
+    }
+    const uint8_t* col = map + ix * 16;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int iy = iy0 + r;
+      const bool ok = x_ok && iy >= 0 && iy < HIN;
+      uint4 xv = POOL ? make_uint4(kNinf, kNinf, kNinf, kNinf) : make_uint4(0u, 0u, 0u, 0u);
+      if (ok) xv = *reinterpret_cast<const uint4*>(col + iy * (HIN * 16));
+      const __half2 x[4] = {*reinterpret_cast<const __half2*>(&xv.x), *reinterpret_cast<const __half2*>(&xv.y),
+                            *reinterpret_cast<const __half2*>(&xv.z), *reinterpret_cast<const __half2*>(&xv.w)};
+#pragma unroll
+      for (int j = 0; j < SH; ++j) {
+        const int ky = r - j * S;            // compile-time after unrolling
+        if (ky >= 0 && ky < K) {
+          if constexpr (POOL) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[j][c] = __hmax2_nan(acc[j][c], x[c]);
+          } else {
+            const __half2 w[4] = {*reinterpret_cast<const __half2*>(&wk[ky].x), *reinterpret_cast<const __half2*>(&wk[ky].y),
+                                  *reinterpret_cast<const __half2*>(&wk[ky].z), *reinterpret_cast<const __half2*>(&wk[ky].w)};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[j][c] = __hfma2(x[c], w[c], acc[j][c]);
+          }
+        }
+      }
+    }
+  }
+  uint8_t* optr = dst + plane * (HOUT * HOUT * 16) + ((ys * SH) * HOUT + ox) * 16;
+  const __half2 hzero = __float2half2_rn(0.f);
+#pragma unroll
+  for (int j = 0; j < SH; ++j) {
+    if (!POOL && relu) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] = __hmax2(acc[j][c], hzero);
+    }
+    *reinterpret_cast<uint4*>(optr + j * (HOUT * 16)) =
+        make_uint4(*reinterpret_cast<const uint32_t*>(&acc[j][0]), *reinterpret_cast<const uint32_t*>(&acc[j][1]),
+                   *reinterpret_cast<const uint32_t*>(&acc[j][2]), *reinterpret_cast<const uint32_t*>(&acc[j][3]));
+  }
+}
+
+// ---- pointwise conv of one patch: MMAs issued by one lane of the warpgroup's first warp, epilogue by its four warps ------
+template <int CIN, int COUT, int ROWS>
+__device__ __forceinline__ void tail_pw(uint8_t* __restrict__ buf, uint32_t buf_addr, const uint8_t* __restrict__ sm, uint32_t base,
+                                        const TailOp& o, uint32_t tmem_wg, uint32_t bar, uint32_t& phase, int q, int lane) {
+  constexpr int TILES = (ROWS + kTileM - 1) / kTileM;
+  constexpr uint32_t PITCH = ROWS * 16;                  // plane pitch of the (equal-sized) source / destination maps
+  static_assert(TILES * COUT <= kTailCols && COUT % 32 == 0 && CIN % 16 == 0, "accumulators of one op fit the warpgroup's columns");
+  if (q == 0) {
+    tc_fence_after();
+    if (elect_one()) {
+      constexpr uint32_t a_hi = noswizzle_desc_hi(128);
+      constexpr uint32_t b_hi = noswizzle_desc_hi(CIN * 16);
+      constexpr uint32_t idesc = make_idesc_f16(kTileM, COUT, 0);
+      const uint32_t a_lo0 = noswizzle_desc_lo(buf_addr + o.src_off, PITCH);
+      const uint32_t b_lo0 = noswizzle_desc_lo(base + o.w_off, 128);
+#pragma unroll
+      for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+        for (int k = 0; k < CIN / 16; ++k)
+          umma_f16_w(tmem_wg + t * COUT, a_lo0 + t * (2048u >> 4) + k * ((2u * PITCH) >> 4), a_hi, b_lo0 + k * 16u, b_hi, idesc, k != 0);
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar, phase);
+  phase ^= 1u;
+  tc_fence_after();
+  const uint8_t* s_bias = sm + o.b_off;                  // [COUT] fp32
+  const bool has_res = o.res_off >= 0;
+#pragma unroll
+  for (int t = 0; t < TILES; ++t) {
+    if (t * kTileM + q * 32 < ROWS) {                    // warp-uniform
+      const int row = t * kTileM + q * 32 + lane;
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_wg + (static_cast<uint32_t>(q * 32) << 16) + t * COUT + c0, r);
+        tmem_ld_wait();
+        if (row < ROWS) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + (c0 + h * 8) * 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + (c0 + h * 8 + 4) * 4);
+            float v[8] = {__uint_as_float(r[8 * h]) + b0.x,     __uint_as_float(r[8 * h + 1]) + b0.y,
+                          __uint_as_float(r[8 * h + 2]) + b0.z, __uint_as_float(r[8 * h + 3]) + b0.w,
+                          __uint_as_float(r[8 * h + 4]) + b1.x, __uint_as_float(r[8 * h + 5]) + b1.y,
+                          __uint_as_float(r[8 * h + 6]) + b1.z, __uint_as_float(r[8 * h + 7]) + b1.w};
+            const uint32_t poff = static_cast<uint32_t>(c0 / 8 + h) * PITCH + row * 16;
+            if (has_res) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(buf + o.res_off + poff);
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                v[2 * e] += f.x;
+                v[2 * e + 1] += f.y;
+              }
+            }
+            uint4 ov;
+            if (o.relu)
+              ov = make_uint4(pack16_relu(v[0], v[1], 0), pack16_relu(v[2], v[3], 0), pack16_relu(v[4], v[5], 0), pack16_relu(v[6], v[7], 0));
+            else
+              ov = make_uint4(pack16(v[0], v[1], 0), pack16(v[2], v[3], 0), pack16(v[4], v[5], 0), pack16(v[6], v[7], 0));
+            *reinterpret_cast<uint4*>(buf + o.dst_off + poff) = ov;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NWG>
+__global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_constant__ TailParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw_addr);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2, q = warp & 3, t = threadIdx.x & 127;
+  const uint32_t bar0 = base + p.bar_off;
+  const uint32_t tmem_slot = bar0 + 8 * kTailMaxWG;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.bar_off + 8 * kTailMaxWG);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < NWG; ++i) mbar_init(bar0 + 8 * i, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  {
+    uint4* dst = reinterpret_cast<uint4*>(sm + p.blob_off);
+    for (int i = threadIdx.x; i < p.blob_bytes / 16; i += NWG * 128) dst[i] = __ldg(p.blob + i);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_wg = *tmem_slot_ptr + wg * kTailCols;
+  const uint32_t bar = bar0 + 8 * wg;
+  uint32_t phase = 0;
+  uint8_t* buf = sm + wg * p.wg_stride;
+  const uint32_t buf_addr = base + wg * p.wg_stride;
+  const size_t in_patch_bytes = static_cast<size_t>(p.in_pix) << (4 + p.in_planes_log2);
+  const size_t out_patch_bytes = static_cast<size_t>(p.out_pix) << (4 + p.out_planes_log2);
+
+  HN_TAIL_T(t_total);
+  for (int patch = blockIdx.x * NWG + wg; patch < p.n; patch += gridDim.x * NWG) {
+    HN_TAIL_T(t_load);
+    // ---- NHWC global -> channel-planar shared memory in 16-byte chunks: chunk i = (pixel block, plane, pixel % 8), so 8
+    // consecutive lanes write 128 contiguous bytes of one plane while the warp reads whole lines of the NHWC tensor ----
+    {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in) + static_cast<size_t>(patch) * in_patch_bytes;
+      const int pl2 = p.in_planes_log2;
+      const uint32_t pitch = static_cast<uint32_t>(p.in_pix) * 16;
+      const uint32_t dst0 = buf_addr + p.in_off;
+      const int chunks = p.in_pix << pl2;
+      for (int i = t; i < chunks; i += 128) {
+        const int blk = i >> (3 + pl2), rem = i & ((8 << pl2) - 1);
+        const int plane = rem >> 3, pixel = blk * 8 + (rem & 7);
+        cp_async_16(dst0 + plane * pitch + pixel * 16, src + ((static_cast<size_t>(pixel) << pl2) + plane) * 16);
+      }
+      cp_async_wait_all();
+    }
+    fence_proxy_async_smem();
+    tail_wg_sync(wg);
+    HN_TAIL_ACC(32, t_load);
+
+    for (int oi = 0; oi < p.n_ops; ++oi) {
+      const TailOp& o = p.ops[oi];
+      HN_TAIL_T(t_op);
+      if (o.kind == TAIL_PW) {
+        switch (o.shape) {
+          case 0: tail_pw<32, 32, 256>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
+          case 1: tail_pw<32, 64, 64>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
+          case 2: tail_pw<64, 64, 64>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
+          case 3: tail_pw<64, 128, 16>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
+          default: tail_pw<128, 128, 16>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
+        }
+      } else if (o.kind == TAIL_DW) {
+        const uint8_t* s = buf + o.src_off;
+        uint8_t* d = buf + o.dst_off;
+        const uint8_t* w = sm + o.w_off;
+        const uint8_t* b = sm + o.b_off;
+        if (o.kernel == 3) {
+          switch (o.shape) {
+            case 0: tail_dw<3, 1, 32, 16, false>(s, d, w, b, o.relu, t); break;
+            case 1: tail_dw<3, 2, 32, 8, false>(s, d, w, b, o.relu, t); break;
+            case 2: tail_dw<3, 1, 64, 8, false>(s, d, w, b, o.relu, t); break;
+            case 3: tail_dw<3, 2, 64, 4, false>(s, d, w, b, o.relu, t); break;
+            default: tail_dw<3, 1, 128, 4, false>(s, d, w, b, o.relu, t); break;
+          }
+        } else {
+          switch (o.shape) {
+            case 0: tail_dw<5, 1, 32, 16, false>(s, d, w, b, o.relu, t); break;
+            case 1: tail_dw<5, 2, 32, 8, false>(s, d, w, b, o.relu, t); break;
+            case 2: tail_dw<5, 1, 64, 8, false>(s, d, w, b, o.relu, t); break;
+            case 3: tail_dw<5, 2, 64, 4, false>(s, d, w, b, o.relu, t); break;
+            default: tail_dw<5, 1, 128, 4, false>(s, d, w, b, o.relu, t); break;
+          }
+        }
+      } else {
+        if (o.shape == 1) tail_dw<3, 2, 32, 8, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, 0, t);
+        else tail_dw<3, 2, 64, 4, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, 0, t);
+      }
+      // the next op reads this one's output through the other proxy (generic <-> tensor core) and may overwrite its
+      // accumulators / source buffer
+      tc_fence_before();
+      fence_proxy_async_smem();
+      tail_wg_sync(wg);
+      HN_TAIL_ACC(oi, t_op);
+    }
+
+    // ---- channel-planar shared memory -> NHWC global (same chunk order as the load) ----
+    HN_TAIL_T(t_store);
+    {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(patch) * out_patch_bytes;
+      const int pl2 = p.out_planes_log2;
+      const uint32_t pitch = static_cast<uint32_t>(p.out_pix) * 16;
+      const uint8_t* s0 = buf + p.out_off;
+      const int chunks = p.out_pix << pl2;
+      for (int i = t; i < chunks; i += 128) {
+        const int blk = i >> (3 + pl2), rem = i & ((8 << pl2) - 1);
+        const int plane = rem >> 3, pixel = blk * 8 + (rem & 7);
+        *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(pixel) << pl2) + plane) * 16) =
+            *reinterpret_cast<const uint4*>(s0 + plane * pitch + pixel * 16);
+      }
+    }
+    tail_wg_sync(wg);   // the buffers are free for the next patch's load
+    HN_TAIL_ACC(33, t_store);
+#ifdef HN_TAIL_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0) hn_tail_trace[35] += 1;
+#endif
+  }
+  HN_TAIL_ACC(34, t_total);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(*tmem_slot_ptr, 512);
+  }
+}
+
+}  // namespace hn
