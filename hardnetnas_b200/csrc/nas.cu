@@ -1285,6 +1285,10 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
   const int n = last - first + 1;
   if (n > kTailMaxOps) return HN_ERR_UNSUPPORTED;
   std::vector<size_t> w_off(n, 0), b_off(n, 0);
+  // constant tiles: "ones" A tile (K plane 0: columns 0, 1 = 1.0; K plane 1 = 2 KB of zeros, also the depthwise zero padding),
+  // 16 bytes of -inf (max-pool padding), 16 x 16 identity B tile
+  const size_t ones_off = take(4096 + 16);
+  const size_t eye_off = take(512);
   for (int i = first; i <= last; ++i) {
     const hn_nas_op& o = st->ops[i];
     const size_t in_b = static_cast<size_t>(o.cin) * o.hin * o.hin * 2, out_b = static_cast<size_t>(o.cout) * o.hout * o.hout * 2;
@@ -1292,7 +1296,7 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
     slot_bytes[o.dst] = std::max(slot_bytes[o.dst], out_b);
     if (o.kind == OP_PW && o.res >= 0) slot_bytes[o.res] = std::max(slot_bytes[o.res], out_b);
     const int k = i - first;
-    if (o.kind == OP_PW) { w_off[k] = take(static_cast<size_t>(o.cin) * o.cout * 2); b_off[k] = take(o.cout * 4); }
+    if (o.kind == OP_PW) w_off[k] = take(static_cast<size_t>(o.cin + 16) * o.cout * 2);   // + 16 K columns: bias as fp16 hi + lo
     if (o.kind == OP_DW) { w_off[k] = take(static_cast<size_t>(o.kernel) * o.kernel * o.cin * 2); b_off[k] = take(o.cin * 2); }
   }
   const size_t blob_bytes = seg_align(off, 16);
@@ -1308,11 +1312,23 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
   TailParams& p = tl.params;
   memset(&p, 0, sizeof(p));
   p.wg_stride = static_cast<int>(wg_stride);
+  p.op_base = first;
+  p.launch_id = static_cast<int>(st->tails.size()) & 7;
   p.blob_off = static_cast<int>(nwg * wg_stride);
   p.blob_bytes = static_cast<int>(blob_bytes);
   p.bar_off = static_cast<int>(seg_align(p.blob_off + std::max<size_t>(blob_bytes, 2048), 128));
   tl.smem = p.bar_off + 64 + 1024;
   std::vector<uint8_t> blob(std::max<size_t>(blob_bytes, 16), 0);
+  p.ones_off = p.blob_off + static_cast<int>(ones_off);
+  p.eye_off = p.blob_off + static_cast<int>(eye_off);
+  {
+    uint16_t* ones = reinterpret_cast<uint16_t*>(blob.data() + ones_off);   // A layout: (k / 8) * 2048 + row * 16 + (k % 8) * 2
+    for (int r = 0; r < 128; ++r) ones[r * 8] = ones[r * 8 + 1] = f2h16(1.0f, 0);
+    uint16_t* ninf = reinterpret_cast<uint16_t*>(blob.data() + ones_off + 4096);
+    for (int j = 0; j < 8; ++j) ninf[j] = 0xFC00;
+    uint16_t* eye = reinterpret_cast<uint16_t*>(blob.data() + eye_off);     // B layout: (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+    for (int d = 0; d < 16; ++d) eye[((d >> 3) * 256 + (d >> 3) * 128 + (d & 7) * 16 + (d & 7) * 2) >> 1] = f2h16(1.0f, 0);
+  }
   for (int i = first; i <= last; ++i) {
     const hn_nas_op& o = st->ops[i];
     const int k = i - first;
@@ -1327,12 +1343,18 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
     to.b_off = p.blob_off + static_cast<int>(b_off[k]);
     uint8_t* b = blob.data();
     if (o.kind == OP_PW) {
-      // UMMA no-swizzle K-major image of W[cout][cin]: element (n, k) at (n / 8) * (cin * 16) + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+      // UMMA no-swizzle K-major image of [W | bias_hi bias_lo 0...] = [cout][K' = cin + 16]:
+      // element (n, k) at (n / 8) * (K' * 16) + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+      const int kp = o.cin + 16;
       uint16_t* w = reinterpret_cast<uint16_t*>(b + w_off[k]);
-      for (int nn = 0; nn < o.cout; ++nn)
-        for (int c = 0; c < o.cin; ++c)
-          w[((nn >> 3) * o.cin * 16 + (c >> 3) * 128 + (nn & 7) * 16 + (c & 7) * 2) >> 1] = f2h16(params[o.w_off + static_cast<size_t>(nn) * o.cin + c], 0);
-      memcpy(b + b_off[k], params + o.b_off, o.cout * 4);
+      auto at = [&](int nn, int c) -> uint16_t& { return w[((nn >> 3) * kp * 16 + (c >> 3) * 128 + (nn & 7) * 16 + (c & 7) * 2) >> 1]; };
+      for (int nn = 0; nn < o.cout; ++nn) {
+        for (int c = 0; c < o.cin; ++c) at(nn, c) = f2h16(params[o.w_off + static_cast<size_t>(nn) * o.cin + c], 0);
+        const float bias = params[o.b_off + nn];
+        const __half hi = __float2half_rn(bias);
+        at(nn, o.cin) = *reinterpret_cast<const uint16_t*>(&hi);
+        at(nn, o.cin + 1) = f2h16(bias - __half2float(hi), 0);
+      }
     } else if (o.kind == OP_DW) {
       uint16_t* w = reinterpret_cast<uint16_t*>(b + w_off[k]);
       for (int j = 0; j < o.kernel * o.kernel * o.cin; ++j) w[j] = f2h16(params[o.w_off + j], 0);
@@ -1930,6 +1952,18 @@ extern "C" int hn_debug_seg_trace(unsigned long long* out256, int reset) {
   if (reset) {
     unsigned long long z[256] = {0};
     HN_CUDA(cudaMemcpyToSymbol(hn::hn_seg_trace, z, sizeof(z)));
+  }
+  return HN_OK;
+}
+#endif
+
+#ifdef HN_TAIL_TRACE
+extern "C" int hn_debug_tail_trace(unsigned long long* out128, int reset) {
+  HN_CUDA(cudaDeviceSynchronize());
+  HN_CUDA(cudaMemcpyFromSymbol(out128, hn::hn_tail_trace, 128 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[128] = {0};
+    HN_CUDA(cudaMemcpyToSymbol(hn::hn_tail_trace, z, sizeof(z)));
   }
   return HN_OK;
 }

@@ -12,8 +12,10 @@
 // compile-time (the search space SEARCH_SPACE2 has five stage shapes behind the front kernel, lookup_table_builder.py:18-45),
 // so the per-thread work split needs no integer division and every thread of a warpgroup has exactly one depthwise item.
 //   PW    1x1 conv: tcgen05 GEMM on the activation IN PLACE (channel-planar [c / 8][pixel][c % 8] = UMMA no-swizzle
-//         K-major, SBO 128 B, LBO = plane pitch) against the resident weight image; epilogue TMEM -> bias (+ residual)
-//         (+ ReLU) -> fp16 -> planar destination. Maps with fewer than 128 pixels issue a full M = 128 tile and ignore the
+//         K-major, SBO 128 B, LBO = plane pitch) against the resident weight image. Bias and residual are added BY THE
+//         TENSOR CORE (one K step of a constant "ones" tile against the bias stored as fp16 hi + lo behind the weights;
+//         16-channel slices of the block input against a 16 x 16 identity), so the epilogue is only TMEM -> [ReLU] -> fp16
+//         -> planar destination. Maps with fewer than 128 pixels issue a full M = 128 tile and ignore the
 //         surplus accumulator rows.
 //   DW    depthwise k x k (3 | 5, stride 1 | 2) in packed half2 arithmetic, the summation order of dw_conv_smem_h2_kernel
 //         (nas.cu); a thread = 8 channels x one output column x a strip of SH rows, SH = C * hout^2 / 1024.
@@ -49,14 +51,18 @@ struct TailParams {
   int n, n_ops;
   int wg_stride;          // bytes of one warpgroup's buffer region (region w starts at w * wg_stride)
   int bar_off;            // kTailMaxWG mbarriers + tensor-memory slot
+  int ones_off;           // constant A tile [128 rows][K = 16]: columns 0, 1 = 1.0 (its second K plane = 2 KB of zeros), then 16 B of -inf
+  int eye_off;            // constant B tile: 16 x 16 identity
   int in_off, in_pix, in_planes_log2;
   int out_off, out_pix, out_planes_log2;
+  int op_base, launch_id; // index of ops[0] in the program / of this launch in the plan (diagnostics)
   TailOp ops[kTailMaxOps];
 };
 
 #ifdef HN_TAIL_TRACE
-// Diagnostic build only: cycles thread 0 of warpgroup 0 of CTA 0 spends per op ([op]), load [32], store [33], total [34], patches [35]
-__device__ unsigned long long hn_tail_trace[64];
+// Diagnostic build only (-DHN_TAIL_TRACE): cycles thread 0 of CTA 0 spends per op ([program op index]; PW: [64 + op] up to
+// "accumulators complete"), load [32 + launch], store [40 + launch], total [48 + launch], patches [56 + launch]
+__device__ unsigned long long hn_tail_trace[128];
 #define HN_TAIL_T(var) const long long var = clock64()
 #define HN_TAIL_ACC(slot, t0) do { if (blockIdx.x == 0 && threadIdx.x == 0) hn_tail_trace[slot] += static_cast<unsigned long long>(clock64() - (t0)); } while (0)
 #else
@@ -69,7 +75,8 @@ __device__ __forceinline__ void tail_wg_sync(int wg) { asm volatile("bar.sync %0
 // ---- depthwise conv / max-pool of one patch by the 128 threads of a warpgroup -------------------------------------------
 template <int K, int S, int C, int HOUT, bool POOL>
 __device__ __forceinline__ void tail_dw(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const uint8_t* __restrict__ s_w /*[K * K][C] fp16*/,
-                                        const uint8_t* __restrict__ s_b /*[C] fp16*/, int relu, int t) {
+                                        const uint8_t* __restrict__ s_b /*[C] fp16*/, const uint8_t* __restrict__ s_pad /*16 B of padding value*/,
+                                        int relu, int t) {
   constexpr int HIN = HOUT * S, PLANES = C / 8, PAD = K >> 1;
   constexpr int SH = PLANES * HOUT * HOUT / 128;
   static_assert(SH >= 1 && SH * 128 == PLANES * HOUT * HOUT && HOUT % SH == 0, "one item per thread");
@@ -101,13 +108,12 @@ __device__ __forceinline__ void tail_dw(const uint8_t* __restrict__ src, uint8_t
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) wk[ky] = *reinterpret_cast<const uint4*>(s_w + ((ky * K + kx) * C + plane * 8) * 2);
     }
-    const uint8_t* col = map + ix * 16;
+    const uint8_t* col = map + ix * 16 + iy0 * (HIN * 16);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      const int iy = iy0 + r;
-      const bool ok = x_ok && iy >= 0 && iy < HIN;
-      uint4 xv = POOL ? make_uint4(kNinf, kNinf, kNinf, kNinf) : make_uint4(0u, 0u, 0u, 0u);
-      if (ok) xv = *reinterpret_cast<const uint4*>(col + iy * (HIN * 16));
+      // out-of-image taps read the padding vector (one select on the address; no predicated load, no register zeroing)
+      const bool ok = x_ok && static_cast<unsigned>(iy0 + r) < static_cast<unsigned>(HIN);
+      const uint4 xv = *reinterpret_cast<const uint4*>(ok ? col + r * (HIN * 16) : s_pad);
       const __half2 x[4] = {*reinterpret_cast<const __half2*>(&xv.x), *reinterpret_cast<const __half2*>(&xv.y),
                             *reinterpret_cast<const __half2*>(&xv.z), *reinterpret_cast<const __half2*>(&xv.w)};
 #pragma unroll
@@ -141,10 +147,19 @@ __device__ __forceinline__ void tail_dw(const uint8_t* __restrict__ src, uint8_t
   }
 }
 
+// {lo, hi} -> two fp16 values saturated to the largest finite value, one instruction
+__device__ __forceinline__ uint32_t tail_pack_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // ---- pointwise conv of one patch: MMAs issued by one lane of the warpgroup's first warp, epilogue by its four warps ------
 template <int CIN, int COUT, int ROWS>
 __device__ __forceinline__ void tail_pw(uint8_t* __restrict__ buf, uint32_t buf_addr, const uint8_t* __restrict__ sm, uint32_t base,
-                                        const TailOp& o, uint32_t tmem_wg, uint32_t bar, uint32_t& phase, int q, int lane) {
+                                        const TailOp& o, int ones_off, int eye_off, uint32_t tmem_wg, uint32_t bar, uint32_t& phase, int q, int lane,
+                                        int trace_op) {
+  HN_TAIL_T(t_pw);
   constexpr int TILES = (ROWS + kTileM - 1) / kTileM;
   constexpr uint32_t PITCH = ROWS * 16;                  // plane pitch of the (equal-sized) source / destination maps
   static_assert(TILES * COUT <= kTailCols && COUT % 32 == 0 && CIN % 16 == 0, "accumulators of one op fit the warpgroup's columns");
@@ -152,15 +167,31 @@ __device__ __forceinline__ void tail_pw(uint8_t* __restrict__ buf, uint32_t buf_
     tc_fence_after();
     if (elect_one()) {
       constexpr uint32_t a_hi = noswizzle_desc_hi(128);
-      constexpr uint32_t b_hi = noswizzle_desc_hi(CIN * 16);
+      constexpr uint32_t b_hi = noswizzle_desc_hi((CIN + 16) * 16);
       constexpr uint32_t idesc = make_idesc_f16(kTileM, COUT, 0);
       const uint32_t a_lo0 = noswizzle_desc_lo(buf_addr + o.src_off, PITCH);
       const uint32_t b_lo0 = noswizzle_desc_lo(base + o.w_off, 128);
+      const uint32_t ones_lo = noswizzle_desc_lo(base + ones_off, 2048);
 #pragma unroll
       for (int t = 0; t < TILES; ++t) {
 #pragma unroll
         for (int k = 0; k < CIN / 16; ++k)
           umma_f16_w(tmem_wg + t * COUT, a_lo0 + t * (2048u >> 4) + k * ((2u * PITCH) >> 4), a_hi, b_lo0 + k * 16u, b_hi, idesc, k != 0);
+        // + bias: a K step of the constant "ones" tile against the weight image's last 16 K columns (bias as fp16 hi + lo)
+        umma_f16_w(tmem_wg + t * COUT, ones_lo, a_hi, b_lo0 + (CIN / 16) * 16u, b_hi, idesc, 1u);
+      }
+      if (o.res_off >= 0) {
+        // + residual: 16-channel slices of the block input against a 16 x 16 identity (exact in the fp32 accumulator)
+        constexpr uint32_t e_hi = noswizzle_desc_hi(256);
+        constexpr uint32_t idesc16 = make_idesc_f16(kTileM, 16, 0);
+        const uint32_t r_lo0 = noswizzle_desc_lo(buf_addr + o.res_off, PITCH);
+        const uint32_t e_lo = noswizzle_desc_lo(base + eye_off, 128);
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+          for (int k = 0; k < COUT / 16; ++k)
+            umma_f16_w(tmem_wg + t * COUT + k * 16, r_lo0 + t * (2048u >> 4) + k * ((2u * PITCH) >> 4), a_hi, e_lo, e_hi, idesc16, 1u);
+        }
       }
       umma_commit(bar);
     }
@@ -169,47 +200,45 @@ __device__ __forceinline__ void tail_pw(uint8_t* __restrict__ buf, uint32_t buf_
   mbar_wait(bar, phase);
   phase ^= 1u;
   tc_fence_after();
-  const uint8_t* s_bias = sm + o.b_off;                  // [COUT] fp32
-  const bool has_res = o.res_off >= 0;
+  HN_TAIL_ACC(64 + trace_op, t_pw);
+  // epilogue: accumulator (bias and residual already inside) -> [ReLU] -> fp16 -> planar destination, two 32-column loads in flight
+  constexpr int CH = COUT / 32;                          // 32-column chunks per tile
+  constexpr int NCH = TILES * CH;
+  static_assert(NCH == 1 || NCH % 2 == 0, "chunks are processed in pairs");
+  constexpr int STEP = NCH >= 2 ? 2 : 1;
+  uint8_t* dstp = buf + o.dst_off;
+  const int relu = o.relu;
 #pragma unroll
-  for (int t = 0; t < TILES; ++t) {
-    if (t * kTileM + q * 32 < ROWS) {                    // warp-uniform
-      const int row = t * kTileM + q * 32 + lane;
+  for (int c = 0; c < NCH; c += STEP) {
+    const int t = c / CH;                                // a pair never straddles tiles (CH is 1 with two tiles, else even)
+    if ((TILES == 1 ? 0 : (c / CH) * kTileM) + q * 32 < ROWS) {   // warp-uniform
+      uint32_t r[STEP][32];
 #pragma unroll
-      for (int c0 = 0; c0 < COUT; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_wg + (static_cast<uint32_t>(q * 32) << 16) + t * COUT + c0, r);
-        tmem_ld_wait();
+      for (int u = 0; u < STEP; ++u) {
+        const int tt = (c + u) / CH, c0 = ((c + u) % CH) * 32;
+        tmem_ld32(tmem_wg + (static_cast<uint32_t>(q * 32) << 16) + tt * COUT + c0, r[u]);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < STEP; ++u) {
+        const int tt = (c + u) / CH, c0 = ((c + u) % CH) * 32;
+        const int row = tt * kTileM + q * 32 + lane;
         if (row < ROWS) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + (c0 + h * 8) * 4);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + (c0 + h * 8 + 4) * 4);
-            float v[8] = {__uint_as_float(r[8 * h]) + b0.x,     __uint_as_float(r[8 * h + 1]) + b0.y,
-                          __uint_as_float(r[8 * h + 2]) + b0.z, __uint_as_float(r[8 * h + 3]) + b0.w,
-                          __uint_as_float(r[8 * h + 4]) + b1.x, __uint_as_float(r[8 * h + 5]) + b1.y,
-                          __uint_as_float(r[8 * h + 6]) + b1.z, __uint_as_float(r[8 * h + 7]) + b1.w};
             const uint32_t poff = static_cast<uint32_t>(c0 / 8 + h) * PITCH + row * 16;
-            if (has_res) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(buf + o.res_off + poff);
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-                v[2 * e] += f.x;
-                v[2 * e + 1] += f.y;
-              }
-            }
+            const float* v = reinterpret_cast<const float*>(&r[u][8 * h]);
             uint4 ov;
-            if (o.relu)
+            if (relu)
               ov = make_uint4(pack16_relu(v[0], v[1], 0), pack16_relu(v[2], v[3], 0), pack16_relu(v[4], v[5], 0), pack16_relu(v[6], v[7], 0));
             else
-              ov = make_uint4(pack16(v[0], v[1], 0), pack16(v[2], v[3], 0), pack16(v[4], v[5], 0), pack16(v[6], v[7], 0));
-            *reinterpret_cast<uint4*>(buf + o.dst_off + poff) = ov;
+              ov = make_uint4(tail_pack_sat(v[0], v[1]), tail_pack_sat(v[2], v[3]), tail_pack_sat(v[4], v[5]), tail_pack_sat(v[6], v[7]));
+            *reinterpret_cast<uint4*>(dstp + poff) = ov;
           }
         }
       }
     }
+    (void)t;
   }
 }
 
@@ -271,51 +300,53 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
     }
     fence_proxy_async_smem();
     tail_wg_sync(wg);
-    HN_TAIL_ACC(32, t_load);
+    HN_TAIL_ACC(32 + p.launch_id, t_load);
 
     for (int oi = 0; oi < p.n_ops; ++oi) {
       const TailOp& o = p.ops[oi];
       HN_TAIL_T(t_op);
       if (o.kind == TAIL_PW) {
         switch (o.shape) {
-          case 0: tail_pw<32, 32, 256>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
-          case 1: tail_pw<32, 64, 64>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
-          case 2: tail_pw<64, 64, 64>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
-          case 3: tail_pw<64, 128, 16>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
-          default: tail_pw<128, 128, 16>(buf, buf_addr, sm, base, o, tmem_wg, bar, phase, q, lane); break;
+          case 0: tail_pw<32, 32, 256>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
+          case 1: tail_pw<32, 64, 64>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
+          case 2: tail_pw<64, 64, 64>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
+          case 3: tail_pw<64, 128, 16>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
+          default: tail_pw<128, 128, 16>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
         }
       } else if (o.kind == TAIL_DW) {
         const uint8_t* s = buf + o.src_off;
         uint8_t* d = buf + o.dst_off;
         const uint8_t* w = sm + o.w_off;
         const uint8_t* b = sm + o.b_off;
+        const uint8_t* pad0 = sm + p.ones_off + 2048;   // zeros
         if (o.kernel == 3) {
           switch (o.shape) {
-            case 0: tail_dw<3, 1, 32, 16, false>(s, d, w, b, o.relu, t); break;
-            case 1: tail_dw<3, 2, 32, 8, false>(s, d, w, b, o.relu, t); break;
-            case 2: tail_dw<3, 1, 64, 8, false>(s, d, w, b, o.relu, t); break;
-            case 3: tail_dw<3, 2, 64, 4, false>(s, d, w, b, o.relu, t); break;
-            default: tail_dw<3, 1, 128, 4, false>(s, d, w, b, o.relu, t); break;
+            case 0: tail_dw<3, 1, 32, 16, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 1: tail_dw<3, 2, 32, 8, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 2: tail_dw<3, 1, 64, 8, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 3: tail_dw<3, 2, 64, 4, false>(s, d, w, b, pad0, o.relu, t); break;
+            default: tail_dw<3, 1, 128, 4, false>(s, d, w, b, pad0, o.relu, t); break;
           }
         } else {
           switch (o.shape) {
-            case 0: tail_dw<5, 1, 32, 16, false>(s, d, w, b, o.relu, t); break;
-            case 1: tail_dw<5, 2, 32, 8, false>(s, d, w, b, o.relu, t); break;
-            case 2: tail_dw<5, 1, 64, 8, false>(s, d, w, b, o.relu, t); break;
-            case 3: tail_dw<5, 2, 64, 4, false>(s, d, w, b, o.relu, t); break;
-            default: tail_dw<5, 1, 128, 4, false>(s, d, w, b, o.relu, t); break;
+            case 0: tail_dw<5, 1, 32, 16, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 1: tail_dw<5, 2, 32, 8, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 2: tail_dw<5, 1, 64, 8, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 3: tail_dw<5, 2, 64, 4, false>(s, d, w, b, pad0, o.relu, t); break;
+            default: tail_dw<5, 1, 128, 4, false>(s, d, w, b, pad0, o.relu, t); break;
           }
         }
       } else {
-        if (o.shape == 1) tail_dw<3, 2, 32, 8, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, 0, t);
-        else tail_dw<3, 2, 64, 4, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, 0, t);
+        const uint8_t* padn = sm + p.ones_off + 4096;   // -inf
+        if (o.shape == 1) tail_dw<3, 2, 32, 8, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
+        else tail_dw<3, 2, 64, 4, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
       }
       // the next op reads this one's output through the other proxy (generic <-> tensor core) and may overwrite its
       // accumulators / source buffer
       tc_fence_before();
       fence_proxy_async_smem();
       tail_wg_sync(wg);
-      HN_TAIL_ACC(oi, t_op);
+      HN_TAIL_ACC(p.op_base + oi, t_op);
     }
 
     // ---- channel-planar shared memory -> NHWC global (same chunk order as the load) ----
@@ -334,12 +365,12 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
       }
     }
     tail_wg_sync(wg);   // the buffers are free for the next patch's load
-    HN_TAIL_ACC(33, t_store);
+    HN_TAIL_ACC(40 + p.launch_id, t_store);
 #ifdef HN_TAIL_TRACE
-    if (blockIdx.x == 0 && threadIdx.x == 0) hn_tail_trace[35] += 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) hn_tail_trace[56 + p.launch_id] += 1;
 #endif
   }
-  HN_TAIL_ACC(34, t_total);
+  HN_TAIL_ACC(48 + p.launch_id, t_total);
 
   tc_fence_before();
   __syncthreads();
