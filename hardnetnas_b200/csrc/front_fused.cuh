@@ -96,7 +96,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
                    int num_patches, int act_bf16, float norm_eps /*added to the std: 1e-7 HardNet, 1e-8 HardNetNeiMask*/,
                    const __grid_constant__ CUtensorMap tm_out /*PW2: [n * 1024, 32] as 32 x 32 boxes, 64B swizzle*/,
                    const float* __restrict__ dw_w = nullptr /*FDW 3 | 5: [k * k][32] folded*/, const float* __restrict__ dw_b = nullptr /*[32]*/,
-                   int dw_relu = 0) {
+                   int dw_relu = 0, int fdw_planar = 0 /*FDW output channel-planar [n][4][16][16][8] (the tail kernel's bulk-copy layout)*/) {
   static_assert(FDW == 0 || PW2, "the fused depthwise stage sits behind the pointwise variant");
   constexpr int NACT1 = FDW ? 1 : 2;   // stage-1 activation buffers
   extern __shared__ uint8_t smem_raw[];
@@ -675,7 +675,9 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
               }
             }
           }
-          uint16_t* optr = out + (static_cast<size_t>(patch) * 256 + (ys * SH) * 16 + ox) * 32 + plane * 8;
+          uint16_t* optr = fdw_planar ? out + static_cast<size_t>(patch) * 8192 + plane * 2048 + ((ys * SH) * 16 + ox) * 8
+                                      : out + (static_cast<size_t>(patch) * 256 + (ys * SH) * 16 + ox) * 32 + plane * 8;
+          const int orow = fdw_planar ? 16 * 8 : 16 * 32;
           const __half2 hzero = __float2half2_rn(0.f);
 #pragma unroll
           for (int j = 0; j < SH; ++j) {
@@ -683,7 +685,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) acc[j][qq] = __hmax2(acc[j][qq], hzero);
             }
-            *reinterpret_cast<uint4*>(optr + static_cast<size_t>(j) * 16 * 32) =
+            *reinterpret_cast<uint4*>(optr + j * orow) =
                 make_uint4(*reinterpret_cast<const uint32_t*>(&acc[j][0]), *reinterpret_cast<const uint32_t*>(&acc[j][1]),
                            *reinterpret_cast<const uint32_t*>(&acc[j][2]), *reinterpret_cast<const uint32_t*>(&acc[j][3]));
           }

@@ -20,10 +20,11 @@ int launch_l1(const void* patches, int in_dtype, uint16_t* out, const float* w, 
 int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUtensorMap& tm_out, const float* w1,
                     const float* bias1, const uint16_t* w2img, const float* bias2_host /*[32], HOST memory*/, int n, int act_bf16, int sm_count,
                     cudaStream_t s);
-// the same with the stride-2 depthwise conv (fdw = 3 | 5) or max-pool (fdw = 1) behind it: output [n][16][16][32] NHWC fp16
+// the same with the stride-2 depthwise conv (fdw = 3 | 5) or max-pool (fdw = 1) behind it: output [n][16][16][32] NHWC fp16, or
+// channel-planar [n][4][16][16][8] (out_planar: what the tail kernel bulk-copies)
 int launch_front_pw_dw(const void* patches, int in_dtype, uint16_t* out, const float* w1, const float* bias1, const uint16_t* w2img,
                        const float* bias2_host, int fdw, const float* dw_w, const float* dw_b, int dw_relu, int n, int sm_count,
-                       cudaStream_t s);
+                       cudaStream_t s, int out_planar = 0);
 void front_pw_weight_image(const uint16_t* w /*[32][32] 16-bit*/, std::vector<uint16_t>& img);
 }  // namespace hn
 

@@ -209,7 +209,7 @@ int launch_front_pw(const void* patches, int in_dtype, uint16_t* out, const CUte
 // (FDW variant of the front kernel): patches -> [n][16][16][32] NHWC fp16; the 64 KB/patch pointwise output stays on chip.
 int launch_front_pw_dw(const void* patches, int in_dtype, uint16_t* out, const float* w1, const float* bias1, const uint16_t* w2img,
                        const float* bias2_host, int fdw, const float* dw_w, const float* dw_b, int dw_relu, int n, int sm_count,
-                       cudaStream_t s) {
+                       cudaStream_t s, int out_planar) {
   static DeviceOnce attr_once;
   if (attr_once.first_time()) {
 #define HN_FDW_ATTR(T, F) HN_CUDA(cudaFuncSetAttribute(front_fused_kernel<T, true, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFfSmem)))
@@ -223,7 +223,7 @@ int launch_front_pw_dw(const void* patches, int in_dtype, uint16_t* out, const f
   static const CUtensorMap no_map = {};
   FfBias bias2;
   memcpy(bias2.v, bias2_host, sizeof(bias2.v));
-#define HN_FDW_LAUNCH(T, F) front_fused_kernel<T, true, F><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const T*>(patches), out, w1, bias1, w2, bias2, 0, n, 0, 0.f, no_map, dw_w, dw_b, dw_relu)
+#define HN_FDW_LAUNCH(T, F) front_fused_kernel<T, true, F><<<grid, kFfThreads, kFfSmem, s>>>(static_cast<const T*>(patches), out, w1, bias1, w2, bias2, 0, n, 0, 0.f, no_map, dw_w, dw_b, dw_relu, out_planar)
   if (in_dtype == HN_F32) {
     if (fdw == 1) HN_FDW_LAUNCH(float, 1); else if (fdw == 3) HN_FDW_LAUNCH(float, 3); else HN_FDW_LAUNCH(float, 5);
   } else {

@@ -881,7 +881,7 @@ struct NasTail {
   int first = 0, last = 0;   // op range [first, last]
   int nwg = 0;               // warpgroups (= patches in flight) per CTA
   size_t smem = 0;
-  int slot_off[3] = {0, 0, 0};   // byte offsets of the three program slots inside a warpgroup's region
+  std::vector<int> dst_off;  // per op of the run: byte offset of its output inside a warpgroup's region
   TailParams params;
   uint8_t* blob = nullptr;   // device copy of the weight image
 };
@@ -889,6 +889,7 @@ struct NasTail {
 struct NasState {
   std::vector<NasTail> tails;
   std::vector<int> tail_of_op;       // index into tails, or -1
+  int head_planar = 0;               // the last tail launch writes the head GEMM's rows channel-planar (head weight K order permuted)
   std::vector<NasSegment> segs;
   std::vector<int> seg_of_op;        // index into segs, or -1: the op runs as its own kernel
   std::vector<hn_nas_op> ops;
@@ -1279,7 +1280,6 @@ static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // Finalises tail launch [first, last]: buffer offsets, warpgroups per CTA, weight image on the device.
 static int tail_build(hn_handle* h, NasState* st, const float* params, int first, int last, NasTail& tl) {
-  size_t slot_bytes[3] = {0, 0, 0};
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t r = off; off = seg_align(off + bytes, 128); return r; };
   const int n = last - first + 1;
@@ -1289,22 +1289,58 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
   // 16 bytes of -inf (max-pool padding), 16 x 16 identity B tile
   const size_t ones_off = take(4096 + 16);
   const size_t eye_off = take(512);
+  size_t region_bytes = 0;
   for (int i = first; i <= last; ++i) {
     const hn_nas_op& o = st->ops[i];
     const size_t in_b = static_cast<size_t>(o.cin) * o.hin * o.hin * 2, out_b = static_cast<size_t>(o.cout) * o.hout * o.hout * 2;
-    slot_bytes[o.src] = std::max(slot_bytes[o.src], in_b);
-    slot_bytes[o.dst] = std::max(slot_bytes[o.dst], out_b);
-    if (o.kind == OP_PW && o.res >= 0) slot_bytes[o.res] = std::max(slot_bytes[o.res], out_b);
+    region_bytes = std::max(region_bytes, std::max(in_b, out_b));
     const int k = i - first;
     if (o.kind == OP_PW) w_off[k] = take(static_cast<size_t>(o.cin + 16) * o.cout * 2);   // + 16 K columns: bias as fp16 hi + lo
     if (o.kind == OP_DW) { w_off[k] = take(static_cast<size_t>(o.kernel) * o.kernel * o.cin * 2); b_off[k] = take(o.cin * 2); }
   }
   const size_t blob_bytes = seg_align(off, 16);
-  size_t wg_stride = 0;
-  for (int k = 0; k < 3; ++k) { tl.slot_off[k] = static_cast<int>(wg_stride); wg_stride += seg_align(slot_bytes[k], 1024); }
+  // Three equal regions per warpgroup, assigned by liveness (not by the program's slot ids): the run's input sits in
+  // region 0 and every output goes to a free region, region 0 last — so region 0 is idle from the last op that touches the
+  // input (or a tensor that had to share its region) onwards and the NEXT patch's input is bulk-copied into it while the
+  // remaining ops run.
+  region_bytes = seg_align(region_bytes, 1024);
+  const size_t wg_stride = 3 * region_bytes;
+  int slot_region[3] = {-1, -1, -1};
+  slot_region[st->ops[first].src] = 0;
+  std::vector<int> src_r(n, 0), dst_r(n, 0), res_r(n, -1);
+  int last_r0 = -1;
+  auto live_after = [&](int slot, int i) {      // is the tensor in program slot `slot` read by an op of the run behind op i?
+    for (int j = i + 1; j <= last; ++j) {
+      const hn_nas_op& o = st->ops[j];
+      if (o.src == slot || (o.kind == OP_PW && o.res == slot)) return true;
+      if (o.dst == slot) return false;
+    }
+    return false;
+  };
+  for (int i = first; i <= last; ++i) {
+    const hn_nas_op& o = st->ops[i];
+    const int k = i - first;
+    src_r[k] = slot_region[o.src];
+    res_r[k] = (o.kind == OP_PW && o.res >= 0) ? slot_region[o.res] : -1;
+    if (src_r[k] < 0 || (o.kind == OP_PW && o.res >= 0 && res_r[k] < 0)) return HN_ERR_UNSUPPORTED;
+    bool busy[3] = {false, false, false};
+    busy[src_r[k]] = true;
+    if (res_r[k] >= 0) busy[res_r[k]] = true;
+    for (int sl = 0; sl < 3; ++sl)
+      if (sl != o.dst && slot_region[sl] >= 0 && live_after(sl, i)) busy[slot_region[sl]] = true;
+    int r = -1;
+    for (int cand : {1, 2, 0})
+      if (!busy[cand]) { r = cand; break; }
+    if (r < 0) return HN_ERR_UNSUPPORTED;
+    dst_r[k] = r;
+    for (int sl = 0; sl < 3; ++sl)
+      if (sl != o.dst && slot_region[sl] == r) slot_region[sl] = -1;   // a dead tensor's region was reused
+    slot_region[o.dst] = r;
+    if (src_r[k] == 0 || res_r[k] == 0 || r == 0) last_r0 = k;
+  }
   // a partial accumulator tile reads up to 2 KB past the end of a source plane: the blob sits behind the last region, so
   // those reads stay inside the CTA's shared memory
-  const size_t fixed = seg_align(std::max<size_t>(blob_bytes, 2048), 128) + 64 + 1024 /*alignment of the base*/;
+  const size_t fixed = seg_align(std::max<size_t>(blob_bytes, 2048), 128) + 128 + 1024 /*alignment of the base*/;
   int nwg = h->env.nas_tail_wg;
   while (nwg >= 1 && nwg * wg_stride + fixed > 227 * 1024) --nwg;
   if (nwg < 1) return HN_ERR_UNSUPPORTED;
@@ -1312,12 +1348,14 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
   TailParams& p = tl.params;
   memset(&p, 0, sizeof(p));
   p.wg_stride = static_cast<int>(wg_stride);
+  p.prefetch_after = last_r0 < n - 1 ? last_r0 : -1;
   p.op_base = first;
   p.launch_id = static_cast<int>(st->tails.size()) & 7;
   p.blob_off = static_cast<int>(nwg * wg_stride);
   p.blob_bytes = static_cast<int>(blob_bytes);
   p.bar_off = static_cast<int>(seg_align(p.blob_off + std::max<size_t>(blob_bytes, 2048), 128));
-  tl.smem = p.bar_off + 64 + 1024;
+  tl.smem = p.bar_off + 128 + 1024;
+  tl.dst_off.assign(n, 0);
   std::vector<uint8_t> blob(std::max<size_t>(blob_bytes, 16), 0);
   p.ones_off = p.blob_off + static_cast<int>(ones_off);
   p.eye_off = p.blob_off + static_cast<int>(eye_off);
@@ -1336,9 +1374,10 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
     to.kind = o.kind == OP_PW ? TAIL_PW : (o.kind == OP_DW ? TAIL_DW : TAIL_POOL);
     to.shape = tail_op_shape(o);
     to.kernel = o.kernel; to.relu = o.relu;
-    to.src_off = tl.slot_off[o.src];
-    to.dst_off = tl.slot_off[o.dst];
-    to.res_off = (o.kind == OP_PW && o.res >= 0) ? tl.slot_off[o.res] : -1;
+    to.src_off = static_cast<int>(src_r[k] * region_bytes);
+    to.dst_off = static_cast<int>(dst_r[k] * region_bytes);
+    to.res_off = res_r[k] >= 0 ? static_cast<int>(res_r[k] * region_bytes) : -1;
+    tl.dst_off[k] = to.dst_off;
     to.w_off = p.blob_off + static_cast<int>(w_off[k]);
     to.b_off = p.blob_off + static_cast<int>(b_off[k]);
     uint8_t* b = blob.data();
@@ -1363,9 +1402,8 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
     }
   }
   const hn_nas_op& of = st->ops[first];
-  p.in_off = tl.slot_off[of.src];
-  p.in_pix = of.hin * of.hin;
-  p.in_planes_log2 = ilog2(of.cin / 8);
+  p.in_off = 0;
+  p.in_bytes = of.cin * of.hin * of.hin * 2;
   HN_CUDA(cudaMalloc(&tl.blob, blob.size()));
   HN_CUDA(cudaMemcpy(tl.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   p.blob = reinterpret_cast<const uint4*>(tl.blob);
@@ -1446,14 +1484,16 @@ static int launch_tail_cfg(const TailParams& p, size_t smem, int sm_count, cudaS
 }
 
 // ops [tl.first, end] of the run for n patches; `out` receives the NHWC output of op `end`
-static int launch_tail(const NasState* st, const NasTail& tl, const uint16_t* in, uint16_t* out, int n, int end, int sm_count, cudaStream_t s) {
+static int launch_tail(const NasState* st, const NasTail& tl, const uint16_t* in, uint16_t* out, int out_planar, int n, int end, int sm_count,
+                       cudaStream_t s) {
   TailParams p = tl.params;
   const hn_nas_op& ol = st->ops[end];
   p.in = in;
   p.out = out;
   p.n = n;
   p.n_ops = end - tl.first + 1;
-  p.out_off = tl.slot_off[ol.dst];
+  p.out_off = tl.dst_off[end - tl.first];
+  p.out_planar = out_planar;
   p.out_pix = ol.hout * ol.hout;
   p.out_planes_log2 = ilog2(ol.cout / 8);
   switch (tl.nwg) {
@@ -1507,7 +1547,8 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
         if (st->front_fdw && nxt <= last_op) {
           HN_TRY(launch_front_pw_dw(src, in_dtype, st->slot[on.dst], st->params + o0.w_off, st->params + o0.b_off, st->front_img,
                                     st->front_bias2, st->front_fdw, on.kind == OP_DW ? st->params + on.w_off : nullptr,
-                                    on.kind == OP_DW ? st->params + on.b_off : nullptr, on.relu, n, h->sm_count, s));
+                                    on.kind == OP_DW ? st->params + on.b_off : nullptr, on.relu, n, h->sm_count, s,
+                                    /*out_planar=*/nxt < last_op && st->tail_of_op[nxt + 1] >= 0));
           first = nxt + 1;
         } else {
         const bool sub = h->env.nas_front_chunk > 0 && h->env.nas_front_chunk < n && nxt <= last_op && nxt < static_cast<int>(st->ops.size()) - 1 &&
@@ -1539,7 +1580,10 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
           const int end = std::min(tl.last, last_op);
           const bool to_head = end == n_total - 2 && last_op == n_total - 1;
           uint16_t* dst = to_head ? st->head_in + static_cast<size_t>(off) * st->head_k : ((out_override && end == last_op) ? out_override : st->slot[st->ops[end].dst]);
-          HN_TRY(launch_tail(st, tl, st->slot[st->ops[tl.first].src], dst, n, end, h->sm_count, s));
+          // channel-planar interchange towards the next tail launch / the head GEMM (permuted weight K order); a run that
+          // stops here (activation dump) writes NHWC like every per-op kernel
+          const int planar = (to_head && st->head_planar) || (end == tl.last && last_op > end && st->tail_of_op[end + 1] >= 0);
+          HN_TRY(launch_tail(st, tl, st->slot[st->ops[tl.first].src], dst, planar, n, end, h->sm_count, s));
           i = to_head ? end + 1 : end;
           continue;
         }
@@ -1901,6 +1945,23 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
     if (rc != HN_OK) return fail(rc);
     rc = tail_partition(h, st, params);
     if (rc != HN_OK) return fail(rc);
+    if (!st->tails.empty() && st->tails.back().last == n_ops - 2) {
+      // the last tail launch bulk-stores its channel-planar output as the head GEMM's input row: K index
+      // plane * (pix * 8) + pixel * 8 + c % 8 instead of NHWC's pixel * C + c
+      const hn_nas_op& oh = ops[n_ops - 1];
+      const int pix = oh.kernel * oh.kernel, C = oh.cin;
+      std::vector<uint16_t> wh(static_cast<size_t>(128) * st->head_k);
+      for (int nn = 0; nn < 128; ++nn)
+        for (int px = 0; px < pix; ++px)
+          for (int c = 0; c < C; ++c)
+            wh[static_cast<size_t>(nn) * st->head_k + (c >> 3) * (pix * 8) + px * 8 + (c & 7)] =
+                f2h16(params[oh.w_off + static_cast<size_t>(nn) * st->head_k + px * C + c], bf);
+      if (cudaMemcpy(st->w16 + st->w16_off[n_ops - 1], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("hn_pack_nas: head weight upload failed");
+        return fail(HN_ERR_CUDA);
+      }
+      st->head_planar = 1;
+    }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) {
     set_error("hn_pack_nas: cudaDeviceSynchronize failed");

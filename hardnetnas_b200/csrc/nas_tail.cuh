@@ -44,17 +44,20 @@ struct TailOp {
 };
 
 struct TailParams {
-  const uint16_t* in;     // [n][in_pix][in_planes * 8] NHWC fp16 (input of ops[0])
-  uint16_t* out;          // [n][out_pix][out_planes * 8] NHWC fp16 (output of ops[n_ops - 1])
+  const uint16_t* in;     // [n][in_planes][in_pix][8] channel-planar fp16 (input of ops[0]): one bulk copy per patch
+  uint16_t* out;          // output of ops[n_ops - 1]: channel-planar like the input (out_planar: another tail launch or the head
+                          // GEMM, whose weight K order is permuted to match, reads it) or [n][out_pix][out_planes * 8] NHWC
   const uint4* blob;      // weight image in global memory (copied once per CTA)
   int blob_off, blob_bytes;
   int n, n_ops;
   int wg_stride;          // bytes of one warpgroup's buffer region (region w starts at w * wg_stride)
-  int bar_off;            // kTailMaxWG mbarriers + tensor-memory slot
+  int bar_off;            // 2 x kTailMaxWG mbarriers ("accumulators complete", "input landed") + tensor-memory slot
   int ones_off;           // constant A tile [128 rows][K = 16]: columns 0, 1 = 1.0 (its second K plane = 2 KB of zeros), then 16 B of -inf
   int eye_off;            // constant B tile: 16 x 16 identity
-  int in_off, in_pix, in_planes_log2;
-  int out_off, out_pix, out_planes_log2;
+  int in_off, in_bytes;   // the patch's input region / bytes
+  int out_off, out_pix, out_planes_log2, out_planar;
+  int prefetch_after;     // index of the last op that touches the input region: the NEXT patch's input is requested right
+                          // behind it and lands while the remaining ops run (-1: the region is busy to the end)
   int op_base, launch_id; // index of ops[0] in the program / of this launch in the plan (diagnostics)
   TailOp ops[kTailMaxOps];
 };
@@ -252,12 +255,15 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const int wg = warp >> 2, q = warp & 3, t = threadIdx.x & 127;
   const uint32_t bar0 = base + p.bar_off;
-  const uint32_t tmem_slot = bar0 + 8 * kTailMaxWG;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.bar_off + 8 * kTailMaxWG);
+  const uint32_t tmem_slot = bar0 + 16 * kTailMaxWG;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.bar_off + 16 * kTailMaxWG);
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < NWG; ++i) mbar_init(bar0 + 8 * i, 1);
+      for (int i = 0; i < NWG; ++i) {
+        mbar_init(bar0 + 8 * i, 1);
+        mbar_init(bar0 + 8 * (kTailMaxWG + i), 1);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -274,31 +280,29 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_wg = *tmem_slot_ptr + wg * kTailCols;
   const uint32_t bar = bar0 + 8 * wg;
-  uint32_t phase = 0;
+  const uint32_t bar_ld = bar0 + 8 * (kTailMaxWG + wg);
+  uint32_t phase = 0, phase_ld = 0;
   uint8_t* buf = sm + wg * p.wg_stride;
   const uint32_t buf_addr = base + wg * p.wg_stride;
-  const size_t in_patch_bytes = static_cast<size_t>(p.in_pix) << (4 + p.in_planes_log2);
   const size_t out_patch_bytes = static_cast<size_t>(p.out_pix) << (4 + p.out_planes_log2);
+  const int stride = gridDim.x * NWG;
+  const int pf = (p.prefetch_after >= 0 && p.prefetch_after < p.n_ops - 1) ? p.prefetch_after : -1;
+  // one thread of the warpgroup requests a patch's input: ONE bulk copy (the global layout is the shared-memory layout)
+  auto request = [&](int patch) {
+    mbar_arrive_expect_tx(bar_ld, static_cast<uint32_t>(p.in_bytes));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_addr + p.in_off),
+                 "l"(reinterpret_cast<const uint8_t*>(p.in) + static_cast<size_t>(patch) * p.in_bytes), "r"(static_cast<uint32_t>(p.in_bytes)), "r"(bar_ld)
+                 : "memory");
+  };
 
   HN_TAIL_T(t_total);
-  for (int patch = blockIdx.x * NWG + wg; patch < p.n; patch += gridDim.x * NWG) {
+  int patch = blockIdx.x * NWG + wg;
+  if (t == 0 && patch < p.n) request(patch);
+  for (; patch < p.n; patch += stride) {
     HN_TAIL_T(t_load);
-    // ---- NHWC global -> channel-planar shared memory in 16-byte chunks: chunk i = (pixel block, plane, pixel % 8), so 8
-    // consecutive lanes write 128 contiguous bytes of one plane while the warp reads whole lines of the NHWC tensor ----
-    {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in) + static_cast<size_t>(patch) * in_patch_bytes;
-      const int pl2 = p.in_planes_log2;
-      const uint32_t pitch = static_cast<uint32_t>(p.in_pix) * 16;
-      const uint32_t dst0 = buf_addr + p.in_off;
-      const int chunks = p.in_pix << pl2;
-      for (int i = t; i < chunks; i += 128) {
-        const int blk = i >> (3 + pl2), rem = i & ((8 << pl2) - 1);
-        const int plane = rem >> 3, pixel = blk * 8 + (rem & 7);
-        cp_async_16(dst0 + plane * pitch + pixel * 16, src + ((static_cast<size_t>(pixel) << pl2) + plane) * 16);
-      }
-      cp_async_wait_all();
-    }
-    fence_proxy_async_smem();
+    if (t == 0) bulk_wait_read<0>();   // the previous patch's output store has left shared memory
+    mbar_wait(bar_ld, phase_ld);
+    phase_ld ^= 1u;
     tail_wg_sync(wg);
     HN_TAIL_ACC(32 + p.launch_id, t_load);
 
@@ -346,12 +350,21 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
       tc_fence_before();
       fence_proxy_async_smem();
       tail_wg_sync(wg);
+      if (oi == pf && t == 0 && patch + stride < p.n) request(patch + stride);
       HN_TAIL_ACC(p.op_base + oi, t_op);
     }
 
-    // ---- channel-planar shared memory -> NHWC global (same chunk order as the load) ----
     HN_TAIL_T(t_store);
-    {
+    if (p.out_planar) {
+      // one bulk store (every thread fenced its writes towards the async proxy behind the last op)
+      if (t == 0) {
+        bulk_store(reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(patch) * out_patch_bytes, buf_addr + p.out_off,
+                   static_cast<uint32_t>(out_patch_bytes));
+        bulk_commit();
+      }
+    } else {
+      // channel-planar shared memory -> NHWC global in 16-byte chunks: chunk i = (pixel block, plane, pixel % 8), so 8
+      // consecutive lanes read 128 contiguous bytes of one plane while the warp writes whole lines of the NHWC tensor
       uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + static_cast<size_t>(patch) * out_patch_bytes;
       const int pl2 = p.out_planes_log2;
       const uint32_t pitch = static_cast<uint32_t>(p.out_pix) * 16;
@@ -363,8 +376,12 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
         *reinterpret_cast<uint4*>(dst + ((static_cast<size_t>(pixel) << pl2) + plane) * 16) =
             *reinterpret_cast<const uint4*>(s0 + plane * pitch + pixel * 16);
       }
+      tail_wg_sync(wg);   // the output region may be overwritten by the next patch
     }
-    tail_wg_sync(wg);   // the buffers are free for the next patch's load
+    if (pf < 0 && t == 0 && patch + stride < p.n) {
+      bulk_wait_read<0>();             // the output may share the input region
+      request(patch + stride);
+    }
     HN_TAIL_ACC(40 + p.launch_id, t_store);
 #ifdef HN_TAIL_TRACE
     if (blockIdx.x == 0 && threadIdx.x == 0) hn_tail_trace[56 + p.launch_id] += 1;
@@ -372,6 +389,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
   }
   HN_TAIL_ACC(48 + p.launch_id, t_total);
 
+  if (t == 0) bulk_wait_all<0>();      // output stores still read this CTA's shared memory
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
