@@ -1287,7 +1287,7 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
   std::vector<size_t> w_off(n, 0), b_off(n, 0);
   // constant tiles: "ones" A tile (K plane 0: columns 0, 1 = 1.0; K plane 1 = 2 KB of zeros, also the depthwise zero padding),
   // 16 bytes of -inf (max-pool padding), 16 x 16 identity B tile
-  const size_t ones_off = take(4096 + 16);
+  const size_t ones_off = take(4096 + 128);
   const size_t eye_off = take(512);
   size_t region_bytes = 0;
   for (int i = first; i <= last; ++i) {
@@ -1363,7 +1363,7 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
     uint16_t* ones = reinterpret_cast<uint16_t*>(blob.data() + ones_off);   // A layout: (k / 8) * 2048 + row * 16 + (k % 8) * 2
     for (int r = 0; r < 128; ++r) ones[r * 8] = ones[r * 8 + 1] = f2h16(1.0f, 0);
     uint16_t* ninf = reinterpret_cast<uint16_t*>(blob.data() + ones_off + 4096);
-    for (int j = 0; j < 8; ++j) ninf[j] = 0xFC00;
+    for (int j = 0; j < 64; ++j) ninf[j] = 0xFC00;
     uint16_t* eye = reinterpret_cast<uint16_t*>(blob.data() + eye_off);     // B layout: (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
     for (int d = 0; d < 16; ++d) eye[((d >> 3) * 256 + (d >> 3) * 128 + (d & 7) * 16 + (d & 7) * 2) >> 1] = f2h16(1.0f, 0);
   }
@@ -1400,6 +1400,14 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
       uint16_t* bb = reinterpret_cast<uint16_t*>(b + b_off[k]);
       for (int j = 0; j < o.cin; ++j) bb[j] = f2h16(params[o.b_off + j], 0);
     }
+  }
+  // a pointwise conv whose output is read only by the stride-2 depthwise conv / max-pool right behind it writes the parity layout
+  for (int i = first + 1; i <= last; ++i) {
+    const hn_nas_op& o = st->ops[i];
+    const hn_nas_op& pr = st->ops[i - 1];
+    if ((o.kind == OP_DW || o.kind == OP_MAXPOOL) && o.stride == 2 && (o.hin == 16 || o.hin == 8) && pr.kind == OP_PW && pr.dst == o.src &&
+        !live_after(o.src, i))
+      p.ops[i - first].parity = p.ops[i - 1 - first].parity = 1;
   }
   const hn_nas_op& of = st->ops[first];
   p.in_off = 0;
@@ -1493,6 +1501,7 @@ static int launch_tail(const NasState* st, const NasTail& tl, const uint16_t* in
   p.n = n;
   p.n_ops = end - tl.first + 1;
   p.out_off = tl.dst_off[end - tl.first];
+  if (ol.kind == OP_PW) p.ops[end - tl.first].parity = 0;   // a run cut short behind the producer (activation dump) stores plain rows
   p.out_planar = out_planar;
   p.out_pix = ol.hout * ol.hout;
   p.out_planes_log2 = ilog2(ol.cout / 8);

@@ -41,6 +41,7 @@ struct TailOp {
   int kernel, relu;
   int src_off, dst_off, res_off;   // byte offsets inside the warpgroup's buffer region (res: -1 = none)
   int w_off, b_off;                // byte offsets from the aligned shared-memory base (weight blob)
+  int parity;                      // PW: the output is written in / DW, POOL (stride 2): the input is read from the "parity layout" below
 };
 
 struct TailParams {
@@ -73,16 +74,29 @@ __device__ unsigned long long hn_tail_trace[128];
 #define HN_TAIL_ACC(slot, t0) do { } while (0)
 #endif
 
+// A map whose only reader is a stride-2 depthwise conv / max-pool is laid out by its producer so that the taps of
+// consecutive output columns are consecutive 16-byte slots (plain rows give a 32-byte lane stride = two shared-memory
+// wavefronts per quarter warp): a row holds its even columns, then its odd columns. 16-wide rows rotate the odd half by four
+// slots so that the producer's eight consecutive pixels still hit eight different bank groups; 8-wide rows swap the halves
+// on every second row pair so that two strips of one quarter warp (rows 2 apart) use different halves.
+template <int W>
+__device__ __forceinline__ int tail_parity_slot(int y, int x) {
+  static_assert(W == 16 || W == 8, "maps read at stride 2 behind the front stage");
+  if constexpr (W == 16) return y * 16 + ((x & 1) ? 8 + (((x >> 1) + 4) & 7) : (x >> 1));
+  else return y * 8 + ((((x & 1) ^ (y >> 1)) & 1) << 2) + (x >> 1);
+}
+
 __device__ __forceinline__ void tail_wg_sync(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
 
 // ---- depthwise conv / max-pool of one patch by the 128 threads of a warpgroup -------------------------------------------
-template <int K, int S, int C, int HOUT, bool POOL>
+template <int K, int S, int C, int HOUT, bool POOL, bool PAR = false>
 __device__ __forceinline__ void tail_dw(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const uint8_t* __restrict__ s_w /*[K * K][C] fp16*/,
                                         const uint8_t* __restrict__ s_b /*[C] fp16*/, const uint8_t* __restrict__ s_pad /*16 B of padding value*/,
                                         int relu, int t) {
   constexpr int HIN = HOUT * S, PLANES = C / 8, PAD = K >> 1;
   constexpr int SH = PLANES * HOUT * HOUT / 128;
   static_assert(SH >= 1 && SH * 128 == PLANES * HOUT * HOUT && HOUT % SH == 0, "one item per thread");
+  static_assert(!PAR || S == 2, "the parity layout serves stride-2 readers");
   constexpr int STRIPS = HOUT / SH, NR = (SH - 1) * S + K;
   const int ox = t % HOUT, ys = (t / HOUT) % STRIPS, plane = t / (HOUT * STRIPS);
   const uint8_t* map = src + plane * (HIN * HIN * 16);
@@ -111,12 +125,18 @@ __device__ __forceinline__ void tail_dw(const uint8_t* __restrict__ src, uint8_t
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) wk[ky] = *reinterpret_cast<const uint4*>(s_w + ((ky * K + kx) * C + plane * 8) * 2);
     }
-    const uint8_t* col = map + ix * 16 + iy0 * (HIN * 16);
+    // out-of-image taps read a padding vector (one select on the address; no predicated load, no register zeroing); its bank
+    // group is one the in-image lanes of the quarter warp cannot use (they end at group 7 on the left border, start at 0 on the right)
+    const uint8_t* pad = s_pad + ((S == 1 && kx < PAD) ? 112 : 0);
+    int xs = ix;
+    if constexpr (PAR && HIN == 16) xs = (ix & 1) ? 8 + (((ix >> 1) + 4) & 7) : (ix >> 1);
+    const uint8_t* col = map + xs * 16 + iy0 * (HIN * 16);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      // out-of-image taps read the padding vector (one select on the address; no predicated load, no register zeroing)
       const bool ok = x_ok && static_cast<unsigned>(iy0 + r) < static_cast<unsigned>(HIN);
-      const uint4 xv = *reinterpret_cast<const uint4*>(ok ? col + r * (HIN * 16) : s_pad);
+      const uint8_t* ptr = col + r * (HIN * 16);
+      if constexpr (PAR && HIN == 8) ptr = map + tail_parity_slot<8>(iy0 + r, ix) * 16;
+      const uint4 xv = *reinterpret_cast<const uint4*>(ok ? ptr : pad);
       const __half2 x[4] = {*reinterpret_cast<const __half2*>(&xv.x), *reinterpret_cast<const __half2*>(&xv.y),
                             *reinterpret_cast<const __half2*>(&xv.z), *reinterpret_cast<const __half2*>(&xv.w)};
 #pragma unroll
@@ -226,10 +246,13 @@ __device__ __forceinline__ void tail_pw(uint8_t* __restrict__ buf, uint32_t buf_
       for (int u = 0; u < STEP; ++u) {
         const int tt = (c + u) / CH, c0 = ((c + u) % CH) * 32;
         const int row = tt * kTileM + q * 32 + lane;
+        int slot = row;
+        if constexpr (ROWS == 256) { if (o.parity) slot = tail_parity_slot<16>(row >> 4, row & 15); }
+        if constexpr (ROWS == 64) { if (o.parity) slot = tail_parity_slot<8>(row >> 3, row & 7); }
         if (row < ROWS) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            const uint32_t poff = static_cast<uint32_t>(c0 / 8 + h) * PITCH + row * 16;
+            const uint32_t poff = static_cast<uint32_t>(c0 / 8 + h) * PITCH + slot * 16;
             const float* v = reinterpret_cast<const float*>(&r[u][8 * h]);
             uint4 ov;
             if (relu)
@@ -326,24 +349,29 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
         if (o.kernel == 3) {
           switch (o.shape) {
             case 0: tail_dw<3, 1, 32, 16, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 1: tail_dw<3, 2, 32, 8, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 1: if (o.parity) tail_dw<3, 2, 32, 8, false, true>(s, d, w, b, pad0, o.relu, t); else tail_dw<3, 2, 32, 8, false>(s, d, w, b, pad0, o.relu, t); break;
             case 2: tail_dw<3, 1, 64, 8, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 3: tail_dw<3, 2, 64, 4, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 3: if (o.parity) tail_dw<3, 2, 64, 4, false, true>(s, d, w, b, pad0, o.relu, t); else tail_dw<3, 2, 64, 4, false>(s, d, w, b, pad0, o.relu, t); break;
             default: tail_dw<3, 1, 128, 4, false>(s, d, w, b, pad0, o.relu, t); break;
           }
         } else {
           switch (o.shape) {
             case 0: tail_dw<5, 1, 32, 16, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 1: tail_dw<5, 2, 32, 8, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 1: if (o.parity) tail_dw<5, 2, 32, 8, false, true>(s, d, w, b, pad0, o.relu, t); else tail_dw<5, 2, 32, 8, false>(s, d, w, b, pad0, o.relu, t); break;
             case 2: tail_dw<5, 1, 64, 8, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 3: tail_dw<5, 2, 64, 4, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 3: if (o.parity) tail_dw<5, 2, 64, 4, false, true>(s, d, w, b, pad0, o.relu, t); else tail_dw<5, 2, 64, 4, false>(s, d, w, b, pad0, o.relu, t); break;
             default: tail_dw<5, 1, 128, 4, false>(s, d, w, b, pad0, o.relu, t); break;
           }
         }
       } else {
         const uint8_t* padn = sm + p.ones_off + 4096;   // -inf
-        if (o.shape == 1) tail_dw<3, 2, 32, 8, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
-        else tail_dw<3, 2, 64, 4, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
+        if (o.shape == 1) {
+          if (o.parity) tail_dw<3, 2, 32, 8, true, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
+          else tail_dw<3, 2, 32, 8, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
+        } else {
+          if (o.parity) tail_dw<3, 2, 64, 4, true, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
+          else tail_dw<3, 2, 64, 4, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
+        }
       }
       // the next op reads this one's output through the other proxy (generic <-> tensor core) and may overwrite its
       // accumulators / source buffer
