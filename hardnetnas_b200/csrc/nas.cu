@@ -1458,7 +1458,7 @@ static int tail_partition(hn_handle* h, NasState* st, const float* params) {
       const hn_nas_op& f = st->ops[start];
       const bool boundary = (o.kind == OP_PW && !o.relu) || o.kind == OP_MAXPOOL || (o.kind == OP_PW && st->ops[i + 1].kind != OP_DW);
       const size_t in_b = static_cast<size_t>(f.cin) * f.hin * f.hin, cut_b = static_cast<size_t>(o.cout) * o.hout * o.hout;
-      cut = boundary && cut_b * h->env.nas_tail_cut <= in_b && closed(start, i) && closed(i + 1, last);
+      cut = boundary && cut_b * h->env.nas_tail_cut <= in_b && last - i >= h->env.nas_tail_minops && closed(start, i) && closed(i + 1, last);
     }
     if (cut) { runs.emplace_back(start, i); start = i + 1; }
   }

@@ -30,6 +30,9 @@
 
 namespace hn {
 
+#ifndef HN_TAIL_UNROLL_LIMIT
+#define HN_TAIL_UNROLL_LIMIT 0
+#endif
 constexpr int kTailMaxOps = 24;
 constexpr int kTailMaxWG = 4;
 constexpr int kTailCols = 128;   // tensor-memory columns per warpgroup
@@ -116,7 +119,10 @@ __device__ __forceinline__ void tail_dw(const uint8_t* __restrict__ src, uint8_t
     }
   }
   const int iy0 = ys * SH * S - PAD;
-#pragma unroll 1
+  // small bodies are unrolled over kx (the loads of the next column overlap this column's arithmetic); the 5x5 stride-1
+  // strip of 8 rows stays rolled: its body alone is ~220 instructions and the kernel's hot code must stay i-cache sized
+  constexpr int UNR = (SH * K * K * 4 <= HN_TAIL_UNROLL_LIMIT) ? K : 1;
+#pragma unroll UNR
   for (int kx = 0; kx < K; ++kx) {
     const int ix = ox * S + kx - PAD;
     const bool x_ok = ix >= 0 && ix < HIN;
