@@ -168,6 +168,55 @@ def test_front_kernel_with_and_without_the_fused_depthwise_stage(arch, monkeypat
     assert (outs[0].float() - outs[1].float()).abs().max().item() <= 5e-4
 
 
-def test_default_plan_is_one_kernel_per_op():
+def test_default_plan_is_front_tail_head():
+    """fp16 nets of expansion-1 blocks (every recorded architecture) run as fused front kernel + warpgroup-per-patch tail
+    launches (csrc/nas_tail.cuh) + head GEMM; HN_NAS_TAIL=0, bf16 activations and wider blocks keep one kernel per op."""
     net, _, _ = build("wang2")
-    assert net.resident_plan() == []
+    assert net.resident_plan() == [(3, 9, 4, 0), (10, 15, 4, 0)]       # (first op, last op, patches in flight per CTA, 0)
+    assert build("wang3")[0].resident_plan() == [(3, 8, 3, 0)]
+    assert build("mixed_se")[0].resident_plan() == []
+    assert build("wang2", act_dtype="bf16")[0].resident_plan() == []
+
+
+@pytest.mark.parametrize("arch,env", [("wang2", {}), ("wang2", {"HN_NAS_TAIL_CUT": "0"}), ("wang2", {"HN_NAS_TAIL_WG": "1"}),
+                                      ("wang2", {"HN_NAS_TAIL_MINOPS": "1", "HN_NAS_TAIL_CUT": "1"}), ("wang3", {}),
+                                      ("wang3", {"HN_NAS_TAIL_MINOPS": "1"}), ("wang4", {}), ("wang4", {"HN_NAS_TAIL_WG": "3", "HN_NAS_TAIL_MINOPS": "1"})])
+def test_tail_kernel_plans(arch, env, monkeypatch):
+    """The tail kernel (IRFBlock pw -> dw -> pwl [+x] and Identity pool / 1x1 conv, fbnet_builder.py:455-570, :202-228, with the
+    patch resident in shared memory; bias and residual added by the tensor core; parity layout in front of stride-2 readers)
+    under several launch plans: descriptors against the oracle for a ragged batch that leaves warpgroups without a patch, and
+    the output of EVERY op (runs cut short behind any op, incl. behind a parity-layout producer) against the one-kernel-per-op
+    path and, at the block boundaries, against the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    net, ops, sd = build(arch, chunk_patches=64, head_rows=256)
+    plan = net.resident_plan()
+    assert plan and all(minb == 0 and 1 <= nwg <= 4 and b >= a for a, b, nwg, minb in plan), plan
+    x = synth.make_patches(203, 6, edge_cases=False)
+    ref, feats = nas_oracle.nas_forward(x, ops, sd, return_features=True)
+    max_abs, cos = _cmp(net(x.cuda()), ref)
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (arch, plan, max_abs, cos)
+    prog = net.compile_program()
+    n_ops = len(prog.ops)
+    xs = x[:37].cuda()
+    outs = [net.forward_op(xs, i).float().cpu() for i in range(n_ops - 1)]
+    for stage, op_index in enumerate(prog.stage_end):
+        r = feats[stage][:37]
+        assert (outs[op_index].permute(0, 3, 1, 2) - r).abs().max().item() <= 6e-3 * r.abs().max().item() + 1e-5, (arch, stage, op_index)
+    monkeypatch.setenv("HN_NAS_TAIL", "0")
+    base, _, _ = build(arch, chunk_patches=64, head_rows=256)
+    assert base.resident_plan() == []
+    for i in range(n_ops - 1):
+        b = base.forward_op(xs, i).float().cpu()
+        assert (outs[i] - b).abs().max().item() <= 6e-3 * b.abs().max().item() + 1e-5, (arch, plan, i)
+    assert (net(x.cuda()).float() - base(x.cuda()).float()).abs().max().item() <= 5e-4
+
+
+def test_tail_kernel_uint8_and_batch_one():
+    net, ops, sd = build("wang2")
+    x8 = (synth.make_patches(150, 8, edge_cases=False) * 255).round().to(torch.uint8)
+    max_abs, cos = _cmp(net(x8.cuda()), nas_oracle.nas_forward(x8.float(), ops, sd))
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+    x = synth.make_patches(1, 3, edge_cases=False)
+    max_abs, cos = _cmp(net(x.cuda()), nas_oracle.nas_forward(x, ops, sd))
+    assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
