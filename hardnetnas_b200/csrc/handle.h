@@ -46,7 +46,7 @@ struct HnEnv {
   int nas_tail_cut = 2;       // HN_NAS_TAIL_CUT: start a new tail launch at a block boundary whose tensor is <= 1/cut of the launch's
                               // input (smaller maps -> smaller buffers -> more warpgroups per SM); 0 = one launch for the whole tail
   int nas_tail_minops = 4;    // HN_NAS_TAIL_MINOPS: ... and only if at least this many ops remain behind the cut
-  int nas_tail_wg = 4;        // HN_NAS_TAIL_WG: cap on warpgroups (patches in flight) per CTA
+  int nas_tail_wg = 6;        // HN_NAS_TAIL_WG: cap on warpgroups (patches in flight) per CTA
   char nas_split[128] = {0};  // HN_NAS_SPLIT="i,j,...": explicit op indices that start a new segment (overrides the heuristic)
 };
 

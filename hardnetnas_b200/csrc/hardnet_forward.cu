@@ -436,7 +436,7 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
     h->env.nas_tail = flag("HN_NAS_TAIL", true);
     h->env.nas_tail_cut = std::max(0, num("HN_NAS_TAIL_CUT", 2));
     h->env.nas_tail_minops = std::max(1, num("HN_NAS_TAIL_MINOPS", 4));
-    h->env.nas_tail_wg = std::min(4, std::max(1, num("HN_NAS_TAIL_WG", 4)));
+    h->env.nas_tail_wg = std::min(6, std::max(1, num("HN_NAS_TAIL_WG", 6)));
     if (const char* e = getenv("HN_NAS_SPLIT")) snprintf(h->env.nas_split, sizeof(h->env.nas_split), "%s", e);
   }
   {

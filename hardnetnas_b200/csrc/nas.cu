@@ -1340,8 +1340,11 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
   }
   // a partial accumulator tile reads up to 2 KB past the end of a source plane: the blob sits behind the last region, so
   // those reads stay inside the CTA's shared memory
-  const size_t fixed = seg_align(std::max<size_t>(blob_bytes, 2048), 128) + 128 + 1024 /*alignment of the base*/;
-  int nwg = h->env.nas_tail_wg;
+  const size_t fixed = seg_align(std::max<size_t>(blob_bytes, 2048), 128) + 256 + 1024 /*alignment of the base*/;
+  // five or six warpgroups (64 tensor-memory columns and 85 registers each) only for runs without 16 x 16 maps
+  bool big_map = false;
+  for (int i = first; i <= last; ++i) big_map = big_map || st->ops[i].hin == 16;
+  int nwg = std::min(h->env.nas_tail_wg, big_map ? 4 : kTailMaxWG);
   while (nwg >= 1 && nwg * wg_stride + fixed > 227 * 1024) --nwg;
   if (nwg < 1) return HN_ERR_UNSUPPORTED;
   tl.first = first; tl.last = last; tl.nwg = nwg;
@@ -1354,7 +1357,7 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
   p.blob_off = static_cast<int>(nwg * wg_stride);
   p.blob_bytes = static_cast<int>(blob_bytes);
   p.bar_off = static_cast<int>(seg_align(p.blob_off + std::max<size_t>(blob_bytes, 2048), 128));
-  tl.smem = p.bar_off + 128 + 1024;
+  tl.smem = p.bar_off + 256 + 1024;
   tl.dst_off.assign(n, 0);
   std::vector<uint8_t> blob(std::max<size_t>(blob_bytes, 16), 0);
   p.ones_off = p.blob_off + static_cast<int>(ones_off);
@@ -1509,7 +1512,9 @@ static int launch_tail(const NasState* st, const NasTail& tl, const uint16_t* in
     case 1: return launch_tail_cfg<1>(p, tl.smem, sm_count, s);
     case 2: return launch_tail_cfg<2>(p, tl.smem, sm_count, s);
     case 3: return launch_tail_cfg<3>(p, tl.smem, sm_count, s);
-    default: return launch_tail_cfg<4>(p, tl.smem, sm_count, s);
+    case 4: return launch_tail_cfg<4>(p, tl.smem, sm_count, s);
+    case 5: return launch_tail_cfg<5>(p, tl.smem, sm_count, s);
+    default: return launch_tail_cfg<6>(p, tl.smem, sm_count, s);
   }
 }
 

@@ -34,8 +34,8 @@ namespace hn {
 #define HN_TAIL_UNROLL_LIMIT 0
 #endif
 constexpr int kTailMaxOps = 24;
-constexpr int kTailMaxWG = 4;
-constexpr int kTailCols = 128;   // tensor-memory columns per warpgroup
+constexpr int kTailMaxWG = 6;    // 768 threads: 85 registers per thread
+constexpr int kTailBars = 8;     // mbarrier slots per kind
 enum : int { TAIL_PW = 1, TAIL_DW = 2, TAIL_POOL = 3 };
 
 struct TailOp {
@@ -184,93 +184,104 @@ __device__ __forceinline__ uint32_t tail_pack_sat(float lo, float hi) {
 }
 
 // ---- pointwise conv of one patch: MMAs issued by one lane of the warpgroup's first warp, epilogue by its four warps ------
-template <int CIN, int COUT, int ROWS>
+// COLS = the warpgroup's tensor-memory columns (128 with up to four warpgroups per CTA, 64 with five or six): an op whose
+// accumulators need more (C_out = 128) runs as two column passes of N = 64, one after the other.
+template <int CIN, int COUT, int ROWS, int COLS, int STEP_MAX>
 __device__ __forceinline__ void tail_pw(uint8_t* __restrict__ buf, uint32_t buf_addr, const uint8_t* __restrict__ sm, uint32_t base,
-                                        const TailOp& o, int ones_off, int eye_off, uint32_t tmem_wg, uint32_t bar, uint32_t& phase, int q, int lane,
-                                        int trace_op) {
+                                        const TailOp& o, int ones_off, int eye_off, uint32_t tmem_wg, uint32_t bar, uint32_t& phase, int wg,
+                                        int q, int lane, int trace_op) {
   HN_TAIL_T(t_pw);
   constexpr int TILES = (ROWS + kTileM - 1) / kTileM;
   constexpr uint32_t PITCH = ROWS * 16;                  // plane pitch of the (equal-sized) source / destination maps
-  static_assert(TILES * COUT <= kTailCols && COUT % 32 == 0 && CIN % 16 == 0, "accumulators of one op fit the warpgroup's columns");
-  if (q == 0) {
-    tc_fence_after();
-    if (elect_one()) {
-      constexpr uint32_t a_hi = noswizzle_desc_hi(128);
-      constexpr uint32_t b_hi = noswizzle_desc_hi((CIN + 16) * 16);
-      constexpr uint32_t idesc = make_idesc_f16(kTileM, COUT, 0);
-      const uint32_t a_lo0 = noswizzle_desc_lo(buf_addr + o.src_off, PITCH);
-      const uint32_t b_lo0 = noswizzle_desc_lo(base + o.w_off, 128);
-      const uint32_t ones_lo = noswizzle_desc_lo(base + ones_off, 2048);
-#pragma unroll
-      for (int t = 0; t < TILES; ++t) {
-#pragma unroll
-        for (int k = 0; k < CIN / 16; ++k)
-          umma_f16_w(tmem_wg + t * COUT, a_lo0 + t * (2048u >> 4) + k * ((2u * PITCH) >> 4), a_hi, b_lo0 + k * 16u, b_hi, idesc, k != 0);
-        // + bias: a K step of the constant "ones" tile against the weight image's last 16 K columns (bias as fp16 hi + lo)
-        umma_f16_w(tmem_wg + t * COUT, ones_lo, a_hi, b_lo0 + (CIN / 16) * 16u, b_hi, idesc, 1u);
-      }
-      if (o.res_off >= 0) {
-        // + residual: 16-channel slices of the block input against a 16 x 16 identity (exact in the fp32 accumulator)
-        constexpr uint32_t e_hi = noswizzle_desc_hi(256);
-        constexpr uint32_t idesc16 = make_idesc_f16(kTileM, 16, 0);
-        const uint32_t r_lo0 = noswizzle_desc_lo(buf_addr + o.res_off, PITCH);
-        const uint32_t e_lo = noswizzle_desc_lo(base + eye_off, 128);
-#pragma unroll
-        for (int t = 0; t < TILES; ++t) {
-#pragma unroll
-          for (int k = 0; k < COUT / 16; ++k)
-            umma_f16_w(tmem_wg + t * COUT + k * 16, r_lo0 + t * (2048u >> 4) + k * ((2u * PITCH) >> 4), a_hi, e_lo, e_hi, idesc16, 1u);
-        }
-      }
-      umma_commit(bar);
-    }
-    __syncwarp();
-  }
-  mbar_wait(bar, phase);
-  phase ^= 1u;
-  tc_fence_after();
-  HN_TAIL_ACC(64 + trace_op, t_pw);
-  // epilogue: accumulator (bias and residual already inside) -> [ReLU] -> fp16 -> planar destination, two 32-column loads in flight
-  constexpr int CH = COUT / 32;                          // 32-column chunks per tile
-  constexpr int NCH = TILES * CH;
-  static_assert(NCH == 1 || NCH % 2 == 0, "chunks are processed in pairs");
-  constexpr int STEP = NCH >= 2 ? 2 : 1;
+  constexpr int NPASS = (TILES * COUT + COLS - 1) / COLS;
+  constexpr int NP = COUT / NPASS;                       // output channels per pass = N of its MMAs
+  static_assert(NP * NPASS == COUT && TILES * NP <= COLS && NP % 32 == 0 && CIN % 16 == 0, "accumulators of one pass fit the warpgroup's columns");
   uint8_t* dstp = buf + o.dst_off;
   const int relu = o.relu;
 #pragma unroll
-  for (int c = 0; c < NCH; c += STEP) {
-    const int t = c / CH;                                // a pair never straddles tiles (CH is 1 with two tiles, else even)
-    if ((TILES == 1 ? 0 : (c / CH) * kTileM) + q * 32 < ROWS) {   // warp-uniform
-      uint32_t r[STEP][32];
+  for (int np = 0; np < NPASS; ++np) {
+    if (np > 0) {                                         // every warp has drained the previous pass from tensor memory
+      tc_fence_before();
+      tail_wg_sync(wg);
+    }
+    if (q == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t a_hi = noswizzle_desc_hi(128);
+        constexpr uint32_t b_hi = noswizzle_desc_hi((CIN + 16) * 16);
+        constexpr uint32_t idesc = make_idesc_f16(kTileM, NP, 0);
+        const uint32_t a_lo0 = noswizzle_desc_lo(buf_addr + o.src_off, PITCH);
+        // weight image rows [np * NP, (np + 1) * NP): 8-row groups are (CIN + 16) * 16 bytes apart
+        const uint32_t b_lo0 = noswizzle_desc_lo(base + o.w_off + np * (NP / 8) * ((CIN + 16) * 16), 128);
+        const uint32_t ones_lo = noswizzle_desc_lo(base + ones_off, 2048);
 #pragma unroll
-      for (int u = 0; u < STEP; ++u) {
-        const int tt = (c + u) / CH, c0 = ((c + u) % CH) * 32;
-        tmem_ld32(tmem_wg + (static_cast<uint32_t>(q * 32) << 16) + tt * COUT + c0, r[u]);
+        for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+          for (int k = 0; k < CIN / 16; ++k)
+            umma_f16_w(tmem_wg + t * NP, a_lo0 + t * (2048u >> 4) + k * ((2u * PITCH) >> 4), a_hi, b_lo0 + k * 16u, b_hi, idesc, k != 0);
+          // + bias: a K step of the constant "ones" tile against the weight image's last 16 K columns (bias as fp16 hi + lo)
+          umma_f16_w(tmem_wg + t * NP, ones_lo, a_hi, b_lo0 + (CIN / 16) * 16u, b_hi, idesc, 1u);
+        }
+        if (o.res_off >= 0) {
+          // + residual: 16-channel slices of the block input against a 16 x 16 identity (exact in the fp32 accumulator)
+          constexpr uint32_t e_hi = noswizzle_desc_hi(256);
+          constexpr uint32_t idesc16 = make_idesc_f16(kTileM, 16, 0);
+          const uint32_t r_lo0 = noswizzle_desc_lo(buf_addr + o.res_off + np * (NP / 8) * PITCH, PITCH);
+          const uint32_t e_lo = noswizzle_desc_lo(base + eye_off, 128);
+#pragma unroll
+          for (int t = 0; t < TILES; ++t) {
+#pragma unroll
+            for (int k = 0; k < NP / 16; ++k)
+              umma_f16_w(tmem_wg + t * NP + k * 16, r_lo0 + t * (2048u >> 4) + k * ((2u * PITCH) >> 4), a_hi, e_lo, e_hi, idesc16, 1u);
+          }
+        }
+        umma_commit(bar);
       }
-      tmem_ld_wait();
+      __syncwarp();
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    tc_fence_after();
+    if (np == 0) HN_TAIL_ACC(64 + trace_op, t_pw);
+    // epilogue: accumulator (bias and residual already inside) -> [ReLU] -> fp16 -> planar destination, up to two 32-column
+    // loads in flight
+    constexpr int CH = NP / 32;                            // 32-column chunks per tile
+    constexpr int NCH = TILES * CH;
+    static_assert(NCH == 1 || NCH % 2 == 0, "chunks are processed in pairs");
+    constexpr int STEP = (NCH >= 2 && STEP_MAX >= 2) ? 2 : 1;
 #pragma unroll
-      for (int u = 0; u < STEP; ++u) {
-        const int tt = (c + u) / CH, c0 = ((c + u) % CH) * 32;
-        const int row = tt * kTileM + q * 32 + lane;
-        int slot = row;
-        if constexpr (ROWS == 256) { if (o.parity) slot = tail_parity_slot<16>(row >> 4, row & 15); }
-        if constexpr (ROWS == 64) { if (o.parity) slot = tail_parity_slot<8>(row >> 3, row & 7); }
-        if (row < ROWS) {
+    for (int c = 0; c < NCH; c += STEP) {
+      if ((TILES == 1 ? 0 : (c / CH) * kTileM) + q * 32 < ROWS) {   // warp-uniform (two tiles only with full maps)
+        uint32_t r[STEP][32];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const uint32_t poff = static_cast<uint32_t>(c0 / 8 + h) * PITCH + slot * 16;
-            const float* v = reinterpret_cast<const float*>(&r[u][8 * h]);
-            uint4 ov;
-            if (relu)
-              ov = make_uint4(pack16_relu(v[0], v[1], 0), pack16_relu(v[2], v[3], 0), pack16_relu(v[4], v[5], 0), pack16_relu(v[6], v[7], 0));
-            else
-              ov = make_uint4(tail_pack_sat(v[0], v[1]), tail_pack_sat(v[2], v[3]), tail_pack_sat(v[4], v[5]), tail_pack_sat(v[6], v[7]));
-            *reinterpret_cast<uint4*>(dstp + poff) = ov;
+        for (int u = 0; u < STEP; ++u) {
+          const int tt = (c + u) / CH, c0 = ((c + u) % CH) * 32;
+          tmem_ld32(tmem_wg + (static_cast<uint32_t>(q * 32) << 16) + tt * NP + c0, r[u]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < STEP; ++u) {
+          const int tt = (c + u) / CH, c0 = np * NP + ((c + u) % CH) * 32;
+          const int row = tt * kTileM + q * 32 + lane;
+          int slot = row;
+          if constexpr (ROWS == 256) { if (o.parity) slot = tail_parity_slot<16>(row >> 4, row & 15); }
+          if constexpr (ROWS == 64) { if (o.parity) slot = tail_parity_slot<8>(row >> 3, row & 7); }
+          if (row < ROWS) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const uint32_t poff = static_cast<uint32_t>(c0 / 8 + h) * PITCH + slot * 16;
+              const float* v = reinterpret_cast<const float*>(&r[u][8 * h]);
+              uint4 ov;
+              if (relu)
+                ov = make_uint4(pack16_relu(v[0], v[1], 0), pack16_relu(v[2], v[3], 0), pack16_relu(v[4], v[5], 0), pack16_relu(v[6], v[7], 0));
+              else
+                ov = make_uint4(tail_pack_sat(v[0], v[1]), tail_pack_sat(v[2], v[3]), tail_pack_sat(v[4], v[5]), tail_pack_sat(v[6], v[7]));
+              *reinterpret_cast<uint4*>(dstp + poff) = ov;
+            }
           }
         }
       }
     }
-    (void)t;
   }
 }
 
@@ -284,14 +295,14 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const int wg = warp >> 2, q = warp & 3, t = threadIdx.x & 127;
   const uint32_t bar0 = base + p.bar_off;
-  const uint32_t tmem_slot = bar0 + 16 * kTailMaxWG;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.bar_off + 16 * kTailMaxWG);
+  const uint32_t tmem_slot = bar0 + 16 * kTailBars;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + p.bar_off + 16 * kTailBars);
 
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < NWG; ++i) {
         mbar_init(bar0 + 8 * i, 1);
-        mbar_init(bar0 + 8 * (kTailMaxWG + i), 1);
+        mbar_init(bar0 + 8 * (kTailBars + i), 1);
       }
       fence_mbar_init();
     }
@@ -307,9 +318,11 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_wg = *tmem_slot_ptr + wg * kTailCols;
+  constexpr int COLS = NWG <= 4 ? 128 : 64;            // tensor-memory columns per warpgroup
+  constexpr int STEPM = NWG <= 4 ? 2 : 1;              // 32-column accumulator loads in flight (register budget)
+  const uint32_t tmem_wg = *tmem_slot_ptr + wg * COLS;
   const uint32_t bar = bar0 + 8 * wg;
-  const uint32_t bar_ld = bar0 + 8 * (kTailMaxWG + wg);
+  const uint32_t bar_ld = bar0 + 8 * (kTailBars + wg);
   uint32_t phase = 0, phase_ld = 0;
   uint8_t* buf = sm + wg * p.wg_stride;
   const uint32_t buf_addr = base + wg * p.wg_stride;
@@ -339,44 +352,60 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
       const TailOp& o = p.ops[oi];
       HN_TAIL_T(t_op);
       if (o.kind == TAIL_PW) {
-        switch (o.shape) {
-          case 0: tail_pw<32, 32, 256>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
-          case 1: tail_pw<32, 64, 64>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
-          case 2: tail_pw<64, 64, 64>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
-          case 3: tail_pw<64, 128, 16>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
-          default: tail_pw<128, 128, 16>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, q, lane, p.op_base + oi); break;
+#define HN_TAIL_PW(CI, CO, R) tail_pw<CI, CO, R, COLS, STEPM>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, wg, q, lane, p.op_base + oi)
+        // five or six warpgroups only fit when no 16 x 16 map is part of the run (8 KB regions): those shapes are not compiled in
+        if constexpr (NWG <= 4) {
+          if (o.shape == 0) HN_TAIL_PW(32, 32, 256);
         }
+        switch (o.shape) {
+          case 0: break;
+          case 1: HN_TAIL_PW(32, 64, 64); break;
+          case 2: HN_TAIL_PW(64, 64, 64); break;
+          case 3: HN_TAIL_PW(64, 128, 16); break;
+          default: HN_TAIL_PW(128, 128, 16); break;
+        }
+#undef HN_TAIL_PW
       } else if (o.kind == TAIL_DW) {
         const uint8_t* s = buf + o.src_off;
         uint8_t* d = buf + o.dst_off;
         const uint8_t* w = sm + o.w_off;
         const uint8_t* b = sm + o.b_off;
         const uint8_t* pad0 = sm + p.ones_off + 2048;   // zeros
+#define HN_TAIL_DW(K_, S_, C_, H_) tail_dw<K_, S_, C_, H_, false>(s, d, w, b, pad0, o.relu, t)
+#define HN_TAIL_DW2(K_, C_, H_) do { if (o.parity) tail_dw<K_, 2, C_, H_, false, true>(s, d, w, b, pad0, o.relu, t); else HN_TAIL_DW(K_, 2, C_, H_); } while (0)
+        if constexpr (NWG <= 4) {                       // 16 x 16 inputs: never with five or six warpgroups (see above)
+          if (o.shape == 0) { if (o.kernel == 3) HN_TAIL_DW(3, 1, 32, 16); else HN_TAIL_DW(5, 1, 32, 16); }
+          if (o.shape == 1) { if (o.kernel == 3) HN_TAIL_DW2(3, 32, 8); else HN_TAIL_DW2(5, 32, 8); }
+        }
         if (o.kernel == 3) {
           switch (o.shape) {
-            case 0: tail_dw<3, 1, 32, 16, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 1: if (o.parity) tail_dw<3, 2, 32, 8, false, true>(s, d, w, b, pad0, o.relu, t); else tail_dw<3, 2, 32, 8, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 2: tail_dw<3, 1, 64, 8, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 3: if (o.parity) tail_dw<3, 2, 64, 4, false, true>(s, d, w, b, pad0, o.relu, t); else tail_dw<3, 2, 64, 4, false>(s, d, w, b, pad0, o.relu, t); break;
-            default: tail_dw<3, 1, 128, 4, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 0: case 1: break;
+            case 2: HN_TAIL_DW(3, 1, 64, 8); break;
+            case 3: HN_TAIL_DW2(3, 64, 4); break;
+            default: HN_TAIL_DW(3, 1, 128, 4); break;
           }
         } else {
           switch (o.shape) {
-            case 0: tail_dw<5, 1, 32, 16, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 1: if (o.parity) tail_dw<5, 2, 32, 8, false, true>(s, d, w, b, pad0, o.relu, t); else tail_dw<5, 2, 32, 8, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 2: tail_dw<5, 1, 64, 8, false>(s, d, w, b, pad0, o.relu, t); break;
-            case 3: if (o.parity) tail_dw<5, 2, 64, 4, false, true>(s, d, w, b, pad0, o.relu, t); else tail_dw<5, 2, 64, 4, false>(s, d, w, b, pad0, o.relu, t); break;
-            default: tail_dw<5, 1, 128, 4, false>(s, d, w, b, pad0, o.relu, t); break;
+            case 0: case 1: break;
+            case 2: HN_TAIL_DW(5, 1, 64, 8); break;
+            case 3: HN_TAIL_DW2(5, 64, 4); break;
+            default: HN_TAIL_DW(5, 1, 128, 4); break;
           }
         }
+#undef HN_TAIL_DW2
+#undef HN_TAIL_DW
       } else {
         const uint8_t* padn = sm + p.ones_off + 4096;   // -inf
+        const uint8_t* s = buf + o.src_off;
+        uint8_t* d = buf + o.dst_off;
         if (o.shape == 1) {
-          if (o.parity) tail_dw<3, 2, 32, 8, true, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
-          else tail_dw<3, 2, 32, 8, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
+          if constexpr (NWG <= 4) {
+            if (o.parity) tail_dw<3, 2, 32, 8, true, true>(s, d, nullptr, nullptr, padn, 0, t);
+            else tail_dw<3, 2, 32, 8, true>(s, d, nullptr, nullptr, padn, 0, t);
+          }
         } else {
-          if (o.parity) tail_dw<3, 2, 64, 4, true, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
-          else tail_dw<3, 2, 64, 4, true>(buf + o.src_off, buf + o.dst_off, nullptr, nullptr, padn, 0, t);
+          if (o.parity) tail_dw<3, 2, 64, 4, true, true>(s, d, nullptr, nullptr, padn, 0, t);
+          else tail_dw<3, 2, 64, 4, true>(s, d, nullptr, nullptr, padn, 0, t);
         }
       }
       // the next op reads this one's output through the other proxy (generic <-> tensor core) and may overwrite its

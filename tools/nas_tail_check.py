@@ -28,7 +28,7 @@ def main():
                     r = {"arch": arch, "env": env, "error": repr(exc), "ok": False}
                 ok = ok and r["ok"]
                 print("PARITY", json.dumps(r), flush=True)
-    tplans = [{}, {"HN_NAS_TAIL_CUT": "0"}, {"HN_NAS_TAIL": "0"}] if fast else \
+    tplans = [{}, {"HN_NAS_TAIL_WG": "5"}, {"HN_NAS_TAIL_WG": "4"}, {"HN_NAS_TAIL": "0"}] if fast else \
         [{}, {"HN_NAS_TAIL_CUT": "0"}, {"HN_NAS_TAIL_WG": "3"}, {"HN_NAS_TAIL_WG": "2"}, {"HN_NAS_TAIL": "0"}]
     for arch in ("wang2", "wang3", "wang4"):
         for env in tplans:
