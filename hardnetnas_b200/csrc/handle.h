@@ -43,6 +43,7 @@ struct HnEnv {
   int nas_cut_ratio = 4;      // HN_NAS_CUT_RATIO: start a new segment at a block boundary whose tensor is <= 1/ratio of the segment input
   int nas_gmax = 8;           // HN_NAS_GMAX: cap on patches per group
   bool nas_tail = true;       // HN_NAS_TAIL=0: no warpgroup-per-patch tail kernel (nas_tail.cuh) behind the fused front stage
+  bool nas_fold = true;       // HN_NAS_FOLD=0: the tail runs the packed ops one by one (no folding of linear 1x1 convs into their consumers)
   int nas_tail_cut = 2;       // HN_NAS_TAIL_CUT: start a new tail launch at a block boundary whose tensor is <= 1/cut of the launch's
                               // input (smaller maps -> smaller buffers -> more warpgroups per SM); 0 = one launch for the whole tail
   int nas_tail_minops = 4;    // HN_NAS_TAIL_MINOPS: ... and only if at least this many ops remain behind the cut

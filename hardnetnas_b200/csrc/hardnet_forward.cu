@@ -434,6 +434,7 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
     h->env.nas_cut_ratio = std::max(1, num("HN_NAS_CUT_RATIO", 4));
     h->env.nas_gmax = std::max(1, num("HN_NAS_GMAX", 8));
     h->env.nas_tail = flag("HN_NAS_TAIL", true);
+    h->env.nas_fold = flag("HN_NAS_FOLD", true);
     h->env.nas_tail_cut = std::max(0, num("HN_NAS_TAIL_CUT", 2));
     h->env.nas_tail_minops = std::max(1, num("HN_NAS_TAIL_MINOPS", 4));
     h->env.nas_tail_wg = std::min(6, std::max(1, num("HN_NAS_TAIL_WG", 6)));

@@ -879,17 +879,27 @@ struct NasSegment {
 // A run of consecutive ops behind the front stage executed by ONE launch of nas_tail_kernel (nas_tail.cuh), a warpgroup per patch.
 struct NasTail {
   int first = 0, last = 0;   // op range [first, last]
+  int last_orig = 0;         // packed op whose output the run's last op produces
   int nwg = 0;               // warpgroups (= patches in flight) per CTA
   size_t smem = 0;
   std::vector<int> dst_off;  // per op of the run: byte offset of its output inside a warpgroup's region
+  std::vector<int> src_r, res_r, dst_r;   // per op: regions of its inputs / output
+  std::vector<int> out_c, out_h, is_pw;   // per op: output channels / side, pointwise?
   TailParams params;
   uint8_t* blob = nullptr;   // device copy of the weight image
 };
 
 struct NasState {
-  std::vector<NasTail> tails;
-  std::vector<int> tail_of_op;       // index into tails, or -1
-  int head_planar = 0;               // the last tail launch writes the head GEMM's rows channel-planar (head weight K order permuted)
+  std::vector<NasTail> tails;        // plain form of the ops behind the front stage (op k of the form = packed op tail_first + k):
+                                     // activation dumps, and the forward when the folded form is unavailable
+  std::vector<int> tail_of_op;       // packed op -> index into tails, or -1
+  int tail_first = 0;
+  int head_planar = 0;               // the last plain tail launch writes the head GEMM's rows channel-planar (head weight K order permuted)
+  std::vector<NasTail> ftails;       // folded form (linear 1x1 convs folded into their consumers): the forward's launches
+  uint16_t* headf_w = nullptr;       // folded head: [128][headf_k] 16-bit, channel-planar K order
+  float* headf_b = nullptr;
+  int headf_k = 0;
+  TcParams headf;
   std::vector<NasSegment> segs;
   std::vector<int> seg_of_op;        // index into segs, or -1: the op runs as its own kernel
   std::vector<hn_nas_op> ops;
@@ -920,6 +930,9 @@ void nas_state_free(NasState* s) {
   cudaFree(s->front_img);
   for (auto& sg : s->segs) cudaFree(sg.blob);
   for (auto& tl : s->tails) cudaFree(tl.blob);
+  for (auto& tl : s->ftails) cudaFree(tl.blob);
+  cudaFree(s->headf_w);
+  cudaFree(s->headf_b);
   delete s;
 }
 
@@ -1249,111 +1262,333 @@ static int seg_partition(hn_handle* h, NasState* st, const float* params) {
 // ------------------------------------------------------------------------------------------------------------
 // warpgroup-per-patch tail launches (nas_tail.cuh)
 // ------------------------------------------------------------------------------------------------------------
-static int tail_pw_shape(const hn_nas_op& o) {
-  const int rows = o.hin * o.hin;
-  if (o.cin == 32 && o.cout == 32 && rows == 256) return 0;
-  if (o.cin == 32 && o.cout == 64 && rows == 64) return 1;
-  if (o.cin == 64 && o.cout == 64 && rows == 64) return 2;
-  if (o.cin == 64 && o.cout == 128 && rows == 16) return 3;
-  if (o.cin == 128 && o.cout == 128 && rows == 16) return 4;
+// The ops behind the front stage as a small SSA program over tensor ids (tensor 0 = the front stage's output). Two forms:
+//   plain   one TOp per packed op, a block's residual as an identity second input (activation dumps run this form, so every
+//           packed op's output can still be inspected), and
+//   folded  every LINEAR 1x1 conv (the `pwl` of an IRFBlock, fbnet_builder.py:455-570: conv + BN, no ReLU) is folded into its
+//           consumers: y = relu(W2 (W1 a + b1 + x) + b2) = relu((W2 W1) a + W2 x + (W2 b1 + b2)) is ONE pointwise op with two
+//           inputs, and the head conv of model_supernet.py:64-68 absorbs the last block's `pwl`. wang2: 13 ops -> 8 (4 pointwise
+//           + 4 depthwise), head K 2048 -> 1024. Products are formed in double precision and rounded once to fp16, so the
+//           folded net drops roundings of intermediate activations rather than adding any.
+struct TOp {
+  int kind = 0;                 // OP_PW / OP_DW / OP_MAXPOOL
+  int cin = 0, cout = 0, kernel = 1, stride = 1, hin = 0, hout = 0, relu = 0;
+  int in0 = -1, in1 = -1, out = -1;   // tensor ids (in1: second input of a pointwise op)
+  int c1 = 0;                   // channels of in1
+  int ident1 = 0;               // in1 is added as it is (identity weights)
+  std::vector<float> w, w1, b;  // PW: [cout][cin], [cout][c1] (unless ident1), [cout]; DW: [k * k][C], [C]
+  int orig = -1;                // packed op whose output this op produces
+};
+
+struct TProg {
+  std::vector<TOp> ops;
+  std::vector<std::pair<int, int>> tensors;   // (channels, side)
+  // head: [128][pix * C] in NHWC K order (pixel * C + c) over tensor `head_in`
+  int head_in = -1, head_c = 0, head_pix = 0;
+  std::vector<float> head_w, head_b;
+  bool folded = false;
+};
+
+static int tail_pw_shape(int cin, int c1w /*weighted second input channels, 0 = none / identity*/, int cout, int rows) {
+  struct S { int cin, c1, cout, rows; };
+  static const S table[] = {{32, 0, 32, 256}, {32, 0, 64, 64}, {64, 0, 64, 64}, {64, 0, 128, 16}, {128, 0, 128, 16},
+                            {32, 32, 32, 256}, {64, 32, 64, 64}, {64, 64, 64, 64}, {128, 64, 128, 16}};
+  for (int i = 0; i < static_cast<int>(sizeof(table) / sizeof(table[0])); ++i)
+    if (table[i].cin == cin && table[i].c1 == c1w && table[i].cout == cout && table[i].rows == rows) return i;
   return -1;
 }
-static int tail_dw_shape(const hn_nas_op& o) {
-  if (o.cin != o.cout || o.hout * o.stride != o.hin) return -1;
-  if (o.cin == 32 && o.hout == 16 && o.stride == 1) return 0;
-  if (o.cin == 32 && o.hout == 8 && o.stride == 2) return 1;
-  if (o.cin == 64 && o.hout == 8 && o.stride == 1) return 2;
-  if (o.cin == 64 && o.hout == 4 && o.stride == 2) return 3;
-  if (o.cin == 128 && o.hout == 4 && o.stride == 1) return 4;
+static int tail_dw_shape(int c, int hin, int hout, int stride) {
+  if (hout * stride != hin) return -1;
+  if (c == 32 && hout == 16 && stride == 1) return 0;
+  if (c == 32 && hout == 8 && stride == 2) return 1;
+  if (c == 64 && hout == 8 && stride == 1) return 2;
+  if (c == 64 && hout == 4 && stride == 2) return 3;
+  if (c == 128 && hout == 4 && stride == 1) return 4;
   return -1;
 }
-static int tail_op_shape(const hn_nas_op& o) {
+static int tail_op_shape(const TOp& o) {
   switch (o.kind) {
-    case OP_PW: return tail_pw_shape(o);
-    case OP_DW: return (o.kernel == 3 || o.kernel == 5) ? tail_dw_shape(o) : -1;
-    case OP_MAXPOOL: { const int sh = tail_dw_shape(o); return (sh == 1 || sh == 3) ? sh : -1; }
+    case OP_PW: return (o.in1 >= 0 && o.ident1 && o.c1 != o.cout) ? -1 : tail_pw_shape(o.cin, (o.in1 >= 0 && !o.ident1) ? o.c1 : 0, o.cout, o.hin * o.hin);
+    case OP_DW: return (o.kernel == 3 || o.kernel == 5) ? tail_dw_shape(o.cin, o.hin, o.hout, o.stride) : -1;
+    case OP_MAXPOOL: { const int sh = tail_dw_shape(o.cin, o.hin, o.hout, o.stride); return (sh == 1 || sh == 3) ? sh : -1; }
     default: return -1;
   }
 }
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-// Finalises tail launch [first, last]: buffer offsets, warpgroups per CTA, weight image on the device.
-static int tail_build(hn_handle* h, NasState* st, const float* params, int first, int last, NasTail& tl) {
+// plain form: one TOp per packed op of [first, n_ops - 2]; false if the program does not have the expected structure
+static bool tail_prog_plain(const std::vector<hn_nas_op>& ops, const float* params, int first, TProg& pr) {
+  const int n_ops = static_cast<int>(ops.size());
+  int slot_t[3] = {-1, -1, -1};
+  const hn_nas_op& of = ops[first];
+  pr.tensors.emplace_back(of.cin, of.hin);
+  slot_t[of.src] = 0;
+  for (int i = first; i <= n_ops - 2; ++i) {
+    const hn_nas_op& o = ops[i];
+    if (o.kind != OP_PW && o.kind != OP_DW && o.kind != OP_MAXPOOL) return false;
+    TOp t;
+    t.kind = o.kind; t.cin = o.cin; t.cout = o.cout; t.kernel = o.kernel; t.stride = o.kind == OP_PW ? 1 : o.stride;
+    t.hin = o.hin; t.hout = o.hout; t.relu = o.relu; t.orig = i;
+    t.in0 = slot_t[o.src];
+    if (t.in0 < 0) return false;
+    if (o.kind == OP_PW && o.res >= 0) {
+      t.in1 = slot_t[o.res];
+      if (t.in1 < 0) return false;
+      t.c1 = o.cout; t.ident1 = 1;
+    }
+    if (o.kind == OP_PW) {
+      t.w.assign(params + o.w_off, params + o.w_off + static_cast<size_t>(o.cin) * o.cout);
+      t.b.assign(params + o.b_off, params + o.b_off + o.cout);
+    } else if (o.kind == OP_DW) {
+      t.w.assign(params + o.w_off, params + o.w_off + static_cast<size_t>(o.kernel) * o.kernel * o.cin);
+      t.b.assign(params + o.b_off, params + o.b_off + o.cin);
+    }
+    t.out = static_cast<int>(pr.tensors.size());
+    pr.tensors.emplace_back(o.cout, o.hout);
+    slot_t[o.dst] = t.out;
+    pr.ops.push_back(std::move(t));
+  }
+  const hn_nas_op& oh = ops[n_ops - 1];
+  pr.head_in = slot_t[oh.src];
+  if (pr.head_in < 0) return false;
+  pr.head_c = oh.cin; pr.head_pix = oh.kernel * oh.kernel;
+  const size_t K = static_cast<size_t>(pr.head_pix) * pr.head_c;
+  pr.head_w.assign(params + oh.w_off, params + oh.w_off + 128 * K);
+  pr.head_b.assign(params + oh.b_off, params + oh.b_off + 128);
+  return true;
+}
+
+// folded form (see above); false if a value would need more than two inputs in a way the pass does not resolve
+static bool tail_prog_folded(const std::vector<hn_nas_op>& ops, const float* params, int first, TProg& pr) {
+  struct Term { int t, ct; std::vector<double> M; };                  // M: [C][ct]
+  struct Val { bool mat = false; int t = -1, C = 0, H = 0; std::vector<Term> terms; std::vector<double> c; bool set = false; };
+  const int n_ops = static_cast<int>(ops.size());
+  Val vals[3];
+  const hn_nas_op& of = ops[first];
+  pr.tensors.emplace_back(of.cin, of.hin);
+  vals[of.src].mat = true; vals[of.src].t = 0; vals[of.src].C = of.cin; vals[of.src].H = of.hin; vals[of.src].set = true;
+  auto is_identity = [](const Term& tm, int C) {
+    if (tm.ct != C) return false;
+    for (int r = 0; r < C; ++r)
+      for (int k = 0; k < C; ++k)
+        if (tm.M[static_cast<size_t>(r) * C + k] != (r == k ? 1.0 : 0.0)) return false;
+    return true;
+  };
+  // emits the pointwise op that computes a linear value (1 or 2 terms) and turns it into a materialised tensor
+  auto materialize = [&](Val& v, int relu, int orig) -> bool {
+    if (v.mat) return true;
+    if (v.terms.empty() || v.terms.size() > 2) return false;
+    if (v.terms.size() == 2 && is_identity(v.terms[0], v.C) && !is_identity(v.terms[1], v.C)) std::swap(v.terms[0], v.terms[1]);
+    TOp t;
+    t.kind = OP_PW; t.cin = v.terms[0].ct; t.cout = v.C; t.hin = t.hout = v.H; t.relu = relu; t.orig = orig;
+    t.in0 = v.terms[0].t;
+    t.w.assign(v.terms[0].M.begin(), v.terms[0].M.end());
+    if (v.terms.size() == 2) {
+      t.in1 = v.terms[1].t; t.c1 = v.terms[1].ct;
+      t.ident1 = is_identity(v.terms[1], v.C) ? 1 : 0;
+      if (!t.ident1) t.w1.assign(v.terms[1].M.begin(), v.terms[1].M.end());
+    }
+    t.b.assign(v.c.begin(), v.c.end());
+    t.out = static_cast<int>(pr.tensors.size());
+    pr.tensors.emplace_back(v.C, v.H);
+    pr.ops.push_back(std::move(t));
+    v.mat = true; v.t = pr.ops.back().out; v.terms.clear(); v.c.clear();
+    return true;
+  };
+  // terms of W * v (v materialised: one term; v linear: W composed with each of its terms), bias W * c
+  auto apply = [&](const std::vector<double>& W, int cout, const Val& v, std::vector<Term>& terms, std::vector<double>& bias) {
+    if (v.mat) {
+      terms.push_back({v.t, v.C, W});
+      return;
+    }
+    for (const Term& tm : v.terms) {
+      Term nt{tm.t, tm.ct, std::vector<double>(static_cast<size_t>(cout) * tm.ct, 0.0)};
+      for (int r = 0; r < cout; ++r)
+        for (int k = 0; k < v.C; ++k) {
+          const double wv = W[static_cast<size_t>(r) * v.C + k];
+          if (wv == 0.0) continue;
+          for (int j = 0; j < tm.ct; ++j) nt.M[static_cast<size_t>(r) * tm.ct + j] += wv * tm.M[static_cast<size_t>(k) * tm.ct + j];
+        }
+      terms.push_back(std::move(nt));
+    }
+    for (int r = 0; r < cout; ++r)
+      for (int k = 0; k < v.C; ++k) bias[r] += W[static_cast<size_t>(r) * v.C + k] * v.c[k];
+  };
+  auto add_terms = [&](std::vector<Term>& terms, const Term& tm) {
+    for (Term& e : terms)
+      if (e.t == tm.t) {
+        for (size_t j = 0; j < e.M.size(); ++j) e.M[j] += tm.M[j];
+        return;
+      }
+    terms.push_back(tm);
+  };
+  for (int i = first; i <= n_ops - 2; ++i) {
+    const hn_nas_op& o = ops[i];
+    if (!vals[o.src].set) return false;
+    if (o.kind == OP_PW) {
+      if (o.res >= 0 && !vals[o.res].set) return false;
+      for (int attempt = 0; attempt < 3; ++attempt) {
+        std::vector<double> W(params + o.w_off, params + o.w_off + static_cast<size_t>(o.cin) * o.cout);
+        std::vector<Term> terms;
+        std::vector<double> bias(params + o.b_off, params + o.b_off + o.cout);
+        apply(W, o.cout, vals[o.src], terms, bias);
+        if (o.res >= 0) {
+          const Val& rv = vals[o.res];
+          if (rv.mat) {
+            Term id{rv.t, rv.C, std::vector<double>(static_cast<size_t>(rv.C) * rv.C, 0.0)};
+            for (int r = 0; r < rv.C; ++r) id.M[static_cast<size_t>(r) * rv.C + r] = 1.0;
+            add_terms(terms, id);
+          } else {
+            for (const Term& tm : rv.terms) add_terms(terms, tm);
+            for (int r = 0; r < o.cout; ++r) bias[r] += rv.c[r];
+          }
+        }
+        if (terms.size() > 2) {     // too many inputs: compute a linear operand for real first, then try again
+          if (!vals[o.src].mat) { if (!materialize(vals[o.src], 0, -1)) return false; }
+          else if (o.res >= 0 && !vals[o.res].mat) { if (!materialize(vals[o.res], 0, -1)) return false; }
+          else return false;
+          continue;
+        }
+        Val out;
+        out.C = o.cout; out.H = o.hin; out.terms = std::move(terms); out.c = std::move(bias); out.set = true;
+        if (o.relu && !materialize(out, 1, i)) return false;
+        vals[o.dst] = std::move(out);
+        break;
+      }
+      if (!vals[o.dst].set) return false;
+    } else if (o.kind == OP_DW || o.kind == OP_MAXPOOL) {
+      if (!materialize(vals[o.src], 0, -1)) return false;
+      TOp t;
+      t.kind = o.kind; t.cin = o.cin; t.cout = o.cout; t.kernel = o.kernel; t.stride = o.stride; t.hin = o.hin; t.hout = o.hout; t.relu = o.relu;
+      t.orig = i; t.in0 = vals[o.src].t;
+      if (o.kind == OP_DW) {
+        t.w.assign(params + o.w_off, params + o.w_off + static_cast<size_t>(o.kernel) * o.kernel * o.cin);
+        t.b.assign(params + o.b_off, params + o.b_off + o.cin);
+      }
+      t.out = static_cast<int>(pr.tensors.size());
+      pr.tensors.emplace_back(o.cout, o.hout);
+      pr.ops.push_back(std::move(t));
+      Val out;
+      out.mat = true; out.t = pr.ops.back().out; out.C = o.cout; out.H = o.hout; out.set = true;
+      vals[o.dst] = std::move(out);
+    } else {
+      return false;
+    }
+  }
+  // head conv: absorbs a linear value with ONE source tensor
+  const hn_nas_op& oh = ops[n_ops - 1];
+  Val& hv = vals[oh.src];
+  if (!hv.set) return false;
+  const int pix = oh.kernel * oh.kernel, C = oh.cin;
+  const float* Wh = params + oh.w_off;           // [128][pix * C]
+  pr.head_pix = pix;
+  pr.head_b.assign(params + oh.b_off, params + oh.b_off + 128);
+  if (!hv.mat && hv.terms.size() == 1 && hv.terms[0].ct % 8 == 0 && (pix * hv.terms[0].ct) % 128 == 0) {
+    const Term& tm = hv.terms[0];
+    pr.head_in = tm.t; pr.head_c = tm.ct;
+    pr.head_w.assign(static_cast<size_t>(128) * pix * tm.ct, 0.f);
+    std::vector<double> acc(tm.ct);
+    for (int o2 = 0; o2 < 128; ++o2) {
+      double bsum = pr.head_b[o2];
+      for (int px = 0; px < pix; ++px) {
+        std::fill(acc.begin(), acc.end(), 0.0);
+        const float* wrow = Wh + (static_cast<size_t>(o2) * pix + px) * C;
+        for (int c = 0; c < C; ++c) {
+          const double wv = wrow[c];
+          bsum += wv * hv.c[c];
+          for (int j = 0; j < tm.ct; ++j) acc[j] += wv * tm.M[static_cast<size_t>(c) * tm.ct + j];
+        }
+        for (int j = 0; j < tm.ct; ++j) pr.head_w[(static_cast<size_t>(o2) * pix + px) * tm.ct + j] = static_cast<float>(acc[j]);
+      }
+      pr.head_b[o2] = static_cast<float>(bsum);
+    }
+  } else {
+    if (!materialize(hv, 0, n_ops - 2)) return false;
+    pr.head_in = hv.t; pr.head_c = C;
+    pr.head_w.assign(Wh, Wh + static_cast<size_t>(128) * pix * C);
+  }
+  pr.folded = true;
+  return true;
+}
+
+// Finalises tail launch [first, last] of `pr`: region offsets, warpgroups per CTA, weight image on the device.
+static int tail_build(hn_handle* h, const TProg& pr, int first, int last, int launch_id, NasTail& tl) {
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t r = off; off = seg_align(off + bytes, 128); return r; };
   const int n = last - first + 1;
   if (n > kTailMaxOps) return HN_ERR_UNSUPPORTED;
   std::vector<size_t> w_off(n, 0), b_off(n, 0);
   // constant tiles: "ones" A tile (K plane 0: columns 0, 1 = 1.0; K plane 1 = 2 KB of zeros, also the depthwise zero padding),
-  // 16 bytes of -inf (max-pool padding), 16 x 16 identity B tile
+  // 128 bytes of -inf (max-pool padding), 16 x 16 identity B tile
   const size_t ones_off = take(4096 + 128);
   const size_t eye_off = take(512);
   size_t region_bytes = 0;
+  bool big_map = false;
+  auto wc1 = [](const TOp& o) { return (o.in1 >= 0 && !o.ident1) ? o.c1 : 0; };   // weighted second-input channels
   for (int i = first; i <= last; ++i) {
-    const hn_nas_op& o = st->ops[i];
+    const TOp& o = pr.ops[i];
+    if (tail_op_shape(o) < 0) return HN_ERR_UNSUPPORTED;
     const size_t in_b = static_cast<size_t>(o.cin) * o.hin * o.hin * 2, out_b = static_cast<size_t>(o.cout) * o.hout * o.hout * 2;
     region_bytes = std::max(region_bytes, std::max(in_b, out_b));
+    if (o.in1 >= 0) region_bytes = std::max(region_bytes, static_cast<size_t>(o.c1) * o.hin * o.hin * 2);
+    big_map = big_map || o.hin == 16;
     const int k = i - first;
-    if (o.kind == OP_PW) w_off[k] = take(static_cast<size_t>(o.cin + 16) * o.cout * 2);   // + 16 K columns: bias as fp16 hi + lo
+    if (o.kind == OP_PW) w_off[k] = take(static_cast<size_t>(o.cin + 16 + wc1(o)) * o.cout * 2);   // + 16 K columns: bias as fp16 hi + lo
     if (o.kind == OP_DW) { w_off[k] = take(static_cast<size_t>(o.kernel) * o.kernel * o.cin * 2); b_off[k] = take(o.cin * 2); }
   }
   const size_t blob_bytes = seg_align(off, 16);
-  // Three equal regions per warpgroup, assigned by liveness (not by the program's slot ids): the run's input sits in
-  // region 0 and every output goes to a free region, region 0 last — so region 0 is idle from the last op that touches the
-  // input (or a tensor that had to share its region) onwards and the NEXT patch's input is bulk-copied into it while the
-  // remaining ops run.
+  // Three equal regions per warpgroup, assigned by liveness: the run's input sits in region 0 and every output goes to a
+  // free region, region 0 last — so region 0 is idle from the last op that touches the input (or a tensor that had to share
+  // its region) onwards and the NEXT patch's input is bulk-copied into it while the remaining ops run.
   region_bytes = seg_align(region_bytes, 1024);
   const size_t wg_stride = 3 * region_bytes;
-  int slot_region[3] = {-1, -1, -1};
-  slot_region[st->ops[first].src] = 0;
-  std::vector<int> src_r(n, 0), dst_r(n, 0), res_r(n, -1);
-  int last_r0 = -1;
-  auto live_after = [&](int slot, int i) {      // is the tensor in program slot `slot` read by an op of the run behind op i?
-    for (int j = i + 1; j <= last; ++j) {
-      const hn_nas_op& o = st->ops[j];
-      if (o.src == slot || (o.kind == OP_PW && o.res == slot)) return true;
-      if (o.dst == slot) return false;
-    }
-    return false;
+  const int in_t = pr.ops[first].in0;
+  auto last_use = [&](int t) {                  // last op of the run that reads tensor t (-1: none); the run's output lives on
+    int lu = -1;
+    for (int j = first; j <= last; ++j)
+      if (pr.ops[j].in0 == t || pr.ops[j].in1 == t) lu = j;
+    return lu;
   };
+  std::vector<int> region(pr.tensors.size(), -1);
+  region[in_t] = 0;
+  int last_r0 = -1;
   for (int i = first; i <= last; ++i) {
-    const hn_nas_op& o = st->ops[i];
-    const int k = i - first;
-    src_r[k] = slot_region[o.src];
-    res_r[k] = (o.kind == OP_PW && o.res >= 0) ? slot_region[o.res] : -1;
-    if (src_r[k] < 0 || (o.kind == OP_PW && o.res >= 0 && res_r[k] < 0)) return HN_ERR_UNSUPPORTED;
+    const TOp& o = pr.ops[i];
+    if (region[o.in0] < 0 || (o.in1 >= 0 && region[o.in1] < 0)) return HN_ERR_UNSUPPORTED;   // reads a tensor from outside the run
     bool busy[3] = {false, false, false};
-    busy[src_r[k]] = true;
-    if (res_r[k] >= 0) busy[res_r[k]] = true;
-    for (int sl = 0; sl < 3; ++sl)
-      if (sl != o.dst && slot_region[sl] >= 0 && live_after(sl, i)) busy[slot_region[sl]] = true;
+    busy[region[o.in0]] = true;
+    if (o.in1 >= 0) busy[region[o.in1]] = true;
+    for (size_t t = 0; t < region.size(); ++t)
+      if (region[t] >= 0 && last_use(static_cast<int>(t)) > i) busy[region[t]] = true;
     int r = -1;
     for (int cand : {1, 2, 0})
       if (!busy[cand]) { r = cand; break; }
     if (r < 0) return HN_ERR_UNSUPPORTED;
-    dst_r[k] = r;
-    for (int sl = 0; sl < 3; ++sl)
-      if (sl != o.dst && slot_region[sl] == r) slot_region[sl] = -1;   // a dead tensor's region was reused
-    slot_region[o.dst] = r;
-    if (src_r[k] == 0 || res_r[k] == 0 || r == 0) last_r0 = k;
+    for (size_t t = 0; t < region.size(); ++t)
+      if (region[t] == r) region[t] = -1;       // a dead tensor's region is reused
+    region[o.out] = r;
+    // re-derive the inputs' regions for the record below (they cannot have been evicted: they were busy)
+    if (region[o.in0] == 0 || (o.in1 >= 0 && region[o.in1] == 0) || r == 0) last_r0 = i - first;
+    tl.src_r.push_back(region[o.in0]);
+    tl.res_r.push_back(o.in1 >= 0 ? region[o.in1] : -1);
+    tl.dst_r.push_back(r);
   }
   // a partial accumulator tile reads up to 2 KB past the end of a source plane: the blob sits behind the last region, so
   // those reads stay inside the CTA's shared memory
   const size_t fixed = seg_align(std::max<size_t>(blob_bytes, 2048), 128) + 256 + 1024 /*alignment of the base*/;
   // five or six warpgroups (64 tensor-memory columns and 85 registers each) only for runs without 16 x 16 maps
-  bool big_map = false;
-  for (int i = first; i <= last; ++i) big_map = big_map || st->ops[i].hin == 16;
   int nwg = std::min(h->env.nas_tail_wg, big_map ? 4 : kTailMaxWG);
   while (nwg >= 1 && nwg * wg_stride + fixed > 227 * 1024) --nwg;
   if (nwg < 1) return HN_ERR_UNSUPPORTED;
   tl.first = first; tl.last = last; tl.nwg = nwg;
+  tl.last_orig = pr.ops[last].orig;
   TailParams& p = tl.params;
   memset(&p, 0, sizeof(p));
   p.wg_stride = static_cast<int>(wg_stride);
   p.prefetch_after = last_r0 < n - 1 ? last_r0 : -1;
-  p.op_base = first;
-  p.launch_id = static_cast<int>(st->tails.size()) & 7;
+  p.op_base = pr.ops[first].orig >= 0 ? pr.ops[first].orig : first;
+  p.launch_id = launch_id & 7;
   p.blob_off = static_cast<int>(nwg * wg_stride);
   p.blob_bytes = static_cast<int>(blob_bytes);
   p.bar_off = static_cast<int>(seg_align(p.blob_off + std::max<size_t>(blob_bytes, 2048), 128));
@@ -1371,113 +1606,104 @@ static int tail_build(hn_handle* h, NasState* st, const float* params, int first
     for (int d = 0; d < 16; ++d) eye[((d >> 3) * 256 + (d >> 3) * 128 + (d & 7) * 16 + (d & 7) * 2) >> 1] = f2h16(1.0f, 0);
   }
   for (int i = first; i <= last; ++i) {
-    const hn_nas_op& o = st->ops[i];
+    const TOp& o = pr.ops[i];
     const int k = i - first;
     TailOp& to = p.ops[k];
     to.kind = o.kind == OP_PW ? TAIL_PW : (o.kind == OP_DW ? TAIL_DW : TAIL_POOL);
     to.shape = tail_op_shape(o);
     to.kernel = o.kernel; to.relu = o.relu;
-    to.src_off = static_cast<int>(src_r[k] * region_bytes);
-    to.dst_off = static_cast<int>(dst_r[k] * region_bytes);
-    to.res_off = res_r[k] >= 0 ? static_cast<int>(res_r[k] * region_bytes) : -1;
+    to.src_off = static_cast<int>(tl.src_r[k] * region_bytes);
+    to.dst_off = static_cast<int>(tl.dst_r[k] * region_bytes);
+    to.res_off = tl.res_r[k] >= 0 ? static_cast<int>(tl.res_r[k] * region_bytes) : -1;
     tl.dst_off[k] = to.dst_off;
     to.w_off = p.blob_off + static_cast<int>(w_off[k]);
     to.b_off = p.blob_off + static_cast<int>(b_off[k]);
+    tl.out_c.push_back(o.cout); tl.out_h.push_back(o.hout); tl.is_pw.push_back(o.kind == OP_PW);
     uint8_t* b = blob.data();
     if (o.kind == OP_PW) {
-      // UMMA no-swizzle K-major image of [W | bias_hi bias_lo 0...] = [cout][K' = cin + 16]:
+      // UMMA no-swizzle K-major image of [W | bias_hi bias_lo 0... | W1] = [cout][K' = cin + 16 + c1w]:
       // element (n, k) at (n / 8) * (K' * 16) + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2
-      const int kp = o.cin + 16;
+      const int c1w = wc1(o);
+      const int kp = o.cin + 16 + c1w;
       uint16_t* w = reinterpret_cast<uint16_t*>(b + w_off[k]);
       auto at = [&](int nn, int c) -> uint16_t& { return w[((nn >> 3) * kp * 16 + (c >> 3) * 128 + (nn & 7) * 16 + (c & 7) * 2) >> 1]; };
       for (int nn = 0; nn < o.cout; ++nn) {
-        for (int c = 0; c < o.cin; ++c) at(nn, c) = f2h16(params[o.w_off + static_cast<size_t>(nn) * o.cin + c], 0);
-        const float bias = params[o.b_off + nn];
+        for (int c = 0; c < o.cin; ++c) at(nn, c) = f2h16(o.w[static_cast<size_t>(nn) * o.cin + c], 0);
+        const float bias = o.b[nn];
         const __half hi = __float2half_rn(bias);
         at(nn, o.cin) = *reinterpret_cast<const uint16_t*>(&hi);
         at(nn, o.cin + 1) = f2h16(bias - __half2float(hi), 0);
+        for (int c = 0; c < c1w; ++c) at(nn, o.cin + 16 + c) = f2h16(o.w1[static_cast<size_t>(nn) * c1w + c], 0);
       }
     } else if (o.kind == OP_DW) {
       uint16_t* w = reinterpret_cast<uint16_t*>(b + w_off[k]);
-      for (int j = 0; j < o.kernel * o.kernel * o.cin; ++j) w[j] = f2h16(params[o.w_off + j], 0);
+      for (int j = 0; j < o.kernel * o.kernel * o.cin; ++j) w[j] = f2h16(o.w[j], 0);
       uint16_t* bb = reinterpret_cast<uint16_t*>(b + b_off[k]);
-      for (int j = 0; j < o.cin; ++j) bb[j] = f2h16(params[o.b_off + j], 0);
+      for (int j = 0; j < o.cin; ++j) bb[j] = f2h16(o.b[j], 0);
     }
   }
   // a pointwise conv whose output is read only by the stride-2 depthwise conv / max-pool right behind it writes the parity layout
   for (int i = first + 1; i <= last; ++i) {
-    const hn_nas_op& o = st->ops[i];
-    const hn_nas_op& pr = st->ops[i - 1];
-    if ((o.kind == OP_DW || o.kind == OP_MAXPOOL) && o.stride == 2 && (o.hin == 16 || o.hin == 8) && pr.kind == OP_PW && pr.dst == o.src &&
-        !live_after(o.src, i))
+    const TOp& o = pr.ops[i];
+    const TOp& pv = pr.ops[i - 1];
+    bool only_reader = true;
+    for (size_t j = 0; j < pr.ops.size(); ++j)
+      if (static_cast<int>(j) != i && (pr.ops[j].in0 == pv.out || pr.ops[j].in1 == pv.out)) only_reader = false;
+    if ((o.kind == OP_DW || o.kind == OP_MAXPOOL) && o.stride == 2 && (o.hin == 16 || o.hin == 8) && pv.kind == OP_PW && pv.out == o.in0 &&
+        only_reader && pr.head_in != pv.out)
       p.ops[i - first].parity = p.ops[i - 1 - first].parity = 1;
   }
-  const hn_nas_op& of = st->ops[first];
+  const TOp& of = pr.ops[first];
   p.in_off = 0;
-  p.in_bytes = of.cin * of.hin * of.hin * 2;
+  p.in_bytes = pr.tensors[in_t].first * pr.tensors[in_t].second * pr.tensors[in_t].second * 2;
+  (void)of;
   HN_CUDA(cudaMalloc(&tl.blob, blob.size()));
   HN_CUDA(cudaMemcpy(tl.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   p.blob = reinterpret_cast<const uint4*>(tl.blob);
   return HN_OK;
 }
 
-// Covers every op between the front stage and the head with tail launches, or none at all (any unsupported op, bf16
-// activations, no fused depthwise front stage: the one-kernel-per-op path stays).
-static int tail_partition(hn_handle* h, NasState* st, const float* params) {
-  const int n_ops = static_cast<int>(st->ops.size());
-  st->tail_of_op.assign(n_ops, -1);
-  st->tails.clear();
-  if (!h->env.nas_tail || st->act_bf16 || !st->front_fdw || !h->env.nas_front) return HN_OK;
-  const int first = st->front_ops + 1, last = n_ops - 2;
-  if (first > last) return HN_OK;
-  for (int i = first; i <= last; ++i)
-    if (tail_op_shape(st->ops[i]) < 0) return HN_OK;
-  // every tensor an op of [a, b] reads must be the run's input or produced inside it, and only the last op's output may
-  // be read behind the run
-  auto closed = [&](int a, int b) {
-    bool defined[3] = {false, false, false};
-    defined[st->ops[a].src] = true;
-    for (int i = a; i <= b; ++i) {
-      const hn_nas_op& o = st->ops[i];
-      if (!defined[o.src] || (o.kind == OP_PW && o.res >= 0 && !defined[o.res])) return false;
-      defined[o.dst] = true;
+// Cuts `pr` into tail launches (all of it or nothing). A launch boundary needs exactly one tensor crossing it.
+static int tail_partition(hn_handle* h, const TProg& pr, std::vector<NasTail>& tails) {
+  tails.clear();
+  const int n = static_cast<int>(pr.ops.size());
+  if (n == 0) return HN_OK;
+  for (const TOp& o : pr.ops)
+    if (tail_op_shape(o) < 0) return HN_OK;
+  auto tensor_bytes = [&](int t) { return static_cast<size_t>(pr.tensors[t].first) * pr.tensors[t].second * pr.tensors[t].second; };
+  // only op k's output may be read behind op k (by later ops or by the head)
+  auto single_crossing = [&](int k) {
+    for (int j = 0; j <= k; ++j) {
+      const int t = pr.ops[j].out;
+      if (j == k) continue;
+      for (int m = k + 1; m < n; ++m)
+        if (pr.ops[m].in0 == t || pr.ops[m].in1 == t) return false;
+      if (pr.head_in == t) return false;
     }
-    bool inside[3] = {false, false, false};
-    for (int i = a; i <= b; ++i) inside[st->ops[i].dst] = true;
-    inside[st->ops[b].dst] = false;
-    for (int j = b + 1; j < n_ops; ++j) {
-      const hn_nas_op& o = st->ops[j];
-      if (inside[o.src] || (o.kind == OP_PW && o.res >= 0 && inside[o.res])) return false;
-      if (o.kind != OP_HEAD) inside[o.dst] = false;
-    }
+    const int t0 = pr.ops[0].in0;   // the front stage's output
+    for (int m = k + 1; m < n; ++m)
+      if (pr.ops[m].in0 == t0 || pr.ops[m].in1 == t0) return false;
     return true;
   };
   std::vector<std::pair<int, int>> runs;
-  int start = first;
-  for (int i = first; i <= last; ++i) {
-    bool cut = i == last;
+  int start = 0;
+  for (int i = 0; i < n; ++i) {
+    bool cut = i == n - 1;
     if (!cut && h->env.nas_tail_cut > 0) {
-      const hn_nas_op& o = st->ops[i];
-      const hn_nas_op& f = st->ops[start];
-      const bool boundary = (o.kind == OP_PW && !o.relu) || o.kind == OP_MAXPOOL || (o.kind == OP_PW && st->ops[i + 1].kind != OP_DW);
-      const size_t in_b = static_cast<size_t>(f.cin) * f.hin * f.hin, cut_b = static_cast<size_t>(o.cout) * o.hout * o.hout;
-      cut = boundary && cut_b * h->env.nas_tail_cut <= in_b && last - i >= h->env.nas_tail_minops && closed(start, i) && closed(i + 1, last);
+      const size_t in_b = tensor_bytes(pr.ops[start].in0), cut_b = tensor_bytes(pr.ops[i].out);
+      cut = cut_b * h->env.nas_tail_cut <= in_b && n - 1 - i >= h->env.nas_tail_minops && single_crossing(i);
     }
     if (cut) { runs.emplace_back(start, i); start = i + 1; }
   }
-  for (auto& r : runs)
-    if (!closed(r.first, r.second)) return HN_OK;
   for (auto& r : runs) {
     NasTail tl;
-    const int rc = tail_build(h, st, params, r.first, r.second, tl);
+    const int rc = tail_build(h, pr, r.first, r.second, static_cast<int>(tails.size()), tl);
     if (rc != HN_OK) {
-      for (auto& t2 : st->tails) cudaFree(t2.blob);
-      st->tails.clear();
-      st->tail_of_op.assign(n_ops, -1);
+      for (auto& t2 : tails) cudaFree(t2.blob);
+      tails.clear();
       return rc == HN_ERR_UNSUPPORTED ? HN_OK : rc;
     }
-    for (int i = r.first; i <= r.second; ++i) st->tail_of_op[i] = static_cast<int>(st->tails.size());
-    st->tails.push_back(tl);
+    tails.push_back(tl);
   }
   return HN_OK;
 }
@@ -1494,20 +1720,19 @@ static int launch_tail_cfg(const TailParams& p, size_t smem, int sm_count, cudaS
   return HN_OK;
 }
 
-// ops [tl.first, end] of the run for n patches; `out` receives the NHWC output of op `end`
-static int launch_tail(const NasState* st, const NasTail& tl, const uint16_t* in, uint16_t* out, int out_planar, int n, int end, int sm_count,
-                       cudaStream_t s) {
+// ops [tl.first, end] of the run for n patches; `out` receives the output of op `end` (channel-planar or NHWC)
+static int launch_tail(const NasTail& tl, const uint16_t* in, uint16_t* out, int out_planar, int n, int end, int sm_count, cudaStream_t s) {
   TailParams p = tl.params;
-  const hn_nas_op& ol = st->ops[end];
+  const int k = end - tl.first;
   p.in = in;
   p.out = out;
   p.n = n;
-  p.n_ops = end - tl.first + 1;
-  p.out_off = tl.dst_off[end - tl.first];
-  if (ol.kind == OP_PW) p.ops[end - tl.first].parity = 0;   // a run cut short behind the producer (activation dump) stores plain rows
+  p.n_ops = k + 1;
+  p.out_off = tl.dst_off[k];
+  if (tl.is_pw[k]) p.ops[k].parity = 0;   // a run cut short behind the producer (activation dump) stores plain rows
   p.out_planar = out_planar;
-  p.out_pix = ol.hout * ol.hout;
-  p.out_planes_log2 = ilog2(ol.cout / 8);
+  p.out_pix = tl.out_h[k] * tl.out_h[k];
+  p.out_planes_log2 = ilog2(tl.out_c[k] / 8);
   switch (tl.nwg) {
     case 1: return launch_tail_cfg<1>(p, tl.smem, sm_count, s);
     case 2: return launch_tail_cfg<2>(p, tl.smem, sm_count, s);
@@ -1588,16 +1813,31 @@ static int run_nas_ops(hn_handle* h, NasState* st, const char* src, int in_dtype
       for (int i = first; i <= last_op; ++i) {
         const hn_nas_op& o = st->ops[i];
         uint16_t* const op_out = (out_override && i == last_op && o.kind != OP_HEAD) ? out_override : (o.kind != OP_HEAD ? st->slot[o.dst] : nullptr);
+        if (i == st->tail_first && last_op == n_total - 1 && !st->ftails.empty()) {
+          // the forward: folded form, launches chained through the slots, the last one writes the head GEMM's rows
+          const uint16_t* cur = st->slot[st->ops[i].src];
+          int cur_slot = st->ops[i].src;
+          for (size_t k = 0; k < st->ftails.size(); ++k) {
+            const NasTail& tl = st->ftails[k];
+            const bool lastl = k + 1 == st->ftails.size();
+            const int nxt_slot = (cur_slot + 1) % 3;
+            uint16_t* dst = lastl ? st->head_in + static_cast<size_t>(off) * st->headf_k : st->slot[nxt_slot];
+            HN_TRY(launch_tail(tl, cur, dst, 1, n, tl.last, h->sm_count, s));
+            cur = dst;
+            cur_slot = nxt_slot;
+          }
+          break;
+        }
         if (st->tail_of_op[i] >= 0) {
-          // warpgroup-per-patch tail launch: ops [i, end]; a run that ends right before the head writes the head GEMM's rows
+          // plain form: packed ops [i, end]; a run that ends right before the head writes the head GEMM's rows
           const NasTail& tl = st->tails[st->tail_of_op[i]];
-          const int end = std::min(tl.last, last_op);
+          const int end = std::min(tl.last + st->tail_first, last_op);
           const bool to_head = end == n_total - 2 && last_op == n_total - 1;
           uint16_t* dst = to_head ? st->head_in + static_cast<size_t>(off) * st->head_k : ((out_override && end == last_op) ? out_override : st->slot[st->ops[end].dst]);
           // channel-planar interchange towards the next tail launch / the head GEMM (permuted weight K order); a run that
           // stops here (activation dump) writes NHWC like every per-op kernel
-          const int planar = (to_head && st->head_planar) || (end == tl.last && last_op > end && st->tail_of_op[end + 1] >= 0);
-          HN_TRY(launch_tail(st, tl, st->slot[st->ops[tl.first].src], dst, planar, n, end, h->sm_count, s));
+          const int planar = (to_head && st->head_planar) || (end == tl.last + st->tail_first && last_op > end && st->tail_of_op[end + 1] >= 0);
+          HN_TRY(launch_tail(tl, st->slot[st->ops[tl.first + st->tail_first].src], dst, planar, n, end - st->tail_first, h->sm_count, s));
           i = to_head ? end + 1 : end;
           continue;
         }
@@ -1957,24 +2197,67 @@ extern "C" int hn_pack_nas(hn_handle* h, const hn_nas_op* ops, int n_ops, const 
   {
     int rc = seg_partition(h, st, params);
     if (rc != HN_OK) return fail(rc);
-    rc = tail_partition(h, st, params);
-    if (rc != HN_OK) return fail(rc);
-    if (!st->tails.empty() && st->tails.back().last == n_ops - 2) {
-      // the last tail launch bulk-stores its channel-planar output as the head GEMM's input row: K index
-      // plane * (pix * 8) + pixel * 8 + c % 8 instead of NHWC's pixel * C + c
-      const hn_nas_op& oh = ops[n_ops - 1];
-      const int pix = oh.kernel * oh.kernel, C = oh.cin;
-      std::vector<uint16_t> wh(static_cast<size_t>(128) * st->head_k);
-      for (int nn = 0; nn < 128; ++nn)
-        for (int px = 0; px < pix; ++px)
-          for (int c = 0; c < C; ++c)
-            wh[static_cast<size_t>(nn) * st->head_k + (c >> 3) * (pix * 8) + px * 8 + (c & 7)] =
-                f2h16(params[oh.w_off + static_cast<size_t>(nn) * st->head_k + px * C + c], bf);
-      if (cudaMemcpy(st->w16 + st->w16_off[n_ops - 1], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
-        set_error("hn_pack_nas: head weight upload failed");
-        return fail(HN_ERR_CUDA);
+    // warpgroup-per-patch tail launches behind the fused front stage (fp16 activations, every op of a supported shape)
+    st->tail_of_op.assign(n_ops, -1);
+    st->tail_first = st->front_ops + 1;
+    if (h->env.nas_tail && !bf && st->front_fdw && h->env.nas_front && st->tail_first <= n_ops - 2) {
+      TProg plain;
+      if (tail_prog_plain(st->ops, params, st->tail_first, plain)) {
+        rc = tail_partition(h, plain, st->tails);
+        if (rc != HN_OK) return fail(rc);
       }
-      st->head_planar = 1;
+      for (size_t k = 0; k < st->tails.size(); ++k)
+        for (int i = st->tails[k].first; i <= st->tails[k].last; ++i) st->tail_of_op[st->tail_first + i] = static_cast<int>(k);
+      TProg fold;
+      if (!st->tails.empty() && h->env.nas_fold && tail_prog_folded(st->ops, params, st->tail_first, fold)) {
+        rc = tail_partition(h, fold, st->ftails);
+        if (rc != HN_OK) return fail(rc);
+      }
+      auto planar_head = [&](const TProg& pr, std::vector<uint16_t>& wh) {
+        // a tail launch bulk-stores its channel-planar output as the head GEMM's input row: K index
+        // plane * (pix * 8) + pixel * 8 + c % 8 instead of NHWC's pixel * C + c
+        const int pix = pr.head_pix, C = pr.head_c;
+        const size_t K = static_cast<size_t>(pix) * C;
+        wh.assign(128 * K, 0);
+        for (int nn = 0; nn < 128; ++nn)
+          for (int px = 0; px < pix; ++px)
+            for (int c = 0; c < C; ++c)
+              wh[nn * K + (c >> 3) * (pix * 8) + px * 8 + (c & 7)] = f2h16(pr.head_w[nn * K + static_cast<size_t>(px) * C + c], 0);
+      };
+      if (!st->tails.empty()) {
+        std::vector<uint16_t> wh;
+        planar_head(plain, wh);
+        if (cudaMemcpy(st->w16 + st->w16_off[n_ops - 1], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+          set_error("hn_pack_nas: head weight upload failed");
+          return fail(HN_ERR_CUDA);
+        }
+        st->head_planar = 1;
+      }
+      if (!st->ftails.empty()) {
+        std::vector<uint16_t> wh;
+        planar_head(fold, wh);
+        st->headf_k = fold.head_pix * fold.head_c;
+        if (cudaMalloc(&st->headf_w, wh.size() * 2) != cudaSuccess || cudaMalloc(&st->headf_b, 128 * sizeof(float)) != cudaSuccess ||
+            cudaMemcpy(st->headf_w, wh.data(), wh.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(st->headf_b, fold.head_b.data(), 128 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+          set_error("hn_pack_nas: folded head upload failed");
+          return fail(HN_ERR_CUDA);
+        }
+        TcParams& hp = st->headf;
+        hp = st->head;
+        const uint64_t K = static_cast<uint64_t>(st->headf_k);
+        const uint64_t dimsA[2] = {K, static_cast<uint64_t>(h->head_rows)};
+        const uint64_t strA[1] = {K * 2};
+        const uint32_t boxA[2] = {64, static_cast<uint32_t>(kTileM)};
+        rc = make_tmap_16bit(&hp.tmA[0], st->head_in, 2, dimsA, strA, boxA, 128);
+        if (rc != HN_OK) return fail(rc);
+        const uint64_t dimsB[2] = {K, 128};
+        const uint32_t boxB[2] = {64, 128};
+        rc = make_tmap_16bit(&hp.tmB, st->headf_w, 2, dimsB, strA, boxB, 128);
+        if (rc != HN_OK) return fail(rc);
+        hp.num_k_stages = static_cast<int>(K / (64 * kHeadG));
+        hp.bias = st->headf_b;
+      }
     }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) {
@@ -2009,7 +2292,7 @@ extern "C" int hn_forward_nas(hn_handle* h, const void* patches, int in_dtype, l
       const char* src = static_cast<const char*>(patches) + static_cast<size_t>(base + off) * 1024 * in_elem;
       HN_TRY(run_nas_ops(h, st, src, in_dtype, n, off, n_ops - 1, s));
     }
-    TcParams p = st->head;
+    TcParams p = st->ftails.empty() ? st->head : st->headf;
     p.total_rows = nb;
     p.num_tiles = static_cast<int>((nb + kTileM - 1) / kTileM);
     p.out_dtype = out_dtype;
@@ -2055,9 +2338,15 @@ extern "C" int hn_nas_plan(hn_handle* h, int* out, int cap) {
     const NasSegment& sg = h->nas->segs[i];
     out[4 * i] = sg.first; out[4 * i + 1] = sg.last; out[4 * i + 2] = sg.G; out[4 * i + 3] = sg.minb;
   }
-  // warpgroup-per-patch tail launches: (first, last, patches in flight per CTA, 0)
-  for (const NasTail& tl : h->nas->tails) {
-    if (n < cap && out) { out[4 * n] = tl.first; out[4 * n + 1] = tl.last; out[4 * n + 2] = tl.nwg; out[4 * n + 3] = 0; }
+  // warpgroup-per-patch tail launches of the forward: (first packed op, last packed op, patches in flight per CTA, 0); in the
+  // folded form a launch starts / ends at the packed op whose output its first / last op produces
+  const bool folded = !h->nas->ftails.empty();
+  for (const NasTail& tl : (folded ? h->nas->ftails : h->nas->tails)) {
+    if (n < cap && out) {
+      out[4 * n] = folded ? tl.params.op_base : tl.first + h->nas->tail_first;
+      out[4 * n + 1] = folded ? tl.last_orig : tl.last + h->nas->tail_first;
+      out[4 * n + 2] = tl.nwg; out[4 * n + 3] = 0;
+    }
     ++n;
   }
   return n;

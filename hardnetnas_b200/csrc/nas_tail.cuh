@@ -186,7 +186,9 @@ __device__ __forceinline__ uint32_t tail_pack_sat(float lo, float hi) {
 // ---- pointwise conv of one patch: MMAs issued by one lane of the warpgroup's first warp, epilogue by its four warps ------
 // COLS = the warpgroup's tensor-memory columns (128 with up to four warpgroups per CTA, 64 with five or six): an op whose
 // accumulators need more (C_out = 128) runs as two column passes of N = 64, one after the other.
-template <int CIN, int COUT, int ROWS, int COLS, int STEP_MAX>
+// RESW > 0: a second input tensor of RESW channels with its own weights (a folded block: y = relu(W a + W1 x + b), nas.cu);
+// RESW == 0 and res_off >= 0: a plain residual, added through 16 x 16 identity slices.
+template <int CIN, int COUT, int ROWS, int COLS, int STEP_MAX, int RESW = 0>
 __device__ __forceinline__ void tail_pw(uint8_t* __restrict__ buf, uint32_t buf_addr, const uint8_t* __restrict__ sm, uint32_t base,
                                         const TailOp& o, int ones_off, int eye_off, uint32_t tmem_wg, uint32_t bar, uint32_t& phase, int wg,
                                         int q, int lane, int trace_op) {
@@ -208,11 +210,12 @@ __device__ __forceinline__ void tail_pw(uint8_t* __restrict__ buf, uint32_t buf_
       tc_fence_after();
       if (elect_one()) {
         constexpr uint32_t a_hi = noswizzle_desc_hi(128);
-        constexpr uint32_t b_hi = noswizzle_desc_hi((CIN + 16) * 16);
+        constexpr int KP = CIN + 16 + RESW;                // K of the weight image: [W | bias hi, lo, 0... | W1]
+        constexpr uint32_t b_hi = noswizzle_desc_hi(KP * 16);
         constexpr uint32_t idesc = make_idesc_f16(kTileM, NP, 0);
         const uint32_t a_lo0 = noswizzle_desc_lo(buf_addr + o.src_off, PITCH);
-        // weight image rows [np * NP, (np + 1) * NP): 8-row groups are (CIN + 16) * 16 bytes apart
-        const uint32_t b_lo0 = noswizzle_desc_lo(base + o.w_off + np * (NP / 8) * ((CIN + 16) * 16), 128);
+        // weight image rows [np * NP, (np + 1) * NP): 8-row groups are KP * 16 bytes apart
+        const uint32_t b_lo0 = noswizzle_desc_lo(base + o.w_off + np * (NP / 8) * (KP * 16), 128);
         const uint32_t ones_lo = noswizzle_desc_lo(base + ones_off, 2048);
 #pragma unroll
         for (int t = 0; t < TILES; ++t) {
@@ -221,8 +224,15 @@ __device__ __forceinline__ void tail_pw(uint8_t* __restrict__ buf, uint32_t buf_
             umma_f16_w(tmem_wg + t * NP, a_lo0 + t * (2048u >> 4) + k * ((2u * PITCH) >> 4), a_hi, b_lo0 + k * 16u, b_hi, idesc, k != 0);
           // + bias: a K step of the constant "ones" tile against the weight image's last 16 K columns (bias as fp16 hi + lo)
           umma_f16_w(tmem_wg + t * NP, ones_lo, a_hi, b_lo0 + (CIN / 16) * 16u, b_hi, idesc, 1u);
+          if constexpr (RESW > 0) {
+            // + W1 x: K steps over the second input (same pixel pitch) against the image's last RESW K columns
+            const uint32_t x_lo0 = noswizzle_desc_lo(buf_addr + o.res_off, PITCH);
+#pragma unroll
+            for (int k = 0; k < RESW / 16; ++k)
+              umma_f16_w(tmem_wg + t * NP, x_lo0 + t * (2048u >> 4) + k * ((2u * PITCH) >> 4), a_hi, b_lo0 + (CIN / 16 + 1 + k) * 16u, b_hi, idesc, 1u);
+          }
         }
-        if (o.res_off >= 0) {
+        if (RESW == 0 && o.res_off >= 0) {
           // + residual: 16-channel slices of the block input against a 16 x 16 identity (exact in the fp32 accumulator)
           constexpr uint32_t e_hi = noswizzle_desc_hi(256);
           constexpr uint32_t idesc16 = make_idesc_f16(kTileM, 16, 0);
@@ -352,17 +362,21 @@ __global__ void __launch_bounds__(NWG * 128, 1) nas_tail_kernel(const __grid_con
       const TailOp& o = p.ops[oi];
       HN_TAIL_T(t_op);
       if (o.kind == TAIL_PW) {
-#define HN_TAIL_PW(CI, CO, R) tail_pw<CI, CO, R, COLS, STEPM>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, wg, q, lane, p.op_base + oi)
+#define HN_TAIL_PW(CI, CO, R, RW) tail_pw<CI, CO, R, COLS, STEPM, RW>(buf, buf_addr, sm, base, o, p.ones_off, p.eye_off, tmem_wg, bar, phase, wg, q, lane, p.op_base + oi)
         // five or six warpgroups only fit when no 16 x 16 map is part of the run (8 KB regions): those shapes are not compiled in
         if constexpr (NWG <= 4) {
-          if (o.shape == 0) HN_TAIL_PW(32, 32, 256);
+          if (o.shape == 0) HN_TAIL_PW(32, 32, 256, 0);
+          if (o.shape == 5) HN_TAIL_PW(32, 32, 256, 32);
         }
-        switch (o.shape) {
-          case 0: break;
-          case 1: HN_TAIL_PW(32, 64, 64); break;
-          case 2: HN_TAIL_PW(64, 64, 64); break;
-          case 3: HN_TAIL_PW(64, 128, 16); break;
-          default: HN_TAIL_PW(128, 128, 16); break;
+        switch (o.shape) {        // (cin, weighted second-input channels, cout, pixels): tail_pw_shape in nas.cu
+          case 0: case 5: break;
+          case 1: HN_TAIL_PW(32, 64, 64, 0); break;
+          case 2: HN_TAIL_PW(64, 64, 64, 0); break;
+          case 3: HN_TAIL_PW(64, 128, 16, 0); break;
+          case 4: HN_TAIL_PW(128, 128, 16, 0); break;
+          case 6: HN_TAIL_PW(64, 64, 64, 32); break;
+          case 7: HN_TAIL_PW(64, 64, 64, 64); break;
+          default: HN_TAIL_PW(128, 128, 16, 64); break;
         }
 #undef HN_TAIL_PW
       } else if (o.kind == TAIL_DW) {
