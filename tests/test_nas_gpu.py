@@ -172,21 +172,26 @@ def test_default_plan_is_front_tail_head():
     """fp16 nets of expansion-1 blocks (every recorded architecture) run as fused front kernel + warpgroup-per-patch tail
     launches (csrc/nas_tail.cuh) + head GEMM; HN_NAS_TAIL=0, bf16 activations and wider blocks keep one kernel per op."""
     net, _, _ = build("wang2")
-    assert net.resident_plan() == [(3, 9, 4, 0), (10, 15, 6, 0)]       # (first op, last op, patches in flight per CTA, 0)
-    assert build("wang3")[0].resident_plan() == [(3, 8, 3, 0)]
+    # (packed op that produces the launch's first / last output, patches in flight per CTA, 0); folded form: the linear
+    # convs 3, 6, 9, 12, 15 are gone (absorbed by ops 4, 7, 10, 13 and the head)
+    assert net.resident_plan() == [(4, 8, 4, 0), (10, 14, 6, 0)]
+    assert build("wang3")[0].resident_plan() == [(4, 8, 3, 0)]
     assert build("mixed_se")[0].resident_plan() == []
     assert build("wang2", act_dtype="bf16")[0].resident_plan() == []
 
 
-@pytest.mark.parametrize("arch,env", [("wang2", {}), ("wang2", {"HN_NAS_TAIL_CUT": "0"}), ("wang2", {"HN_NAS_TAIL_WG": "1"}),
-                                      ("wang2", {"HN_NAS_TAIL_MINOPS": "1", "HN_NAS_TAIL_CUT": "1"}), ("wang3", {}),
-                                      ("wang3", {"HN_NAS_TAIL_MINOPS": "1"}), ("wang4", {}), ("wang4", {"HN_NAS_TAIL_WG": "3", "HN_NAS_TAIL_MINOPS": "1"})])
+@pytest.mark.parametrize("arch,env", [("wang2", {}), ("wang2", {"HN_NAS_FOLD": "0"}), ("wang2", {"HN_NAS_TAIL_CUT": "0"}), ("wang2", {"HN_NAS_TAIL_WG": "1"}),
+                                      ("wang2", {"HN_NAS_TAIL_MINOPS": "1", "HN_NAS_TAIL_CUT": "1"}),
+                                      ("wang2", {"HN_NAS_TAIL_MINOPS": "1", "HN_NAS_TAIL_CUT": "1", "HN_NAS_FOLD": "0"}), ("wang3", {}),
+                                      ("wang3", {"HN_NAS_TAIL_MINOPS": "1"}), ("wang3", {"HN_NAS_FOLD": "0"}), ("wang4", {}),
+                                      ("wang4", {"HN_NAS_TAIL_WG": "3", "HN_NAS_TAIL_MINOPS": "1"}), ("wang4", {"HN_NAS_FOLD": "0"})])
 def test_tail_kernel_plans(arch, env, monkeypatch):
     """The tail kernel (IRFBlock pw -> dw -> pwl [+x] and Identity pool / 1x1 conv, fbnet_builder.py:455-570, :202-228, with the
-    patch resident in shared memory; bias and residual added by the tensor core; parity layout in front of stride-2 readers)
-    under several launch plans: descriptors against the oracle for a ragged batch that leaves warpgroups without a patch, and
-    the output of EVERY op (runs cut short behind any op, incl. behind a parity-layout producer) against the one-kernel-per-op
-    path and, at the block boundaries, against the oracle."""
+    patch resident in shared memory; bias and second input added by the tensor core; parity layout in front of stride-2
+    readers) under several launch plans, with the linear 1x1 convs folded into their consumers (default) and op by op
+    (HN_NAS_FOLD=0): descriptors against the oracle for a ragged batch that leaves warpgroups without a patch, and the output
+    of EVERY packed op (the dump runs the unfolded form cut short behind that op, incl. behind a parity-layout producer)
+    against the one-kernel-per-op path and, at the block boundaries, against the oracle."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     net, ops, sd = build(arch, chunk_patches=64, head_rows=256)
