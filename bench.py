@@ -631,7 +631,10 @@ def bench_nas(device, peaks, with_cpu):
     rec = {"metric": "nas_descriptor_patches_per_sec", "unit": "patches/s", "value": rate, "ms_per_step": ms,
            "workload": f"BASELINE configs[4]: sampled NAS descriptor net wang2 (hardnetNAS fbnet_building_blocks), eval forward at batch {B}, "
                        "fp32 in / fp32 out, fp16 activations",
-           "resident_plan": nas.resident_plan(),
+           "launch_plan": {"tail_launches": nas.resident_plan(), "launches_per_pass": 2 + len(nas.resident_plan()),
+                           "note": "fused front kernel (stem + pw + stride-2 dw) + warpgroup-per-patch tail launches (first packed op, last packed op, "
+                                   "patches in flight per CTA, 0) with the linear 1x1 convs folded into their consumers + head GEMM; "
+                                   "ncu launch list profiles/r2_nas_launch_table_tail.txt"},
            "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"],
                         "achieved": rate * NAS_ALGO_BYTES_PER_PATCH / 1e9, "frac": rate * NAS_ALGO_BYTES_PER_PATCH / 1e9 / peaks["hbm_gbs"],
                         "algorithmic_bytes_per_patch": NAS_ALGO_BYTES_PER_PATCH,
@@ -652,6 +655,19 @@ def bench_nas(device, peaks, with_cpu):
     dt = (time.perf_counter() - t0) / 5
     rec["e2e"] = {"value": B / dt, "unit": "patches/s", "h2d_bytes_per_step": B * 4096, "d2h_bytes_per_step": B * 512,
                   "api": "hardnetnas_b200.extract.DescriptorExtractor(SampledDescriptorNet('wang2')) on pinned host buffers"}
+    # the same pipeline fed with uint8 patches (1 KB instead of 4 KB per patch over PCIe: the fp32 line is bound by the host link)
+    h_u8 = torch.empty((B, 1, 32, 32), dtype=torch.uint8, pin_memory=True)
+    h_u8.copy_((h_in * 255.0).round_().clamp_(0, 255))
+    ext8 = DescriptorExtractor(nas, device=device, in_dtype=torch.uint8)
+    ext8(h_u8, h_out)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ext8(h_u8, h_out)
+    torch.cuda.synchronize()
+    dt8 = (time.perf_counter() - t0) / 5
+    rec["e2e_u8"] = {"value": B / dt8, "unit": "patches/s", "h2d_bytes_per_step": B * 1024, "d2h_bytes_per_step": B * 512,
+                     "input": "uint8 patches (dataset storage format)"}
+    del ext8, h_u8
     if with_cpu:
         from oracle import nas_oracle
         from hardnetnas_b200.nas.fbnet_modeldef import arch_ops
