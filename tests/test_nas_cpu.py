@@ -69,3 +69,21 @@ def test_load_from_supernet_state_dict():
     other.load_from_supernet({k: v for k, v in fake.items() if "thetas" not in k}, CANDIDATE_BLOCKS)
     for k, v in other.state_dict().items():
         assert torch.equal(v, sd[k])
+
+
+def test_latency_table_text_format_round_trip(tmp_path):
+    """lookup_table_builder.py:160-188: op names on the first line, one line of latencies per searched layer."""
+    from hardnetnas_b200.nas.lookup_table import CANDIDATE_BLOCKS, LookUpTable
+    t = LookUpTable()
+    assert t.lookup_table_latency is None and t.cnt_layers == 6
+    t.lookup_table_latency = [{op: float(100 * i + k) + 0.25 for k, op in enumerate(CANDIDATE_BLOCKS)} for i in range(6)]
+    path = tmp_path / "lookup_table.txt"
+    t._write_lookup_table_to_file(path)
+    lines = path.read_text().split("\n")
+    assert lines[0] == " ".join(CANDIDATE_BLOCKS) and len(lines) == 7
+    assert LookUpTable(path_to_file=path).lookup_table_latency == t.lookup_table_latency
+    # a file in the layout the reference ships (supernet_functions/lookup_table.txt: same header, float rows)
+    ref_like = tmp_path / "ref.txt"
+    ref_like.write_text(" ".join(CANDIDATE_BLOCKS) + "\n" + "\n".join(" ".join(str(2.38 + j + i) for j in range(17)) for i in range(6)))
+    got = LookUpTable(path_to_file=ref_like).lookup_table_latency
+    assert got[0]["skip"] == 2.38 and got[5]["ir_k5_s2_se"] == 2.38 + 16 + 5

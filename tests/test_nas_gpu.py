@@ -225,3 +225,19 @@ def test_tail_kernel_uint8_and_batch_one():
     x = synth.make_patches(1, 3, edge_cases=False)
     max_abs, cos = _cmp(net(x.cuda()), nas_oracle.nas_forward(x, ops, sd))
     assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (max_abs, cos)
+
+
+def test_latency_table_on_the_engine(tmp_path):
+    """lookup_table_builder.py:121-158 measured on this library's kernels (differential whole-net timing) and, as the reference
+    does it, on the candidates' torch modules; the written file reads back."""
+    from hardnetnas_b200.nas.lookup_table import LookUpTable
+    cands = ["skip", "ir_k3_e1", "ir_k5_s2", "ir_k3_e3_se"]
+    path = tmp_path / "lookup_table.txt"
+    t = LookUpTable(candidate_blocks=cands, calulate_latency=True, path_to_file=path, cnt_of_runs=3, engine="b200")
+    assert len(t.lookup_table_latency) == 6
+    for row in t.lookup_table_latency:
+        assert row["skip"] == 0.0 and all(np.isfinite(v) and 0.0 <= v < 50.0 for v in row.values()), row
+    assert any(row["ir_k3_e3_se"] > 0.0 for row in t.lookup_table_latency)
+    assert LookUpTable(candidate_blocks=cands, path_to_file=path).lookup_table_latency == t.lookup_table_latency
+    tt = LookUpTable(candidate_blocks=cands[:2], calulate_latency=True, cnt_of_runs=2, engine="torch")
+    assert all(v > 0.0 and np.isfinite(v) for row in tt.lookup_table_latency for v in row.values())
