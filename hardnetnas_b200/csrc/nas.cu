@@ -1529,6 +1529,13 @@ static int tail_build(hn_handle* h, const TProg& pr, int first, int last, int la
   for (int i = first; i <= last; ++i) {
     const TOp& o = pr.ops[i];
     if (tail_op_shape(o) < 0) return HN_ERR_UNSUPPORTED;
+    // weights and biases are stored as fp16 (the bias as hi + lo): values outside its range keep the per-op path (fp32 biases)
+    auto fits16 = [](const std::vector<float>& v) {
+      for (float x : v)
+        if (!(std::fabs(x) < 60000.f)) return false;
+      return true;
+    };
+    if (!fits16(o.w) || !fits16(o.w1) || !fits16(o.b)) return HN_ERR_UNSUPPORTED;
     const size_t in_b = static_cast<size_t>(o.cin) * o.hin * o.hin * 2, out_b = static_cast<size_t>(o.cout) * o.hout * o.hout * 2;
     region_bytes = std::max(region_bytes, std::max(in_b, out_b));
     if (o.in1 >= 0) region_bytes = std::max(region_bytes, static_cast<size_t>(o.c1) * o.hin * o.hin * 2);
