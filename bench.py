@@ -350,8 +350,9 @@ def run_b200(args):
             ms_all, n_all = model.profile_read()
             model.profile_enable(0)
     torch.cuda.synchronize()
+    stage_names, stage_macs = HardNet.stage_table(n_all)   # conv3 + conv4 are one kernel when the engine fuses them
     dom = max(range(7), key=lambda i: ms_all[i])
-    stage_share = {HardNet.STAGE_NAMES[i]: round(ms_all[i] / max(sum(ms_all), 1e-9), 4) for i in range(7)}
+    stage_share = {stage_names[i]: round(ms_all[i] / max(sum(ms_all), 1e-9), 4) for i in range(7) if stage_macs[i] or ms_all[i]}
 
     # ---- timed region: device-resident inputs ------------------------------------------------------------
     model.profile_enable(1 << dom)
@@ -375,12 +376,12 @@ def run_b200(args):
     value = world * P * args.steps / (ms_total / 1e3)
 
     peaks = load_peaks()
-    dom_flops = 2.0 * HardNet.STAGE_MACS[dom] * P * args.steps      # algorithmic FLOPs of that stage over the region
+    dom_flops = 2.0 * stage_macs[dom] * P * args.steps      # algorithmic FLOPs of that stage over the region
     achieved_tflops = dom_flops / (dom_ms[dom] / 1e3) / 1e12
     flops_per_launch = dom_flops / max(dom_n[dom], 1)
     roofline = {
-        "kernel": HardNet.STAGE_NAMES[dom], "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["tflops_sustained"],
-        "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops_sustained"], "traffic": load_traffic(HardNet.STAGE_NAMES[dom]),
+        "kernel": stage_names[dom], "bound": "tensor", "achieved": achieved_tflops, "peak": peaks["tflops_sustained"],
+        "unit": "TFLOP/s", "frac": achieved_tflops / peaks["tflops_sustained"], "traffic": load_traffic(stage_names[dom]),
         "peak_source": peaks["source"] + ", sustained bf16 dense (kernel timed inside a long step)",
         "launches": dom_n[dom], "avg_launch_ms": dom_ms[dom] / max(dom_n[dom], 1), "algorithmic_flop_per_launch": flops_per_launch,
         "stage_time_share_warmup": stage_share,

@@ -7,6 +7,7 @@
 
 #include "../../include/hardnet_b200.h"
 #include "tc_conv.cuh"
+#include "tc_conv34.cuh"
 
 namespace hn {
 struct NasState;
@@ -74,6 +75,10 @@ struct hn_handle {
   hn::TcParams pair_params[5];   // same layers for the CTA-pair kernels (tc_conv_pair.cuh)
   unsigned pair_mask = 0;        // bit li: layer li runs on CTA pairs
   hn::TcParams head_params;
+  int fuse34 = 0;                // HN_FUSE34: conv3 + conv4 in one kernel (tc_conv34.cuh): 0 = off, 1 = one load per tap, 2 = one load
+                                 // per (row parity, kx); the deeper layers then read / write the other ping-pong buffer
+  int fuse34_sched = 1;          // HN_FUSE34_SCHED
+  hn::Conv34Params c34;
   // optional per-stage CUDA-event timing (stage 0 = L1, 1..5 = 3x3 convs, 6 = head)
   unsigned profile_mask = 0;
   std::vector<cudaEvent_t> ev[7];

@@ -16,6 +16,7 @@
 #include "l1_tc.cuh"
 #include "tc_conv.cuh"
 #include "tc_conv_pair.cuh"
+#include "tc_conv34.cuh"
 
 namespace hn {
 
@@ -109,6 +110,7 @@ static const bool kRowShift[5] = {true, false, true, false, true};
 static const bool kPairRowShift[5] = {false, false, true, false, true};
 static const int kPairKcb[5] = {64, 64, 128, 128, 128};
 static const unsigned kDefaultPairMask = 0x1c;   // conv4, conv5, conv6 (conv3 is faster with two independent CTAs per SM)
+static const int kDefaultFuse34 = 2;
 static const int kKcb[5] = {64, 64, 128, 128, 64};   // bytes of one pixel's channel chunk per k-block (ConvCfg::KCB)
 
 static int launch_conv_pair(int li, const TcParams& p, int sm_count, cudaStream_t s) {
@@ -129,6 +131,69 @@ static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) 
     case 4: return HN_CONV_L6(p, sm_count, s);
   }
   return HN_ERR_INVALID;
+}
+
+// conv3 + conv4 in one kernel (tc_conv34.cuh): conv2 output in act[1] -> conv4 output in `out`.
+template <bool SIX, int SCHED, int PF>
+static int launch_conv34_cfg(const Conv34Params& p, int sm_count, cudaStream_t stream) {
+  using C = C34Cfg<SIX>;
+  auto kern = conv34_pair_kernel<SIX, SCHED, PF>;
+  static DeviceOnce attr_once;  // per instantiation
+  if (attr_once.first_time()) {
+    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
+  }
+  if (p.n_patches <= 0) return HN_OK;
+  const int groups = (p.n_patches + 1) / 2;
+  const int grid = 2 * std::min(groups, sm_count / 2);   // whole CTA pairs (__cluster_dims__(2, 1, 1))
+  kern<<<grid, kC34Threads, C::SMEM, stream>>>(p);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
+static int build_conv34_params(hn_handle* h) {
+  Conv34Params& p = h->c34;
+  memset(&p, 0, sizeof(p));
+  if (!h->fuse34) return HN_OK;
+  const uint16_t* in = h->act[1];   // conv2 output: parity sub-planes [patch][4 planes][ypar][xpar][16][16][8]
+  const uint32_t rows = h->fuse34 == 2 ? 9u : 8u;
+  const uint32_t box[4] = {16 * 8, rows, 1, 4};
+  for (int ypar = 0; ypar < 2; ++ypar)
+    for (int xpar = 0; xpar < 2; ++xpar) {
+      const uint64_t dims[4] = {16 * 8, 16, static_cast<uint64_t>(h->chunk), 4};
+      const uint64_t str[3] = {16 * 16, 32ull * 32 * 32 * 2, 32 * 32 * 16};
+      HN_TRY(make_tmap_16bit(&p.tmA[ypar * 2 + xpar], in + (ypar * 2 + xpar) * 16 * 16 * 8, 4, dims, str, box, 0));
+    }
+  {
+    const uint64_t dims[2] = {9 * 32, 64};
+    const uint64_t str[1] = {9 * 32 * 2};
+    const uint32_t wbox[2] = {32, 32};
+    HN_TRY(make_tmap_16bit(&p.tmB3, h->wconv[1], 2, dims, str, wbox, 64));
+  }
+  {
+    const uint64_t dims[2] = {9 * 64, 64};
+    const uint64_t str[1] = {9 * 64 * 2};
+    const uint32_t wbox[2] = {64, 32};
+    HN_TRY(make_tmap_16bit(&p.tmB4, h->wconv[2], 2, dims, str, wbox, 128));
+  }
+  return HN_OK;
+}
+
+static int run_conv34(hn_handle* h, int n, void* out, cudaStream_t s) {
+  Conv34Params p = h->c34;
+  p.n_patches = n;
+  p.act_bf16 = h->act_bf16;
+  p.out = out;
+  StageTimer timer(h, 2, s);   // reported as the conv3 stage; the conv4 stage then has no launches of its own
+  if (h->fuse34 == 1) return launch_conv34_cfg<false, 0, 0>(p, h->sm_count, s);
+  switch (h->fuse34_sched) {   // <interleaved conv3 load units, prefetch distance>
+    case 0: return launch_conv34_cfg<true, 0, 0>(p, h->sm_count, s);
+    case 6: return launch_conv34_cfg<true, 6, 0>(p, h->sm_count, s);
+    case 10: return launch_conv34_cfg<true, 0, 2>(p, h->sm_count, s);
+    case 12: return launch_conv34_cfg<true, 2, 2>(p, h->sm_count, s);
+    case 14: return launch_conv34_cfg<true, 4, 2>(p, h->sm_count, s);
+    default: return launch_conv34_cfg<true, 6, 2>(p, h->sm_count, s);
+  }
 }
 
 // Stage 1 (input_norm + conv 1->32 + BN + ReLU) on the tensor core; do_norm = 0 gives the NAS stem.
@@ -292,7 +357,9 @@ static int build_conv_params(hn_handle* h, int li, int kcb, bool rowshift, bool 
   const ConvLayer& L = kConv[li];
   memset(&p, 0, sizeof(p));
   const int kc = kcb / 2;
-  const uint16_t* in = h->act[li & 1];  // the front kernel writes act[1]; layers alternate
+  // the front kernel writes act[1]; layers alternate. With conv3 + conv4 fused the conv4 output lands in act[0] (the fused
+  // kernel cannot write the buffer it reads), so conv5 / conv6 use the opposite buffers.
+  const uint16_t* in = h->act[(li & 1) ^ ((h->fuse34 && li >= 3) ? 1 : 0)];
   const int pix_out = L.hout * L.hout;
   const int rows_per_tile = pix_out >= kTileM ? kTileM / L.hout : L.hout;
   const int patches_per_tile = pix_out >= kTileM ? 1 : kTileM / pix_out;
@@ -353,6 +420,7 @@ static int build_params(hn_handle* h) {
     p.bias = h->bias + 128 * 6;
     p.l2_eps = 1e-10f;
   }
+  HN_TRY(build_conv34_params(h));
   return HN_OK;
 }
 
@@ -380,6 +448,7 @@ static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n
   // `front_chunk` patches over the SAME head of act[1], so it is produced and consumed inside the 126 MB L2 instead of
   // making an HBM round trip; conv3 writes into the full-size act[0] and the deeper stages run once over the whole pass.
   const int front = last_layer >= 3 ? std::min(h->front_chunk, n) : n;
+  const bool fuse = h->fuse34 != 0 && last_layer >= 4;   // a dump of conv3's own output runs the layer on its own
   const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
   for (int off = 0; off < n; off += front) {
     const int m = std::min(front, n - off);
@@ -388,10 +457,11 @@ static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n
       HN_TRY(launch_front_fused(h, static_cast<const char*>(patches) + static_cast<size_t>(off) * 1024 * in_elem, in_dtype,
                                 h->act[1], m, s));
     }
-    if (last_layer >= 3) HN_TRY(run_one_conv(h, 1, m, h->act[0] + static_cast<size_t>(off) * 16 * 16 * 64, s));
+    if (fuse) HN_TRY(run_conv34(h, m, h->act[0] + static_cast<size_t>(off) * 16 * 16 * 64, s));
+    else if (last_layer >= 3) HN_TRY(run_one_conv(h, 1, m, h->act[0] + static_cast<size_t>(off) * 16 * 16 * 64, s));
   }
-  for (int li = 2; li < 5 && li + 2 <= last_layer; ++li)
-    HN_TRY(run_one_conv(h, li, n, (li == 4) ? static_cast<void*>(h->l6 + l6_row * kHeadK) : static_cast<void*>(h->act[(li + 1) & 1]), s));
+  for (int li = fuse ? 3 : 2; li < 5 && li + 2 <= last_layer; ++li)
+    HN_TRY(run_one_conv(h, li, n, (li == 4) ? static_cast<void*>(h->l6 + l6_row * kHeadK) : static_cast<void*>(h->act[((li + 1) & 1) ^ (fuse ? 1 : 0)]), s));
   return HN_OK;
 }
 
@@ -443,6 +513,12 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   {
     const char* e = getenv("HN_FRONT_CHUNK");   // patches per front-kernel + conv3 sub-pass
     h->front_chunk = e ? std::max(2, atoi(e)) : chunk_patches;
+  }
+  {
+    const char* e = getenv("HN_FUSE34");   // conv3 + conv4 in one kernel: 0 = off, 1 = a load per tap, 2 = a load per (row parity, kx)
+    h->fuse34 = e ? std::min(2, std::max(0, atoi(e))) : kDefaultFuse34;
+    const char* e2 = getenv("HN_FUSE34_SCHED");   // 1: conv3 load units dealt between the conv4 MMA groups (tc_conv34.cuh)
+    h->fuse34_sched = e2 ? atoi(e2) : 6;
   }
   {
     const char* e = getenv("HN_PAIR_MASK");   // bit li: run 3x3 layer li (1 = conv3 .. 4 = conv6) on CTA pairs
@@ -572,6 +648,8 @@ extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const floa
   (void)cout;
   HN_CUDA(cudaMemcpy(h->bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
   memcpy(h->bias2_host, bias.data() + 128, sizeof(h->bias2_host));
+  memcpy(h->c34.bias3, bias.data() + 128 * 2, sizeof(h->c34.bias3));
+  memcpy(h->c34.bias4, bias.data() + 128 * 3, sizeof(h->c34.bias4));
   for (int li = 0; li < 5; ++li) {   // by-value copies for the conv kernels' epilogues
     memcpy(h->conv_params[li].bias_v, bias.data() + 128 * (li + 1), sizeof(h->conv_params[li].bias_v));
     memcpy(h->pair_params[li].bias_v, bias.data() + 128 * (li + 1), sizeof(h->pair_params[li].bias_v));
@@ -632,7 +710,7 @@ extern "C" int hn_forward_dump(hn_handle* h, const void* patches, int in_dtype, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   HN_TRY(run_conv_stack(h, patches, in_dtype, static_cast<int>(B), 0, layer, s));
   static const size_t per_patch[7] = {0, 32 * 32 * 32, 32 * 32 * 32, 16 * 16 * 64, 16 * 16 * 64, 8 * 8 * 128, 8 * 8 * 128};
-  const uint16_t* src = layer == 6 ? h->l6 : h->act[(layer - 1) & 1];
+  const uint16_t* src = layer == 6 ? h->l6 : h->act[((layer - 1) & 1) ^ ((h->fuse34 && layer >= 4) ? 1 : 0)];
   HN_CUDA(cudaMemcpyAsync(act_out, src, per_patch[layer] * 2 * static_cast<size_t>(B), cudaMemcpyDeviceToDevice, s));
   return HN_OK;
 }
@@ -661,6 +739,18 @@ extern "C" int hn_profile_read(hn_handle* h, double ms_out[7], long long launche
   }
   return HN_OK;
 }
+
+#ifdef HN_C34_TRACE
+extern "C" int hn_debug_c34_trace(unsigned long long* out16, int reset) {
+  HN_CUDA(cudaDeviceSynchronize());
+  HN_CUDA(cudaMemcpyFromSymbol(out16, hn::hn_c34_trace, 16 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    HN_CUDA(cudaMemcpyToSymbol(hn::hn_c34_trace, z, sizeof(z)));
+  }
+  return HN_OK;
+}
+#endif
 
 #ifdef HN_FF_TRACE
 extern "C" int hn_debug_ff_trace(unsigned long long* out32, int reset) {

@@ -216,6 +216,17 @@ class HardNet(_EngineOwner, nn.Module):
     # multiply-accumulates per patch of each stage; stage 1 = a2 + a3
     STAGE_MACS = (294912, 294912 + 9437184, 4718592, 9437184, 4718592, 9437184, 1048576)
 
+    @classmethod
+    def stage_table(cls, launches):
+        """(names, MACs per patch) of the seven timed stages for an engine whose per-stage launch counts are `launches`:
+        with conv3 + conv4 fused into one kernel (csrc/tc_conv34.cuh, the default) stage 2 carries both layers and stage 3
+        launches nothing."""
+        names, macs = list(cls.STAGE_NAMES), list(cls.STAGE_MACS)
+        if launches[2] > 0 and launches[3] == 0 and launches[4] > 0:
+            names[2], macs[2] = "conv3_conv4_fused", macs[2] + macs[3]
+            names[3], macs[3] = "conv4_64 (inside the fused kernel)", 0
+        return names, macs
+
     def profile_enable(self, stage_mask: int):
         if self._engine is None:
             raise _lib.HardnetB200Error("profile_enable: run one eval forward first")

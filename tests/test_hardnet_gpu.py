@@ -203,10 +203,39 @@ def test_single_cta_and_cta_pair_conv_kernels(mask, monkeypatch):
     """HN_PAIR_MASK selects per 3x3 layer the single-CTA or the CTA-pair (cta_group::2) kernel (default: conv4-conv6 on
     pairs). Both variants of every layer must reproduce the oracle, also on ragged pass sizes."""
     monkeypatch.setenv("HN_PAIR_MASK", mask)
+    monkeypatch.setenv("HN_FUSE34", "0")   # conv3 and conv4 as kernels of their own (the default fuses them)
     model, (w, m, v) = _model(3, chunk_patches=96, head_rows=256)
     x = synth.make_patches(333, 31, edge_cases=False)
     max_abs, cos = _cmp(model(x.cuda()), hardnet_oracle.hardnet_forward(x, w, m, v))
     assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (mask, max_abs, cos)
+
+
+@pytest.mark.parametrize("n,chunk", [(1, 0), (2, 0), (301, 0), (1000, 256), (4097, 0)])
+def test_fused_conv3_conv4_kernel_against_the_separate_kernels(n, chunk, monkeypatch):
+    """conv3 + conv4 in one kernel (csrc/tc_conv34.cuh; HN_FUSE34: 2 = default, 1 = a TMA load per tap, 0 = two kernels).
+    Mode 1 feeds the tensor core the same operands in the same K order as the separate kernels: every later activation and the
+    descriptors are bit-identical. Mode 2 accumulates conv3's taps in another order: conv4's output differs by at most one
+    fp16 rounding step here and there, the descriptors by ~2e-5; all modes meet the oracle gate. Odd batch sizes leave one CTA
+    of the last pair without a patch; chunk 256 makes several passes."""
+    x = synth.make_patches(n, 77 + n, edge_cases=False)
+    xg = x.cuda()
+    outs = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("HN_FUSE34", mode)
+        model, (w, m, v) = _model(3, chunk_patches=chunk, head_rows=0 if chunk == 0 else 1024)
+        outs[mode] = {"desc": model(xg)}
+        if n <= 512:
+            for layer in (4, 5, 6):
+                outs[mode][layer] = model.forward_stage(xg, layer)
+        torch.cuda.synchronize()
+    for k, ref in outs["0"].items():
+        assert torch.equal(outs["1"][k], ref), f"mode 1, {k}"
+        d = (outs["2"][k].float() - ref.float()).abs().max().item()
+        assert d <= (5e-5 if k == "desc" else 5e-4), f"mode 2, {k}: {d:.3e}"
+    ref = hardnet_oracle.hardnet_forward(x[:256], w, m, v)
+    for mode in ("1", "2"):
+        max_abs, cos = _cmp(outs[mode]["desc"][:256], ref)
+        assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (mode, max_abs, cos)
 
 
 def test_second_gpu_in_the_same_process():
