@@ -75,9 +75,9 @@ struct hn_handle {
   hn::TcParams pair_params[5];   // same layers for the CTA-pair kernels (tc_conv_pair.cuh)
   unsigned pair_mask = 0;        // bit li: layer li runs on CTA pairs
   hn::TcParams head_params;
-  int fuse34 = 0;                // HN_FUSE34: conv3 + conv4 in one kernel (tc_conv34.cuh): 0 = off, 1 = one load per tap, 2 = one load
-                                 // per (row parity, kx); the deeper layers then read / write the other ping-pong buffer
-  int fuse34_sched = 1;          // HN_FUSE34_SCHED
+  int fuse34 = 0;                // HN_FUSE34: conv3 + conv4 in one kernel (tc_conv34.cuh): 0 = off, 1 / 2 = shifted-copies kernel,
+                                 // 3 = stacked-N kernel (default); the deeper layers then read / write the other ping-pong buffer
+  int fuse34_sched = 2;          // HN_FUSE34_SCHED (mode 3: bit 0 = fp16-pair shuffles, bit 1 = two TMA producer warps)
   hn::Conv34Params c34;
   // optional per-stage CUDA-event timing (stage 0 = L1, 1..5 = 3x3 convs, 6 = head)
   unsigned profile_mask = 0;

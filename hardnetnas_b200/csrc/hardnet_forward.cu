@@ -110,7 +110,7 @@ static const bool kRowShift[5] = {true, false, true, false, true};
 static const bool kPairRowShift[5] = {false, false, true, false, true};
 static const int kPairKcb[5] = {64, 64, 128, 128, 128};
 static const unsigned kDefaultPairMask = 0x1c;   // conv4, conv5, conv6 (conv3 is faster with two independent CTAs per SM)
-static const int kDefaultFuse34 = 2;
+static const int kDefaultFuse34 = 3;
 static const int kKcb[5] = {64, 64, 128, 128, 64};   // bytes of one pixel's channel chunk per k-block (ConvCfg::KCB)
 
 static int launch_conv_pair(int li, const TcParams& p, int sm_count, cudaStream_t s) {
@@ -134,10 +134,10 @@ static int launch_conv(int li, const TcParams& p, int sm_count, cudaStream_t s) 
 }
 
 // conv3 + conv4 in one kernel (tc_conv34.cuh): conv2 output in act[1] -> conv4 output in `out`.
-template <bool SIX, int SCHED, int PF>
+template <bool SIX, int SCHED>
 static int launch_conv34_cfg(const Conv34Params& p, int sm_count, cudaStream_t stream) {
   using C = C34Cfg<SIX>;
-  auto kern = conv34_pair_kernel<SIX, SCHED, PF>;
+  auto kern = conv34_pair_kernel<SIX, SCHED>;
   static DeviceOnce attr_once;  // per instantiation
   if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C::SMEM)));
@@ -151,12 +151,28 @@ static int launch_conv34_cfg(const Conv34Params& p, int sm_count, cudaStream_t s
   return HN_OK;
 }
 
+template <int SHFL16, int NPROD>
+static int launch_conv34_stack(const Conv34Params& p, int sm_count, cudaStream_t stream) {
+  auto kern = conv34_stack_kernel<SHFL16, NPROD>;
+  static DeviceOnce attr_once;  // per instantiation
+  if (attr_once.first_time()) {
+    HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C34SCfg::SMEM)));
+  }
+  if (p.n_patches <= 0) return HN_OK;
+  const int groups = (p.n_patches + 1) / 2;
+  const int grid = 2 * std::min(groups, sm_count / 2);   // whole CTA pairs (__cluster_dims__(2, 1, 1))
+  kern<<<grid, kC34SThreads, C34SCfg::SMEM, stream>>>(p);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
+}
+
 static int build_conv34_params(hn_handle* h) {
   Conv34Params& p = h->c34;
   memset(&p, 0, sizeof(p));
   if (!h->fuse34) return HN_OK;
   const uint16_t* in = h->act[1];   // conv2 output: parity sub-planes [patch][4 planes][ypar][xpar][16][16][8]
-  const uint32_t rows = h->fuse34 == 2 ? 9u : 8u;
+  const uint32_t rows = h->fuse34 >= 2 ? 9u : 8u;
   const uint32_t box[4] = {16 * 8, rows, 1, 4};
   for (int ypar = 0; ypar < 2; ++ypar)
     for (int xpar = 0; xpar < 2; ++xpar) {
@@ -185,15 +201,16 @@ static int run_conv34(hn_handle* h, int n, void* out, cudaStream_t s) {
   p.act_bf16 = h->act_bf16;
   p.out = out;
   StageTimer timer(h, 2, s);   // reported as the conv3 stage; the conv4 stage then has no launches of its own
-  if (h->fuse34 == 1) return launch_conv34_cfg<false, 0, 0>(p, h->sm_count, s);
-  switch (h->fuse34_sched) {   // <interleaved conv3 load units, prefetch distance>
-    case 0: return launch_conv34_cfg<true, 0, 0>(p, h->sm_count, s);
-    case 6: return launch_conv34_cfg<true, 6, 0>(p, h->sm_count, s);
-    case 10: return launch_conv34_cfg<true, 0, 2>(p, h->sm_count, s);
-    case 12: return launch_conv34_cfg<true, 2, 2>(p, h->sm_count, s);
-    case 14: return launch_conv34_cfg<true, 4, 2>(p, h->sm_count, s);
-    default: return launch_conv34_cfg<true, 6, 2>(p, h->sm_count, s);
+  if (h->fuse34 == 3) {   // HN_FUSE34_SCHED: bit 0 = fp16-pair shuffles, bit 1 = two TMA producer warps
+    switch (h->fuse34_sched & 3) {
+      case 0: return launch_conv34_stack<0, 1>(p, h->sm_count, s);
+      case 1: return launch_conv34_stack<1, 1>(p, h->sm_count, s);
+      case 2: return launch_conv34_stack<0, 2>(p, h->sm_count, s);
+      default: return launch_conv34_stack<1, 2>(p, h->sm_count, s);
+    }
   }
+  if (h->fuse34 == 1) return launch_conv34_cfg<false, 0>(p, h->sm_count, s);
+  return launch_conv34_cfg<true, 6>(p, h->sm_count, s);
 }
 
 // Stage 1 (input_norm + conv 1->32 + BN + ReLU) on the tensor core; do_norm = 0 gives the NAS stem.
@@ -515,10 +532,12 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
     h->front_chunk = e ? std::max(2, atoi(e)) : chunk_patches;
   }
   {
-    const char* e = getenv("HN_FUSE34");   // conv3 + conv4 in one kernel: 0 = off, 1 = a load per tap, 2 = a load per (row parity, kx)
-    h->fuse34 = e ? std::min(2, std::max(0, atoi(e))) : kDefaultFuse34;
-    const char* e2 = getenv("HN_FUSE34_SCHED");   // 1: conv3 load units dealt between the conv4 MMA groups (tc_conv34.cuh)
-    h->fuse34_sched = e2 ? atoi(e2) : 6;
+    // conv3 + conv4 in one kernel (tc_conv34.cuh): 0 = off, 1 = three x-shifted copies of the activation, a load per tap,
+    // 2 = the same with a load per (row parity, kx), 3 = conv4's kx taps stacked on N (default)
+    const char* e = getenv("HN_FUSE34");
+    h->fuse34 = e ? std::min(3, std::max(0, atoi(e))) : kDefaultFuse34;
+    const char* e2 = getenv("HN_FUSE34_SCHED");   // mode 3: bit 0 = fp16-pair shuffles, bit 1 = two TMA producer warps
+    h->fuse34_sched = e2 ? atoi(e2) : 2;
   }
   {
     const char* e = getenv("HN_PAIR_MASK");   // bit li: run 3x3 layer li (1 = conv3 .. 4 = conv6) on CTA pairs

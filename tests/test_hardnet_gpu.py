@@ -212,16 +212,18 @@ def test_single_cta_and_cta_pair_conv_kernels(mask, monkeypatch):
 
 @pytest.mark.parametrize("n,chunk", [(1, 0), (2, 0), (301, 0), (1000, 256), (4097, 0)])
 def test_fused_conv3_conv4_kernel_against_the_separate_kernels(n, chunk, monkeypatch):
-    """conv3 + conv4 in one kernel (csrc/tc_conv34.cuh; HN_FUSE34: 2 = default, 1 = a TMA load per tap, 0 = two kernels).
+    """conv3 + conv4 in one kernel (csrc/tc_conv34.cuh; HN_FUSE34: 3 = default, conv4's kx taps stacked on N and finished by
+    tcgen05.shift + warp shuffles; 1 / 2 = three x-shifted copies of the activation in shared memory; 0 = two kernels).
     Mode 1 feeds the tensor core the same operands in the same K order as the separate kernels: every later activation and the
-    descriptors are bit-identical. Mode 2 accumulates conv3's taps in another order: conv4's output differs by at most one
-    fp16 rounding step here and there, the descriptors by ~2e-5; all modes meet the oracle gate. Odd batch sizes leave one CTA
-    of the last pair without a patch; chunk 256 makes several passes."""
+    descriptors are bit-identical. Modes 2 and 3 accumulate in another order: conv4's output differs by at most one fp16
+    rounding step here and there, the descriptors by ~2e-5; all modes meet the oracle gate. Odd batch sizes leave one CTA of the
+    last pair without a patch; chunk 256 makes several passes. HN_FUSE34_SCHED=3 (mode 3): fp16-pair shuffles."""
     x = synth.make_patches(n, 77 + n, edge_cases=False)
     xg = x.cuda()
     outs = {}
-    for mode in ("0", "1", "2"):
-        monkeypatch.setenv("HN_FUSE34", mode)
+    for mode in ("0", "1", "2", "3", "3p"):
+        monkeypatch.setenv("HN_FUSE34", mode[0])
+        monkeypatch.setenv("HN_FUSE34_SCHED", "3" if mode == "3p" else ("6" if mode == "2" else "2"))
         model, (w, m, v) = _model(3, chunk_patches=chunk, head_rows=0 if chunk == 0 else 1024)
         outs[mode] = {"desc": model(xg)}
         if n <= 512:
@@ -230,10 +232,17 @@ def test_fused_conv3_conv4_kernel_against_the_separate_kernels(n, chunk, monkeyp
         torch.cuda.synchronize()
     for k, ref in outs["0"].items():
         assert torch.equal(outs["1"][k], ref), f"mode 1, {k}"
-        d = (outs["2"][k].float() - ref.float()).abs().max().item()
-        assert d <= (5e-5 if k == "desc" else 5e-4), f"mode 2, {k}: {d:.3e}"
+        for mode in ("2", "3", "3p"):
+            d = (outs[mode][k].float() - ref.float()).abs().max().item()
+            assert d <= (1e-4 if k == "desc" else 1e-3), f"mode {mode}, {k}: {d:.3e}"
+    if n == 4097:
+        # races between the kernel's roles (producer / issuer / shifter / epilogue warps of two CTAs) would show as run-to-run
+        # differences: the default kernel is bit-reproducible over a full pass and a large batch
+        big = synth.make_patches(40000, 5, edge_cases=False).cuda()
+        a = model(big)
+        assert torch.equal(model(big), a) and torch.equal(model(big[:4097]), a[:4097])
     ref = hardnet_oracle.hardnet_forward(x[:256], w, m, v)
-    for mode in ("1", "2"):
+    for mode in ("1", "2", "3", "3p"):
         max_abs, cos = _cmp(outs[mode]["desc"][:256], ref)
         assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (mode, max_abs, cos)
 

@@ -35,11 +35,10 @@ lib.hn_debug_c34_trace.restype = C.c_int
 lib.hn_debug_c34_trace.argtypes = [C.c_void_p, C.c_int]
 x = torch.randn(18944 * 4, 1, 32, 32, device="cuda")
 out = torch.empty(x.size(0), 128, device="cuda")
-names = {0: "issuer: full (loads)", 1: "issuer: mid ready", 2: "issuer: t4empty", 5: "epi warp 2: t3full", 6: "epi warp 2: t4full (mid free)",
-         7: "epi warp 2: conv3 epilogue", 8: "epi warp 2: conv3 + conv4 epilogue", 9: "producer: empty"}
-for sched in [a for a in sys.argv[1:] if not a.startswith("-")] or ["0", "6", "10", "16"]:
-    os.environ["HN_FUSE34"] = "2"
-    os.environ["HN_FUSE34_SCHED"] = sched
+names = {0: "issuer: full (loads)", 1: "issuer: mid ready", 2: "issuer: t4empty (v2: t3empty)", 10: "issuer: t4empty (v2)", 11: "shifter: mma4 (v2)", 5: "epi warp 2: t3full", 6: "epi warp 2: t4full (mid free)",
+         7: "epi warp 2: conv3 epilogue", 8: "epi warp 2: conv3 + conv4 epilogue", 9: "producer: empty", 12: "producer 0: issue section"}
+for sched in [a for a in sys.argv[1:] if not a.startswith("-")] or ["2:6", "3:0"]:
+    os.environ["HN_FUSE34"], os.environ["HN_FUSE34_SCHED"] = sched.split(":")
     m = HardNet().cuda().eval()
     for _ in range(2):
         m(x, out=out)
