@@ -716,6 +716,23 @@ def bench_config1(device, model, with_cpu):
     da, dp = model(a), model(p)
     rec["b200_loss_only_ms"] = timeit(lambda: loss_HardNet(da, dp, anchor_swap=True), 50)
 
+    # The same step with the anchors and positives in ONE forward of 2048 patches (eval-mode BatchNorm: identical descriptors;
+    # the concatenation is inside the timed step). Seven kernel prologues instead of fourteen.
+    def step_one_forward():
+        d = model(torch.cat([a, p]))
+        return loss_HardNet(d[:1024], d[1024:], anchor_swap=True)
+    try:
+        rec["b200_one_forward_of_2048_eager_ms"] = timeit(step_one_forward, 20)
+        # (the split-K factor of the head GEMM follows the batch size: last-bit differences between the two forms)
+        rec["one_forward_vs_two_max_abs_diff"] = float((model(torch.cat([a, p])) - torch.cat([da, dp])).abs().max().item())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_one_forward()
+        rec["b200_one_forward_of_2048_cuda_graph_ms"] = timeit(graph.replay, 50)
+        del graph
+    except Exception as exc:
+        print(f"[bench] single-forward variant of the config-1 step failed: {exc}", file=sys.stderr)
+
     # the reference's own op sequence on the same GPU (stock torch modules: cuDNN / cuBLAS, TF32 allowed) for the same step
     def stock_step():
         with torch.no_grad():

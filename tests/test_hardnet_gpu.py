@@ -240,7 +240,9 @@ def test_fused_conv3_conv4_kernel_against_the_separate_kernels(n, chunk, monkeyp
         # differences: the default kernel is bit-reproducible over a full pass and a large batch
         big = synth.make_patches(40000, 5, edge_cases=False).cuda()
         a = model(big)
-        assert torch.equal(model(big), a) and torch.equal(model(big[:4097]), a[:4097])
+        assert torch.equal(model(big), a)
+        # (a 4097-patch batch runs the head GEMM split-K: another fp32 summation order, hence a tolerance instead of equality)
+        assert (model(big[:4097]) - a[:4097]).abs().max().item() <= 1e-6
     ref = hardnet_oracle.hardnet_forward(x[:256], w, m, v)
     for mode in ("1", "2", "3", "3p"):
         max_abs, cos = _cmp(outs[mode]["desc"][:256], ref)

@@ -38,3 +38,13 @@ def test_copies_drop_the_engine(make):
     assert rep._engine is None and m._engine is not None
     assert m.repack() is m and m._packed_key is None
     m._engine = None
+
+
+def test_stage_table_follows_the_launch_counts():
+    """bench.py attributes FLOPs per timed stage: with conv3 + conv4 fused into one kernel (the default engine) stage 2
+    carries both layers' MACs and stage 3 none; with separate kernels the table is the per-layer one."""
+    names, macs = HardNet.stage_table([0, 28, 28, 0, 28, 28, 1])
+    assert names[2] == "conv3_conv4_fused" and macs[2] == 4718592 + 9437184 and macs[3] == 0
+    assert sum(macs[1:]) == sum(HardNet.STAGE_MACS[1:])
+    names, macs = HardNet.stage_table([0, 28, 28, 28, 28, 28, 1])
+    assert tuple(names) == HardNet.STAGE_NAMES and tuple(macs) == HardNet.STAGE_MACS
