@@ -85,18 +85,16 @@ struct FfBias {
   float v[32];
 };
 
-// FDW: 0 = none; 3 / 5 = depthwise 3x3 / 5x5 stride 2 (+ bias, optional ReLU) behind the pointwise stage; 1 = MaxPool 3x3
-// stride 2 pad 1 (hardnetNAS fbnet_builder.py:455-570 IRFBlock `dw`, :202-228 Identity). fp16 activations only.
-template <typename TIn, bool PW2 = false, int FDW = 0>
-__global__ void __launch_bounds__(kFfThreads, 1)
-front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]; PW2: NHWC; FDW: NHWC [n][16][16][32]*/,
-                   const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
-                   const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
-                   const __grid_constant__ FfBias bias2 /*[32]*/, int do_norm /*0: no input normalisation*/,
-                   int num_patches, int act_bf16, float norm_eps /*added to the std: 1e-7 HardNet, 1e-8 HardNetNeiMask*/,
-                   const __grid_constant__ CUtensorMap tm_out /*PW2: [n * 1024, 32] as 32 x 32 boxes, 64B swizzle*/,
-                   const float* __restrict__ dw_w = nullptr /*FDW 3 | 5: [k * k][32] folded*/, const float* __restrict__ dw_b = nullptr /*[32]*/,
-                   int dw_relu = 0, int fdw_planar = 0 /*FDW output channel-planar [n][4][16][16][8] (the tail kernel's bulk-copy layout)*/) {
+// The kernel body as a device function: `blk` of `nblk` CTAs work on patches blk, blk + nblk, ... (the stand-alone kernel passes
+// blockIdx.x / gridDim.x; the co-scheduled front + conv3/conv4 launch of front_c34.cuh gives this role a sub-range of the grid).
+// ready != nullptr (HardNet variant only): each of the eight conv2 epilogue warps stamps ready[patch * 8 + its index] = 1 once
+// its part of the patch is in global memory (release at gpu scope) - the consumer role of the same launch polls these flags.
+template <typename TIn, bool PW2, int FDW>
+__device__ __forceinline__ void front_fused_body(const TIn* __restrict__ in, uint16_t* __restrict__ out, const float* __restrict__ w1,
+                                                 const float* __restrict__ bias1, const uint4* __restrict__ w2img, const FfBias& bias2,
+                                                 int do_norm, int num_patches, int act_bf16, float norm_eps, const CUtensorMap& tm_out,
+                                                 const float* __restrict__ dw_w, const float* __restrict__ dw_b, int dw_relu, int fdw_planar,
+                                                 const int blk, const int nblk, int* __restrict__ ready) {
   static_assert(FDW == 0 || PW2, "the fused depthwise stage sits behind the pointwise variant");
   constexpr int NACT1 = FDW ? 1 : 2;   // stage-1 activation buffers
   extern __shared__ uint8_t smem_raw[];
@@ -205,12 +203,12 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     const int lw = warp - kFfLoader0;      // rows 8 * lw .. 8 * lw + 7
     const uint32_t one16 = act_bf16 ? 0x3F80u : 0x3C00u;
     constexpr uint32_t RAW_BYTES = 1024 * sizeof(TIn);
-    const int n_loc = (num_patches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int n_loc = (num_patches - blk + nblk - 1) / nblk;
     auto prefetch = [&](int j) {           // lane 0 of loader warp 0 only
       const int d = j % kFfRawDepth;
       mbar_wait(raw_empty(d), ((j / kFfRawDepth) & 1) ^ 1u);
       mbar_arrive_expect_tx(raw_full(d), RAW_BYTES);
-      const TIn* g = in + (static_cast<size_t>(blockIdx.x) + static_cast<size_t>(j) * gridDim.x) * 1024;
+      const TIn* g = in + (static_cast<size_t>(blk) + static_cast<size_t>(j) * nblk) * 1024;
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                        raw_addr0 + d * 4096), "l"(g), "r"(RAW_BYTES), "r"(raw_full(d))
                    : "memory");
@@ -219,7 +217,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
       for (int j = 0; j < kFfRawDepth - 1 && j < n_loc; ++j) prefetch(j);
     float* s_red = reinterpret_cast<float*>(gbase + (bar_base + 384 - base));   // [sum | sum of squares][patch parity][4 warps]
     int it = 0;
-    for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
+    for (int patch = blk; patch < num_patches; patch += nblk, ++it) {
       if (lw == 0 && lane == 0 && it + kFfRawDepth - 1 < n_loc) prefetch(it + kFfRawDepth - 1);
       __syncwarp();
       const int d = it % kFfRawDepth;
@@ -298,7 +296,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     // epilogue). The shift is NOT ordered behind earlier MMAs by itself, so it waits for the tile's mma_done barrier.
     if constexpr (!PW2) {
       const int g = warp - kFfShift0;
-      const int n_local = (num_patches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+      const int n_local = (num_patches - blk + nblk - 1) / nblk;
       for (int it = 0; it < n_local; ++it) {
 #pragma unroll
         for (int tt = 0; tt < 4; ++tt) {
@@ -327,7 +325,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     const uint32_t b1_lo = noswizzle_desc_lo(w1_addr, 128);
     const uint32_t act_lo0 = noswizzle_desc_lo(act1_addr, kFfPlane);
     const uint32_t w2_lo = noswizzle_desc_lo(w2_addr, 128);
-    const int n_local = (num_patches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+    const int n_local = (num_patches - blk + nblk - 1) / nblk;
     auto issue_l1_half = [&](int half) {
       HN_FF_SECTION_BEGIN();
       if (elect_one()) {
@@ -441,7 +439,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     // ============================== stage-1 epilogue: TMEM -> bias, ReLU, pack -> act1 (smem) ==============================
     const int q = warp;
     int it = 0;
-    for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x, ++it) {
+    for (int patch = blk; patch < num_patches; patch += nblk, ++it) {
       const int b = FDW ? 0 : it & 1;
       HN_FF_WAIT(8, act1_empty(b), (FDW ? (it & 1) : ((it >> 1) & 1)) ^ 1u);
       uint8_t* act = gbase + (act1_addr - base) + b * kFfAct1;
@@ -505,7 +503,7 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
     const uint32_t t_row0 = tm_c2 + (static_cast<uint32_t>(q * 32) << 16);
     const float m_left = lane == 0 ? 0.f : 1.f;     // x - 1 / x + 1 outside the row = the conv's zero padding
     const float m_right = lane == 31 ? 0.f : 1.f;
-    for (int patch = blockIdx.x; patch < num_patches; patch += gridDim.x) {
+    for (int patch = blk; patch < num_patches; patch += nblk) {
       uint16_t* opatch = out + static_cast<size_t>(patch) * 32768;
 #pragma unroll 1
       for (int tt = 0; tt < 4; ++tt) {
@@ -610,6 +608,13 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
         __syncwarp();
         if (lane == 0) mbar_arrive(c2_empty(a));
       }
+      if constexpr (!PW2) {
+        if (ready != nullptr) {   // this warp's four tiles of the patch are stored: publish them to the consumer role
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ready + static_cast<size_t>(patch) * 8 + (warp - 4)), "r"(1) : "memory");
+        }
+      }
       if constexpr (FDW != 0) {
         // ---- stride-2 depthwise conv / max-pool of the patch-resident tile by the same eight warps: a thread owns 8
         // channels x one output column x a strip of 4 output rows (4 planes x 16 columns x 4 strips = 256 items) ----
@@ -706,15 +711,31 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
   tc_fence_before();
   __syncthreads();
 #ifdef HN_FF_TRACE
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blk == 0 && threadIdx.x == 0) {
     atomicAdd(&hn_ff_trace[15], static_cast<unsigned long long>(clock64() - hn_ff_start));
-    atomicAdd(&hn_ff_trace[16], static_cast<unsigned long long>((num_patches + gridDim.x - 1) / gridDim.x));
+    atomicAdd(&hn_ff_trace[16], static_cast<unsigned long long>((num_patches + nblk - 1) / nblk));
   }
 #endif
   if (warp == kFfIssuer) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// FDW: 0 = none; 3 / 5 = depthwise 3x3 / 5x5 stride 2 (+ bias, optional ReLU) behind the pointwise stage; 1 = MaxPool 3x3
+// stride 2 pad 1 (hardnetNAS fbnet_builder.py:455-570 IRFBlock `dw`, :202-228 Identity). fp16 activations only.
+template <typename TIn, bool PW2 = false, int FDW = 0>
+__global__ void __launch_bounds__(kFfThreads, 1)
+front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][4 planes][2][2][16][16][8]; PW2: NHWC; FDW: NHWC [n][16][16][32]*/,
+                   const float* __restrict__ w1 /*[9][32] folded*/, const float* __restrict__ bias1 /*[32]*/,
+                   const uint4* __restrict__ w2img /*kFfW2 bytes, shared-memory image*/,
+                   const __grid_constant__ FfBias bias2 /*[32]*/, int do_norm /*0: no input normalisation*/,
+                   int num_patches, int act_bf16, float norm_eps /*added to the std: 1e-7 HardNet, 1e-8 HardNetNeiMask*/,
+                   const __grid_constant__ CUtensorMap tm_out /*PW2: [n * 1024, 32] as 32 x 32 boxes, 64B swizzle*/,
+                   const float* __restrict__ dw_w = nullptr /*FDW 3 | 5: [k * k][32] folded*/, const float* __restrict__ dw_b = nullptr /*[32]*/,
+                   int dw_relu = 0, int fdw_planar = 0 /*FDW output channel-planar [n][4][16][16][8] (the tail kernel's bulk-copy layout)*/) {
+  front_fused_body<TIn, PW2, FDW>(in, out, w1, bias1, w2img, bias2, do_norm, num_patches, act_bf16, norm_eps, tm_out, dw_w, dw_b, dw_relu,
+                                  fdw_planar, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), nullptr);
 }
 
 }  // namespace hn

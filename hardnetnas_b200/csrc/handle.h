@@ -79,6 +79,10 @@ struct hn_handle {
                                  // 3 = stacked-N kernel (default); the deeper layers then read / write the other ping-pong buffer
   int fuse34_sched = 2;          // HN_FUSE34_SCHED (mode 3: bit 0 = fp16-pair shuffles, bit 1 = two TMA producer warps)
   hn::Conv34Params c34;
+  int cosched = 0;               // HN_COSCHED=1: front kernel and fused conv3 + conv4 kernel as the two roles of ONE launch (front_c34.cuh):
+                                 // the conv2 output is consumed out of L2 a few microseconds after it was written
+  int cosched_nf = 72;           // HN_COSCHED_NF: CTAs of the front role (even)
+  int* c34_ready = nullptr;      // [chunk][8] producer -> consumer flags of that launch (all zero between launches)
   // optional per-stage CUDA-event timing (stage 0 = L1, 1..5 = 3x3 convs, 6 = head)
   unsigned profile_mask = 0;
   std::vector<cudaEvent_t> ev[7];

@@ -17,6 +17,7 @@
 #include "tc_conv.cuh"
 #include "tc_conv_pair.cuh"
 #include "tc_conv34.cuh"
+#include "front_c34.cuh"
 
 namespace hn {
 
@@ -111,6 +112,7 @@ static const bool kPairRowShift[5] = {false, false, true, false, true};
 static const int kPairKcb[5] = {64, 64, 128, 128, 128};
 static const unsigned kDefaultPairMask = 0x1c;   // conv4, conv5, conv6 (conv3 is faster with two independent CTAs per SM)
 static const int kDefaultFuse34 = 3;
+static const int kDefaultCosched = 0;
 static const int kKcb[5] = {64, 64, 128, 128, 64};   // bytes of one pixel's channel chunk per k-block (ConvCfg::KCB)
 
 static int launch_conv_pair(int li, const TcParams& p, int sm_count, cudaStream_t s) {
@@ -211,6 +213,38 @@ static int run_conv34(hn_handle* h, int n, void* out, cudaStream_t s) {
   }
   if (h->fuse34 == 1) return launch_conv34_cfg<false, 0>(p, h->sm_count, s);
   return launch_conv34_cfg<true, 6>(p, h->sm_count, s);
+}
+
+// Front kernel + fused conv3 + conv4 kernel as the two roles of one launch (front_c34.cuh): patches -> conv4 output in `out`.
+static int run_front_c34(hn_handle* h, const void* patches, int in_dtype, int n, void* out, cudaStream_t s) {
+  static DeviceOnce attr_once;
+  if (attr_once.first_time()) {
+    HN_CUDA(cudaFuncSetAttribute(front_c34_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFrontC34Smem)));
+    HN_CUDA(cudaFuncSetAttribute(front_c34_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFrontC34Smem)));
+  }
+  FrontC34Params P;
+  P.in = patches;
+  P.conv2_out = h->act[1];
+  P.w1 = h->w1;
+  P.bias1 = h->bias;
+  P.w2img = reinterpret_cast<const uint4*>(h->w2img);
+  memcpy(P.bias2.v, h->bias2_host, sizeof(P.bias2.v));
+  P.norm_eps = h->norm_eps;
+  P.n_patches = n;
+  P.act_bf16 = h->act_bf16;
+  const int grid = h->sm_count & ~1;
+  P.nf = std::min(std::max(2, h->cosched_nf & ~1), grid - 2);
+  P.ready = h->c34_ready;
+  P.c34 = h->c34;
+  P.c34.n_patches = n;
+  P.c34.act_bf16 = h->act_bf16;
+  P.c34.out = out;
+  StageTimer timer(h, 1, s);   // reported as the front stage; the conv3 / conv4 stages then have no launches of their own
+  if (in_dtype == HN_F32) front_c34_kernel<float><<<grid, kFfThreads, kFrontC34Smem, s>>>(P);
+  else front_c34_kernel<uint8_t><<<grid, kFfThreads, kFrontC34Smem, s>>>(P);
+  HN_CUDA(cudaGetLastError());
+  count_launch();
+  return HN_OK;
 }
 
 // Stage 1 (input_norm + conv 1->32 + BN + ReLU) on the tensor core; do_norm = 0 gives the NAS stem.
@@ -469,6 +503,12 @@ static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n
   const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
   for (int off = 0; off < n; off += front) {
     const int m = std::min(front, n - off);
+    // both roles need enough patches to fill their share of the SMs; small batches keep the two launches (every SM on each stage)
+    if (fuse && h->fuse34 == 3 && h->cosched && m >= 32 * h->sm_count) {
+      HN_TRY(run_front_c34(h, static_cast<const char*>(patches) + static_cast<size_t>(off) * 1024 * in_elem, in_dtype, m,
+                           h->act[0] + static_cast<size_t>(off) * 16 * 16 * 64, s));
+      continue;
+    }
     {
       StageTimer timer(h, 1, s);  // stage 1 + conv2 (the stage-1 activation never reaches global memory)
       HN_TRY(launch_front_fused(h, static_cast<const char*>(patches) + static_cast<size_t>(off) * 1024 * in_elem, in_dtype,
@@ -536,6 +576,8 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
     // 2 = the same with a load per (row parity, kx), 3 = conv4's kx taps stacked on N (default)
     const char* e = getenv("HN_FUSE34");
     h->fuse34 = e ? std::min(3, std::max(0, atoi(e))) : kDefaultFuse34;
+    h->cosched = getenv("HN_COSCHED") ? atoi(getenv("HN_COSCHED")) : kDefaultCosched;
+    h->cosched_nf = getenv("HN_COSCHED_NF") ? atoi(getenv("HN_COSCHED_NF")) : 72;
     const char* e2 = getenv("HN_FUSE34_SCHED");   // mode 3: bit 0 = fp16-pair shuffles, bit 1 = two TMA producer warps
     h->fuse34_sched = e2 ? atoi(e2) : 2;
   }
@@ -567,6 +609,8 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   HN_CUDA_H(cudaMalloc(&h->w2img, kFfW2));
   HN_CUDA_H(cudaMalloc(&h->bias, 7 * 128 * sizeof(float)));
   HN_CUDA_H(cudaMalloc(&h->stats, static_cast<size_t>(chunk_patches) * sizeof(float2)));
+  HN_CUDA_H(cudaMalloc(&h->c34_ready, static_cast<size_t>(chunk_patches) * 8 * sizeof(int)));
+  HN_CUDA_H(cudaMemset(h->c34_ready, 0, static_cast<size_t>(chunk_patches) * 8 * sizeof(int)));
   // split-K partials of the head at small batches: tiles x splits <= #SM work items of 128 x 128 fp32 each
   HN_CUDA_H(cudaMalloc(&h->head_partial, static_cast<size_t>(h->sm_count) * kTileM * kHeadN * sizeof(float)));
 #undef HN_CUDA_H
@@ -587,6 +631,7 @@ extern "C" int hn_destroy(hn_handle* h) {
   cudaFree(h->w2img);
   cudaFree(h->bias);
   cudaFree(h->stats);
+  cudaFree(h->c34_ready);
   cudaFree(h->head_partial);
   for (auto& v : h->ev)
     for (cudaEvent_t e : v) cudaEventDestroy(e);

@@ -444,9 +444,12 @@ struct C34SCfg {
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
+// The kernel body as a device function: CTA `blk` of `nblk` (whole pairs) - the stand-alone kernel passes blockIdx.x / gridDim.x,
+// the co-scheduled front + conv3/conv4 launch (front_c34.cuh) gives this role the tail of its grid. ready != nullptr: the conv2
+// output of patch i is being produced by the front role of the SAME launch; the producer warp polls the eight flags
+// ready[i * 8 ..] (acquire at gpu scope) before the patch's first TMA load and clears them for the next launch.
 template <int SHFL16, int NPROD>   // SHFL16 = 1: D0 crosses lanes as fp16 pairs (half the shuffles; fp16 activations only)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC34SThreads, 1)
-conv34_stack_kernel(const __grid_constant__ Conv34Params p) {
+__device__ __forceinline__ void conv34_stack_body(const Conv34Params& p, const int blk, const int nblk, int* __restrict__ ready) {
   using C = C34SCfg;
   constexpr int STAGES = C::STAGES;
 
@@ -467,15 +470,16 @@ conv34_stack_kernel(const __grid_constant__ Conv34Params p) {
   auto mma4_bar = [&](int t) { return bar_base + 8u * (2 * STAGES + 8 + t); };
   const uint32_t mid_bar = bar_base + 8u * (2 * STAGES + 10);
   const uint32_t w_bar = bar_base + 8u * (2 * STAGES + 11);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 12);
+  const uint32_t pready_bar = bar_base + 8u * (2 * STAGES + 12);   // co-scheduled launch: producer 0 -> producer 1, "the patch is in global memory"
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 13);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int pr = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int pr = blk >> 1, num_pairs = nblk >> 1;
   const int num_groups = (p.n_patches + 1) / 2;                    // a group = two consecutive patches, one per CTA
-  const int n_it = (num_groups - pr + num_pairs - 1) / num_pairs;  // groups of this pair (the host launches <= num_groups pairs)
+  const int n_it = pr < num_groups ? (num_groups - pr + num_pairs - 1) / num_pairs : 0;  // groups of this pair
 
 #ifdef HN_C34_TRACE
   const long long c34_start = clock64();
@@ -503,6 +507,7 @@ conv34_stack_kernel(const __grid_constant__ Conv34Params p) {
       }
       mbar_init(mid_bar, 32);            // sixteen epilogue warps of each CTA (leader's copy)
       mbar_init(w_bar, 2);
+      mbar_init(pready_bar, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -549,6 +554,31 @@ conv34_stack_kernel(const __grid_constant__ Conv34Params p) {
       for (int it = 0; it < n_it; ++it) {
         // a patch index past the batch reads stale or out-of-range (zero-filled) data; its results are never stored
         const int patch = 2 * (pr + it * num_pairs) + static_cast<int>(rank);
+        if (ready != nullptr) {
+          if (pw == 0) {
+            if (patch < p.n_patches) {
+              const int* f = ready + static_cast<size_t>(patch) * 8 + (lane & 7);
+              const uint64_t t0 = globaltimer_ns();
+              uint32_t spins = 0;
+              for (;;) {
+                int v;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (!__any_sync(0xffffffffu, v != 1)) break;
+                if ((++spins & 255u) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
+                  if (lane == 0) printf("hardnet_b200: conv2 output of patch %d never became ready (block %d)\n", patch, blockIdx.x);
+                  __trap();
+                }
+              }
+              __syncwarp();
+              if (lane < 8) ready[static_cast<size_t>(patch) * 8 + lane] = 0;   // consumed; the next launch stamps it again
+              asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes of the front role -> this CTA's TMA reads
+            }
+            __syncwarp();
+            if (NPROD == 2 && lane == 0) mbar_arrive(pready_bar);
+          } else {
+            mbar_wait(pready_bar, it & 1);
+          }
+        }
 #pragma unroll 1
         for (int tu = (NPROD == 2 ? pw * C::UNITS : 0); tu < (NPROD == 2 ? (pw + 1) * C::UNITS : 2 * C::UNITS); ++tu) {
           const int t = tu / C::UNITS, u = tu - t * C::UNITS;
@@ -771,7 +801,7 @@ conv34_stack_kernel(const __grid_constant__ Conv34Params p) {
       if (it > 0) epilogue4(it - 1);
       if (e == 0) C34_ACC(8);
     }
-    epilogue4(n_it - 1);
+    if (n_it > 0) epilogue4(n_it - 1);
   }
 
   // nobody leaves (and frees shared / tensor memory) while the peer may still read it or signal its barriers
@@ -788,6 +818,12 @@ conv34_stack_kernel(const __grid_constant__ Conv34Params p) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
   }
+}
+
+template <int SHFL16, int NPROD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC34SThreads, 1)
+conv34_stack_kernel(const __grid_constant__ Conv34Params p) {
+  conv34_stack_body<SHFL16, NPROD>(p, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), nullptr);
 }
 
 }  // namespace hn

@@ -249,6 +249,22 @@ def test_fused_conv3_conv4_kernel_against_the_separate_kernels(n, chunk, monkeyp
         assert max_abs <= DESC_MAX_ABS and cos >= DESC_MIN_COS, (mode, max_abs, cos)
 
 
+def test_coscheduled_front_and_conv34_roles_are_bit_identical(monkeypatch):
+    """HN_COSCHED=1 (opt-in, csrc/front_c34.cuh): the front kernel and the fused conv3 + conv4 kernel run as the two roles of
+    ONE launch, patches handed over through per-patch ready flags in global memory. Same kernels' arithmetic: descriptors are
+    bit-identical to the default path over full passes, a ragged tail pass and two consecutive calls (the flags are cleared by
+    the consumer); batches below 32 patches per SM keep the two launches."""
+    x = synth.make_patches(30001, 9, edge_cases=False).cuda()
+    monkeypatch.setenv("HN_COSCHED", "0")
+    ref_model, _ = _model(3, chunk_patches=9472, head_rows=0)
+    ref = ref_model(x)
+    monkeypatch.setenv("HN_COSCHED", "1")
+    model, _ = _model(3, chunk_patches=9472, head_rows=0)
+    assert torch.equal(model(x), ref)
+    assert torch.equal(model(x), ref)
+    assert torch.equal(model(x[:5000]), ref_model(x[:5000]))
+
+
 def test_second_gpu_in_the_same_process():
     """Kernel attributes (dynamic shared memory limits) are per device: a process may use more than one GPU."""
     if torch.cuda.device_count() < 2:
