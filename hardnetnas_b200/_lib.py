@@ -73,14 +73,15 @@ def load(build_if_missing: bool | None = None) -> C.CDLL:
         return _lib
     if build_if_missing is None:
         build_if_missing = os.environ.get("HARDNET_B200_AUTOBUILD", "0") == "1"
-    if not LIB_PATH.exists():
+    lib_path = Path(os.environ["HARDNET_B200_LIB"]) if os.environ.get("HARDNET_B200_LIB") else LIB_PATH   # developer switch: A/B builds
+    if not lib_path.exists():
         if not build_if_missing:
             raise HardnetB200Error(
-                f"{LIB_PATH} is missing: build it with `python -m hardnetnas_b200.build` "
+                f"{lib_path} is missing: build it with `python -m hardnetnas_b200.build` "
                 "(there is no CPU or PyTorch fallback for the accelerated path)")
         from . import build as _build
         _build.build()
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(lib_path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

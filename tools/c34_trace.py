@@ -17,7 +17,7 @@ if "--build" in sys.argv:
     from hardnetnas_b200 import build as B
     B.build()
     obj = B.OBJ / "hardnet_forward_c34trace.o"
-    subprocess.run([B._nvcc(), *B.NVCC_FLAGS, "-DHN_C34_TRACE", "-c", str(B.CSRC / "hardnet_forward.cu"), "-o", str(obj)], check=True,
+    subprocess.run([B._nvcc(), *B.NVCC_FLAGS, "-DHN_C34_TRACE", "-DHN_FF_TRACE", "-c", str(B.CSRC / "hardnet_forward.cu"), "-o", str(obj)], check=True,
                    capture_output=True)
     objs = [str(o) for o in B.OBJ.glob("*.o") if o.name not in ("hardnet_forward.o", obj.name)] + [str(obj)]
     subprocess.run([B._nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(TRACE_LIB), *objs], check=True)

@@ -9,7 +9,12 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from hardnetnas_b200 import _lib  # noqa: E402
 from hardnetnas_b200.hardnet import HardNet  # noqa: E402
 
+import os  # noqa: E402
+if os.environ.get("HN_TRACE_LIB"):   # a trace build next to the normal library (tools/c34_trace.py --build makes one with both trace flags)
+    _lib.LIB_PATH = Path(os.environ["HN_TRACE_LIB"])
 lib = _lib.load()
+lib.hn_debug_ff_trace.restype = C.c_int
+lib.hn_debug_ff_trace.argtypes = [C.c_void_p, C.c_int]
 torch.manual_seed(0)
 x = torch.nn.functional.avg_pool2d(torch.rand(18944 * 4, 1, 32, 32, device="cuda"), 5, 1, 2)
 if len(sys.argv) > 1 and sys.argv[1] == "nas":       # the PW2 variant (NAS stem + first pointwise conv)
