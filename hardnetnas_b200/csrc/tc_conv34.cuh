@@ -3,7 +3,12 @@
 // with the 32 KB/patch activation between them resident in shared memory (never written to HBM: the two layers as
 // separate kernels move 96 + 64 KB per patch, this kernel 64 + 32 KB).
 //
-// Work split: a CTA pair (tcgen05.mma.cta_group::2, M = 256) works on TWO patches at a time, one per CTA. A 16 x 16
+// Two kernels live here. conv34_stack_kernel (second half of the file) is the DEFAULT: conv4's kx taps stacked on N.
+// conv34_pair_kernel (first half, HN_FUSE34=1 / 2) was the first version and is kept as the bit-exact cross-check of the
+// layer arithmetic (mode 1 reproduces the two separate kernels bit for bit) and as the record of why the default looks the
+// way it does: it is bound by the shared-memory pipe.
+//
+// Common to both. Work split: a CTA pair (tcgen05.mma.cta_group::2, M = 256) works on TWO patches at a time, one per CTA. A 16 x 16
 // output map is two 128-pixel tiles (image rows 0-7 / 8-15); an MMA covers tile t of both CTAs' patches. Each CTA keeps
 // half of the weight rows of BOTH layers resident (18 + 36 KB), as in conv3x3_pair_kernel.
 //
@@ -12,6 +17,7 @@
 //   SIX = true : one 9 KB box per (row parity, kx) - rows y0-1 .. y0+7 of a parity sub-plane, shifted by the kx column
 //                offset; the ky taps of that parity are descriptor offsets of whole image rows (6 loads per tile, 108
 //                instead of 144 KB per patch through the SM's L2 port).
+// First version (conv34_pair_kernel):
 // conv3's epilogue (bias + ReLU + 16-bit pack) does not store to global memory: it writes the activation into the `mid`
 // region of shared memory in the channel-planar layout = UMMA no-swizzle K-major operand, [plane][row -1..16][16 px][8 ch],
 // THREE times: as is, shifted one pixel right and one pixel left (the halo rows and the border column of the shifted copies
@@ -20,7 +26,8 @@
 // core matrices, so a one-pixel shift would wrap into the neighbouring row.)
 //
 // Schedule of the single issuing thread (leader CTA), per pair of patches i:
-//     conv4(i)  [72 MMAs]   then   conv3(i + 2)  [36 MMAs]
+//     conv4(i)  [72 MMAs]   then   conv3(i + 2)  [36 MMAs]     (SCHED > 0: that many of conv3's tile-0 load units are dealt
+//                                                               between the six (tile, kx) groups of conv4)
 // and of the eight epilogue warps of each CTA:
 //     wait conv4(i - 1) retired (= mid free)  ->  conv3 epilogue of i (TMEM -> mid)  ->  signal "mid ready"  ->
 //     conv4 epilogue of i - 1 (TMEM -> global)
