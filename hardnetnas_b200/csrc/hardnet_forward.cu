@@ -367,6 +367,8 @@ int launch_head(const TcParams& p_in, int sm_count, cudaStream_t stream) {
   if (attr_once.first_time()) {
     HN_CUDA(cudaFuncSetAttribute(gemm_l2norm_kernel<kHeadN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(kHeadSmem)));
+    HN_CUDA(cudaFuncSetAttribute(gemm_l2norm_kernel<kHeadN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(kHeadSmem)));
   }
   if (p_in.num_tiles <= 0) return HN_OK;
   TcParams p = p_in;
@@ -380,6 +382,14 @@ int launch_head(const TcParams& p_in, int sm_count, cudaStream_t stream) {
   }
   p.k_splits = splits;
   const int items = p.num_tiles * splits;
+  static const bool two_tiles = [] { const char* e = getenv("HN_HEAD_TILES"); return e ? atoi(e) == 2 : true; }();   // read once
+  if (splits == 1 && two_tiles && p.num_tiles > sm_count) {
+    // bulk batches: two row tiles per streamed weight block (the kernel is bound by the L2 -> SM traffic)
+    gemm_l2norm_kernel<kHeadN, 2><<<std::min((p.num_tiles + 1) / 2, sm_count), kTcThreads, kHeadSmem, stream>>>(p);
+    HN_CUDA(cudaGetLastError());
+    count_launch();
+    return HN_OK;
+  }
   gemm_l2norm_kernel<kHeadN><<<std::min(items, sm_count), kTcThreads, kHeadSmem, stream>>>(p);
   HN_CUDA(cudaGetLastError());
   count_launch();
@@ -542,7 +552,7 @@ extern "C" int hn_create(hn_handle** out, int chunk_patches, long long head_rows
   if (st != HN_OK) { delete h; return st; }
   if (chunk_patches <= 0) chunk_patches = h->sm_count * 128;  // measured: larger passes amortise launch + prologue cost
   chunk_patches = (chunk_patches + 1) & ~1;
-  if (head_rows <= 0) head_rows = static_cast<long long>(h->sm_count) * kTileM;
+  if (head_rows <= 0) head_rows = 2ll * h->sm_count * kTileM;   // two row tiles per CTA and head launch (gemm_l2norm_kernel<N, 2>)
   head_rows = std::max<long long>(head_rows, chunk_patches);
   head_rows = (head_rows + chunk_patches - 1) / chunk_patches * chunk_patches;
   h->chunk = chunk_patches;

@@ -403,11 +403,16 @@ constexpr int kHeadStages = 3;
 constexpr uint32_t kHeadBlk = kTileM * 128;  // one 128 x 64 fp16 operand tile
 constexpr size_t kHeadSmem = size_t(kHeadStages) * kHeadG * 2 * kHeadBlk + 1024 + 256 + kHeadN * 4;
 
-template <int N>
+// TILES = 2 (bulk batches, no split-K): a work item is two consecutive 128-row tiles that share every streamed weight block.
+// At the bulk rate all 148 CTAs stream the same 2 MB of weights out of L2 per tile next to 2 MB of activations - the kernel is
+// bound by that traffic (32 KB per patch through the L2 -> SM fabric for 1 MMAC per patch); two tiles per weight stream make it 24 KB.
+template <int N, int TILES = 1>
 __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid_constant__ TcParams p) {
-  constexpr int STAGES = kHeadStages, G = kHeadG;
+  constexpr int STAGES = TILES == 2 ? 2 : kHeadStages, G = kHeadG;
   static_assert(N == kHeadN, "descriptor head is 128 wide");
-  constexpr uint32_t STAGE_BYTES = G * 2 * kHeadBlk;
+  static_assert(TILES == 1 || TILES == 2, "one or two row tiles per work item");
+  constexpr uint32_t STAGE_BYTES = G * (TILES + 1) * kHeadBlk;   // per k-block: TILES activation tiles + one weight tile
+  static_assert(size_t(STAGES) * STAGE_BYTES + 1024 + 256 + kHeadN * 4 <= kHeadSmem, "shared memory budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -419,7 +424,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw_addr));
   float* s_bias = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - raw_addr));
-  constexpr uint32_t TMEM_COLS = tmem_cols_for(N);
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(TILES * N);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -455,10 +460,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
-    const int splits = p.k_splits > 1 ? p.k_splits : 1;
+    const int splits = (TILES == 1 && p.k_splits > 1) ? p.k_splits : 1;
     const int nks = p.num_k_stages / splits;                 // k-stages per work item
-    for (int item = blockIdx.x; item < p.num_tiles * splits; item += gridDim.x) {
-      const int tile = item / splits, ks0 = (item - tile * splits) * nks;
+    const int n_items = TILES == 2 ? (p.num_tiles + 1) / 2 : p.num_tiles * splits;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int tile = TILES == 2 ? item * 2 : item / splits, ks0 = TILES == 2 ? 0 : (item - tile * splits) * nks;
 #pragma unroll 1
       for (int ksi = 0; ksi < nks; ++ksi) {
         const int ks = ks0 + ksi;
@@ -468,8 +474,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
           mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            tma_load_2d(st_base + g * kHeadBlk, &p.tmA[0], full_bar(stage), (ks * G + g) * 64, tile * kTileM);
-            tma_load_2d(st_base + (G + g) * kHeadBlk, &p.tmB, full_bar(stage), (ks * G + g) * 64, 0);
+#pragma unroll
+            for (int tl = 0; tl < TILES; ++tl)   // a tile past the end of the batch reads out-of-range rows: TMA zero-fills them
+              tma_load_2d(st_base + (g * TILES + tl) * kHeadBlk, &p.tmA[0], full_bar(stage), (ks * G + g) * 64, (tile + tl) * kTileM);
+            tma_load_2d(st_base + (G * TILES + g) * kHeadBlk, &p.tmB, full_bar(stage), (ks * G + g) * 64, 0);
           }
         }
         __syncwarp();
@@ -483,14 +491,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    const int splits = p.k_splits > 1 ? p.k_splits : 1;
+    const int splits = (TILES == 1 && p.k_splits > 1) ? p.k_splits : 1;
     const int nks = p.num_k_stages / splits;
-    for (int item = blockIdx.x; item < p.num_tiles * splits; item += gridDim.x, ++it) {
+    const int n_items = TILES == 2 ? (p.num_tiles + 1) / 2 : p.num_tiles * splits;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * N;
+      const uint32_t d_tmem = tmem_base + acc * (TILES * N);
 #pragma unroll 1
       for (int ks = 0; ks < nks; ++ks) {
         mbar_wait(full_bar(stage), phase);
@@ -500,9 +509,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
 #pragma unroll
           for (int g = 0; g < G; ++g) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_w(d_tmem, lo + ((g * kHeadBlk) >> 4) + 2u * k, HI, lo + (((G + g) * kHeadBlk) >> 4) + 2u * k, HI, idesc,
-                         (ks | g | k) != 0);
+            for (int tl = 0; tl < TILES; ++tl) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_w(d_tmem + tl * N, lo + (((g * TILES + tl) * kHeadBlk) >> 4) + 2u * k, HI,
+                           lo + (((G * TILES + g) * kHeadBlk) >> 4) + 2u * k, HI, idesc, (ks | g | k) != 0);
+            }
           }
           umma_commit(empty_bar(stage));
           if (ks == nks - 1) umma_commit(tfull_bar(acc));
@@ -515,14 +527,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
     int it = 0;
-    const int splits = p.k_splits > 1 ? p.k_splits : 1;
-    for (int item = blockIdx.x; item < p.num_tiles * splits; item += gridDim.x, ++it) {
-      const int tile = item / splits, split = item - tile * splits;
+    const int splits = (TILES == 1 && p.k_splits > 1) ? p.k_splits : 1;
+    const int n_items = TILES == 2 ? (p.num_tiles + 1) / 2 : p.num_tiles * splits;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * N;
+#pragma unroll 1
+      for (int tl = 0; tl < TILES; ++tl) {
+      const int tile = TILES == 2 ? item * 2 + tl : item / splits, split = TILES == 2 ? 0 : item - tile * splits;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (TILES * N) + tl * N;
       const long long row = static_cast<long long>(tile) * kTileM + row_in_tile;
       const bool valid = row < p.total_rows;
       if (splits > 1) {
@@ -543,7 +558,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
-        continue;
+        continue;   // (TILES == 1 on this path: the tile loop has one trip)
       }
       // bias, then x / sqrt(sum(x*x) + eps) over the N columns of the row (Utils.py:19-22)
       float ss = 0.f;
@@ -582,6 +597,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_l2norm_kernel(const __grid
           }
         }
       }
+      }   // tile loop
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
