@@ -265,6 +265,19 @@ def test_coscheduled_front_and_conv34_roles_are_bit_identical(monkeypatch):
     assert torch.equal(model(x[:5000]), ref_model(x[:5000]))
 
 
+def test_head_gemm_two_tiles_per_weight_stream_is_bit_identical():
+    """Bulk batches run the head GEMM with two 128-row tiles per streamed weight block (gemm_l2norm_kernel<N, 2>, used when a head
+    launch has more tiles than SMs; default head batch = 2 x #SM x 128 patches). Same K order per tile: bit-identical to the
+    one-tile kernel, also with an odd tile count (the phantom tile reads zero-filled rows and stores nothing)."""
+    x = synth.make_patches(37888, 21, edge_cases=False).cuda()
+    one_tile, _ = _model(3, head_rows=18944)     # 148 + <= 148 tiles per head launch: one tile per work item, K not split
+    two_tiles, _ = _model(3)                     # one head launch of up to 296 tiles: two tiles per work item
+    ref = one_tile(x)
+    assert torch.equal(two_tiles(x), ref)                                # 296 tiles
+    n = 37888 - 128 - 55                                                 # 295 tiles (odd), ragged last tile
+    assert torch.equal(two_tiles(x[:n]), one_tile(x[:n]))
+
+
 def test_second_gpu_in_the_same_process():
     """Kernel attributes (dynamic shared memory limits) are per device: a process may use more than one GPU."""
     if torch.cuda.device_count() < 2:
