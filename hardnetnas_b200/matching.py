@@ -11,6 +11,20 @@ import torch
 from . import _ops
 
 
+def assert_unit_norm(des, tol: float = 1e-3):
+    """Precondition of the fused matching kernels (include/hardnet_b200.h, hn_match): rows are L2-normalised descriptors, the
+    only input the FDLNet distance form `sqrt(2 - 2 a.b)` is defined for. The kernels do not check it (their fp16 operand
+    packing and the re-rank margin assume |x| <= 1); call this once on descriptors of unknown origin - one device
+    synchronisation, raises ValueError naming the first offending row."""
+    n = des.float().norm(dim=1)
+    bad = ((n - 1.0).abs() > tol) & (n > 0)        # all-zero rows (constant patches) are legal and match nothing
+    if bool(bad.any()):
+        i = int(bad.nonzero()[0])
+        raise ValueError(f"descriptor row {i} has L2 norm {float(n[i]):.6f}: the matching kernels need unit-norm rows "
+                         f"(|norm - 1| <= {tol})")
+    return des
+
+
 def distance_matrix_vector(anchor, positive):
     """Materialising API for small inputs (FDLNet-master/utils/math_utils.py:8-19)."""
     m = 2 - 2 * torch.mm(anchor, positive.t())

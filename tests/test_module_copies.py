@@ -48,3 +48,13 @@ def test_stage_table_follows_the_launch_counts():
     assert sum(macs[1:]) == sum(HardNet.STAGE_MACS[1:])
     names, macs = HardNet.stage_table([0, 28, 28, 28, 28, 28, 1])
     assert tuple(names) == HardNet.STAGE_NAMES and tuple(macs) == HardNet.STAGE_MACS
+
+
+def test_assert_unit_norm_guards_the_matching_precondition():
+    from hardnetnas_b200.matching import assert_unit_norm
+    d = torch.nn.functional.normalize(torch.randn(64, 128), dim=1)
+    d[5] = 0                                   # a constant patch's descriptor
+    assert assert_unit_norm(d) is d
+    d[7] *= 1.5
+    with pytest.raises(ValueError, match="row 7"):
+        assert_unit_norm(d)
