@@ -412,7 +412,7 @@ static int launch_dist(const DistParams& p, int grid_x, int grid_y, cudaStream_t
   static DeviceOnce attr_once;
   if (attr_once.first_time())
     HN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dist_smem_bytes<MB>(MB == 1 ? 6 : 2))));
-  kern<<<dim3(grid_x, grid_y), 64 + 128 * MB, smem, s>>>(p);
+  kern<<<dim3(grid_x, grid_y), 64 + 128 * MB * dist_col_split<EPI>(), smem, s>>>(p);
   HN_CUDA(cudaGetLastError());
   count_launch();
   return HN_OK;

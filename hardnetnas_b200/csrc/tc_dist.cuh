@@ -88,9 +88,18 @@ __device__ __forceinline__ float warp_chunk_max8(const float (&c)[8], int lane) 
   return v;
 }
 
+// Epilogue warps per accumulator lane quarter. The exact epilogues (loss kernels) cost ~80 instructions per column and a loss-sized
+// problem (N = 1024) gives every CTA exactly ONE 128 x 128 tile: with one warp per quarter a thread walked 128 columns alone
+// (~10 k dependent instructions = 13 us of a 28 us kernel). Four warps per quarter take 32 columns each and merge through the
+// packed atomicMin the segments already use.
+template <int EPI>
+constexpr int dist_col_split() { return (EPI == EPI_EXACT || EPI == EPI_EXACT_NEI) ? 4 : 1; }
+
 template <int MB, int EPI>
-__global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_constant__ DistParams p) {
+__global__ void __launch_bounds__(64 + 128 * MB * dist_col_split<EPI>(), 1) dist_kernel(const __grid_constant__ DistParams p) {
   constexpr bool EXACT = EPI == EPI_EXACT || EPI == EPI_EXACT_NEI;
+  constexpr int CS = dist_col_split<EPI>();
+  static_assert(CS == 1 || MB == 1, "the column split is for the single-M-block loss kernels");
   constexpr bool NEI = EPI == EPI_EXACT_NEI;   // compile-time: the plain loss kernel carries none of the mask code
   constexpr uint32_t BLK_BYTES = kDistTile * 128;  // 128 rows x 64 fp16
   constexpr uint32_t TMEM_COLS = 2 * MB * kDistTile;
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(tfull_bar(a), 1);
-        mbar_init(tempty_bar(a), 4 * MB);
+        mbar_init(tempty_bar(a), 4 * MB * CS);
       }
       mbar_init(afull_bar, 1);
       mbar_init(aempty_bar, 1);
@@ -232,8 +241,9 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
   } else {
     // ============================== epilogue ==============================
     const int q = warp & 3;
-    const int mb = (warp - 2) >> 2;
-    const int ep_tid = threadIdx.x - 64;  // 0 .. 128*MB-1
+    const int mb = CS == 1 ? (warp - 2) >> 2 : 0;
+    const int cs = CS == 1 ? 0 : (warp - 2) >> 2;   // which 32 of the tile's 128 columns (exact epilogues)
+    const int ep_tid = threadIdx.x - 64;  // 0 .. 128*MB*CS-1
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int mblk = item / p.segments, seg = item - mblk * p.segments;
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
             const long long c = col0 + ep_tid;
             s_nb[acc * kDistTile + ep_tid] = c < sd.Nb ? sd.norm_b[c] : 0.f;
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(128 * MB) : "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * MB * CS) : "memory");
         }
         if (NEI) {
           if (ep_tid < kDistTile) {
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
             if (c < sd.Nb) { const float2 a = sd.xy_a_cols[c], b = sd.xy_p_cols[c]; v = make_float4(a.x, a.y, b.x, b.y); }
             s_xy[acc * kDistTile + ep_tid] = v;
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(128 * MB) : "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(128 * MB * CS) : "memory");
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
@@ -328,8 +338,11 @@ __global__ void __launch_bounds__(64 + 128 * MB, 1) dist_kernel(const __grid_con
             }
           }
         } else {
-#pragma unroll
-        for (int c0 = 0; c0 < kDistTile; c0 += 32) {
+        // NOT unrolled: the exact epilogue is ~80 instructions per column and a loss-sized problem (N = 1024) runs it ONCE per CTA,
+        // so four unrolled copies were 10 k instructions of straight-line code fetched cold - the instruction fetch (stall reason
+        // no_inst in ncu) was most of the kernel's 28 us; one copy of the 32-column body stays in the instruction cache.
+#pragma unroll 1
+        for (int c0 = CS == 1 ? 0 : cs * 32; c0 < (CS == 1 ? kDistTile : cs * 32 + 32); c0 += 32) {
           uint32_t r[32];
           tmem_ld32(t_row + c0, r);
           tmem_ld_wait();
