@@ -35,7 +35,7 @@ def graphed(fn):
 
 
 lib = _lib.load()
-for n in (128, 1024):
+for n in (128, 512, 1024, 2048, 4096, 8192):
     a = torch.nn.functional.normalize(torch.randn(n, 128, device="cuda"), dim=1)
     p = torch.nn.functional.normalize(a + 0.1 * torch.randn_like(a), dim=1)
     out16 = torch.empty(n * 384, dtype=torch.float16, device="cuda")
