@@ -55,6 +55,7 @@ SIGNATURES = {
     "hn_pair_distances": (C.c_int, [_P, _P, C.c_longlong, _P, _P]),
     "hn_fpr95": (C.c_int, [_P, _P, C.c_longlong, _P, _P]),
     "hn_clip_patches": (C.c_int, [_P, C.c_longlong, C.c_int, C.c_int, _P, _P, _P, _P, C.c_longlong, C.c_int, _P, _P]),
+    "hn_forward_clip": (C.c_int, [_P, _P, C.c_int, C.c_longlong, C.c_int, C.c_int, _P, _P, _P, _P, C.c_longlong, _P, C.c_int, _P]),
 }
 
 

@@ -25,6 +25,7 @@
 // two issuers and the shifts to two more warps those latencies overlap each other and the MMAs.
 #pragma once
 
+#include "clip.cuh"
 #include "common.cuh"
 #include "l1_tc.cuh"
 #include "tc_conv.cuh"
@@ -89,13 +90,19 @@ struct FfBias {
 // blockIdx.x / gridDim.x; the co-scheduled front + conv3/conv4 launch of front_c34.cuh gives this role a sub-range of the grid).
 // ready != nullptr (HardNet variant only): each of the eight conv2 epilogue warps stamps ready[patch * 8 + its index] = 1 once
 // its part of the patch is in global memory (release at gpu scope) - the consumer role of the same launch polls these flags.
-template <typename TIn, bool PW2, int FDW>
+// CLIP (HardNet variant, TIn = float): there is no patch tensor - `in` is unused and patch clip->n0 + i is cropped around its
+// keypoint from the image stack (the reference's clip_patch, FDLNet-master/utils/image_utils.py:11-158, arithmetic in clip.cuh) by
+// the stage-1 epilogue warps, which otherwise wait for the stage-1 MMAs most of the time: they fill the raw ring two patches
+// ahead, in place of the bulk copies, and the loader warps run unchanged.
+template <typename TIn, bool PW2, int FDW, bool CLIP = false>
 __device__ __forceinline__ void front_fused_body(const TIn* __restrict__ in, uint16_t* __restrict__ out, const float* __restrict__ w1,
                                                  const float* __restrict__ bias1, const uint4* __restrict__ w2img, const FfBias& bias2,
                                                  int do_norm, int num_patches, int act_bf16, float norm_eps, const CUtensorMap& tm_out,
                                                  const float* __restrict__ dw_w, const float* __restrict__ dw_b, int dw_relu, int fdw_planar,
-                                                 const int blk, const int nblk, int* __restrict__ ready) {
+                                                 const int blk, const int nblk, int* __restrict__ ready,
+                                                 const ClipSrc* __restrict__ clip = nullptr) {
   static_assert(FDW == 0 || PW2, "the fused depthwise stage sits behind the pointwise variant");
+  static_assert(!CLIP || (sizeof(TIn) == 4 && !PW2), "the cropped patch is fp32 in the raw ring; HardNet variant only");
   constexpr int NACT1 = FDW ? 1 : 2;   // stage-1 activation buffers
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -143,7 +150,7 @@ __device__ __forceinline__ void front_fused_body(const TIn* __restrict__ in, uin
         mbar_init(mma_done(a), 1);
       }
       for (int d = 0; d < kFfRawDepth; ++d) {
-        mbar_init(raw_full(d), 1);    // arrive.expect_tx of the prefetching lane + the copy's complete_tx
+        mbar_init(raw_full(d), CLIP ? 4 : 1);   // arrive.expect_tx of the prefetching lane + the copy's complete_tx; CLIP: the four cropping warps
         mbar_init(raw_empty(d), 4);   // one arrive per loader warp
       }
       fence_mbar_init();
@@ -213,12 +220,12 @@ __device__ __forceinline__ void front_fused_body(const TIn* __restrict__ in, uin
                        raw_addr0 + d * 4096), "l"(g), "r"(RAW_BYTES), "r"(raw_full(d))
                    : "memory");
     };
-    if (lw == 0 && lane == 0)
+    if (!CLIP && lw == 0 && lane == 0)
       for (int j = 0; j < kFfRawDepth - 1 && j < n_loc; ++j) prefetch(j);
     float* s_red = reinterpret_cast<float*>(gbase + (bar_base + 384 - base));   // [sum | sum of squares][patch parity][4 warps]
     int it = 0;
     for (int patch = blk; patch < num_patches; patch += nblk, ++it) {
-      if (lw == 0 && lane == 0 && it + kFfRawDepth - 1 < n_loc) prefetch(it + kFfRawDepth - 1);
+      if (!CLIP && lw == 0 && lane == 0 && it + kFfRawDepth - 1 < n_loc) prefetch(it + kFfRawDepth - 1);
       __syncwarp();
       const int d = it % kFfRawDepth;
       HN_FF_WAIT(0, raw_full(d), (it / kFfRawDepth) & 1);
@@ -439,8 +446,59 @@ __device__ __forceinline__ void front_fused_body(const TIn* __restrict__ in, uin
     // ============================== stage-1 epilogue: TMEM -> bias, ReLU, pack -> act1 (smem) ==============================
     const int q = warp;
     int it = 0;
+    // CLIP: crop rows 8 q + 4 h .. + 3 of local patch jg into ring slot jg % depth, 16 gathers in flight per thread. A warp-wide
+    // load covers a compact 4 x 8 pixel block of the patch, not a row: under rotation a 32-pixel row crosses ~32 image rows = 32
+    // cache lines = 32 L1 wavefronts per instruction, a block ~10 (the kernel's shared-memory traffic shares that pipe).
+    // The keypoint of the next patch is fetched as soon as a patch is finished, so its loads are off the next crop's critical path.
+    [[maybe_unused]] int jg = 0;
+    [[maybe_unused]] ClipKp kp = {};
+    [[maybe_unused]] const int n_crop = (num_patches - blk + nblk - 1) / nblk;
+    [[maybe_unused]] auto crop_half = [&](int h) {
+      if (jg >= n_crop) return;
+      const int d = jg % kFfRawDepth;
+      if (h == 0) mbar_wait(raw_empty(d), ((jg / kFfRawDepth) & 1) ^ 1u);
+      const int prow = 8 * q + 4 * h + (lane >> 3), pcol = lane & 7;   // pixel (prow, 8 r + pcol), r = 0..3
+      float* slot = reinterpret_cast<float*>(gbase + (raw_addr0 - base) + d * 4096) + prow * 32 + pcol;
+      const bool ok = kp.b >= 0 && kp.b < clip->B;   // image index out of range: NaN patch, like the stand-alone kernel
+      const size_t img_off = static_cast<size_t>(ok ? kp.b : 0) * (static_cast<size_t>(clip->H) * clip->W);
+      ClipTaps t[4];
+      float I[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) t[r] = clip_taps(kp, 8 * r + pcol, prow, 32, clip->H, clip->W);
+      if (clip->img_u8) {
+        const uint8_t* img = static_cast<const uint8_t*>(clip->images) + img_off;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          I[r][0] = clip_pixel(img, t[r].ia); I[r][1] = clip_pixel(img, t[r].ib);
+          I[r][2] = clip_pixel(img, t[r].ic); I[r][3] = clip_pixel(img, t[r].id);
+        }
+      } else {
+        const float* img = static_cast<const float*>(clip->images) + img_off;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          I[r][0] = clip_pixel(img, t[r].ia); I[r][1] = clip_pixel(img, t[r].ib);
+          I[r][2] = clip_pixel(img, t[r].ic); I[r][3] = clip_pixel(img, t[r].id);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        slot[r * 8] = ok ? clip_blend(t[r], I[r][0], I[r][1], I[r][2], I[r][3]) : __int_as_float(0x7fc00000);
+      if (h == 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(raw_full(d));
+        if (++jg < n_crop)
+          kp = clip_keypoint(clip->kpts_byxc, clip->kpts_scale, clip->kpts_ori, clip->im_info, clip->kp_per_image,
+                             clip->n0 + blk + static_cast<long long>(jg) * nblk);
+      }
+    };
+    if constexpr (CLIP) {
+      if (n_crop > 0)
+        kp = clip_keypoint(clip->kpts_byxc, clip->kpts_scale, clip->kpts_ori, clip->im_info, clip->kp_per_image, clip->n0 + blk);
+      for (int j = 0; j < 2; ++j) { crop_half(0); crop_half(1); }   // two patches ahead of the loaders
+    }
     for (int patch = blk; patch < num_patches; patch += nblk, ++it) {
       const int b = FDW ? 0 : it & 1;
+      if constexpr (CLIP) crop_half(0);
       HN_FF_WAIT(8, act1_empty(b), (FDW ? (it & 1) : ((it >> 1) & 1)) ^ 1u);
       uint8_t* act = gbase + (act1_addr - base) + b * kFfAct1;
       if constexpr (PW2) {
@@ -470,6 +528,7 @@ __device__ __forceinline__ void front_fused_body(const TIn* __restrict__ in, uin
       }
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
+        if constexpr (CLIP) { if (half == 1) crop_half(1); }
         HN_FF_WAIT(9, l1_full, half);
         tc_fence_after();
 #pragma unroll 1
@@ -736,6 +795,15 @@ front_fused_kernel(const TIn* __restrict__ in, uint16_t* __restrict__ out /*[n][
                    int dw_relu = 0, int fdw_planar = 0 /*FDW output channel-planar [n][4][16][16][8] (the tail kernel's bulk-copy layout)*/) {
   front_fused_body<TIn, PW2, FDW>(in, out, w1, bias1, w2img, bias2, do_norm, num_patches, act_bf16, norm_eps, tm_out, dw_w, dw_b, dw_relu,
                                   fdw_planar, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), nullptr);
+}
+
+// The HardNet front kernel fed by clip_patch on the fly (hn_forward_clip): same stages, patches cropped inside the kernel.
+__global__ void __launch_bounds__(kFfThreads, 1)
+front_fused_clip_kernel(const __grid_constant__ ClipSrc clip, uint16_t* __restrict__ out, const float* __restrict__ w1,
+                        const float* __restrict__ bias1, const uint4* __restrict__ w2img, const __grid_constant__ FfBias bias2,
+                        int num_patches, int act_bf16, float norm_eps, const __grid_constant__ CUtensorMap tm_out) {
+  front_fused_body<float, false, 0, true>(nullptr, out, w1, bias1, w2img, bias2, 1, num_patches, act_bf16, norm_eps, tm_out, nullptr,
+                                          nullptr, 0, 0, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), nullptr, &clip);
 }
 
 }  // namespace hn

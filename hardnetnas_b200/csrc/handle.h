@@ -10,6 +10,9 @@
 #include "tc_conv34.cuh"
 
 namespace hn {
+// internal value of `in_dtype` next to HN_F32 / HN_U8: the input pointer is a HOST ClipSrc (clip.cuh) and the patches are cropped
+// from the image stack by the front kernel's loader warps (hn_forward_clip)
+constexpr int kInClip = 100;
 struct NasState;
 void nas_state_free(NasState* s);
 // [rows, K] x [K, 128] + bias + L2 normalisation (hardnet_forward.cu); shared by the HardNet and NAS heads

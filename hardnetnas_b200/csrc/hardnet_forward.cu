@@ -285,7 +285,13 @@ static int launch_front_fused(hn_handle* h, const void* patches, int in_dtype, u
   static const CUtensorMap no_map = {};   // output tensor map: only the pointwise (NAS) variant stores through TMA
   FfBias b2;
   memcpy(b2.v, h->bias2_host, sizeof(b2.v));
-  if (in_dtype == HN_F32) {
+  if (in_dtype == kInClip) {   // `patches` is a HOST ClipSrc: the loader warps crop the patches from the image stack
+    static DeviceOnce clip_once;
+    if (clip_once.first_time())
+      HN_CUDA(cudaFuncSetAttribute(front_fused_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFfSmem)));
+    front_fused_clip_kernel<<<grid, kFfThreads, kFfSmem, s>>>(*static_cast<const ClipSrc*>(patches), out, h->w1, h->bias, w2, b2, n,
+                                                             h->act_bf16, h->norm_eps, no_map);
+  } else if (in_dtype == HN_F32) {
     const float* x = static_cast<const float*>(patches);
     front_fused_kernel<float><<<grid, kFfThreads, kFfSmem, s>>>(x, out, h->w1, h->bias, w2, b2, 1, n, h->act_bf16, h->norm_eps, no_map);
   } else {
@@ -499,9 +505,24 @@ static int run_one_conv(hn_handle* h, int li, int n, void* out, cudaStream_t s) 
   return pair ? launch_conv_pair(li, p, h->sm_count, s) : launch_conv(li, p, h->sm_count, s);
 }
 
+// The input `off` patches further on: a pointer into the patch tensor, or (kInClip) a copy of the host ClipSrc whose first
+// keypoint is moved on.
+static const void* input_at(const void* patches, int in_dtype, long long off, ClipSrc* tmp) {
+  if (in_dtype == kInClip) {
+    *tmp = *static_cast<const ClipSrc*>(patches);
+    tmp->n0 += off;
+    return tmp;
+  }
+  return static_cast<const char*>(patches) + static_cast<size_t>(off) * 1024 * (in_dtype == HN_F32 ? 4 : 1);
+}
+
 static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n, long long l6_row, int last_layer,
                           cudaStream_t s) {
   if (last_layer < 2) {
+    if (in_dtype == kInClip) {
+      set_error("the stage-1 activation dump takes a patch tensor (crop with hn_clip_patches first)");
+      return HN_ERR_INVALID;
+    }
     StageTimer timer(h, 0, s);  // stage 1 alone (activation dump only), NHWC
     return launch_l1(patches, in_dtype, h->act[0], h->w1, h->bias, h->stats, n, h->act_bf16, h->sm_count, s, h->norm_eps);
   }
@@ -510,19 +531,18 @@ static int run_conv_stack(hn_handle* h, const void* patches, int in_dtype, int n
   // making an HBM round trip; conv3 writes into the full-size act[0] and the deeper stages run once over the whole pass.
   const int front = last_layer >= 3 ? std::min(h->front_chunk, n) : n;
   const bool fuse = h->fuse34 != 0 && last_layer >= 4;   // a dump of conv3's own output runs the layer on its own
-  const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
   for (int off = 0; off < n; off += front) {
     const int m = std::min(front, n - off);
+    ClipSrc clip_at;
+    const void* src = input_at(patches, in_dtype, off, &clip_at);
     // both roles need enough patches to fill their share of the SMs; small batches keep the two launches (every SM on each stage)
-    if (fuse && h->fuse34 == 3 && h->cosched && m >= 32 * h->sm_count) {
-      HN_TRY(run_front_c34(h, static_cast<const char*>(patches) + static_cast<size_t>(off) * 1024 * in_elem, in_dtype, m,
-                           h->act[0] + static_cast<size_t>(off) * 16 * 16 * 64, s));
+    if (fuse && h->fuse34 == 3 && h->cosched && m >= 32 * h->sm_count && in_dtype != kInClip) {
+      HN_TRY(run_front_c34(h, src, in_dtype, m, h->act[0] + static_cast<size_t>(off) * 16 * 16 * 64, s));
       continue;
     }
     {
       StageTimer timer(h, 1, s);  // stage 1 + conv2 (the stage-1 activation never reaches global memory)
-      HN_TRY(launch_front_fused(h, static_cast<const char*>(patches) + static_cast<size_t>(off) * 1024 * in_elem, in_dtype,
-                                h->act[1], m, s));
+      HN_TRY(launch_front_fused(h, src, in_dtype, h->act[1], m, s));
     }
     if (fuse) HN_TRY(run_conv34(h, m, h->act[0] + static_cast<size_t>(off) * 16 * 16 * 64, s));
     else if (last_layer >= 3) HN_TRY(run_one_conv(h, 1, m, h->act[0] + static_cast<size_t>(off) * 16 * 16 * 64, s));
@@ -736,6 +756,8 @@ extern "C" int hn_pack_hardnet(hn_handle* h, const float* const w[7], const floa
   return HN_OK;
 }
 
+static int forward_passes(hn_handle* h, const void* patches, int in_dtype, long long B, void* desc_out, int out_dtype, cudaStream_t s);
+
 extern "C" int hn_forward(hn_handle* h, const void* patches, int in_dtype, long long B, void* desc_out, int out_dtype,
                           void* stream) {
   HN_REQUIRE(h, "hn_forward: NULL handle");
@@ -748,15 +770,48 @@ extern "C" int hn_forward(hn_handle* h, const void* patches, int in_dtype, long 
   HN_REQUIRE(out_dtype == HN_F32 || out_dtype == HN_F16 || out_dtype == HN_BF16, "hn_forward: bad out_dtype");
   if (B == 0) return HN_OK;
   HN_REQUIRE(patches && desc_out, "hn_forward: NULL data pointer");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t in_elem = in_dtype == HN_F32 ? 4 : 1;
+  return forward_passes(h, patches, in_dtype, B, desc_out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+// Descriptors of patches that are cropped from the images on the fly: hn_clip_patches + hn_forward without the fp32 patch tensor
+// (reference caller FDLNet-master/.../rf_net_so.py:160-180 -> image_utils.py:11-158 -> des()).
+extern "C" int hn_forward_clip(hn_handle* h, const void* images, int img_dtype, long long B, int H, int W, const long long* kpts_byxc,
+                               const float* kpts_scale, const float* kpts_ori, const float* im_info, long long N, void* desc_out,
+                               int out_dtype, void* stream) {
+  HN_REQUIRE(h, "hn_forward_clip: NULL handle");
+  if (!h->packed) {
+    set_error("hn_forward_clip: weights not packed (call hn_pack_hardnet first)");
+    return HN_ERR_STATE;
+  }
+  HN_REQUIRE(img_dtype == HN_F32 || img_dtype == HN_U8, "hn_forward_clip: img_dtype must be HN_F32 or HN_U8");
+  HN_REQUIRE(out_dtype == HN_F32 || out_dtype == HN_F16 || out_dtype == HN_BF16, "hn_forward_clip: bad out_dtype");
+  HN_REQUIRE(B >= 1 && H >= 1 && W >= 1 && static_cast<long long>(H) * W < (1ll << 31), "hn_forward_clip: bad image size");
+  HN_REQUIRE(N >= 0 && N % B == 0, "hn_forward_clip: the reference's view(B, -1) needs N (%lld) to be a multiple of B (%lld)", N, B);
+  if (N == 0) return HN_OK;
+  HN_REQUIRE(images && kpts_byxc && kpts_scale && im_info && desc_out, "hn_forward_clip: NULL argument");
+  ClipSrc c;
+  c.images = images;
+  c.kpts_byxc = kpts_byxc;
+  c.kpts_scale = kpts_scale;
+  c.kpts_ori = kpts_ori;
+  c.im_info = im_info;
+  c.B = B;
+  c.kp_per_image = N / B;
+  c.n0 = 0;
+  c.H = H;
+  c.W = W;
+  c.img_u8 = img_dtype == HN_U8;
+  return forward_passes(h, &c, kInClip, N, desc_out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+static int forward_passes(hn_handle* h, const void* patches, int in_dtype, long long B, void* desc_out, int out_dtype, cudaStream_t s) {
   const size_t out_elem = out_dtype == HN_F32 ? 4 : 2;
   for (long long base = 0; base < B; base += h->head_rows) {
     const long long nb = std::min<long long>(h->head_rows, B - base);
     for (long long off = 0; off < nb; off += h->chunk) {
       const int n = static_cast<int>(std::min<long long>(h->chunk, nb - off));
-      const char* src = static_cast<const char*>(patches) + static_cast<size_t>(base + off) * 1024 * in_elem;
-      HN_TRY(run_conv_stack(h, src, in_dtype, n, off, 6, s));
+      ClipSrc clip_at;
+      HN_TRY(run_conv_stack(h, input_at(patches, in_dtype, base + off, &clip_at), in_dtype, n, off, 6, s));
     }
     TcParams p = h->head_params;
     p.total_rows = nb;

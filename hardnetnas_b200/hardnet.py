@@ -209,6 +209,37 @@ class HardNet(_EngineOwner, nn.Module):
                                           _OUT_DTYPES[out_dtype], C.c_void_p(stream)), "hn_forward")
         return out
 
+    def forward_clip(self, kpts_byxc, kpts_scale, kpts_ori, im_info, images, out_dtype: torch.dtype = torch.float32):
+        """`self(clip_patch(kpts_byxc, kpts_scale, kpts_ori, im_info, images, 32))` in one call (eval mode): the crop runs in the
+        loader warps of the first conv kernel, so the [N,1,32,32] patch tensor is never materialised, and `images` may be uint8.
+        Replaces the two calls of RFNetSO.inference (FDLNet-master/latency/rfnet/model/rf_net_so.py:160-180). Descriptors are
+        bit-identical to the two-call form on `images.float()`."""
+        if self.training:
+            raise _lib.HardnetB200Error("forward_clip is the eval-mode path; in train mode call clip_patch and the module")
+        if not (isinstance(images, torch.Tensor) and images.is_cuda):
+            raise _lib.HardnetB200Error("forward_clip runs on B200 CUDA tensors only (no CPU fallback)")
+        assert kpts_byxc.size(0) == kpts_scale.size(0)   # image_utils.py:22
+        dev = images.device
+        B, Cc, H, W = images.size()
+        if Cc != 1:
+            raise ValueError("forward_clip expects single-channel images [B,1,H,W] (the reference flattens them as such)")
+        img_dt = _lib.HN_U8 if images.dtype == torch.uint8 else _lib.HN_F32
+        img = images.detach().contiguous() if images.dtype == torch.uint8 else images.detach().to(torch.float32).contiguous()
+        n = kpts_byxc.size(0)
+        byxc = kpts_byxc.detach().to(device=dev, dtype=torch.int64).contiguous()
+        scale = kpts_scale.detach().to(device=dev, dtype=torch.float32).contiguous().view(-1)
+        ori = None if kpts_ori is None else kpts_ori.detach().to(device=dev, dtype=torch.float32).contiguous()
+        info = im_info.detach().to(device=dev, dtype=torch.float32).contiguous()
+        self._ensure_packed(dev)
+        out = torch.empty((n, 128), dtype=out_dtype, device=dev)
+        eng = self._engine
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(eng.lib.hn_forward_clip(eng.handle, img.data_ptr(), img_dt, B, H, W, byxc.data_ptr(), scale.data_ptr(),
+                                               None if ori is None else ori.data_ptr(), info.data_ptr(), n, out.data_ptr(),
+                                               _OUT_DTYPES[out_dtype], C.c_void_p(stream)), "hn_forward_clip")
+        return out
+
     # ---- measurement hooks (bench.py) ---------------------------------------------------------------
     # stage 0 (input_norm + conv1 on its own) only runs for activation dumps: the forward path fuses it into stage 1
     STAGE_NAMES = ("conv1_only_dump_path", "front_fused_norm_conv1_conv2", "conv3_s2_64", "conv4_64", "conv5_s2_128", "conv6_128",

@@ -240,6 +240,15 @@ int hn_fpr95(const float* scores, const unsigned char* labels, long long n, long
 int hn_clip_patches(const float* images, long long B, int H, int W, const long long* kpts_byxc,
                     const float* kpts_scale, const float* kpts_ori, const float* im_info, long long N,
                     int psize, float* out, void* stream);
+/* hn_clip_patches (psize 32) + hn_forward in one call, with the crop done by the loader warps of the first conv kernel: the
+ * [N,1,32,32] fp32 patch tensor never exists in device memory. Replaces the pair of calls in RFNetSO.inference
+ * (FDLNet-master/latency/rfnet/model/rf_net_so.py:160-180: clip_patch(...) then self.des(patches)). images [B,1,H,W] of
+ * img_dtype HN_F32 or HN_U8 (uint8 pixels are converted to fp32 before the interpolation, i.e. the result equals the fp32 call on
+ * images.float()); keypoint arguments as hn_clip_patches; desc_out [N,128] of out_dtype. Descriptors are bit-identical to
+ * hn_clip_patches followed by hn_forward. A keypoint whose image index is outside [0, B) yields a NaN descriptor. */
+int hn_forward_clip(hn_handle* h, const void* images, int img_dtype, long long B, int H, int W, const long long* kpts_byxc,
+                    const float* kpts_scale, const float* kpts_ori, const float* im_info, long long N, void* desc_out,
+                    int out_dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,3 +56,59 @@ def test_cpu_tensors_fail_loudly():
     byxc, scale, ori, im_info, images = clip_oracle.make_clip_inputs()
     with pytest.raises(HardnetB200Error):
         clip_patch(byxc, scale, ori, im_info, images, 32)
+
+
+def _hardnet(**kw):
+    """HardNet with the reference init and randomised BN statistics (oracle/synth.py), as the descriptor parity tests use."""
+    from hardnetnas_b200.hardnet import HardNet
+    from oracle import synth
+    w, m, v = synth.hardnet_weights_from_seed(0, 3)
+    torch.manual_seed(0)
+    model = HardNet(**kw)
+    sd = model.state_dict()
+    for i, bi in enumerate(synth.BN_IDX):
+        sd[f"features.{bi}.running_mean"] = m[i]
+        sd[f"features.{bi}.running_var"] = v[i]
+    model.load_state_dict(sd)
+    return model.cuda().eval(), (w, m, v)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_ori", [True, False])
+def test_forward_clip_is_bit_identical_to_clip_then_forward(with_ori):
+    """hn_forward_clip (crop inside the front kernel's loader warps, no patch tensor) == hn_clip_patches + hn_forward, bit for
+    bit; and against the CPU oracle of both steps within the descriptor tolerance of BASELINE.json (max-abs 1e-3). The small
+    chunk makes the 2048 keypoints span several passes and head launches (keypoint offsets) with a ragged last pass."""
+    from oracle import hardnet_oracle
+    from hardnetnas_b200.image_utils import clip_patch
+    byxc, scale, ori, im_info, images = clip_oracle.make_clip_inputs(seed=5, B=8, H=240, W=320, k=256)
+    ori_c = ori.cuda() if with_ori else None
+    for chunk in (0, 300):
+        model, (w, m, v) = _hardnet(chunk_patches=chunk, head_rows=600 if chunk else 0)
+        two = model(clip_patch(byxc.cuda(), scale.cuda(), ori_c, im_info.cuda(), images.cuda(), 32))
+        one = model.forward_clip(byxc.cuda(), scale.cuda(), ori_c, im_info.cuda(), images.cuda())
+        assert one.shape == (2048, 128)
+        assert torch.equal(one, two)
+    patches = clip_oracle.clip_patch(byxc, scale, ori if with_ori else None, im_info, images, 32)[:256]
+    ref = hardnet_oracle.hardnet_forward(patches, w, m, v)
+    assert (one[:256].cpu() - ref).abs().max().item() <= 1e-3
+
+
+@pytest.mark.gpu
+def test_forward_clip_uint8_images_and_bad_image_index():
+    from hardnetnas_b200.image_utils import clip_patch
+    byxc, scale, ori, im_info, images = clip_oracle.make_clip_inputs(seed=9, B=4, H=200, W=264, k=75)
+    img8 = (images * 255).round().clamp(0, 255).to(torch.uint8)
+    model, _ = _hardnet()
+    two = model(clip_patch(byxc.cuda(), scale.cuda(), ori.cuda(), im_info.cuda(), img8.float().cuda(), 32))
+    one = model.forward_clip(byxc.cuda(), scale.cuda(), ori.cuda(), im_info.cuda(), img8.cuda())
+    assert torch.equal(one, two) and torch.isfinite(one).all()
+    half = model.forward_clip(byxc.cuda(), scale.cuda(), ori.cuda(), im_info.cuda(), img8.cuda(), out_dtype=torch.float16)
+    assert (half.float() - one).abs().max().item() <= 1e-3
+    bad = byxc.clone()
+    bad[7, 0] = 4          # image index out of range: NaN descriptor for that keypoint only, no out-of-bounds read
+    out = model.forward_clip(bad.cuda(), scale.cuda(), ori.cuda(), im_info.cuda(), img8.cuda())
+    assert torch.isnan(out[7]).all() and torch.equal(out[:7], one[:7]) and torch.equal(out[8:], one[8:])
+    from hardnetnas_b200._lib import HardnetB200Error
+    with pytest.raises(HardnetB200Error):
+        model.train().forward_clip(byxc.cuda(), scale.cuda(), ori.cuda(), im_info.cuda(), img8.cuda())
