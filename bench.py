@@ -434,12 +434,13 @@ def run_b200(args):
     del h_in, h_out
     torch.cuda.empty_cache()
 
-    matching = nas = config1 = None
+    matching = nas = config1 = keypoints = None
     if not args.no_extras:
         matching = bench_matching(device, rank, world, D, peaks, with_cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
         if rank == 0:
             nas = bench_nas(device, peaks, with_cpu=(world == 1 and not args.no_cpu_baseline))
             config1 = bench_config1(device, model, with_cpu=(world == 1 and not args.no_cpu_baseline))
+            keypoints = bench_keypoints(device, model, with_cpu=(world == 1 and not args.no_cpu_baseline))
         D.barrier()
 
     cpu_baseline = None
@@ -457,7 +458,7 @@ def run_b200(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
             "e2e_u8": e2e_u8, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "matching": matching, "nas": nas, "config1": config1,
+            "matching": matching, "nas": nas, "config1": config1, "keypoints": keypoints,
         }
         emit(line)
     if world > 1:
@@ -762,6 +763,62 @@ def bench_config1(device, model, with_cpu):
             cpu_step()
         rec["cpu_ms"] = (time.perf_counter() - t0) / 3 * 1e3
         rec["cpu_kind"] = f"{kind} forward ({desc}) + oracle loss (hardnet/Losses.py:87-154 without its hard-coded .cuda()), {torch.get_num_threads()} threads"
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------------------
+# keypoints -> descriptors (the caller right upstream of the descriptor in RFNetSO.inference,
+# FDLNet-master/latency/rfnet/model/rf_net_so.py:160-180: clip_patch, then des(patches))
+# ---------------------------------------------------------------------------------------------------------
+def bench_keypoints(device, model, with_cpu):
+    from hardnetnas_b200.image_utils import clip_patch
+    B, k, H, W = 16, 16384, 480, 640
+    g = torch.Generator().manual_seed(1)
+    images = torch.nn.functional.avg_pool2d(torch.rand(B, 1, H, W, generator=g), 5, 1, 2)
+    img8 = (images * 255).round().to(torch.uint8).to(device)
+    imgf = img8.float()
+    ys, xs = torch.randint(0, H // 2, (B, k), generator=g), torch.randint(0, W // 2, (B, k), generator=g)
+    bs = torch.arange(B)[:, None].expand(B, k)
+    byxc_h = torch.stack([bs, ys, xs, torch.zeros_like(ys)], dim=-1).view(-1, 4).long()
+    scale_h = 6.0 + 34.0 * torch.rand(B * k, generator=g)
+    ang = 6.2831853 * torch.rand(B * k, generator=g)
+    ori_h = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1)
+    info_h = torch.full((B, 2), 0.5)
+    byxc, scale, ori, info = byxc_h.to(device), scale_h.to(device), ori_h.to(device), info_h.to(device)
+    n = B * k
+    two = model(clip_patch(byxc, scale, ori, info, imgf, 32))
+    one = model.forward_clip(byxc, scale, ori, info, img8)
+    patches = clip_patch(byxc, scale, ori, info, imgf, 32)
+    t_clip = timeit(lambda: clip_patch(byxc, scale, ori, info, imgf, 32), 5)
+    t_fwd = timeit(lambda: model(patches), 5)
+    del patches
+    t_two = timeit(lambda: model(clip_patch(byxc, scale, ori, info, imgf, 32)), 5)
+    t_one = timeit(lambda: model.forward_clip(byxc, scale, ori, info, img8), 5)
+    rec = {"workload": f"keypoints -> descriptors: clip_patch (scale / orientation / bilinear, psize 32) + HardNet forward, {n} keypoints "
+                       f"on {B} images of {H}x{W} (scales 6-40 px, random orientation), images resident on the device",
+           "metric": "keypoint_descriptors_per_sec", "unit": "keypoints/s",
+           "value": n / t_two * 1e3,
+           "ms_clip_patch_then_forward": t_two, "ms_clip_patch_alone": t_clip, "ms_forward_of_ready_patches": t_fwd,
+           "forward_clip": {"value": n / t_one * 1e3, "ms": t_one, "input": "uint8 images, no patch tensor (crop inside the front kernel)",
+                            "bit_identical_to_two_calls": bool(torch.equal(one, two)),
+                            "device_memory_saved_bytes": n * 4096},
+           "roofline": {"kernel": "clip_patch32_kernel", "bound": "hbm", "unit": "GB/s", "achieved": n * 4096 / t_clip / 1e6,
+                        "peak": load_peaks()["hbm_gbs"], "traffic": None,
+                        "note": "algorithmic bytes = the 4 KiB patch written (the gathered image pixels stay in L2)"}}
+    if rec["roofline"]["peak"]:
+        rec["roofline"]["frac"] = rec["roofline"]["achieved"] / rec["roofline"]["peak"]
+    if with_cpu:
+        from oracle import clip_oracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        m = 4096
+        fwd, kind, desc = reference_forward_fn()
+        t0 = time.perf_counter()
+        pc = clip_oracle.clip_patch(byxc_h[:m], scale_h[:m], ori_h[:m], info_h[:1], images[:1], 32)
+        with torch.no_grad():
+            fwd(pc)
+        dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"value": m / dt, "unit": "keypoints/s", "cores": torch.get_num_threads(), "kind": "port+" + kind,
+                               "sample": f"{m} keypoints of image 0 ({dt:.1f} s): oracle/clip_oracle.py (restatement of image_utils.py:11-158) + {desc}"}
     return rec
 
 
