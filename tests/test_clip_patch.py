@@ -112,3 +112,19 @@ def test_forward_clip_uint8_images_and_bad_image_index():
     from hardnetnas_b200._lib import HardnetB200Error
     with pytest.raises(HardnetB200Error):
         model.train().forward_clip(byxc.cuda(), scale.cuda(), ori.cuda(), im_info.cuda(), img8.cuda())
+
+
+@pytest.mark.gpu
+def test_forward_clip_on_the_rf_net_descriptor():
+    """RFNetSO.inference (FDLNet-master/latency/rfnet/model/rf_net_so.py:160-180) calls clip_patch and then its descriptor
+    `self.des` = HardNetNeiMask (input_norm eps 1e-8, plain x / ||x|| head): the fused call carries both epsilons."""
+    from hardnetnas_b200.image_utils import clip_patch
+    from hardnetnas_b200.rf_des import HardNetNeiMask
+    byxc, scale, ori, im_info, images = clip_oracle.make_clip_inputs(seed=3, B=2, H=96, W=128, k=40)
+    torch.manual_seed(1)
+    des = HardNetNeiMask(1.0, 8).cuda().eval()
+    args = (byxc.cuda(), scale.cuda(), ori.cuda(), im_info.cuda(), images.cuda())
+    two = des(clip_patch(*args, 32))
+    one = des.forward_clip(*args)
+    assert torch.equal(one, two) and torch.isfinite(one).all()
+    assert (one.norm(dim=1) - 1).abs().max().item() <= 1e-5
