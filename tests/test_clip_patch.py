@@ -128,3 +128,31 @@ def test_forward_clip_on_the_rf_net_descriptor():
     one = des.forward_clip(*args)
     assert torch.equal(one, two) and torch.isfinite(one).all()
     assert (one.norm(dim=1) - 1).abs().max().item() <= 1e-5
+
+
+def test_float_domain_clamp_gives_the_reference_taps():
+    """csrc/clip.cuh clamps floor(x) in the float domain (fminf / fmaxf) where the reference clamps int64 indices
+    (image_utils.py:98-112): same taps x0, x1 for every finite coordinate, incl. far outside the image and at integers."""
+    rng = np.random.default_rng(0)
+    for W in (1, 2, 17, 640, 4096):
+        x = np.concatenate([rng.uniform(-3 * W - 5, 3 * W + 5, 20000), np.arange(-4, W + 4, dtype=np.float64),
+                            np.array([-1e9, -2.0 ** 31, 2.0 ** 31, 1e9, 3e18, -3e18, -0.0, np.nextafter(0, -1), W - 1 - 1e-6])]).astype(np.float32)
+        fx = np.floor(x)
+        ref0 = np.clip(fx.astype(np.int64), 0, W - 1)
+        ref1 = np.clip(fx.astype(np.int64) + 1, 0, W - 1)
+        got0 = np.minimum(np.maximum(fx, np.float32(0)), np.float32(W - 1))
+        got1 = np.minimum(np.maximum(fx + np.float32(1), np.float32(0)), np.float32(W - 1))
+        assert np.array_equal(got0.astype(np.int64), ref0) and np.array_equal(got1.astype(np.int64), ref1)
+        # the weights use the clamped taps as floats: identical values
+        assert np.array_equal(got0, ref0.astype(np.float32)) and np.array_equal(got1, ref1.astype(np.float32))
+
+
+def test_forward_clip_rejects_cpu_tensors_and_train_mode():
+    from hardnetnas_b200._lib import HardnetB200Error
+    from hardnetnas_b200.hardnet import HardNet
+    byxc, scale, ori, im_info, images = clip_oracle.make_clip_inputs()
+    model = HardNet().eval()
+    with pytest.raises(HardnetB200Error):
+        model.forward_clip(byxc, scale, ori, im_info, images)          # no CPU fallback
+    with pytest.raises(HardnetB200Error):
+        model.train().forward_clip(byxc, scale, ori, im_info, images)  # eval-mode path only
