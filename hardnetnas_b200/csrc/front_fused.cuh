@@ -447,8 +447,8 @@ __device__ __forceinline__ void front_fused_body(const TIn* __restrict__ in, uin
     const int q = warp;
     int it = 0;
     // CLIP: crop rows 8 q + 4 h .. + 3 of local patch jg into ring slot jg % depth, 16 gathers in flight per thread. A warp-wide
-    // load covers a compact 4 x 8 pixel block of the patch, not a row: under rotation a 32-pixel row crosses ~32 image rows = 32
-    // cache lines = 32 L1 wavefronts per instruction, a block ~10 (the kernel's shared-memory traffic shares that pipe).
+    // load covers a compact 4 x 8 pixel block of the patch, not a row (under rotation a 32-pixel row crosses ~32 image rows; ncu:
+    // ~14 sectors per request with blocks). The gathers share the l1tex pipe with the MMAs' operand reads: DESIGN.md section 4.
     // The keypoint of the next patch is fetched as soon as a patch is finished, so its loads are off the next crop's critical path.
     [[maybe_unused]] int jg = 0;
     [[maybe_unused]] ClipKp kp = {};
